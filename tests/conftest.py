@@ -1,0 +1,32 @@
+import os
+import sys
+import tarfile
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def root():
+    return ROOT
+
+
+@pytest.fixture(scope="session")
+def db_dirs(tmp_path_factory):
+    """Unpack the clustered ARG databases shipped under data/db (copied from the reference's
+    db/clustered-ARG-databases/1.1/) and return {name: msa_dir}."""
+    base = tmp_path_factory.mktemp("db")
+    out = {}
+    for name in ("arg-annot.90", "card.90"):
+        tar = os.path.join(ROOT, "data", "db", name + ".tar")
+        with tarfile.open(tar) as t:
+            t.extractall(base)
+        out[name] = str(base / name)
+    return out
