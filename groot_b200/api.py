@@ -1,0 +1,316 @@
+"""ctypes binding of libgrootgpu.so (include/grootgpu.h) — the host-side mirror used by the tests, the
+bench and the Python driver. There is no fallback: if the CUDA library is missing or no device is
+usable every call raises.
+
+Names follow the reference's pipeline (src/pipeline): an `Index` is what `groot index` writes and
+`groot align` loads (Info + ContainmentIndex); `Index.map_reads` is theBoss.mapReads for one batch of
+FASTQ reads; `Index.project` is the graph weighting the graph minions do.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgrootgpu.so")
+
+ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_IO", -4: "ERR_FORMAT", -5: "ERR_SHORT_READ",
+             -6: "ERR_BAD_BASE", -7: "ERR_CAPACITY", -8: "ERR_EMPTY"}
+
+
+class GrootGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("%s: %s" % (ERR_NAMES.get(code, code), msg))
+        self.code = code
+
+
+class IndexParams(C.Structure):
+    _fields_ = [("kmer_size", C.c_uint32), ("sketch_size", C.c_uint32), ("window_size", C.c_uint32),
+                ("num_part", C.c_uint32), ("max_k", C.c_uint32)]
+
+
+class IndexInfo(C.Structure):
+    _fields_ = [("params", IndexParams), ("n_graphs", C.c_uint32), ("n_masked_graphs", C.c_uint32), ("n_paths", C.c_uint32),
+                ("n_nodes", C.c_uint32), ("n_path_bases", C.c_uint64), ("n_raw_windows", C.c_uint64), ("n_windows", C.c_uint32),
+                ("max_merge_span", C.c_uint32), ("max_paths_per_graph", C.c_uint32)]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [("containment_threshold", C.c_double), ("no_align", C.c_int32), ("keep_sketches", C.c_int32),
+                ("results_on_device", C.c_int32)]
+
+
+class Pair(C.Structure):
+    _fields_ = [("read", C.c_uint32), ("graph", C.c_uint32), ("hit_begin", C.c_uint32), ("hit_count", C.c_uint32),
+                ("n_incremented", C.c_uint32), ("rec_begin", C.c_uint32), ("rec_count", C.c_uint32),
+                ("reverse", C.c_uint8), ("clip_start", C.c_uint8), ("clip_end", C.c_uint8), ("stage", C.c_uint8)]
+
+
+PAIR_DTYPE = np.dtype([("read", "<u4"), ("graph", "<u4"), ("hit_begin", "<u4"), ("hit_count", "<u4"), ("n_incremented", "<u4"),
+                       ("rec_begin", "<u4"), ("rec_count", "<u4"), ("reverse", "u1"), ("clip_start", "u1"), ("clip_end", "u1"),
+                       ("stage", "u1")])
+assert PAIR_DTYPE.itemsize == C.sizeof(Pair) == 32
+
+
+class BatchResultC(C.Structure):
+    _fields_ = [("n_reads", C.c_uint32), ("n_hits", C.c_uint64), ("n_pairs", C.c_uint64), ("n_records", C.c_uint64),
+                ("hit_off", C.POINTER(C.c_uint32)), ("hits", C.POINTER(C.c_uint32)), ("pairs", C.POINTER(Pair)),
+                ("rec_path", C.POINTER(C.c_uint32)), ("rec_pos", C.POINTER(C.c_int32)), ("sketches", C.POINTER(C.c_uint64)),
+                ("received", C.c_uint64), ("mapped", C.c_uint64), ("multimapped", C.c_uint64), ("alignments", C.c_uint64),
+                ("ms", C.c_float * 4), ("kernel_launches", C.c_uint32),
+                ("d_hit_off", C.c_void_p), ("d_hits", C.c_void_p), ("d_pairs", C.c_void_p), ("d_rec_path", C.c_void_p),
+                ("d_rec_pos", C.c_void_p)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libgrootgpu.so; raises if it has not been built (python -m groot_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GrootGpuError(-2, "libgrootgpu.so is not built (run `python -m groot_b200.build`); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        L.grootgpu_last_error.restype = C.c_char_p
+        L.grootgpu_version.restype = C.c_char_p
+        L.grootgpu_device_count.argtypes = [C.POINTER(C.c_int)]
+        L.grootgpu_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+        L.grootgpu_host_free.argtypes = [vp]
+        L.grootgpu_index_build.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(IndexParams), C.c_int, C.POINTER(vp)]
+        L.grootgpu_index_build_dir.argtypes = [C.c_char_p, C.POINTER(IndexParams), C.c_int, C.POINTER(vp)]
+        L.grootgpu_graphs_dump.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(IndexParams), C.c_char_p, C.POINTER(C.c_uint64)]
+        L.grootgpu_index_save.argtypes = [vp, C.c_char_p]
+        L.grootgpu_index_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.grootgpu_index_destroy.argtypes = [vp]
+        L.grootgpu_index_destroy.restype = None
+        L.grootgpu_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
+        L.grootgpu_index_dump_file.argtypes = [vp, C.c_char_p]
+        L.grootgpu_index_dump_hash.argtypes = [vp, C.POINTER(C.c_uint64)]
+        L.grootgpu_index_ref.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
+        L.grootgpu_index_query_params.argtypes = [vp, C.c_uint32, C.c_double, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.grootgpu_align_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(AlignParams), C.POINTER(BatchResultC)]
+        L.grootgpu_align_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(AlignParams), vp, C.POINTER(BatchResultC)]
+        L.grootgpu_project_batch.argtypes = [vp, C.POINTER(BatchResultC), vp]
+        L.grootgpu_weights.argtypes = [vp, vp, vp]
+        L.grootgpu_reset_weights.argtypes = [vp]
+        L.grootgpu_sketch_batch.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+        L.grootgpu_prune.argtypes = [vp, C.c_double, vp]
+        L.grootgpu_graph_save_gfa.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int64, C.POINTER(C.c_int)]
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = [
+    "grootgpu_index_build", "grootgpu_index_build_dir", "grootgpu_index_save", "grootgpu_index_load", "grootgpu_index_destroy",
+    "grootgpu_index_get_info", "grootgpu_graphs_dump", "grootgpu_index_dump_file", "grootgpu_index_dump_hash", "grootgpu_index_ref",
+    "grootgpu_index_query_params", "grootgpu_align_batch", "grootgpu_align_batch_device", "grootgpu_project_batch",
+    "grootgpu_weights", "grootgpu_reset_weights", "grootgpu_sketch_batch", "grootgpu_prune", "grootgpu_graph_save_gfa",
+    "grootgpu_host_alloc", "grootgpu_host_free", "grootgpu_device_count", "grootgpu_last_error", "grootgpu_version",
+]
+
+
+def _check(rc):
+    if rc != 0:
+        raise GrootGpuError(rc, lib().grootgpu_last_error().decode(errors="replace"))
+
+
+def device_count():
+    n = C.c_int()
+    rc = lib().grootgpu_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def _np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).view(dtype).copy()
+
+
+class BatchResult:
+    """Host copy of one batch's result (see grootgpu_batch_result). `raw` stays valid until the next
+    map_reads on the same index and is what `Index.project` consumes."""
+
+    def __init__(self, raw: BatchResultC, S: int, copied: bool):
+        self.raw = raw
+        self.n_reads = raw.n_reads
+        self.n_hits, self.n_pairs, self.n_records = int(raw.n_hits), int(raw.n_pairs), int(raw.n_records)
+        self.counts = dict(received=int(raw.received), mapped=int(raw.mapped), multimapped=int(raw.multimapped),
+                           alignments=int(raw.alignments))
+        self.ms = dict(total=raw.ms[0], seed=raw.ms[1], align=raw.ms[2], other=raw.ms[3])
+        self.kernel_launches = raw.kernel_launches
+        if copied:
+            self.hit_off = _np(raw.hit_off, raw.n_reads + 1, np.uint32)
+            self.hits = _np(raw.hits, raw.n_hits, np.uint32)
+            self.pairs = (np.ctypeslib.as_array(C.cast(raw.pairs, C.POINTER(C.c_uint8)), shape=(self.n_pairs * 32,)).view(PAIR_DTYPE).copy()
+                          if self.n_pairs else np.zeros(0, dtype=PAIR_DTYPE))
+            self.rec_path = _np(raw.rec_path, raw.n_records, np.uint32)
+            self.rec_pos = _np(raw.rec_pos, raw.n_records, np.int32)
+            self.sketches = (_np(raw.sketches, raw.n_reads * S, np.uint64).reshape(raw.n_reads, S) if raw.sketches else None)
+
+    def records_table(self):
+        """(read, graph, path, pos, flags, startClip, endClip, seqLength-less) rows in (read, graph, emission) order,
+        the same layout the oracle reports (flags: 0x100 on all but the first record of a pair, 0x10 when reverse)."""
+        out = np.zeros((self.n_records, 7), dtype=np.int64)
+        o = 0
+        for p in self.pairs:
+            n = int(p["rec_count"])
+            if n == 0:
+                continue
+            b = int(p["rec_begin"])
+            flags = np.full(n, 0x10 if p["reverse"] else 0, dtype=np.int64)
+            if n > 1:
+                flags[1:] |= 0x100
+            out[o:o + n, 0] = p["read"]
+            out[o:o + n, 1] = p["graph"]
+            out[o:o + n, 2] = self.rec_path[b:b + n]
+            out[o:o + n, 3] = self.rec_pos[b:b + n]
+            out[o:o + n, 4] = flags
+            out[o:o + n, 5] = p["clip_start"]
+            out[o:o + n, 6] = p["clip_end"]
+            o += n
+        return out
+
+
+class Index:
+    """The graph store + containment index on one GPU (grootgpu_index)."""
+
+    def __init__(self, handle, device):
+        self.h = C.c_void_p(handle)
+        self.device = device
+        self._info = None
+
+    # -- bring-up ---------------------------------------------------------------------------------
+    @classmethod
+    def build(cls, msa_dir=None, msa_files=None, k=31, S=21, w=100, num_part=8, max_k=4, device=0):
+        """`groot index -m <msa_dir> -k -s -w -x -y` (cmd/index.go:45-51; src/pipeline/index.go:37-211)."""
+        p = IndexParams(k, S, w, num_part, max_k)
+        h = C.c_void_p()
+        if msa_files is not None:
+            arr = (C.c_char_p * len(msa_files))(*[f.encode() for f in msa_files])
+            _check(lib().grootgpu_index_build(arr, len(msa_files), C.byref(p), device, C.byref(h)))
+        else:
+            _check(lib().grootgpu_index_build_dir(msa_dir.encode(), C.byref(p), device, C.byref(h)))
+        return cls(h.value, device)
+
+    @classmethod
+    def load(cls, path, device=0):
+        h = C.c_void_p()
+        _check(lib().grootgpu_index_load(path.encode(), device, C.byref(h)))
+        return cls(h.value, device)
+
+    def save(self, path):
+        _check(lib().grootgpu_index_save(self.h, path.encode()))
+
+    def close(self):
+        if self.h:
+            lib().grootgpu_index_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self):
+        if self._info is None:
+            i = IndexInfo()
+            _check(lib().grootgpu_index_get_info(self.h, C.byref(i)))
+            self._info = dict(k=i.params.kmer_size, S=i.params.sketch_size, w=i.params.window_size, num_part=i.params.num_part,
+                              max_k=i.params.max_k, graphs=i.n_graphs, masked=i.n_masked_graphs, paths=i.n_paths, nodes=i.n_nodes,
+                              path_bases=i.n_path_bases, raw_windows=i.n_raw_windows, windows=i.n_windows,
+                              max_merge_span=i.max_merge_span, max_paths_per_graph=i.max_paths_per_graph)
+        return self._info
+
+    def dump_hash(self):
+        h = C.c_uint64()
+        _check(lib().grootgpu_index_dump_hash(self.h, C.byref(h)))
+        return h.value
+
+    def dump_file(self, path):
+        _check(lib().grootgpu_index_dump_file(self.h, path.encode()))
+
+    def ref(self, graph, path):
+        name, ln = C.c_char_p(), C.c_int32()
+        _check(lib().grootgpu_index_ref(self.h, graph, path, C.byref(name), C.byref(ln)))
+        return name.value.decode(), ln.value
+
+    def query_params(self, query_kmers, threshold):
+        K, L, e = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        _check(lib().grootgpu_index_query_params(self.h, query_kmers, threshold, C.byref(K), C.byref(L), C.byref(e)))
+        return K.value, L.value, e.value
+
+    # -- the hot path -----------------------------------------------------------------------------
+    def map_reads(self, seqs, off, threshold=0.99, no_align=False, keep_sketches=False, project=False):
+        """theBoss.mapReads for one batch (src/pipeline/boss.go:108-242): host buffers in, host result out."""
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        prm = AlignParams(threshold, int(no_align), int(keep_sketches), 0)
+        raw = BatchResultC()
+        _check(lib().grootgpu_align_batch(self.h, seqs.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(prm), C.byref(raw)))
+        res = BatchResult(raw, self.info()["S"], True)
+        if project:
+            self.project(res, off)
+        return res
+
+    def map_reads_raw(self, seq_ptr, off_ptr, n_reads, threshold=0.99, no_align=False):
+        """Same call on raw host pointers (pinned buffers), returning only the C struct: what bench.py times."""
+        prm = AlignParams(threshold, int(no_align), 0, 0)
+        raw = BatchResultC()
+        _check(lib().grootgpu_align_batch(self.h, seq_ptr, off_ptr, n_reads, C.byref(prm), C.byref(raw)))
+        return raw
+
+    def map_reads_device(self, d_seq_ptr, d_off_ptr, n_reads, min_len, max_len, threshold=0.99, no_align=False, stream=None, copy_back=False):
+        """Reads already resident in HBM (device pointers as ints)."""
+        prm = AlignParams(threshold, int(no_align), 0, 0 if copy_back else 1)
+        raw = BatchResultC()
+        _check(lib().grootgpu_align_batch_device(self.h, d_seq_ptr, d_off_ptr, n_reads, min_len, max_len, C.byref(prm), stream,
+                                                 C.byref(raw)))
+        return BatchResult(raw, self.info()["S"], True) if copy_back else raw
+
+    def project(self, res, off):
+        """Ordered replay of GrootGraph.IncrementSubPath (src/graph/graph.go:401-451)."""
+        off = np.ascontiguousarray(off, dtype=np.uint64)
+        raw = res.raw if isinstance(res, BatchResult) else res
+        _check(lib().grootgpu_project_batch(self.h, C.byref(raw), off.ctypes.data))
+
+    def weights(self):
+        i = self.info()
+        kf = np.zeros(i["nodes"], dtype=np.float64)
+        kt = np.zeros(i["graphs"], dtype=np.uint64)
+        _check(lib().grootgpu_weights(self.h, kf.ctypes.data, kt.ctypes.data))
+        return kf, kt
+
+    def reset_weights(self):
+        _check(lib().grootgpu_reset_weights(self.h))
+
+    def prune(self, min_kmer_coverage):
+        kept = np.zeros(self.info()["graphs"], dtype=np.uint8)
+        _check(lib().grootgpu_prune(self.h, min_kmer_coverage, kept.ctypes.data))
+        return kept
+
+    def save_gfa(self, graph, path, total_kmers):
+        w = C.c_int()
+        _check(lib().grootgpu_graph_save_gfa(self.h, graph, path.encode(), total_kmers, C.byref(w)))
+        return bool(w.value)
+
+
+def graphs_dump(msa_files, dump_path=None, k=31, S=21, w=100, num_part=8, max_k=4):
+    """Host-only MSA -> graph step (no GPU needed); returns the FNV-1a-64 hash of the dump."""
+    p = IndexParams(k, S, w, num_part, max_k)
+    arr = (C.c_char_p * len(msa_files))(*[f.encode() for f in msa_files])
+    h = C.c_uint64()
+    _check(lib().grootgpu_graphs_dump(arr, len(msa_files), C.byref(p), dump_path.encode() if dump_path else None, C.byref(h)))
+    return h.value
+
+
+def sketch_batch(seqs, off, k, S, device=0):
+    """Sequence.RunMinHash(k, S, false, nil) for a batch (src/seqio/seqio.go:40-68)."""
+    seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
+    off = np.ascontiguousarray(off, dtype=np.uint64)
+    n = len(off) - 1
+    out = np.zeros((n, S), dtype=np.uint64)
+    _check(lib().grootgpu_sketch_batch(device, seqs.ctypes.data, off.ctypes.data, n, k, S, out.ctypes.data))
+    return out

@@ -1,0 +1,39 @@
+"""Builds libgrootgpu.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m groot_b200.build [--force]
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libgrootgpu.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+
+CU = ["capi.cu"]
+CPP = ["host/graph_build.cpp", "host/index_io.cpp", "host/lshe_params.cpp", "host/replay.cpp"]
+
+
+def sources():
+    out = []
+    for root, _, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".cpp", ".h"))]
+    out.append(os.path.join(os.path.dirname(HERE), "include", "grootgpu.h"))
+    return out
+
+
+def build(force=False, verbose=False):
+    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(s) for s in sources()):
+        return OUT
+    cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
+           "-Xcompiler", "-fPIC,-O2,-Wall,-pthread", "--expt-extended-lambda", "-o", OUT]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(CSRC, f) for f in CU + CPP]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

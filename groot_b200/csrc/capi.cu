@@ -1,0 +1,785 @@
+// libgrootgpu.so — C ABI implementation (include/grootgpu.h): index bring-up on the device, the
+// batch pipeline  seed (sketch+probe+verify) -> scan -> fill -> segment -> align search -> scan -> emit,
+// result transfer, and the host-side ordered weight replay.
+//
+// There is no CPU fallback anywhere in this file: every compute entry point needs a CUDA device and
+// fails with GROOTGPU_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <dirent.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/grootgpu.h"
+#include "align_kernels.cuh"
+#include "device_types.cuh"
+#include "flat_index.h"
+#include "seed_kernels.cuh"
+
+using namespace groot;
+
+static_assert(sizeof(PairOut) == sizeof(grootgpu_pair), "PairOut and grootgpu_pair must match");
+static_assert(offsetof(PairOut, rec_count) == offsetof(grootgpu_pair, rec_count), "PairOut layout");
+static_assert(offsetof(PairOut, stage) == offsetof(grootgpu_pair, stage), "PairOut layout");
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+// grow-only device / pinned-host buffers
+struct DBuf {
+    void* p = nullptr; size_t cap = 0;
+    void need(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+    ~DBuf() { if (p) cudaFree(p); }
+};
+struct HBuf {
+    void* p = nullptr; size_t cap = 0;
+    void need(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        CK(cudaHostAlloc(&p, want, cudaHostAllocDefault));
+        cap = want;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+    ~HBuf() { if (p) cudaFreeHost(p); }
+};
+
+template <class T>
+T* upload(const std::vector<T>& v, std::vector<void*>& owned) {
+    void* d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(16, v.size() * sizeof(T))));
+    owned.push_back(d);
+    if (!v.empty()) CK(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return static_cast<T*>(d);
+}
+
+MultTable make_mult(uint32_t k) {
+    MultTable m;
+    for (uint64_t i = 0; i < 32; i++) m.c[i] = i ^ (static_cast<uint64_t>(k) * GROOT_MULTI_SEED);
+    return m;
+}
+
+int pick_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw CudaError("no CUDA device available (libgrootgpu has no CPU fallback)");
+    if (device < 0 || device >= n) throw CudaError("device ordinal out of range");
+    CK(cudaSetDevice(device));
+    return device;
+}
+
+// ---- sketch-only launcher (index windows, grootgpu_sketch_batch) --------------------------------
+template <int S>
+void launch_sketch(const uint8_t* d_seq, const uint64_t* d_off, const uint32_t* d_lens, uint32_t fixed_len, uint32_t n, uint32_t k,
+                   uint64_t* d_out, int* d_err, cudaStream_t st) {
+    int blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, 148ull * 16));
+    sketch_kernel<S><<<std::max(blocks, 1), kSeedThreads, 0, st>>>(d_seq, d_off, d_lens, fixed_len, n, k, make_mult(k), d_out, d_err);
+}
+#define GROOT_S_LIST(X) X(8) X(10) X(16) X(20) X(21) X(24) X(30) X(32)
+bool sketch_dispatch(uint32_t S, const uint8_t* d_seq, const uint64_t* d_off, const uint32_t* d_lens, uint32_t fixed_len, uint32_t n,
+                     uint32_t k, uint64_t* d_out, int* d_err, cudaStream_t st) {
+    switch (S) {
+#define X(s) case s: launch_sketch<s>(d_seq, d_off, d_lens, fixed_len, n, k, d_out, d_err, st); return true;
+        GROOT_S_LIST(X)
+#undef X
+        default: return false;
+    }
+}
+const char* kSupportedS = "8, 10, 16, 20, 21, 24, 30, 32";
+
+// sketches n sequences (host in, host out) on the current device
+void sketch_host(const uint8_t* seqs, size_t seqs_len, const uint64_t* off, const uint32_t* lens, uint32_t fixed_len, uint32_t n,
+                 uint32_t k, uint32_t S, uint64_t* out) {
+    DBuf d_seq, d_off, d_lens, d_out, d_err;
+    d_seq.need(seqs_len + 64); d_off.need(sizeof(uint64_t) * n); d_out.need(sizeof(uint64_t) * n * S); d_err.need(8);
+    CK(cudaMemcpy(d_seq.p, seqs, seqs_len, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_off.p, off, sizeof(uint64_t) * n, cudaMemcpyHostToDevice));
+    if (lens) { d_lens.need(sizeof(uint32_t) * n); CK(cudaMemcpy(d_lens.p, lens, sizeof(uint32_t) * n, cudaMemcpyHostToDevice)); }
+    CK(cudaMemset(d_err.p, 0, 8));
+    if (!sketch_dispatch(S, d_seq.as<uint8_t>(), d_off.as<uint64_t>(), lens ? d_lens.as<uint32_t>() : nullptr, fixed_len, n, k,
+                         d_out.as<uint64_t>(), d_err.as<int>(), 0))
+        throw std::runtime_error(std::string("unsupported sketch size (compiled: ") + kSupportedS + ")");
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    int err[2];
+    CK(cudaMemcpy(err, d_err.p, 8, cudaMemcpyDeviceToHost));
+    if (err[0] != 0) throw std::runtime_error("sequence " + std::to_string(err[1]) + " is shorter than k");
+    CK(cudaMemcpy(out, d_out.p, sizeof(uint64_t) * n * S, cudaMemcpyDeviceToHost));
+}
+void sketch_cb(void*, const uint8_t* seqs, size_t seqs_len, const uint64_t* off, uint32_t n, uint32_t w, uint32_t k, uint32_t S, uint64_t* out) {
+    sketch_host(seqs, seqs_len, off, nullptr, w, n, k, S, out);
+}
+
+std::string slurp(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    if (!f) throw std::runtime_error("cannot open " + path);
+    std::stringstream ss; ss << f.rdbuf();
+    return ss.str();
+}
+
+}  // namespace
+
+// =================================================================================================
+struct grootgpu_index {
+    FlatIndex h;
+    int device = 0;
+    DevIndex d{};
+    std::vector<void*> owned;          // device allocations freed on destroy
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    // LSH tables, built lazily per K (all bands)
+    std::vector<LshTable> h_tables;    // [(K-1)*n_bands + band]
+    LshTable* d_tables = nullptr;
+    bool tables_built[8] = {};
+    // per (q, threshold) parameter cache
+    std::map<std::pair<uint32_t, double>, LenParam> param_cache;
+    // workspaces
+    DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off,
+        rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error;
+    HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_scal;
+    std::vector<LenParam> h_len_params;
+    double lp_threshold = -1; uint32_t lp_min = 1, lp_max = 0;
+
+    ~grootgpu_index() {
+        for (void* p : owned) cudaFree(p);
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+void index_to_device(grootgpu_index* ix) {
+    pick_device(ix->device);
+    FlatIndex& h = ix->h;
+    if (h.p.max_k < 1 || h.p.max_k > 4) throw std::runtime_error("max_k must be in 1..4 (documented limit)");
+    if (h.p.S / h.p.max_k < 1) throw std::runtime_error("sketch size must be >= max_k");
+    DevIndex& d = ix->d;
+    d.nodes = upload(h.nodes, ix->owned);
+    std::vector<uint8_t> seq_padded = h.node_seq; seq_padded.resize(seq_padded.size() + 16, 0);
+    d.node_seq = upload(seq_padded, ix->owned);
+    d.edges = upload(h.edges, ix->owned);
+    d.node_path_id = upload(h.node_path_id, ix->owned);
+    d.node_path_pos = upload(h.node_path_pos, ix->owned);
+    d.node_mask = upload(h.node_mask, ix->owned);
+    d.wins = upload(h.wins, ix->owned);
+    d.cn_node = upload(h.cn_node, ix->owned);
+    d.sketches = upload(h.sketches, ix->owned);
+    d.graph_mask_words = upload(h.graph_mask_words, ix->owned);
+    d.k = h.p.k; d.S = h.p.S; d.max_k = h.p.max_k; d.n_bands = h.p.S / h.p.max_k; d.n_wins = static_cast<uint32_t>(h.wins.size());
+    ix->h_tables.assign(static_cast<size_t>(h.p.max_k) * d.n_bands, LshTable{nullptr, nullptr, 0, 0});
+    void* dt = nullptr;
+    CK(cudaMalloc(&dt, ix->h_tables.size() * sizeof(LshTable)));
+    ix->owned.push_back(dt);
+    ix->d_tables = static_cast<LshTable*>(dt);
+    CK(cudaMemcpy(dt, ix->h_tables.data(), ix->h_tables.size() * sizeof(LshTable), cudaMemcpyHostToDevice));
+    d.tables = ix->d_tables;
+    CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    for (auto& e : ix->ev) CK(cudaEventCreate(&e));
+    if (h.kmer_freq.size() != h.nodes.size()) h.kmer_freq.assign(h.nodes.size(), 0.0);
+    if (h.kmer_total.size() != h.n_graphs) h.kmer_total.assign(h.n_graphs, 0);
+    if (h.node_marked.size() != h.nodes.size()) h.node_marked.assign(h.nodes.size(), 0);
+}
+
+// Flattened CSR of the lshensemble index for prefix length K: for every band, group the windows by the
+// low 32 bits of their first K band hashes (LshForest with 32-bit hash values; the forest's binary-search
+// prefix probe returns exactly one such group) into an open-addressing table of 32-byte slots.
+void build_tables(grootgpu_index* ix, uint32_t K) {
+    if (ix->tables_built[K]) return;
+    FlatIndex& h = ix->h;
+    const uint32_t S = h.p.S, maxk = h.p.max_k, nb = ix->d.n_bands, W = static_cast<uint32_t>(h.wins.size());
+    for (uint32_t b = 0; b < nb; b++) {
+        std::vector<uint32_t> order(W);
+        for (uint32_t i = 0; i < W; i++) order[i] = i;
+        auto keyof = [&](uint32_t w, uint32_t key[4]) {
+            for (uint32_t j = 0; j < 4; j++) key[j] = j < K ? static_cast<uint32_t>(h.sketches[static_cast<size_t>(w) * S + b * maxk + j]) : 0u;
+        };
+        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            uint32_t kx[4], ky[4]; keyof(x, kx); keyof(y, ky);
+            for (int j = 0; j < 4; j++) if (kx[j] != ky[j]) return kx[j] < ky[j];
+            return x < y;  // window ids ascending inside a bucket
+        });
+        uint32_t uniq = 0;
+        for (uint32_t i = 0; i < W; i++) {
+            uint32_t a[4], c[4];
+            if (i == 0) { uniq++; continue; }
+            keyof(order[i], a); keyof(order[i - 1], c);
+            if (memcmp(a, c, 16) != 0) uniq++;
+        }
+        uint32_t cap = 16;
+        while (cap < 2 * uniq) cap <<= 1;
+        std::vector<LshSlot> slots(cap);
+        memset(slots.data(), 0, slots.size() * sizeof(LshSlot));
+        uint32_t i = 0;
+        while (i < W) {
+            uint32_t key[4]; keyof(order[i], key);
+            uint32_t j = i + 1;
+            while (j < W) { uint32_t k2[4]; keyof(order[j], k2); if (memcmp(key, k2, 16) != 0) break; j++; }
+            uint32_t hsh = band_key_hash(key) & (cap - 1);
+            while (slots[hsh].count != 0) hsh = (hsh + 1) & (cap - 1);
+            memcpy(slots[hsh].key, key, 16); slots[hsh].start = i; slots[hsh].count = j - i;
+            i = j;
+        }
+        LshTable t;
+        t.slots = upload(slots, ix->owned);
+        t.wins = upload(order, ix->owned);
+        t.mask = cap - 1; t.pad = 0;
+        ix->h_tables[(K - 1) * nb + b] = t;
+    }
+    CK(cudaMemcpy(ix->d_tables, ix->h_tables.data(), ix->h_tables.size() * sizeof(LshTable), cudaMemcpyHostToDevice));
+    ix->tables_built[K] = true;
+}
+
+LenParam param_for(grootgpu_index* ix, uint32_t q, double t) {
+    auto key = std::make_pair(q, t);
+    auto it = ix->param_cache.find(key);
+    if (it != ix->param_cache.end()) return it->second;
+    const FlatIndex& h = ix->h;
+    int K = 0, L = 0;
+    int x = static_cast<int>(h.p.w - h.p.k + 1);  // NumWindowKmers == every partition's Upper (lshe.go:108-146)
+    optimal_kl(static_cast<int>(h.p.max_k), static_cast<int>(h.p.S / h.p.max_k), x, static_cast<int>(q), t, &K, &L);
+    LenParam lp;
+    lp.K = static_cast<uint8_t>(K); lp.L = static_cast<uint8_t>(L);
+    lp.eq_min = static_cast<uint16_t>(eq_min_for(static_cast<int>(h.p.S), static_cast<int>(q), x, t));
+    ix->param_cache[key] = lp;
+    return lp;
+}
+
+// make sure len_params[len] is on the device for every len in [min_len, max_len] and the tables exist
+void prepare_params(grootgpu_index* ix, uint32_t min_len, uint32_t max_len, double t) {
+    const uint32_t k = ix->h.p.k;
+    if (ix->lp_threshold == t && min_len >= ix->lp_min && max_len <= ix->lp_max) return;
+    uint32_t lo = std::min(min_len, ix->lp_threshold == t ? ix->lp_min : min_len);
+    uint32_t hi = std::max(max_len, ix->lp_threshold == t ? ix->lp_max : max_len);
+    ix->h_len_params.assign(static_cast<size_t>(hi) + 1, LenParam{0, 0, 0xffff});
+    for (uint32_t len = std::max(lo, k); len <= hi; len++) {
+        LenParam lp = param_for(ix, len - k + 1, t);
+        ix->h_len_params[len] = lp;
+        if (lp.eq_min <= ix->h.p.S && lp.K >= 1) build_tables(ix, lp.K);
+    }
+    ix->len_params.need(ix->h_len_params.size() * sizeof(LenParam));
+    CK(cudaMemcpy(ix->len_params.p, ix->h_len_params.data(), ix->h_len_params.size() * sizeof(LenParam), cudaMemcpyHostToDevice));
+    ix->lp_threshold = t; ix->lp_min = lo; ix->lp_max = hi;
+}
+
+// ---- kernel dispatch on the compile-time sketch size ---------------------------------------------
+struct SeedLaunch {
+    template <int S>
+    static void seed(const DevIndex& d, const SeedArgs& a, uint32_t k, size_t smem, int blocks, cudaStream_t st) {
+        CK(cudaFuncSetAttribute(seed_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        seed_kernel<S, 4><<<blocks, kSeedThreads, smem, st>>>(d, a, make_mult(k));
+    }
+    template <int S>
+    static void fill(const DevIndex& d, const FillArgs& a, uint32_t k, int blocks, cudaStream_t st) {
+        fill_kernel<S, 4><<<blocks, kSeedThreads, 0, st>>>(d, a, make_mult(k));
+    }
+    template <int S>
+    static int seed_occupancy(size_t smem) {
+        int nb = 0;
+        cudaFuncSetAttribute(seed_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_kernel<S, 4>, kSeedThreads, smem);
+        return nb;
+    }
+};
+// MAXK is a template parameter of the probe (static register indexing); the slot layout always holds 4
+// key words, so max_k < 4 indexes run the MAXK=4 code with the unused words zero... only when the band
+// stride matches: bands are max_k apart, hence a separate instantiation per max_k would be needed.
+// Round 1 compiles max_k == 4 (the reference default, cmd/index.go:49); other values are rejected.
+bool seed_dispatch(uint32_t S, const DevIndex& d, const SeedArgs& a, uint32_t k, size_t smem, int blocks, cudaStream_t st) {
+    switch (S) {
+#define X(s) case s: SeedLaunch::seed<s>(d, a, k, smem, blocks, st); return true;
+        GROOT_S_LIST(X)
+#undef X
+        default: return false;
+    }
+}
+bool fill_dispatch(uint32_t S, const DevIndex& d, const FillArgs& a, uint32_t k, int blocks, cudaStream_t st) {
+    switch (S) {
+#define X(s) case s: SeedLaunch::fill<s>(d, a, k, blocks, st); return true;
+        GROOT_S_LIST(X)
+#undef X
+        default: return false;
+    }
+}
+int seed_occupancy_dispatch(uint32_t S, size_t smem) {
+    switch (S) {
+#define X(s) case s: return SeedLaunch::seed_occupancy<s>(smem);
+        GROOT_S_LIST(X)
+#undef X
+        default: return 0;
+    }
+}
+
+int g_num_sms(int device) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    return n;
+}
+
+// The batch pipeline on the device. d_seq / d_off already resident.
+void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, uint32_t n, uint32_t min_len, uint32_t max_len,
+               const grootgpu_align_params* prm, cudaStream_t st, grootgpu_batch_result* out) {
+    const bool copy_back = out && !prm->results_on_device;
+    const FlatIndex& h = ix->h;
+    const uint32_t S = h.p.S, k = h.p.k;
+    if (h.p.max_k != 4) throw std::runtime_error("this build supports max_k == 4 only (documented limit)");
+    if (max_len > 60000) throw std::runtime_error("read longer than 60000 bases (documented limit)");
+    prepare_params(ix, std::max(min_len, 1u), max_len, prm->containment_threshold);
+    const int sms = g_num_sms(ix->device);
+    uint32_t launches = 0;
+
+    ix->n_hits.need(4ull * n); ix->hit_off.need(4ull * (n + 1)); ix->stage.need(4ull * HSTAGE * n);
+    ix->scalars.need(64); ix->tile_counter.need(16); ix->error.need(16);
+    // scalars: [0]=n_segs (u32), counters as u64 at +8: [0]=mapped,[1]=multimapped,[2]=records
+    CK(cudaMemsetAsync(ix->scalars.p, 0, 64, st));
+    CK(cudaMemsetAsync(ix->tile_counter.p, 0, 16, st));
+    CK(cudaMemsetAsync(ix->error.p, 0, 16, st));
+    uint32_t* d_nsegs = ix->scalars.as<uint32_t>();
+    unsigned long long* d_counters = reinterpret_cast<unsigned long long*>(ix->scalars.as<uint8_t>() + 8);
+    uint64_t* d_sk = nullptr;
+    if (prm->keep_sketches) { ix->sketches.need(8ull * S * n); d_sk = ix->sketches.as<uint64_t>(); }
+
+    // ---- K1+K2: sketch + probe + verify ----
+    SeedArgs sa{};
+    sa.seq = d_seq; sa.off = d_off; sa.n_reads = n; sa.max_len = max_len; sa.len_params = ix->len_params.as<LenParam>();
+    sa.n_hits = ix->n_hits.as<uint32_t>(); sa.stage = ix->stage.as<uint32_t>(); sa.sketches_out = d_sk;
+    sa.tile_counter = ix->tile_counter.as<uint32_t>(); sa.error = ix->error.as<int>();
+    uint32_t tile_bytes = ((static_cast<uint32_t>(kSeedThreads) * max_len + 31u) & ~15u) + 16u;
+    if (tile_bytes > 96 * 1024) tile_bytes = 0;  // very long reads: no staging, threads read global memory
+    sa.tile_bytes = tile_bytes;
+    const size_t seed_smem = sizeof(SeedTabs) + 64 + 2ull * tile_bytes;
+    int occ = seed_occupancy_dispatch(S, seed_smem);
+    if (occ <= 0) throw std::runtime_error(std::string("unsupported sketch size (compiled: ") + kSupportedS + ")");
+    const uint32_t n_tiles = (n + kSeedThreads - 1) / kSeedThreads;
+    int seed_blocks = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(sms) * occ));
+    CK(cudaEventRecord(ix->ev[0], st));
+    seed_dispatch(S, ix->d, sa, k, seed_smem, std::max(seed_blocks, 1), st); launches++;
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ix->ev[1], st));
+
+    // ---- exclusive scan of per-read hit counts ----
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ix->n_hits.as<uint32_t>(), ix->hit_off.as<uint32_t>(), static_cast<int>(n), st);
+    ix->cub_tmp.need(tmp_bytes + 16);
+    cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, tmp_bytes, ix->n_hits.as<uint32_t>(), ix->hit_off.as<uint32_t>(), static_cast<int>(n), st);
+    uint32_t last_off = 0, last_cnt = 0;
+    CK(cudaMemcpyAsync(&last_off, ix->hit_off.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&last_cnt, ix->n_hits.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    {
+        int err[2];
+        CK(cudaMemcpy(err, ix->error.p, 8, cudaMemcpyDeviceToHost));
+        if (err[0] == GROOTGPU_ERR_SHORT_READ) throw std::invalid_argument("read " + std::to_string(err[1]) + " is shorter than k (the reference panics at boss.go:164-166)");
+        if (err[0] != 0) throw std::length_error("read " + std::to_string(err[1]) + " exceeds the declared maximum length");
+    }
+    const uint32_t H = last_off + last_cnt;
+    CK(cudaMemcpyAsync(ix->hit_off.as<uint32_t>() + n, &H, 4, cudaMemcpyHostToDevice, st));
+
+    uint32_t n_segs = 0;
+    uint64_t R = 0;
+    if (H > 0) {
+        ix->hits.need(4ull * H); ix->hit_read.need(4ull * H); ix->seg_flag.need(H); ix->seg_begin.need(4ull * H);
+        FillArgs fa{};
+        fa.seq = d_seq; fa.off = d_off; fa.n_reads = n; fa.len_params = ix->len_params.as<LenParam>(); fa.n_hits = ix->n_hits.as<uint32_t>();
+        fa.hit_off = ix->hit_off.as<uint32_t>(); fa.stage = ix->stage.as<uint32_t>(); fa.hits = ix->hits.as<uint32_t>();
+        fa.hit_read = ix->hit_read.as<uint32_t>(); fa.seg_flag = ix->seg_flag.as<uint8_t>(); fa.counters = d_counters;
+        int fill_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
+        fill_dispatch(S, ix->d, fa, k, fill_blocks, st); launches++;
+        CK(cudaGetLastError());
+        // ---- (read, graph) segment starts ----
+        thrust::counting_iterator<uint32_t> counting(0);
+        size_t sel_bytes = 0;
+        cub::DeviceSelect::Flagged(nullptr, sel_bytes, counting, ix->seg_flag.as<uint8_t>(), ix->seg_begin.as<uint32_t>(), d_nsegs, static_cast<int>(H), st);
+        ix->cub_tmp.need(sel_bytes + 16);
+        cub::DeviceSelect::Flagged(ix->cub_tmp.p, sel_bytes, counting, ix->seg_flag.as<uint8_t>(), ix->seg_begin.as<uint32_t>(), d_nsegs, static_cast<int>(H), st);
+        CK(cudaMemcpyAsync(&n_segs, d_nsegs, 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+
+        // ---- K3: align search ----
+        ix->pairs.need(sizeof(PairOut) * static_cast<size_t>(n_segs)); ix->seg_nrec.need(4ull * n_segs); ix->seg_locus.need(8ull * n_segs);
+        ix->rec_off.need(4ull * (n_segs + 1));
+        const uint32_t stride = (max_len + 16) & ~15u;
+        const size_t align_smem = static_cast<size_t>(kAlignWarps) * 2 * stride;
+        if (align_smem > 200 * 1024) throw std::runtime_error("read too long for the align kernel's shared-memory staging (documented limit)");
+        int align_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + kAlignWarps - 1) / kAlignWarps, static_cast<uint64_t>(sms) * 6));
+        align_blocks = std::max(align_blocks, 1);
+        const int emit_threads = 128;
+        int emit_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + emit_threads - 1) / emit_threads, static_cast<uint64_t>(sms) * 4));
+        emit_blocks = std::max(emit_blocks, 1);
+        const size_t lanes = std::max<size_t>(static_cast<size_t>(align_blocks) * kAlignWarps * 32, static_cast<size_t>(emit_blocks) * emit_threads);
+        ix->stack_ws.need(lanes * (max_len + 2) * sizeof(DfsFrame));
+        // H as a device scalar for the kernel: reuse hit_off[n]
+        AlignArgs aa{};
+        aa.seq = d_seq; aa.off = d_off; aa.hits = ix->hits.as<uint32_t>(); aa.hit_read = ix->hit_read.as<uint32_t>();
+        aa.seg_begin = ix->seg_begin.as<uint32_t>(); aa.n_segs_ptr = d_nsegs; aa.n_hits_ptr = ix->hit_off.as<uint32_t>() + n;
+        aa.pairs = ix->pairs.as<PairOut>(); aa.seg_nrec = ix->seg_nrec.as<uint32_t>(); aa.seg_locus = ix->seg_locus.as<uint2>();
+        aa.stack_ws = ix->stack_ws.as<DfsFrame>(); aa.max_len = max_len; aa.no_align = prm->no_align; aa.error = ix->error.as<int>();
+        CK(cudaFuncSetAttribute(align_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(align_smem)));
+        CK(cudaEventRecord(ix->ev[2], st));
+        align_search_kernel<<<align_blocks, kAlignWarps * 32, align_smem, st>>>(ix->d, aa); launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ix->ev[3], st));
+        // ---- scan record counts, emit ----
+        size_t scan2 = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, scan2, ix->seg_nrec.as<uint32_t>(), ix->rec_off.as<uint32_t>(), static_cast<int>(n_segs), st);
+        ix->cub_tmp.need(scan2 + 16);
+        cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, scan2, ix->seg_nrec.as<uint32_t>(), ix->rec_off.as<uint32_t>(), static_cast<int>(n_segs), st);
+        uint32_t lo = 0, lc = 0;
+        CK(cudaMemcpyAsync(&lo, ix->rec_off.as<uint32_t>() + (n_segs - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&lc, ix->seg_nrec.as<uint32_t>() + (n_segs - 1), 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        {
+            int err[2];
+            CK(cudaMemcpy(err, ix->error.p, 8, cudaMemcpyDeviceToHost));
+            if (err[0] == GROOTGPU_ERR_BAD_BASE) throw std::domain_error("read " + std::to_string(err[1]) + " holds a base > 'T' and had to be reverse complemented (the reference panics at seqio.go:122)");
+        }
+        R = static_cast<uint64_t>(lo) + lc;
+        ix->rec_path.need(4ull * std::max<uint64_t>(R, 1)); ix->rec_pos.need(4ull * std::max<uint64_t>(R, 1));
+        EmitArgs ea{};
+        ea.seq = d_seq; ea.off = d_off; ea.n_segs_ptr = d_nsegs; ea.pairs = ix->pairs.as<PairOut>(); ea.rec_off = ix->rec_off.as<uint32_t>();
+        ea.seg_locus = ix->seg_locus.as<uint2>(); ea.rec_path = ix->rec_path.as<uint32_t>(); ea.rec_pos = ix->rec_pos.as<int32_t>();
+        ea.stack_ws = ix->stack_ws.as<DfsFrame>(); ea.max_len = max_len; ea.counters = d_counters;
+        align_emit_kernel<<<emit_blocks, emit_threads, 0, st>>>(ix->d, ea); launches++;
+        CK(cudaGetLastError());
+    } else {
+        CK(cudaEventRecord(ix->ev[2], st));
+        CK(cudaEventRecord(ix->ev[3], st));
+    }
+    CK(cudaEventRecord(ix->ev[4], st));
+
+    // ---- results ----
+    unsigned long long counters[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(counters, d_counters, 24, cudaMemcpyDeviceToHost, st));
+    if (copy_back) {
+        ix->r_hit_off.need(4ull * (n + 1)); ix->r_hits.need(4ull * std::max<uint32_t>(H, 1)); ix->r_pairs.need(sizeof(PairOut) * std::max<size_t>(n_segs, 1));
+        ix->r_rec_path.need(4ull * std::max<uint64_t>(R, 1)); ix->r_rec_pos.need(4ull * std::max<uint64_t>(R, 1));
+        CK(cudaMemcpyAsync(ix->r_hit_off.p, ix->hit_off.p, 4ull * (n + 1), cudaMemcpyDeviceToHost, st));
+        if (H) CK(cudaMemcpyAsync(ix->r_hits.p, ix->hits.p, 4ull * H, cudaMemcpyDeviceToHost, st));
+        if (n_segs) CK(cudaMemcpyAsync(ix->r_pairs.p, ix->pairs.p, sizeof(PairOut) * static_cast<size_t>(n_segs), cudaMemcpyDeviceToHost, st));
+        if (R) {
+            CK(cudaMemcpyAsync(ix->r_rec_path.p, ix->rec_path.p, 4ull * R, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ix->r_rec_pos.p, ix->rec_pos.p, 4ull * R, cudaMemcpyDeviceToHost, st));
+        }
+        if (prm->keep_sketches) { ix->r_sketches.need(8ull * S * n); CK(cudaMemcpyAsync(ix->r_sketches.p, ix->sketches.p, 8ull * S * n, cudaMemcpyDeviceToHost, st)); }
+    }
+    CK(cudaEventRecord(ix->ev[5], st));
+    CK(cudaStreamSynchronize(st));
+    if (out) {
+        memset(out, 0, sizeof *out);
+        out->n_reads = n; out->n_hits = H; out->n_pairs = n_segs; out->n_records = R;
+        if (copy_back) {
+            out->hit_off = ix->r_hit_off.as<uint32_t>(); out->hits = ix->r_hits.as<uint32_t>();
+            out->pairs = reinterpret_cast<const grootgpu_pair*>(ix->r_pairs.p);
+            out->rec_path = ix->r_rec_path.as<uint32_t>(); out->rec_pos = ix->r_rec_pos.as<int32_t>();
+            out->sketches = prm->keep_sketches ? ix->r_sketches.as<uint64_t>() : nullptr;
+        }
+        out->received = n; out->mapped = counters[0]; out->multimapped = counters[1]; out->alignments = R;
+        float seed_ms = 0, align_ms = 0, dev_ms = 0, all_ms = 0;
+        cudaEventElapsedTime(&seed_ms, ix->ev[0], ix->ev[1]);
+        cudaEventElapsedTime(&align_ms, ix->ev[2], ix->ev[3]);
+        cudaEventElapsedTime(&dev_ms, ix->ev[0], ix->ev[4]);
+        cudaEventElapsedTime(&all_ms, ix->ev[0], ix->ev[5]);
+        out->ms[0] = all_ms; out->ms[1] = seed_ms; out->ms[2] = align_ms; out->ms[3] = dev_ms - seed_ms - align_ms;
+        out->kernel_launches = launches;
+        out->d_hit_off = ix->hit_off.as<uint32_t>(); out->d_hits = ix->hits.as<uint32_t>();
+        out->d_pairs = reinterpret_cast<const grootgpu_pair*>(ix->pairs.p);
+        out->d_rec_path = ix->rec_path.as<uint32_t>(); out->d_rec_pos = ix->rec_pos.as<int32_t>();
+    }
+}
+
+void fnv_sink(void* ctx, const char* d, size_t n) { uint64_t& hsh = *static_cast<uint64_t*>(ctx); for (size_t i = 0; i < n; i++) { hsh ^= static_cast<uint8_t>(d[i]); hsh *= 1099511628211ULL; } }
+void file_sink(void* ctx, const char* d, size_t n) { fwrite(d, 1, n, static_cast<FILE*>(ctx)); }
+
+template <class F>
+int guarded(F f) {
+    try { f(); return GROOTGPU_OK; }
+    catch (CudaError& e) { return fail(GROOTGPU_ERR_CUDA, e.what()); }
+    catch (std::invalid_argument& e) { return fail(GROOTGPU_ERR_SHORT_READ, e.what()); }
+    catch (std::domain_error& e) { return fail(GROOTGPU_ERR_BAD_BASE, e.what()); }
+    catch (std::length_error& e) { return fail(GROOTGPU_ERR_CAPACITY, e.what()); }
+    catch (std::bad_alloc&) { return fail(GROOTGPU_ERR_CAPACITY, "out of host memory"); }
+    catch (std::ios_base::failure& e) { return fail(GROOTGPU_ERR_IO, e.what()); }
+    catch (std::exception& e) { return fail(GROOTGPU_ERR_FORMAT, e.what()); }
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* grootgpu_last_error(void) { return g_err.c_str(); }
+const char* grootgpu_version(void) { return GROOTGPU_VERSION " (groot " GROOTGPU_REFERENCE_VERSION " align path, sm_100a)"; }
+int grootgpu_device_count(int* n) {
+    if (!n) return fail(GROOTGPU_ERR_ARG, "null argument");
+    *n = 0;
+    if (cudaGetDeviceCount(n) != cudaSuccess) { *n = 0; return fail(GROOTGPU_ERR_CUDA, "cudaGetDeviceCount failed (no driver / no device)"); }
+    return GROOTGPU_OK;
+}
+int grootgpu_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return fail(GROOTGPU_ERR_ARG, "null argument");
+    if (cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) != cudaSuccess) return fail(GROOTGPU_ERR_CUDA, "cudaHostAlloc failed");
+    return GROOTGPU_OK;
+}
+int grootgpu_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? GROOTGPU_OK : fail(GROOTGPU_ERR_CUDA, "cudaFreeHost failed"); }
+
+int grootgpu_index_build(const char* const* msa_paths, uint32_t n_msa, const grootgpu_index_params* params, int device, grootgpu_index** out) {
+    if (!msa_paths || !params || !out || n_msa == 0) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    *out = nullptr;
+    grootgpu_index* ix = new grootgpu_index();
+    int rc = guarded([&] {
+        pick_device(device);
+        ix->device = device;
+        ix->h.p.k = params->kmer_size; ix->h.p.S = params->sketch_size; ix->h.p.w = params->window_size;
+        ix->h.p.num_part = params->num_part; ix->h.p.max_k = params->max_k;
+        if (ix->h.p.k < 1 || ix->h.p.w < ix->h.p.k) throw std::runtime_error("need 1 <= k <= window size");
+        for (uint32_t i = 0; i < n_msa; i++) {
+            std::string text;
+            try { text = slurp(msa_paths[i]); } catch (std::exception& e) { throw std::ios_base::failure(e.what()); }
+            append_graph_from_msa(ix->h, text);
+        }
+        build_windows(ix->h, sketch_cb, nullptr);
+        index_to_device(ix);
+    });
+    if (rc != GROOTGPU_OK) { delete ix; return rc; }
+    *out = ix;
+    return GROOTGPU_OK;
+}
+
+int grootgpu_index_build_dir(const char* msa_dir, const grootgpu_index_params* params, int device, grootgpu_index** out) {
+    if (!msa_dir) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    std::vector<std::string> files;
+    DIR* d = opendir(msa_dir);
+    if (!d) return fail(GROOTGPU_ERR_IO, std::string("cannot open MSA directory ") + msa_dir);
+    while (dirent* e = readdir(d)) {
+        std::string nme = e->d_name;
+        if (nme.rfind("cluster", 0) == 0 && nme.size() > 4 && nme.compare(nme.size() - 4, 4, ".msa") == 0) files.push_back(std::string(msa_dir) + "/" + nme);
+    }
+    closedir(d);
+    if (files.empty()) return fail(GROOTGPU_ERR_EMPTY, "no MSA files in the supplied directory (must be named cluster-DD.msa)");
+    std::sort(files.begin(), files.end());
+    std::vector<const char*> p;
+    for (auto& f : files) p.push_back(f.c_str());
+    return grootgpu_index_build(p.data(), static_cast<uint32_t>(p.size()), params, device, out);
+}
+
+// Host-only: MSA -> graphs (no windows, no device). Dumps the graph section (G/P/N lines) of the canonical
+// text form; lets the CPU-only test-suite check the graph builder against the oracle without a GPU.
+int grootgpu_graphs_dump(const char* const* msa_paths, uint32_t n_msa, const grootgpu_index_params* params, const char* dump_path, uint64_t* hash) {
+    if (!msa_paths || !params || n_msa == 0) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    return guarded([&] {
+        FlatIndex h;
+        h.p.k = params->kmer_size; h.p.S = params->sketch_size; h.p.w = params->window_size; h.p.num_part = params->num_part; h.p.max_k = params->max_k;
+        for (uint32_t i = 0; i < n_msa; i++) {
+            std::string text;
+            try { text = slurp(msa_paths[i]); } catch (std::exception& e) { throw std::ios_base::failure(e.what()); }
+            append_graph_from_msa(h, text);
+        }
+        if (hash) { *hash = 1469598103934665603ULL; dump_index(h, fnv_sink, hash); }
+        if (dump_path) {
+            FILE* f = fopen(dump_path, "wb");
+            if (!f) throw std::ios_base::failure(std::string("cannot create ") + dump_path);
+            dump_index(h, file_sink, f);
+            fclose(f);
+        }
+    });
+}
+
+int grootgpu_index_save(const grootgpu_index* idx, const char* path) {
+    if (!idx || !path) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    try { save_index(idx->h, path); } catch (std::exception& e) { return fail(GROOTGPU_ERR_IO, e.what()); }
+    return GROOTGPU_OK;
+}
+int grootgpu_index_load(const char* path, int device, grootgpu_index** out) {
+    if (!path || !out) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    *out = nullptr;
+    grootgpu_index* ix = new grootgpu_index();
+    int rc = guarded([&] { pick_device(device); ix->device = device; load_index(ix->h, path); index_to_device(ix); });
+    if (rc != GROOTGPU_OK) { delete ix; return rc; }
+    *out = ix;
+    return GROOTGPU_OK;
+}
+void grootgpu_index_destroy(grootgpu_index* idx) {
+    if (!idx) return;
+    cudaSetDevice(idx->device);
+    delete idx;
+}
+
+int grootgpu_index_get_info(const grootgpu_index* idx, grootgpu_index_info* o) {
+    if (!idx || !o) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    const FlatIndex& h = idx->h;
+    memset(o, 0, sizeof *o);
+    o->params.kmer_size = h.p.k; o->params.sketch_size = h.p.S; o->params.window_size = h.p.w; o->params.num_part = h.p.num_part; o->params.max_k = h.p.max_k;
+    o->n_graphs = h.n_graphs; o->n_paths = static_cast<uint32_t>(h.path_name.size()); o->n_nodes = static_cast<uint32_t>(h.nodes.size());
+    o->n_windows = static_cast<uint32_t>(h.wins.size());
+    for (uint32_t g = 0; g < h.n_graphs; g++) {
+        o->n_masked_graphs += h.graph_masked[g]; o->n_raw_windows += h.graph_raw_windows[g];
+        o->max_paths_per_graph = std::max(o->max_paths_per_graph, h.n_paths_of(g));
+        for (uint32_t p = h.graph_path_base[g]; p < h.graph_path_base[g + 1]; p++) o->n_path_bases += static_cast<uint64_t>(h.path_len[p]);
+    }
+    for (auto& w : h.wins) o->max_merge_span = std::max(o->max_merge_span, w.merge_span);
+    return GROOTGPU_OK;
+}
+
+int grootgpu_index_dump_hash(const grootgpu_index* idx, uint64_t* hash) {
+    if (!idx || !hash) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    *hash = 1469598103934665603ULL;
+    dump_index(idx->h, fnv_sink, hash);
+    return GROOTGPU_OK;
+}
+int grootgpu_index_dump_file(const grootgpu_index* idx, const char* path) {
+    if (!idx || !path) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(GROOTGPU_ERR_IO, std::string("cannot create ") + path);
+    dump_index(idx->h, file_sink, f);
+    fclose(f);
+    return GROOTGPU_OK;
+}
+int grootgpu_index_ref(const grootgpu_index* idx, uint32_t g, uint32_t p, const char** name, int32_t* length) {
+    if (!idx || g >= idx->h.n_graphs || p >= idx->h.n_paths_of(g)) return fail(GROOTGPU_ERR_ARG, "graph / path id out of range");
+    uint32_t gp = idx->h.graph_path_base[g] + p;
+    if (name) *name = idx->h.path_name[gp].c_str();
+    if (length) *length = idx->h.path_len[gp];
+    return GROOTGPU_OK;
+}
+int grootgpu_index_query_params(grootgpu_index* idx, uint32_t q, double t, uint32_t* K, uint32_t* L, uint32_t* eq_min) {
+    if (!idx || q == 0) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    LenParam lp = param_for(idx, q, t);
+    if (K) *K = lp.K; if (L) *L = lp.L; if (eq_min) *eq_min = lp.eq_min;
+    return GROOTGPU_OK;
+}
+
+int grootgpu_align_batch_device(grootgpu_index* idx, const uint8_t* d_seq, const uint32_t* d_seq_off, uint32_t n_reads, uint32_t min_len,
+                                uint32_t max_len, const grootgpu_align_params* params, void* stream, grootgpu_batch_result* out) {
+    if (!idx || !d_seq || !d_seq_off || !params || n_reads == 0 || max_len < min_len) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    return guarded([&] {
+        pick_device(idx->device);
+        run_batch(idx, d_seq, d_seq_off, n_reads, min_len, max_len, params, stream ? static_cast<cudaStream_t>(stream) : idx->stream, out);
+    });
+}
+
+int grootgpu_align_batch(grootgpu_index* idx, const uint8_t* seq, const uint64_t* seq_off, uint32_t n_reads, const grootgpu_align_params* params,
+                         grootgpu_batch_result* out) {
+    if (!idx || !seq || !seq_off || !params || !out || n_reads == 0) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    const uint64_t total = seq_off[n_reads] - seq_off[0];
+    if (total >= (1ull << 32) - 64) return fail(GROOTGPU_ERR_CAPACITY, "a batch holds at most 4 GiB of bases: split it");
+    return guarded([&] {
+        pick_device(idx->device);
+        cudaStream_t st = idx->stream;
+        std::vector<uint32_t> off32(n_reads + 1);
+        uint32_t mn = 0xffffffffu, mx = 0;
+        for (uint32_t i = 0; i <= n_reads; i++) off32[i] = static_cast<uint32_t>(seq_off[i] - seq_off[0]);
+        for (uint32_t i = 0; i < n_reads; i++) { uint32_t l = off32[i + 1] - off32[i]; mn = std::min(mn, l); mx = std::max(mx, l); }
+        if (mn < idx->h.p.k) throw std::invalid_argument("a read is shorter than k (the reference panics at boss.go:164-166)");
+        idx->seq.need(total + 64); idx->off.need(4ull * (n_reads + 1));
+        CK(cudaMemcpyAsync(idx->seq.p, seq + seq_off[0], total, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(idx->seq.as<uint8_t>() + total, 0, 64, st));
+        CK(cudaMemcpyAsync(idx->off.p, off32.data(), 4ull * (n_reads + 1), cudaMemcpyHostToDevice, st));
+        run_batch(idx, idx->seq.as<uint8_t>(), idx->off.as<uint32_t>(), n_reads, mn, mx, params, st, out);
+    });
+}
+
+int grootgpu_project_batch(grootgpu_index* idx, const grootgpu_batch_result* res, const uint64_t* seq_off) {
+    if (!idx || !res || !seq_off) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    if (res->n_pairs && (!res->pairs || !res->hits)) return fail(GROOTGPU_ERR_ARG, "result holds no host arrays");
+    return guarded([&] {
+        FlatIndex& h = idx->h;
+        // pairs are ordered by (read, graph): bucketing by graph keeps read order inside every graph,
+        // which is the only order the f64 accumulation of a graph depends on (one minion per graph).
+        std::vector<uint32_t> cnt(h.n_graphs + 1, 0);
+        for (uint64_t i = 0; i < res->n_pairs; i++) cnt[res->pairs[i].graph + 1]++;
+        for (uint32_t g = 0; g < h.n_graphs; g++) cnt[g + 1] += cnt[g];
+        std::vector<uint32_t> order(res->n_pairs), cur(cnt.begin(), cnt.end() - 1);
+        for (uint64_t i = 0; i < res->n_pairs; i++) order[cur[res->pairs[i].graph]++] = static_cast<uint32_t>(i);
+        std::vector<uint32_t> active;
+        for (uint32_t g = 0; g < h.n_graphs; g++) if (cnt[g + 1] > cnt[g]) active.push_back(g);
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            while (true) {
+                size_t a = next.fetch_add(1);
+                if (a >= active.size()) break;
+                uint32_t g = active[a];
+                for (uint32_t o = cnt[g]; o < cnt[g + 1]; o++) {
+                    const grootgpu_pair& p = res->pairs[order[o]];
+                    double kmers = static_cast<double>(static_cast<int64_t>(seq_off[p.read + 1] - seq_off[p.read]) - static_cast<int64_t>(h.p.k)) + 1.0;  // graphminion.go:60
+                    for (uint32_t m = 0; m < p.n_incremented; m++) increment_sub_path(h, res->hits[p.hit_begin + m], kmers);
+                }
+            }
+        };
+        unsigned T = std::max(1u, std::min<unsigned>(std::thread::hardware_concurrency(), 16u));
+        if (res->n_pairs < 4096 || T == 1) work();
+        else { std::vector<std::thread> th; for (unsigned t = 0; t < T; t++) th.emplace_back(work); for (auto& x : th) x.join(); }
+    });
+}
+
+int grootgpu_weights(const grootgpu_index* idx, double* kmer_freq, uint64_t* kmer_total) {
+    if (!idx) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    if (kmer_freq) memcpy(kmer_freq, idx->h.kmer_freq.data(), idx->h.kmer_freq.size() * sizeof(double));
+    if (kmer_total) memcpy(kmer_total, idx->h.kmer_total.data(), idx->h.kmer_total.size() * sizeof(uint64_t));
+    return GROOTGPU_OK;
+}
+int grootgpu_reset_weights(grootgpu_index* idx) {
+    if (!idx) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    std::fill(idx->h.kmer_freq.begin(), idx->h.kmer_freq.end(), 0.0);
+    std::fill(idx->h.kmer_total.begin(), idx->h.kmer_total.end(), 0);
+    return GROOTGPU_OK;
+}
+
+int grootgpu_sketch_batch(int device, const uint8_t* seq, const uint64_t* seq_off, uint32_t n, uint32_t k, uint32_t S, uint64_t* out) {
+    if (!seq || !seq_off || !out || n == 0 || k == 0) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    return guarded([&] {
+        pick_device(device);
+        std::vector<uint32_t> lens(n);
+        for (uint32_t i = 0; i < n; i++) {
+            lens[i] = static_cast<uint32_t>(seq_off[i + 1] - seq_off[i]);
+            if (lens[i] < k) throw std::invalid_argument("sequence " + std::to_string(i) + " is shorter than k (khf.go:38-41)");
+        }
+        sketch_host(seq, seq_off[n], seq_off, lens.data(), 0, n, k, S, out);
+    });
+}
+
+int grootgpu_prune(grootgpu_index* idx, double min_cov, uint8_t* kept) {
+    if (!idx) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    return guarded([&] { for (uint32_t g = 0; g < idx->h.n_graphs; g++) { bool k = prune_graph(idx->h, g, min_cov); if (kept) kept[g] = k ? 1 : 0; } });
+}
+int grootgpu_graph_save_gfa(const grootgpu_index* idx, uint32_t g, const char* path, int64_t total_kmers, int* written) {
+    if (!idx || !path || g >= idx->h.n_graphs) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    std::string s = graph_to_gfa(idx->h, g, total_kmers);
+    if (written) *written = s.empty() ? 0 : 1;
+    if (s.empty()) return GROOTGPU_OK;
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(GROOTGPU_ERR_IO, std::string("cannot create ") + path);
+    fwrite(s.data(), 1, s.size(), f);
+    fclose(f);
+    return GROOTGPU_OK;
+}
+
+}  // extern "C"

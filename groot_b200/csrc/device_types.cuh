@@ -1,0 +1,71 @@
+// Device-side views shared by the kernels (sm_100a). Integer / byte work only — no tensor cores.
+#pragma once
+#include <cstdint>
+
+#include "flat_index.h"
+
+namespace groot {
+
+// ntHash v1 constants (will-rowe/nthash v0.2.0; see oracle/nthash.hpp for the provenance notes)
+#define GROOT_SEED_A 0x3c8bfbb395c60474ULL
+#define GROOT_SEED_C 0x3193c18562a02b4cULL
+#define GROOT_SEED_G 0x20323ed082572324ULL
+#define GROOT_SEED_T 0x295549f54be24456ULL
+#define GROOT_MULTI_SEED 0x90b45d39fb6da1faULL
+#define GROOT_MULTI_SHIFT 27
+
+// One 32-byte slot of an open-addressing table over LSH band keys: the "flattened CSR of the
+// lshensemble index". key = low 32 bits of K consecutive sketch slots (lshensemble's 32-bit
+// hashKeyFunc), [start, start+count) = bucket in LshTable::wins (window ids ascending).
+struct LshSlot {
+    uint32_t key[4];
+    uint32_t start;
+    uint32_t count;  // 0 == empty slot
+    uint32_t pad[2];
+};
+static_assert(sizeof(LshSlot) == 32, "LshSlot must be one 32-byte sector");
+
+struct LshTable {
+    const LshSlot* slots;
+    const uint32_t* wins;
+    uint32_t mask;  // capacity - 1 (power of two)
+    uint32_t pad;
+};
+
+// per query length: what the host optimiser chose (lshe_params.cpp)
+struct LenParam {
+    uint8_t K;        // hashes per band probed
+    uint8_t L;        // bands probed
+    uint16_t eq_min;  // equal sketch slots needed to pass the containment threshold; > S == never
+};
+
+__host__ __device__ inline uint32_t band_key_hash(const uint32_t key[4]) {
+    uint32_t h = key[0] * 0x9E3779B1u;
+    h = (h ^ (h >> 15)) + key[1] * 0x85EBCA77u;
+    h = (h ^ (h >> 13)) + key[2] * 0xC2B2AE3Du;
+    h = (h ^ (h >> 16)) + key[3] * 0x27D4EB2Fu;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; h *= 0x297A2D39u; h ^= h >> 15;
+    return h;
+}
+
+struct DevIndex {
+    const NodeRec* nodes;
+    const uint8_t* node_seq;
+    const uint32_t* edges;
+    const uint32_t* node_path_id;
+    const int32_t* node_path_pos;
+    const uint32_t* node_mask;
+    const WinRec* wins;
+    const uint32_t* cn_node;
+    const uint64_t* sketches;
+    const uint32_t* graph_mask_words;
+    const LshTable* tables;  // [(K-1)*n_bands + band]; slots == nullptr when not built yet
+    uint32_t k, S, max_k, n_bands, n_wins;
+};
+
+// multi-hash multipliers i ^ (k * multiSeed), passed by value => they live in the constant bank
+struct MultTable { uint64_t c[32]; };
+
+enum : int { HSTAGE = 4 };  // hits per read staged by the seed kernel before the exact-size fill
+
+}  // namespace groot

@@ -1,0 +1,296 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Every test drives the CUDA path through the C ABI
+(libgrootgpu.so via groot_b200.api) and compares it, bit for bit, with the CPU oracle on the same inputs,
+with the committed golden fixtures, or through size-independent properties at full size.
+
+Parity bar: integer / byte / index work -> bit-exact. The f64 graph weights are compared bit-exactly too,
+because the host replay performs the additions in the reference's (read) order.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from groot_b200 import api, synth
+from oracle import pyoracle as po
+from tests.util import load_fastq, pack_reads, revcomp
+
+pytestmark = pytest.mark.gpu
+
+
+def _have_gpu():
+    try:
+        return api.device_count() > 0
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _require_gpu():
+    if not _have_gpu():
+        pytest.fail("no CUDA device: the gpu-marked tests must run on the B200 box (there is no CPU fallback)")
+
+
+def oracle_records_table(res):
+    return res.records[:, :7].astype(np.int64)
+
+
+def assert_same_result(g, o, check_records=True):
+    """g: api.BatchResult, o: pyoracle.MapResult"""
+    assert g.counts == o.counts
+    assert np.array_equal(g.hit_off.astype(np.uint64), o.hit_off)
+    assert np.array_equal(g.hits, o.hits)
+    assert g.n_pairs == len(o.pairs)
+    assert np.array_equal(g.pairs["read"], o.pairs[:, 0])
+    assert np.array_equal(g.pairs["graph"], o.pairs[:, 1])
+    assert np.array_equal(g.pairs["n_incremented"], o.pairs[:, 2])
+    assert np.array_equal(g.pairs["rec_count"], o.pairs[:, 3])
+    if check_records:
+        assert np.array_equal(g.records_table(), oracle_records_table(o))
+
+
+# ------------------------------------------------------------------------------------------------- sketches
+def test_sketch_golden_vectors(root):
+    vec = json.load(open(os.path.join(root, "tests", "golden", "sketch_vectors.json")))
+    for name, v in vec.items():
+        blob, off = pack_reads([v["seq"].encode()])
+        got = api.sketch_batch(blob, off, v["k"], v["S"])[0]
+        assert ["%016x" % int(x) for x in got] == v["sketch"], name
+
+
+def test_sketch_matches_oracle_random():
+    rng = np.random.default_rng(5)
+    for k, S in [(7, 10), (31, 21), (51, 30), (31, 20), (41, 21), (31, 32), (15, 8), (31, 16), (31, 24)]:
+        seqs = []
+        for i in range(300):
+            ln = int(rng.integers(k, 260))
+            alphabet = b"ACGT" if i % 3 else b"ACGTNacgtRY"
+            seqs.append(bytes(rng.choice(np.frombuffer(alphabet, dtype=np.uint8), size=ln)))
+        seqs.append(seqs[0][:k])     # len == k: a single k-mer
+        blob, off = pack_reads(seqs)
+        got = api.sketch_batch(blob, off, k, S)
+        for i, s in enumerate(seqs):
+            assert np.array_equal(got[i], po.sketch(s, k, S)), (k, S, i)
+        # RC invariance on the ACGT-only ones (src/minhash/minhash_test.go:111-157)
+        acgt = [s for s in seqs if set(s) <= set(b"ACGT")]
+        b2, o2 = pack_reads([revcomp(s) for s in acgt])
+        b1, o1 = pack_reads(acgt)
+        assert np.array_equal(api.sketch_batch(b1, o1, k, S), api.sketch_batch(b2, o2, k, S))
+
+
+def test_sketch_short_sequence_is_an_error():
+    blob, off = pack_reads([b"ACGTACGTAC", b"ACG"])
+    with pytest.raises(api.GrootGpuError) as e:
+        api.sketch_batch(blob, off, 7, 10)
+    assert e.value.code == -5       # minhash_test.go:86: AddSequence must fail when len < k
+
+
+# ------------------------------------------------------------------------------------------------- index
+@pytest.fixture(scope="module")
+def oxa(root):
+    f = [os.path.join(root, "data", "graph", "test-genes.msa")]
+    return api.Index.build(msa_files=f, k=51, S=30, w=100), po.Index(msa_files=f, k=51, S=30, w=100)
+
+
+def test_index_parity_oxa_cluster(oxa, tmp_path):
+    g, o = oxa
+    g.dump_file(str(tmp_path / "g.txt"))
+    o.dump_file(str(tmp_path / "o.txt"))
+    assert open(tmp_path / "g.txt").read() == open(tmp_path / "o.txt").read()
+    assert g.dump_hash() == o.dump_hash()
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "oxa_small_align.npz"))
+    assert g.dump_hash() == int(golden["index_hash"][0])
+
+
+@pytest.fixture(scope="module")
+def argannot(db_dirs):
+    d = db_dirs["arg-annot.90"]
+    return api.Index.build(msa_dir=d, k=31, S=21, w=100), po.Index(msa_dir=d, k=31, S=21, w=100)
+
+
+def test_index_parity_argannot(argannot):
+    g, o = argannot
+    gi, oi = g.info(), o.stats()
+    for key in ("graphs", "masked", "paths", "nodes", "path_bases", "windows", "raw_windows", "max_merge_span"):
+        assert gi[key] == oi[key], key
+    assert gi["graphs"] == 583 and gi["paths"] == 1749 and gi["raw_windows"] == 1356246   # SURVEY.md §8 sizes
+    assert g.dump_hash() == o.dump_hash()
+    assert g.query_params(70, 0.99) == (4, 1, 21)
+    assert g.query_params(60, 0.99) == (4, 1, 18)
+    assert g.query_params(80, 0.99)[2] == 22
+
+
+def test_index_save_load_roundtrip(oxa, tmp_path):
+    g, _ = oxa
+    p = str(tmp_path / "oxa.grootb200")
+    g.save(p)
+    g2 = api.Index.load(p)
+    assert g2.dump_hash() == g.dump_hash()
+    with pytest.raises(api.GrootGpuError):
+        api.Index.load(str(tmp_path / "missing.grootb200"))
+
+
+# ------------------------------------------------------------------------------------------------- align
+def test_align_golden_oxa(oxa, root):
+    g, o = oxa
+    golden = np.load(os.path.join(root, "tests", "golden", "oxa_small_align.npz"))
+    names, seqs, quals = load_fastq(os.path.join(root, "data", "reads", "test-reads-OXA90-OXA106-100bp-with-errors.fastq"))
+    blob, off = pack_reads(seqs[:300])
+    g.reset_weights()
+    res = g.map_reads(blob, off, 0.99, keep_sketches=True, project=True)
+    assert np.array_equal(res.hit_off.astype(np.uint64), golden["hit_off"])
+    assert np.array_equal(res.hits, golden["hits"])
+    assert np.array_equal(res.records_table(), golden["records"][:, :7].astype(np.int64))
+    assert [res.counts[k] for k in ("received", "mapped", "multimapped", "alignments")] == golden["counts"].tolist()
+    assert np.array_equal(g.weights()[0], golden["weights"])          # bit-exact f64
+    for i in (0, 17, 299):
+        assert np.array_equal(res.sketches[i], po.sketch(seqs[i], 51, 30))
+
+
+def test_align_parity_oxa_full_and_prune(oxa, root):
+    g, o = oxa
+    names, seqs, quals = load_fastq(os.path.join(root, "data", "reads", "test-reads-OXA90-OXA106-100bp-with-errors.fastq"))
+    blob, off = pack_reads(seqs)
+    g.reset_weights(); o.reset_weights()
+    gr = g.map_reads(blob, off, 0.99, project=True)
+    orr = o.map_reads(blob, off, 0.99)
+    assert_same_result(gr, orr)
+    gw, gt = g.weights(); ow, ot = o.weights()
+    assert np.array_equal(gw, ow) and np.array_equal(gt, ot)
+    # the reference's own assertion (src/pipeline/3_sketch_test.go:49-58): OXA-90 survives pruning at 10
+    kept = g.prune(10.0)
+    assert kept[0] == 1
+    assert "argannot~~~(Bla)OXA-90~~~EU547443:1-825" in [g.ref(0, p)[0] for p in range(g.info()["paths"])]
+
+
+def _c1_reads(db_dir, n, L, seed=42):
+    return synth.synth_reads(n, L, synth.db_sequences(db_dir), seed=seed)
+
+
+def test_align_parity_argannot_c1(argannot, db_dirs, root):
+    """Config C1: 1k x 100 bp vs arg-annot.90 — the reference's shipped perfect reads and the synthetic mix."""
+    g, o = argannot
+    names, seqs, quals = load_fastq(os.path.join(root, "data", "reads", "full-argannot-perfect-reads-small.fq.gz"))
+    for blob, off in (pack_reads(seqs), _c1_reads(db_dirs["arg-annot.90"], 4000, 100)):
+        g.reset_weights(); o.reset_weights()
+        gr = g.map_reads(blob, off, 0.99, project=True)
+        orr = o.map_reads(blob, off, 0.99, threads=8)
+        assert orr.counts["mapped"] > 0.4 * orr.counts["received"]
+        assert_same_result(gr, orr)
+        assert np.array_equal(g.weights()[0], o.weights()[0])
+        assert np.array_equal(g.weights()[1], o.weights()[1])
+
+
+def test_align_parity_variable_length_and_thresholds(argannot, root):
+    g, o = argannot
+    names, seqs, quals = load_fastq(os.path.join(root, "data", "reads", "full-argannot-perfect-reads-small-variable-rl.fq.gz"))
+    seqs = [s for s in seqs if len(s) >= 31]
+    blob, off = pack_reads(seqs)
+    for t in (0.99, 0.97, 0.9):
+        g.reset_weights(); o.reset_weights()
+        gr = g.map_reads(blob, off, t, project=True)
+        orr = o.map_reads(blob, off, t, threads=8)
+        assert_same_result(gr, orr)
+        assert np.array_equal(g.weights()[0], o.weights()[0])
+
+
+def test_align_no_align_mode(argannot, db_dirs):
+    g, o = argannot
+    blob, off = _c1_reads(db_dirs["arg-annot.90"], 2000, 100, seed=7)
+    g.reset_weights(); o.reset_weights()
+    gr = g.map_reads(blob, off, 0.99, no_align=True, project=True)
+    orr = o.map_reads(blob, off, 0.99, no_align=True)
+    assert gr.n_records == 0
+    assert_same_result(gr, orr)
+    assert np.array_equal(g.weights()[0], o.weights()[0])       # graphminion.go:70-72: every mapping is weighted
+
+
+def test_align_edge_cases(argannot):
+    g, o = argannot
+    k = 31
+    # a read shorter than k: the reference panics (boss.go:164-166) -> error code, nothing computed
+    blob, off = pack_reads([b"ACGT" * 25, b"ACGTACGT"])
+    with pytest.raises(api.GrootGpuError) as e:
+        g.map_reads(blob, off)
+    assert e.value.code == -5
+    # empty batch
+    with pytest.raises(api.GrootGpuError):
+        g.map_reads(np.zeros(0, dtype=np.uint8), np.zeros(1, dtype=np.uint64))
+    # reads that cannot seed: longer than the window (eq_min unsatisfiable), exactly k long, all-N, single read
+    rng = np.random.default_rng(3)
+    long_read = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=180))
+    for seqs in ([long_read], [long_read[:k]], [b"N" * 100], [long_read[:100]] * 3):
+        blob, off = pack_reads(seqs)
+        gr = g.map_reads(blob, off)
+        orr = o.map_reads(blob, off)
+        assert_same_result(gr, orr)
+
+
+def test_align_lowercase_read_needing_revcomp_is_an_error(argannot, db_dirs):
+    """seqio.go:17-23,122: complementBases is indexed by the base; a byte > 'T' panics. Lower-case reads hash
+    like upper-case ones (nthash seed table), so a lower-case copy of a reverse-strand read seeds, fails the
+    forward alignment and reaches RevComplement."""
+    g, o = argannot
+    seqs = synth.db_sequences(db_dirs["arg-annot.90"])
+    s = bytes(seqs[10][40:140])
+    blob, off = pack_reads([revcomp(s).lower()])
+    with pytest.raises(api.GrootGpuError) as e:
+        g.map_reads(blob, off)
+    assert e.value.code == -6
+    with pytest.raises(RuntimeError):
+        o.map_reads(blob, off)
+
+
+def test_align_parity_card_150bp(db_dirs):
+    """Config C4 (reduced): 150 bp reads vs card.90 -w 150 (masked graph, larger merge spans)."""
+    d = db_dirs["card.90"]
+    g = api.Index.build(msa_dir=d, k=31, S=21, w=150)
+    o = po.Index(msa_dir=d, k=31, S=21, w=150)
+    assert g.info()["masked"] == o.stats()["masked"] >= 1
+    assert g.dump_hash() == o.dump_hash()
+    blob, off = synth.synth_reads(3000, 150, synth.db_sequences(d), seed=11)
+    gr = g.map_reads(blob, off, 0.99, project=True)
+    orr = o.map_reads(blob, off, 0.99, threads=8)
+    assert_same_result(gr, orr)
+    assert np.array_equal(g.weights()[0], o.weights()[0])
+
+
+# ------------------------------------------------------------------------------------------------- full size
+def test_full_size_properties(argannot, db_dirs):
+    """BASELINE config sizes through size-independent properties: (1) batch-split invariance — a 2M-read batch
+    equals the concatenation of its halves; (2) strand symmetry — reverse-complementing every read leaves the
+    sketches' hits unchanged and flips the reverse flag of every aligned pair; (3) idempotence; (4) a sampled
+    slice equals the oracle."""
+    g, o = argannot
+    n, L = 2_000_000, 100
+    blob, off = synth.synth_reads(n, L, synth.db_sequences(db_dirs["arg-annot.90"]), seed=42)
+    full = g.map_reads(blob, off, 0.99)
+    assert full.counts["received"] == n
+    assert 0.45 * n < full.counts["mapped"] < 0.55 * n          # 50 % exact substrings minus the W2 quirk
+    again = g.map_reads(blob, off, 0.99)
+    assert np.array_equal(full.hits, again.hits) and np.array_equal(full.rec_pos, again.rec_pos)
+    assert np.array_equal(full.pairs, again.pairs)
+    h = n // 2
+    a = g.map_reads(blob[:h * L], off[:h + 1], 0.99)
+    b = g.map_reads(blob[h * L:], off[h:] - off[h], 0.99)
+    assert np.array_equal(np.concatenate([a.hits, b.hits]), full.hits)
+    assert np.array_equal(np.concatenate([a.rec_path, b.rec_path]), full.rec_path)
+    assert np.array_equal(np.concatenate([a.rec_pos, b.rec_pos]), full.rec_pos)
+    assert a.counts["mapped"] + b.counts["mapped"] == full.counts["mapped"]
+    # strand symmetry on a 200k slice
+    m = 200_000
+    comp = synth._COMP
+    rc = comp[blob[:m * L].reshape(m, L)][:, ::-1].reshape(-1).copy()
+    fwd = g.map_reads(blob[:m * L], off[:m + 1], 0.99)
+    rev = g.map_reads(rc, off[:m + 1], 0.99)
+    assert np.array_equal(fwd.hit_off, rev.hit_off) and np.array_equal(fwd.hits, rev.hits)
+    both = (fwd.pairs["rec_count"] > 0) & (rev.pairs["rec_count"] > 0)
+    assert both.sum() > 0.9 * len(fwd.pairs)
+    # a palindromic placement can align on both strands; everything else must flip
+    flipped = fwd.pairs["reverse"][both] != rev.pairs["reverse"][both]
+    assert flipped.mean() > 0.999
+    # sampled slice vs oracle
+    s0, s1 = 1_234_000, 1_240_000
+    sub = g.map_reads(blob[s0 * L:s1 * L], off[s0:s1 + 1] - off[s0], 0.99)
+    orr = o.map_reads(blob[s0 * L:s1 * L], off[s0:s1 + 1] - off[s0], 0.99, threads=8)
+    assert_same_result(sub, orr)
