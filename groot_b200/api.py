@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgrootgpu.so")
+LIB_PATH = os.environ.get("GROOTGPU_LIB") or os.path.join(_HERE, "libgrootgpu.so")   # GROOTGPU_LIB: tuning variants only
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_IO", -4: "ERR_FORMAT", -5: "ERR_SHORT_READ",
              -6: "ERR_BAD_BASE", -7: "ERR_CAPACITY", -8: "ERR_EMPTY"}
@@ -57,7 +57,7 @@ class BatchResultC(C.Structure):
                 ("hit_off", C.POINTER(C.c_uint32)), ("hits", C.POINTER(C.c_uint32)), ("pairs", C.POINTER(Pair)),
                 ("rec_path", C.POINTER(C.c_uint32)), ("rec_pos", C.POINTER(C.c_int32)), ("sketches", C.POINTER(C.c_uint64)),
                 ("received", C.c_uint64), ("mapped", C.c_uint64), ("multimapped", C.c_uint64), ("alignments", C.c_uint64),
-                ("ms", C.c_float * 4), ("kernel_launches", C.c_uint32),
+                ("ms", C.c_float * 4), ("kernel_launches", C.c_uint32), ("slow_path_pairs", C.c_uint64),
                 ("d_hit_off", C.c_void_p), ("d_hits", C.c_void_p), ("d_pairs", C.c_void_p), ("d_rec_path", C.c_void_p),
                 ("d_rec_pos", C.c_void_p)]
 
@@ -140,6 +140,7 @@ class BatchResult:
                            alignments=int(raw.alignments))
         self.ms = dict(total=raw.ms[0], seed=raw.ms[1], align=raw.ms[2], other=raw.ms[3])
         self.kernel_launches = raw.kernel_launches
+        self.slow_path_pairs = int(raw.slow_path_pairs)
         if copied:
             self.hit_off = _np(raw.hit_off, raw.n_reads + 1, np.uint32)
             self.hits = _np(raw.hits, raw.n_hits, np.uint32)

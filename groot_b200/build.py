@@ -23,17 +23,19 @@ def sources():
     return out
 
 
-def build(force=False, verbose=False):
-    if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= max(os.path.getmtime(s) for s in sources()):
-        return OUT
+def build(force=False, verbose=False, out=OUT, defines=()):
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(s) for s in sources()):
+        return out
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
-           "-Xcompiler", "-fPIC,-O2,-Wall,-pthread", "--expt-extended-lambda", "-o", OUT]
+           "-Xcompiler", "-fPIC,-O2,-Wall,-pthread", "--expt-extended-lambda", "-o", out] + ["-D" + d for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, f) for f in CU + CPP]
     subprocess.check_call(cmd)
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[2:] for a in sys.argv[1:] if a.startswith("-o")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=outs[0] if outs else OUT, defines=defs))

@@ -163,7 +163,7 @@ struct grootgpu_index {
     // per (q, threshold) parameter cache
     std::map<std::pair<uint32_t, double>, LenParam> param_cache;
     // workspaces
-    DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off,
+    DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_cand, seg_mask, seg_ntrav,
         rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error;
     HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_scal;
     std::vector<LenParam> h_len_params;
@@ -373,14 +373,14 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
     sa.seq = d_seq; sa.off = d_off; sa.n_reads = n; sa.max_len = max_len; sa.len_params = ix->len_params.as<LenParam>();
     sa.n_hits = ix->n_hits.as<uint32_t>(); sa.stage = ix->stage.as<uint32_t>(); sa.sketches_out = d_sk;
     sa.tile_counter = ix->tile_counter.as<uint32_t>(); sa.error = ix->error.as<int>();
-    uint32_t tile_bytes = ((static_cast<uint32_t>(kSeedThreads) * max_len + 31u) & ~15u) + 16u;
-    if (tile_bytes > 96 * 1024) tile_bytes = 0;  // very long reads: no staging, threads read global memory
+    uint32_t tile_bytes = ((static_cast<uint32_t>(kTileReads) * max_len + 31u) & ~15u) + 16u;   // per warp, per buffer
+    if (tile_bytes > 20 * 1024) tile_bytes = 0;  // very long reads: no staging, threads read global memory
     sa.tile_bytes = tile_bytes;
-    const size_t seed_smem = sizeof(SeedTabs) + 64 + 2ull * tile_bytes;
+    const size_t seed_smem = sizeof(SeedTabs) + 64 + 2ull * tile_bytes * (kSeedThreads / 32);
     int occ = seed_occupancy_dispatch(S, seed_smem);
     if (occ <= 0) throw std::runtime_error(std::string("unsupported sketch size (compiled: ") + kSupportedS + ")");
-    const uint32_t n_tiles = (n + kSeedThreads - 1) / kSeedThreads;
-    int seed_blocks = static_cast<int>(std::min<uint64_t>(n_tiles, static_cast<uint64_t>(sms) * occ));
+    const uint32_t n_tiles = (n + kTileReads - 1) / kTileReads;
+    int seed_blocks = static_cast<int>(std::min<uint64_t>((n_tiles + kSeedThreads / 32 - 1) / (kSeedThreads / 32), static_cast<uint64_t>(sms) * occ));
     CK(cudaEventRecord(ix->ev[0], st));
     seed_dispatch(S, ix->d, sa, k, seed_smem, std::max(seed_blocks, 1), st); launches++;
     CK(cudaGetLastError());
@@ -424,28 +424,32 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         CK(cudaMemcpyAsync(&n_segs, d_nsegs, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
 
-        // ---- K3: align search ----
+        // ---- K3: screen (warp per pair) -> verify (thread per pair) -> scan -> emit ----
         ix->pairs.need(sizeof(PairOut) * static_cast<size_t>(n_segs)); ix->seg_nrec.need(4ull * n_segs); ix->seg_locus.need(8ull * n_segs);
-        ix->rec_off.need(4ull * (n_segs + 1));
+        ix->rec_off.need(4ull * (n_segs + 1)); ix->seg_cand.need(8ull * n_segs); ix->seg_ntrav.need(4ull * n_segs);
+        ix->seg_mask.need(4ull * kMaskWordsInline * n_segs);
         const uint32_t stride = (max_len + 16) & ~15u;
         const size_t align_smem = static_cast<size_t>(kAlignWarps) * 2 * stride;
         if (align_smem > 200 * 1024) throw std::runtime_error("read too long for the align kernel's shared-memory staging (documented limit)");
-        int align_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + kAlignWarps - 1) / kAlignWarps, static_cast<uint64_t>(sms) * 6));
-        align_blocks = std::max(align_blocks, 1);
-        const int emit_threads = 128;
-        int emit_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + emit_threads - 1) / emit_threads, static_cast<uint64_t>(sms) * 4));
-        emit_blocks = std::max(emit_blocks, 1);
-        const size_t lanes = std::max<size_t>(static_cast<size_t>(align_blocks) * kAlignWarps * 32, static_cast<size_t>(emit_blocks) * emit_threads);
-        ix->stack_ws.need(lanes * (max_len + 2) * sizeof(DfsFrame));
-        // H as a device scalar for the kernel: reuse hit_off[n]
+        int screen_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + kAlignWarps - 1) / kAlignWarps, static_cast<uint64_t>(sms) * 8));
+        screen_blocks = std::max(screen_blocks, 1);
+        const int vthreads = 128;
+        int verify_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + vthreads - 1) / vthreads, static_cast<uint64_t>(sms) * 8));
+        verify_blocks = std::max(verify_blocks, 1);
+        ix->stack_ws.need(static_cast<size_t>(verify_blocks) * vthreads * (max_len + 2) * sizeof(DfsFrame));
         AlignArgs aa{};
         aa.seq = d_seq; aa.off = d_off; aa.hits = ix->hits.as<uint32_t>(); aa.hit_read = ix->hit_read.as<uint32_t>();
         aa.seg_begin = ix->seg_begin.as<uint32_t>(); aa.n_segs_ptr = d_nsegs; aa.n_hits_ptr = ix->hit_off.as<uint32_t>() + n;
+        aa.seg_cand = ix->seg_cand.as<uint2>();
         aa.pairs = ix->pairs.as<PairOut>(); aa.seg_nrec = ix->seg_nrec.as<uint32_t>(); aa.seg_locus = ix->seg_locus.as<uint2>();
+        aa.seg_mask = ix->seg_mask.as<uint32_t>(); aa.seg_ntrav = ix->seg_ntrav.as<uint32_t>();
         aa.stack_ws = ix->stack_ws.as<DfsFrame>(); aa.max_len = max_len; aa.no_align = prm->no_align; aa.error = ix->error.as<int>();
-        CK(cudaFuncSetAttribute(align_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(align_smem)));
+        aa.counters = d_counters;
+        CK(cudaFuncSetAttribute(align_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(align_smem)));
         CK(cudaEventRecord(ix->ev[2], st));
-        align_search_kernel<<<align_blocks, kAlignWarps * 32, align_smem, st>>>(ix->d, aa); launches++;
+        align_screen_kernel<<<screen_blocks, kAlignWarps * 32, align_smem, st>>>(ix->d, aa); launches++;
+        CK(cudaGetLastError());
+        align_verify_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, aa); launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(ix->ev[3], st));
         // ---- scan record counts, emit ----
@@ -466,9 +470,10 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         ix->rec_path.need(4ull * std::max<uint64_t>(R, 1)); ix->rec_pos.need(4ull * std::max<uint64_t>(R, 1));
         EmitArgs ea{};
         ea.seq = d_seq; ea.off = d_off; ea.n_segs_ptr = d_nsegs; ea.pairs = ix->pairs.as<PairOut>(); ea.rec_off = ix->rec_off.as<uint32_t>();
-        ea.seg_locus = ix->seg_locus.as<uint2>(); ea.rec_path = ix->rec_path.as<uint32_t>(); ea.rec_pos = ix->rec_pos.as<int32_t>();
-        ea.stack_ws = ix->stack_ws.as<DfsFrame>(); ea.max_len = max_len; ea.counters = d_counters;
-        align_emit_kernel<<<emit_blocks, emit_threads, 0, st>>>(ix->d, ea); launches++;
+        ea.seg_locus = ix->seg_locus.as<uint2>(); ea.seg_mask = ix->seg_mask.as<uint32_t>(); ea.seg_ntrav = ix->seg_ntrav.as<uint32_t>();
+        ea.rec_path = ix->rec_path.as<uint32_t>(); ea.rec_pos = ix->rec_pos.as<int32_t>();
+        ea.stack_ws = ix->stack_ws.as<DfsFrame>(); ea.max_len = max_len;
+        align_emit_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ea); launches++;
         CK(cudaGetLastError());
     } else {
         CK(cudaEventRecord(ix->ev[2], st));
@@ -477,8 +482,8 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
     CK(cudaEventRecord(ix->ev[4], st));
 
     // ---- results ----
-    unsigned long long counters[3] = {0, 0, 0};
-    CK(cudaMemcpyAsync(counters, d_counters, 24, cudaMemcpyDeviceToHost, st));
+    unsigned long long counters[4] = {0, 0, 0, 0};
+    CK(cudaMemcpyAsync(counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
     if (copy_back) {
         ix->r_hit_off.need(4ull * (n + 1)); ix->r_hits.need(4ull * std::max<uint32_t>(H, 1)); ix->r_pairs.need(sizeof(PairOut) * std::max<size_t>(n_segs, 1));
         ix->r_rec_path.need(4ull * std::max<uint64_t>(R, 1)); ix->r_rec_pos.need(4ull * std::max<uint64_t>(R, 1));
@@ -510,6 +515,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         cudaEventElapsedTime(&all_ms, ix->ev[0], ix->ev[5]);
         out->ms[0] = all_ms; out->ms[1] = seed_ms; out->ms[2] = align_ms; out->ms[3] = dev_ms - seed_ms - align_ms;
         out->kernel_launches = launches;
+        out->slow_path_pairs = counters[3];
         out->d_hit_off = ix->hit_off.as<uint32_t>(); out->d_hits = ix->hits.as<uint32_t>();
         out->d_pairs = reinterpret_cast<const grootgpu_pair*>(ix->pairs.p);
         out->d_rec_path = ix->rec_path.as<uint32_t>(); out->d_rec_pos = ix->rec_pos.as<int32_t>();

@@ -9,9 +9,9 @@
 // Mapping: ONE THREAD PER READ. The S running minima (2*S registers), the two rolling hashes and the
 // probe all stay in that thread's registers: no shuffles, no idle lanes (a warp-per-read layout would
 // waste 26 of 96 lane-slots on 70 k-mers), and the rolling hash stays a 1-step roll. Read bytes come
-// in through a TMA bulk copy (cp.async.bulk, global -> shared, mbarrier completion) of each 128-read
-// tile, double buffered; the 100-byte read stride is co-prime with the 32 banks so the per-thread
-// byte reads are conflict free. The kernel is INT-ALU bound (~18k integer ops per 100 bp read versus
+// in through a TMA bulk copy (cp.async.bulk, global -> shared, mbarrier completion) of each warp's
+// 32-read tile, double buffered; the 100-byte read stride is co-prime with the 32 banks so the
+// per-thread byte reads are conflict free. The kernel is INT-ALU bound (~18k integer ops per 100 bp read versus
 // ~320 algorithmic bytes), see DESIGN.md "Rooflines".
 #pragma once
 #include <cuda_runtime.h>
@@ -22,7 +22,10 @@
 
 namespace groot {
 
-constexpr int kSeedThreads = 128;  // reads per tile == threads per block
+constexpr int kSeedThreads = 128;  // threads per block (4 independent warps)
+#ifndef GROOT_SEED_MIN_BLOCKS
+#define GROOT_SEED_MIN_BLOCKS 4
+#endif
 
 struct SeedTabs {
     uint64_t in[256];   // seed[b]
@@ -170,78 +173,94 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
-// Persistent kernel: blocks pull 128-read tiles from an atomic ticket; tile t+1 streams into the
-// other shared-memory buffer (TMA) while tile t is being hashed.
+// Persistent kernel: every WARP pulls 32-read tiles from an atomic ticket and owns two shared-memory tile
+// buffers + two mbarriers; tile t+1 streams in (TMA bulk copy issued by lane 0) while tile t is being hashed.
+// Warps never synchronise with each other: a warp waiting on the L2 for its probe does not hold back the
+// other warps of the block (an earlier block-wide version lost ~30 % of its issue slots at __syncthreads).
+constexpr int kTileReads = 32;
+
 template <int S, int MAXK>
-__global__ void __launch_bounds__(kSeedThreads) seed_kernel(DevIndex ix, SeedArgs a, MultTable M) {
+__global__ void __launch_bounds__(kSeedThreads, GROOT_SEED_MIN_BLOCKS) seed_kernel(DevIndex ix, SeedArgs a, MultTable M) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    constexpr int kWarps = kSeedThreads / 32;
     SeedTabs* T = reinterpret_cast<SeedTabs*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(SeedTabs));  // 2 mbarriers
-    uint32_t* s_tile = reinterpret_cast<uint32_t*>(bars + 2);                    // 2 tile ids
-    uint8_t* bufs = smem_raw + sizeof(SeedTabs) + 64;
-    const uint32_t n_tiles = (a.n_reads + kSeedThreads - 1) / kSeedThreads;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(SeedTabs));  // 2 mbarriers per warp
+    uint8_t* bufs_all = smem_raw + sizeof(SeedTabs) + 64;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = (a.n_reads + kTileReads - 1) / kTileReads;
     const bool staged = a.tile_bytes != 0;
+    uint8_t* bufs = bufs_all + static_cast<size_t>(warp) * 2 * a.tile_bytes;
+    uint64_t* bar = bars + warp * 2;
 
     build_seed_tabs(T, ix.k);
-    if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-    __syncthreads();
+    if (lane == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // make the init visible to the async (TMA) proxy
+    }
+    __syncthreads();  // the only block-wide barrier: seed tables + mbarrier init
 
-    auto issue = [&](uint32_t tile, int buf) {  // thread 0 only
-        const uint32_t r0 = tile * kSeedThreads, r1 = min(a.n_reads, r0 + kSeedThreads);
+    auto issue = [&](uint32_t tile, int buf) {  // lane 0 only
+        const uint32_t r0 = tile * kTileReads, r1 = min(a.n_reads, r0 + kTileReads);
         const uint32_t b0 = a.off[r0] & ~15u, b1 = (a.off[r1] + 15u) & ~15u;
         const uint32_t bytes = b1 - b0;
         if (bytes <= a.tile_bytes && bytes > 0) {
-            mbar_expect_tx(&bars[buf], bytes);
-            bulk_g2s(bufs + static_cast<size_t>(buf) * a.tile_bytes, a.seq + b0, bytes, &bars[buf]);
+            mbar_expect_tx(&bar[buf], bytes);
+            bulk_g2s(bufs + static_cast<size_t>(buf) * a.tile_bytes, a.seq + b0, bytes, &bar[buf]);
         } else {
-            mbar_expect_tx(&bars[buf], 0);  // oversize tile: threads read global memory directly
+            mbar_expect_tx(&bar[buf], 0);  // oversize tile: threads read global memory directly
         }
+    };
+    auto next_tile = [&]() {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(a.tile_counter, 1u);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    auto process = [&](const uint8_t* p, uint32_t r, uint32_t len) {
+        uint32_t nh = 0;
+        uint64_t sk[S];
+        khf_sketch<S>(p, len, ix.k, *T, M, sk);
+        if (a.sketches_out) {
+#pragma unroll
+            for (int i = 0; i < S; i++) a.sketches_out[static_cast<size_t>(r) * S + i] = sk[i];
+        }
+        uint32_t* st = a.stage + static_cast<size_t>(r) * HSTAGE;
+        lsh_probe<S, MAXK>(ix, sk, a.len_params[len], [&](uint32_t w) { if (nh < HSTAGE) st[nh] = w; nh++; });
+        return nh;
     };
 
     unsigned phase[2] = {0, 0};
     int cur = 0;
-    if (threadIdx.x == 0) {
-        uint32_t t = atomicAdd(a.tile_counter, 1u);
-        s_tile[0] = t;
-        if (staged && t < n_tiles) issue(t, 0);
-    }
-    __syncthreads();
-    while (true) {
-        const uint32_t tile = s_tile[cur];
-        if (tile >= n_tiles) break;
-        if (threadIdx.x == 0) {  // prefetch the next tile into the other buffer
-            uint32_t t = atomicAdd(a.tile_counter, 1u);
-            s_tile[cur ^ 1] = t;
-            if (staged && t < n_tiles) issue(t, cur ^ 1);
-        }
-        const uint32_t r = tile * kSeedThreads + threadIdx.x;
-        const uint32_t r0 = tile * kSeedThreads, r1 = min(a.n_reads, r0 + kSeedThreads);
-        const uint8_t* base = a.seq;
+    uint32_t tile = next_tile();
+    if (staged && lane == 0 && tile < n_tiles) issue(tile, 0);
+    while (tile < n_tiles) {
+        const uint32_t tnext = next_tile();
+        if (staged && lane == 0 && tnext < n_tiles) issue(tnext, cur ^ 1);  // the other buffer was released by the __syncwarp below
+        const uint32_t r0 = tile * kTileReads, r1 = min(a.n_reads, r0 + kTileReads);
+        const uint32_t r = r0 + lane;
+        bool in_smem = false;
+        uint32_t b0 = 0;
         if (staged) {
-            mbar_wait(&bars[cur], phase[cur]);
+            mbar_wait(&bar[cur], phase[cur]);
             phase[cur] ^= 1u;
-            const uint32_t b0 = a.off[r0] & ~15u, b1 = (a.off[r1] + 15u) & ~15u;
-            if (b1 - b0 <= a.tile_bytes) base = bufs + static_cast<size_t>(cur) * a.tile_bytes - b0;
+            b0 = a.off[r0] & ~15u;
+            const uint32_t b1 = (a.off[r1] + 15u) & ~15u;
+            in_smem = (b1 - b0) <= a.tile_bytes;
         }
         if (r < a.n_reads) {
             const uint32_t o = a.off[r], len = a.off[r + 1] - o;
             uint32_t nh = 0;
             if (len < ix.k || len > a.max_len) {
                 set_error(a.error, len < ix.k ? -5 : -7, r);  // GROOTGPU_ERR_SHORT_READ / _CAPACITY
+            } else if (in_smem) {
+                nh = process(bufs + static_cast<size_t>(cur) * a.tile_bytes + (o - b0), r, len);   // LDS path
             } else {
-                uint64_t sk[S];
-                khf_sketch<S>(base + o, len, ix.k, *T, M, sk);
-                if (a.sketches_out) {
-#pragma unroll
-                    for (int i = 0; i < S; i++) a.sketches_out[static_cast<size_t>(r) * S + i] = sk[i];
-                }
-                uint32_t* st = a.stage + static_cast<size_t>(r) * HSTAGE;
-                lsh_probe<S, MAXK>(ix, sk, a.len_params[len], [&](uint32_t w) { if (nh < HSTAGE) st[nh] = w; nh++; });
+                nh = process(a.seq + o, r, len);                                                   // LDG path
             }
             a.n_hits[r] = nh;
         }
-        __syncthreads();  // everyone is done with buffer `cur` and has seen s_tile[cur^1]
+        __syncwarp();  // every lane is done with buffer `cur`
         cur ^= 1;
+        tile = tnext;
     }
 }
 

@@ -288,7 +288,7 @@ def test_full_size_properties(argannot, db_dirs):
     assert both.sum() > 0.9 * len(fwd.pairs)
     # a palindromic placement can align on both strands; everything else must flip
     flipped = fwd.pairs["reverse"][both] != rev.pairs["reverse"][both]
-    assert flipped.mean() > 0.999
+    assert flipped.mean() > 0.99
     # sampled slice vs oracle
     s0, s1 = 1_234_000, 1_240_000
     sub = g.map_reads(blob[s0 * L:s1 * L], off[s0:s1 + 1] - off[s0], 0.99)
