@@ -12,7 +12,7 @@ OUT = os.path.join(HERE, "libgrootgpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU = ["capi.cu"]
-CPP = ["host/graph_build.cpp", "host/index_io.cpp", "host/lshe_params.cpp", "host/replay.cpp"]
+CPP = ["host/graph_build.cpp", "host/index_io.cpp", "host/lshe_params.cpp", "host/replay.cpp", "host/prefix_table.cpp"]
 
 
 def sources():

@@ -10,17 +10,23 @@
 // The reference walks an ordered list of candidate starts per mapping and strand ("tries"): offsets
 // OffSet..OffSet+MergeSpan+WindowSize on the seed node, then offsets 0..10 on every contained node, then a
 // 1-base start clip and a 1-base end clip; forward strand first, then the reverse complement; mappings in
-// (Node, OffSet) order. It stops at the first try whose DFS yields at least one path id. Three kernels:
+// (Node, OffSet) order. It stops at the first try whose DFS yields at least one path id.
 //
-//   align_screen_kernel  ONE WARP PER PAIR. The 32 lanes evaluate 32 consecutive tries of that list at once
-//                        with a DFS bounded to the first kScreenBases read bases (a necessary condition for
-//                        the full match); a ballot picks the lowest-numbered survivor == the first try the
-//                        sequential loop could possibly stop at. Almost every try dies on its first base.
-//   align_verify_kernel  ONE THREAD PER PAIR. Runs the full DFS on that try (32 independent walks per warp
-//                        instead of one lane walking while 31 wait); if it fails — low-complexity sequence —
-//                        the thread simply continues the reference's sequential enumeration from there.
-//                        Path membership is a bitset per node, so "a path id is assigned iff it occurs in
-//                        every node of the traversal" (alignment.go:301-307) is an AND over the DFS stack.
+//   align_init_kernel    one thread per pair: default (unaligned) result, cursor at the first try, pair queued.
+//   align_screen_kernel  ONE WARP PER QUEUED PAIR. From the pair's cursor, the 32 lanes test 32 consecutive tries at
+//                        once against the prefix table (host/prefix_table.cpp: the read's first 8 bases must equal
+//                        one of the 8-base traversal prefixes of the start position — a necessary condition for
+//                        dfsRecursive to succeed there, two loads and a masked XOR per try, no DFS); a ballot picks
+//                        the lowest-numbered survivor == the next try the sequential loop could stop at.
+//   align_walk_kernel    ONE THREAD PER QUEUED PAIR, 32 independent walks per warp in a FLAT loop (<= 8 bases of
+//                        the current node per iteration, node changes as per-lane events) with the path bitset
+//                        carried as a running AND. A pair whose walk yields no path id is re-queued with its cursor
+//                        just past that try. The host runs a fixed number of screen/walk rounds over the shrinking,
+//                        compacted queue (no host sync: counts live on the device), then
+//   align_finish_kernel  one thread per leftover pair continues the reference's sequential enumeration to the end.
+//                        (Earlier layouts — a warp per pair doing everything, one thread per pair doing everything,
+//                        in-kernel warp-synchronous rounds — lost 5-10x to lanes idling on each other; see
+//                        profiles/r01_notes.md.)
 //   align_emit_kernel    ONE THREAD PER PAIR, after an exclusive scan of the record counts: expands the
 //                        traversal's path bitset into (path, pos) records at the pair's exact offset.
 #pragma once
@@ -32,8 +38,6 @@
 
 namespace groot {
 
-constexpr int kAlignWarps = 8;      // warps per block in the screen kernel
-constexpr int kScreenBases = 16;    // read bases a try must match to survive the screen
 constexpr int kMaskWordsInline = 8; // path bitsets of up to 256 paths travel from verify to emit without a second DFS
 
 struct DfsFrame {
@@ -65,21 +69,6 @@ struct GlobalRead {  // forward or reverse-complement view of a read in global m
         return rc ? complement_base(p[len - 1 - i]) : p[i];
     }
 };
-
-// ---- the ordered list of tries of one (mapping, strand) ------------------------------------------
-__device__ __forceinline__ uint32_t tries_per_strand(const WinRec& wr) {
-    return (wr.merge_span + wr.win_size + 1u) + wr.cn_cnt * 11u + 2u;
-}
-// try t -> start node, start offset, hierarchy stage (1..4)
-__device__ __forceinline__ void decode_try(const DevIndex& ix, const WinRec& wr, uint32_t t, uint32_t* node, uint32_t* off, uint32_t* stage) {
-    const uint32_t t1 = wr.merge_span + wr.win_size + 1u;          // alignment.go:35-45
-    if (t < t1) { *node = wr.node; *off = wr.offset + t; *stage = 1; return; }
-    t -= t1;
-    const uint32_t t2 = wr.cn_cnt * 11u;                           // alignment.go:48-70 (ContainedNodes ascending SegmentID)
-    if (t < t2) { *node = ix.cn_node[wr.cn_off + t / 11u]; *off = t % 11u; *stage = 2; return; }
-    t -= t2;
-    *node = wr.node; *off = wr.offset; *stage = 3 + t;             // alignment.go:73-85 (start clip), 88-103 (end clip)
-}
 
 enum { DFS_EXISTS = 0, DFS_COUNT = 1, DFS_EMIT = 2 };
 
@@ -178,145 +167,386 @@ struct AlignArgs {
     const uint32_t* seg_begin;     // [n_segs] index into hits of each (read, graph) segment start
     const uint32_t* n_segs_ptr;    // device scalar
     const uint32_t* n_hits_ptr;    // device scalar (total hits)
-    uint2* seg_cand;               // [n_segs] screen result: x = mapping index inside the pair (0xffffffff = none), y = strand<<31 | try
     PairOut* pairs;                // [n_segs]
     uint32_t* seg_nrec;            // [n_segs]
     uint2* seg_locus;              // [n_segs] (node, offset) of the successful start
     uint32_t* seg_mask;            // [n_segs * kMaskWordsInline] path bitset when exactly one traversal carried ids
     uint32_t* seg_ntrav;           // [n_segs]
     DfsFrame* stack_ws;            // [threads * (max_len + 2)]
+    uint32_t* mask_ws;             // [threads * (max_len + 2) * kMaskWordsInline]
     uint32_t max_len;
     int no_align;
     int* error;
     unsigned long long* counters;  // [3] += pairs that needed the sequential continuation (diagnostic)
 };
 
-// ---- screen: one warp per pair, 32 tries at a time ------------------------------------------------
-__global__ void __launch_bounds__(kAlignWarps * 32) align_screen_kernel(DevIndex ix, AlignArgs a) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t stride = (a.max_len + 16) & ~15u;
-    uint8_t* fwd = smem_raw + static_cast<size_t>(warp) * 2 * stride;
-    uint8_t* rcb = fwd + stride;
-    const uint32_t n_segs = *a.n_segs_ptr, n_hits = *a.n_hits_ptr;
-    const uint32_t gwarp = blockIdx.x * kAlignWarps + warp, total_warps = gridDim.x * kAlignWarps;
-    DfsFrame stack[kScreenBases + 2];
+// Read view of one thread: forward or reverse complement (computed on the fly through a shared LUT),
+// optionally skipping the first base (start clip).
+struct ReadView {
+    const uint8_t* p;
+    const uint8_t* lut;  // shared-memory complement table (src/seqio/seqio.go:17-23: everything else -> 0)
+    uint32_t len;        // full read length
+    uint32_t shift;
+    bool rc;
+    __device__ __forceinline__ uint8_t operator()(uint32_t i) const {
+        i += shift;
+        return rc ? lut[p[len - 1 - i]] : p[i];
+    }
+};
 
-    for (uint32_t s = gwarp; s < n_segs; s += total_warps) {
-        // segments tile hits[]: a segment ends where the next one starts
-        const uint32_t hb = a.seg_begin[s];
-        const uint32_t he = (s + 1 < n_segs) ? a.seg_begin[s + 1] : n_hits;
-        uint2 cand = make_uint2(0xffffffffu, 0u);
-        if (!a.no_align) {                                     // graphminion.go:70-72
-            const uint32_t r = a.hit_read[hb];
-            const uint32_t o = a.off[r], len = a.off[r + 1] - o;
-            __syncwarp();
-            for (uint32_t i = lane; i < len; i += 32) fwd[i] = a.seq[o + i];
-            __syncwarp();
-            bool rc_ready = false, found = false;
-            for (uint32_t m = hb; m < he && !found; m++) {
-                const WinRec wr = ix.wins[a.hits[m]];
-                const uint32_t T = tries_per_strand(wr);
-                for (uint32_t strand = 0; strand < 2 && !found; strand++) {
-                    if (strand == 1 && !rc_ready) {            // graphminion.go:94 RevComplement (forward found nothing)
-                        bool bad = false;
-                        for (uint32_t i = lane; i < len; i += 32) {
-                            uint8_t b = fwd[len - 1 - i];
-                            if (b > 'T') bad = true;           // Go: index out of range on complementBases
-                            rcb[i] = complement_base(b);
-                        }
-                        if (__any_sync(0xffffffffu, bad) && lane == 0) { if (atomicCAS(a.error, 0, -6) == 0) a.error[1] = static_cast<int>(r); }
-                        __syncwarp();
-                        rc_ready = true;
-                    }
-                    const uint8_t* rd = strand ? rcb : fwd;
-                    for (uint32_t base = 0; base < T && !found; base += 32) {
-                        const uint32_t t = base + lane;
-                        bool ok = false;
-                        if (t < T) {
-                            uint32_t node, off0, stage;
-                            decode_try(ix, wr, t, &node, &off0, &stage);
-                            const uint32_t view_len = stage >= 3 ? len - 1 : len;
-                            const uint32_t pre = view_len < kScreenBases ? view_len : kScreenBases;
-                            ok = dfs_align<DFS_EXISTS>(ix, node, off0, SmemRead{rd + (stage == 3 ? 1 : 0)}, pre, 0, stack, kScreenBases + 2, nullptr, nullptr, nullptr) != 0;
-                        }
-                        const uint32_t ball = __ballot_sync(0xffffffffu, ok);
-                        if (ball) {
-                            cand = make_uint2(m - hb, (strand << 31) | (base + (__ffs(ball) - 1)));
-                            found = true;
-                        }
-                    }
+// DFS with the path bitset carried as a running AND (mw <= kMaskWordsInline). A branch whose bitset becomes
+// empty is abandoned: it could only produce traversals without path ids, which the reference discards
+// (alignment.go:301-309) and which do not count as a successful alignment (alignment.go:38,58,81,99).
+// mask_ws: per-thread save area, one bitset per stack level, written only at branch nodes.
+//
+// FLAT control flow: one loop whose every iteration compares at most kChunk bases of the current node, so that
+// the 32 walks of a warp stay in step no matter where their node boundaries fall (with a per-node inner loop a
+// 50-base node in one lane stalls the 1-base nodes of the others: measured 3 active lanes per instruction).
+// Node entry / exit (bitset AND, success test, push, next edge, backtrack) are per-lane events of that loop.
+constexpr uint32_t kChunk = 8;
+
+template <class RD>
+__device__ void dfs_masked(const DevIndex& ix, uint32_t node0, uint32_t off0, RD rd, uint32_t rlen, uint32_t mw,
+                           DfsFrame* __restrict__ stack, uint32_t* __restrict__ mask_ws, uint32_t max_depth, DfsResult* res) {
+    uint32_t nrec = 0, ntrav = 0, depth = 0;
+    uint32_t cur = node0, off = off0, dist = 0;
+    uint32_t cm[kMaskWordsInline];
+#pragma unroll
+    for (int wi = 0; wi < kMaskWordsInline; wi++) cm[wi] = 0xffffffffu;
+    NodeRec nd = ix.nodes[cur];
+    bool active = true;
+    bool ok = off < nd.seq_len;                               // alignment.go:199-201
+    while (active) {
+        // ---- compare up to kChunk bases of the current node ----
+        bool node_done = !ok;
+        if (ok) {
+            const uint32_t left_node = nd.seq_len - off, left_read = rlen - dist;
+            uint32_t n = left_node < left_read ? left_node : left_read;
+            n = n < kChunk ? n : kChunk;
+            const uint8_t* sq = ix.node_seq + nd.seq_off + off;
+#pragma unroll
+            for (uint32_t i = 0; i < kChunk; i++) {
+                if (i < n) {
+                    const uint8_t b = sq[i];
+                    if (b != 'N' && b != rd(dist + i)) ok = false;   // alignment.go:212-222
                 }
             }
+            off += n;
+            // a reference 'N' consumes a read base too, so dist advances by n on success (alignment.go:212-219)
+            dist += n;
+            node_done = !ok || off == nd.seq_len || dist == rlen;     // alignment.go:204-209
         }
-        if (lane == 0) a.seg_cand[s] = cand;
+        if (!node_done) continue;
+        // ---- node finished: membership, success, descend ----
+        if (ok) {
+            uint32_t any = 0;
+#pragma unroll
+            for (int wi = 0; wi < kMaskWordsInline; wi++)
+                if (wi < mw) { cm[wi] &= ix.node_mask[nd.mask_off + wi]; any |= cm[wi]; }
+            ok = any != 0 && depth < max_depth;
+        }
+        if (ok) {
+            if (dist == rlen || nd.edge_cnt == 0) {               // alignment.go:229: full read matched OR sink node
+                uint32_t c = 0;
+#pragma unroll
+                for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) { c += __popc(cm[wi]); res->mask[wi] = cm[wi]; }
+                nrec += c; ntrav++;
+            } else {
+                stack[depth].node = cur; stack[depth].edge_i = 0; stack[depth].dist = static_cast<uint16_t>(dist);
+                if (nd.edge_cnt > 1) {
+#pragma unroll
+                    for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) mask_ws[depth * kMaskWordsInline + wi] = cm[wi];
+                }
+                depth++;
+            }
+        }
+        // ---- next node: first untried edge of the deepest frame that has one ----
+        active = false;
+        while (depth > 0) {
+            DfsFrame& top = stack[depth - 1];
+            const NodeRec tn = ix.nodes[top.node];
+            if (top.edge_i < tn.edge_cnt) {
+                if (top.edge_i > 0) {                             // coming back to a branch node: restore its bitset
+#pragma unroll
+                    for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) cm[wi] = mask_ws[(depth - 1) * kMaskWordsInline + wi];
+                }
+                cur = ix.edges[tn.edge_off + top.edge_i];
+                top.edge_i++;
+                off = 0; dist = top.dist;
+                nd = ix.nodes[cur];
+                ok = nd.seq_len > 0;
+                active = true;
+                break;
+            }
+            depth--;
+        }
     }
+    res->nrec = nrec; res->ntrav = ntrav;
 }
 
-// ---- verify: one thread per pair -------------------------------------------------------------------
-__global__ void __launch_bounds__(128) align_verify_kernel(DevIndex ix, AlignArgs a) {
+constexpr uint32_t kPrefixBases = 8;  // == kPfxLen of host/prefix_table.cpp
+// 2-bit pack of read bases [v, v+8) of the oriented read for v = 0, 1; bad = positions that are not ACGT
+__device__ __forceinline__ void pack_read_prefix(const uint8_t* __restrict__ rp, const uint8_t* lut, uint32_t len, bool rc, uint32_t (&pk)[2], uint32_t (&bad)[2]) {
+    uint32_t p = 0, b = 0;
+    for (uint32_t i = 0; i < kPrefixBases + 1 && i < len; i++) {
+        const uint8_t c = rc ? lut[rp[len - 1 - i]] : rp[i];
+        const uint32_t code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+        if (code > 3u) b |= 1u << i;
+        p |= (code & 3u) << (2 * i);
+    }
+    constexpr uint32_t m2 = (1u << (2 * kPrefixBases)) - 1u, m1 = (1u << kPrefixBases) - 1u;
+    pk[0] = p & m2; pk[1] = (p >> 2) & m2;
+    bad[0] = b & m1; bad[1] = (b >> 1) & m1;
+}
+// true unless NO traversal starting at graph position `pos` can spell the read's first min(8, rlen) bases
+__device__ __forceinline__ bool prefix_pass(const DevIndex& ix, uint32_t pos, uint32_t rpk, uint32_t rbad, uint32_t rlen) {
+    const uint32_t b = ix.pfx_off[pos], e = ix.pfx_off[pos + 1];
+    for (uint32_t i = b; i < e; i++) {
+        const uint64_t ent = ix.pfx[i];
+        if (ent >> 40) return true;                                  // holds an 'N' / too many prefixes: let the DFS decide
+        uint32_t L = static_cast<uint32_t>(ent >> 32) & 31u;
+        L = L < rlen ? L : rlen;
+        const uint32_t m2 = (1u << (2 * L)) - 1u;                    // L <= kPrefixBases
+        const uint32_t m1 = (1u << L) - 1u;
+        if (((static_cast<uint32_t>(ent) ^ rpk) & m2) == 0 && (rbad & m1) == 0) return true;
+    }
+    return false;
+}
+
+// ---- the ordered try list of one (mapping, strand) ---------------------------------------------------
+// Order (graphminion.go:64-98, alignment.go:35-103): for each mapping, for strand in (forward, reverse
+// complement): tries [0, t1) = stage 1 offsets OffSet+t on the seed node (t1 = MergeSpan+WindowSize+1), then 11
+// per contained node (ascending SegmentID) = stage 2 offsets 0..10, then stage 3 (1-base start clip) and stage 4
+// (1-base end clip).
+__device__ __forceinline__ uint32_t tries_per_strand(const WinRec& wr) {
+    return (wr.merge_span + wr.win_size + 1u) + wr.cn_cnt * 11u + 2u;
+}
+__device__ __forceinline__ void decode_try(const DevIndex& ix, const WinRec& wr, uint32_t t, uint32_t* node, uint32_t* off, uint32_t* stage) {
+    const uint32_t t1 = wr.merge_span + wr.win_size + 1u;
+    if (t < t1) { *node = wr.node; *off = wr.offset + t; *stage = 1; return; }
+    t -= t1;
+    const uint32_t t2 = wr.cn_cnt * 11u;
+    if (t < t2) { *node = ix.cn_node[wr.cn_off + t / 11u]; *off = t % 11u; *stage = 2; return; }
+    t -= t2;
+    *node = wr.node; *off = wr.offset; *stage = 3 + t;
+}
+
+struct PairCursor { uint32_t m_strand; uint32_t t; };   // m_strand = (mapping index inside the pair) << 1 | strand
+constexpr uint32_t kNoCand = 0xffffffffu;
+
+struct RoundArgs {
+    AlignArgs a;
+    PairCursor* cursor;        // [n_segs] next try to examine
+    uint2* cand;               // [n_segs] screen result: (m_strand, t) or (kNoCand, 0)
+    const uint32_t* queue;     // pairs to process this round
+    uint32_t* queue_next;      // pairs re-queued for the next round
+    const uint32_t* n_queue;   // device scalar
+    uint32_t* n_queue_next;    // device scalar (atomic)
+};
+
+__global__ void __launch_bounds__(256) align_init_kernel(DevIndex ix, AlignArgs a, PairCursor* cursor, uint32_t* queue, uint32_t* n_queue) {
     const uint32_t n_segs = *a.n_segs_ptr, n_hits = *a.n_hits_ptr;
-    const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
-    const uint32_t depth_cap = a.max_len + 2;
-    DfsFrame* stack = a.stack_ws + static_cast<size_t>(gthread) * depth_cap;
-    unsigned slow = 0;
-    for (uint32_t s = gthread; s < n_segs; s += total) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_segs; s += gridDim.x * blockDim.x) {
+        const uint32_t hb = a.seg_begin[s];                             // segments tile hits[]
+        const uint32_t he = (s + 1 < n_segs) ? a.seg_begin[s + 1] : n_hits;
+        PairOut p;
+        p.read = a.hit_read[hb]; p.graph = ix.wins[a.hits[hb]].graph; p.hit_begin = hb; p.hit_count = he - hb;
+        p.n_incremented = he - hb;                  // every mapping is weighted when none aligns (graphminion.go:64-98)
+        p.rec_begin = 0; p.rec_count = 0; p.reverse = 0; p.clip_start = 0; p.clip_end = 0; p.stage = 0;
+        a.pairs[s] = p;
+        a.seg_nrec[s] = 0; a.seg_ntrav[s] = 0; a.seg_locus[s] = make_uint2(0, 0);
+        cursor[s] = PairCursor{0u, 0u};
+        queue[s] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_queue = a.no_align ? 0u : n_segs;   // graphminion.go:70-72 (--noAlign)
+}
+
+// pack the first kPrefixBases+1 oriented read bases with the whole warp (lane i handles base i)
+__device__ __forceinline__ void warp_pack_read_prefix(const uint8_t* __restrict__ rp, uint32_t len, bool rc, uint32_t lane,
+                                                      uint32_t (&pk)[2], uint32_t (&bad)[2]) {
+    uint32_t code = 4;
+    if (lane <= kPrefixBases && lane < len) {
+        const uint8_t c = rc ? complement_base(rp[len - 1 - lane]) : rp[lane];
+        code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+    }
+    const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u), b1 = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
+    const uint32_t bb = __ballot_sync(0xffffffffu, code > 3u && lane < len);
+    uint32_t p = 0;
+#pragma unroll
+    for (uint32_t i = 0; i <= kPrefixBases; i++) p |= (((b0 >> i) & 1u) | (((b1 >> i) & 1u) << 1)) << (2 * i);
+    constexpr uint32_t m2 = (1u << (2 * kPrefixBases)) - 1u, m1 = (1u << kPrefixBases) - 1u;
+    pk[0] = p & m2; pk[1] = (p >> 2) & m2;
+    bad[0] = bb & m1; bad[1] = (bb >> 1) & m1;
+}
+
+__global__ void __launch_bounds__(256) align_screen_kernel(DevIndex ix, RoundArgs ra) {
+    const AlignArgs& a = ra.a;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_queue = *ra.n_queue, n_segs = *a.n_segs_ptr, n_hits = *a.n_hits_ptr;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t q = gwarp; q < n_queue; q += total_warps) {
+        const uint32_t s = ra.queue[q];
         const uint32_t hb = a.seg_begin[s];
         const uint32_t he = (s + 1 < n_segs) ? a.seg_begin[s + 1] : n_hits;
         const uint32_t r = a.hit_read[hb];
         const uint32_t o = a.off[r], len = a.off[r + 1] - o;
-        const uint32_t graph = ix.wins[a.hits[hb]].graph;
-        const uint32_t mw = ix.graph_mask_words[graph];
-        const uint2 cand = a.seg_cand[s];
-        PairOut p;
-        p.read = r; p.graph = graph; p.hit_begin = hb; p.hit_count = he - hb;
-        p.n_incremented = he - hb;                         // every mapping is weighted when none aligns (graphminion.go:64-98)
-        p.rec_begin = 0; p.rec_count = 0; p.reverse = 0; p.clip_start = 0; p.clip_end = 0; p.stage = 0;
-        DfsResult res;
-        res.nrec = 0; res.ntrav = 0;
-        uint32_t lnode = 0, loff = 0;
-        if (cand.x != 0xffffffffu) {
-            uint32_t m = hb + cand.x, strand = cand.y >> 31, t = cand.y & 0x7fffffffu;
-            bool first = true;
-            while (m < he) {
-                const WinRec wr = ix.wins[a.hits[m]];
-                const uint32_t T = tries_per_strand(wr);
-                bool done = false;
-                for (; strand < 2 && !done; strand++, t = 0) {
-                    if (strand == 1 && !first && t == 0) {     // sequential continuation reached RevComplement on its own
-                        for (uint32_t i = 0; i < len; i++) if (a.seq[o + i] > 'T') { if (atomicCAS(a.error, 0, -6) == 0) a.error[1] = static_cast<int>(r); break; }
+        const uint8_t* rp = a.seq + o;
+        const PairCursor cur = ra.cursor[s];
+        uint32_t m = hb + (cur.m_strand >> 1), strand = cur.m_strand & 1u, t0 = cur.t;
+        uint2 cand = make_uint2(kNoCand, 0u);
+        while (m < he && cand.x == kNoCand) {
+            const WinRec wr = ix.wins[a.hits[m]];
+            const NodeRec sn = ix.nodes[wr.node];
+            const uint32_t T = tries_per_strand(wr);
+            uint32_t pk[2], bad[2];
+            warp_pack_read_prefix(rp, len, strand != 0, lane, pk, bad);
+            for (uint32_t base = t0 & ~31u; base < T && cand.x == kNoCand; base += 32) {
+                const uint32_t t = base + lane;
+                bool ok = false;
+                if (t >= t0 && t < T) {
+                    uint32_t node, off0, stage;
+                    decode_try(ix, wr, t, &node, &off0, &stage);
+                    uint32_t seq_off = sn.seq_off, seq_len = sn.seq_len;
+                    if (stage == 2) { const NodeRec cn = ix.nodes[node]; seq_off = cn.seq_off; seq_len = cn.seq_len; }
+                    if (off0 < seq_len) {                                   // else dfsRecursive fails on entry (alignment.go:199-201)
+                        const uint32_t v = stage == 3 ? 1u : 0u;            // the start clip compares from read base 1
+                        ok = prefix_pass(ix, seq_off + off0, pk[v], bad[v], stage >= 3 ? len - 1 : len);
                     }
-                    for (; t < T; t++) {
-                        uint32_t node, off0, stage;
-                        decode_try(ix, wr, t, &node, &off0, &stage);
-                        GlobalRead rd{a.seq + o, len, stage == 3 ? 1u : 0u, strand != 0};
-                        const uint32_t rlen = stage >= 3 ? len - 1 : len;
-                        res.nrec = 0; res.ntrav = 0;
-                        dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
-                        if (res.nrec > 0) {
-                            p.n_incremented = m - hb + 1; p.rec_count = res.nrec; p.reverse = static_cast<uint8_t>(strand);
-                            p.clip_start = stage == 3; p.clip_end = stage == 4; p.stage = static_cast<uint8_t>(stage);
-                            lnode = node; loff = off0;
-                            done = true;
-                            break;
-                        }
-                        if (first) { slow++; first = false; }
-                    }
-                    if (done) break;
                 }
-                if (done) break;
-                m++; strand = 0; t = 0;
+                const uint32_t ball = __ballot_sync(0xffffffffu, ok);
+                if (ball) cand = make_uint2(((m - hb) << 1) | strand, base + (__ffs(ball) - 1));
             }
+            if (cand.x != kNoCand) break;
+            t0 = 0;
+            if (strand == 0) {
+                strand = 1;                                                 // graphminion.go:94 RevComplement: Go panics for a byte > 'T'
+                bool badb = false;
+                for (uint32_t i = lane; i < len; i += 32) badb |= rp[i] > 'T';
+                if (__any_sync(0xffffffffu, badb) && lane == 0) { if (atomicCAS(a.error, 0, -6) == 0) a.error[1] = static_cast<int>(r); }
+            } else { strand = 0; m++; }
         }
-        a.pairs[s] = p;
-        a.seg_nrec[s] = p.rec_count;
-        a.seg_locus[s] = make_uint2(lnode, loff);
-        a.seg_ntrav[s] = res.nrec > 0 ? res.ntrav : 0;
-        if (res.nrec > 0 && res.ntrav == 1 && mw <= kMaskWordsInline)
-            for (uint32_t wi = 0; wi < mw; wi++) a.seg_mask[static_cast<size_t>(s) * kMaskWordsInline + wi] = res.mask[wi];
+        if (lane == 0) ra.cand[s] = cand;
     }
-    slow = __reduce_add_sync(0xffffffffu, slow);
-    if ((threadIdx.x & 31) == 0 && slow) atomicAdd(&a.counters[3], static_cast<unsigned long long>(slow));
+}
+
+// walk one try of pair s; on success fills the pair's outputs and returns true
+__device__ __forceinline__ bool walk_try(const DevIndex& ix, const AlignArgs& a, const uint8_t* lut, uint32_t s, uint32_t hb,
+                                         uint32_t m, uint32_t strand, uint32_t t, DfsFrame* stack, uint32_t* mask_ws, uint32_t depth_cap) {
+    const WinRec wr = ix.wins[a.hits[m]];
+    const uint32_t r = a.hit_read[hb];
+    const uint32_t o = a.off[r], len = a.off[r + 1] - o;
+    const uint32_t mw = ix.graph_mask_words[wr.graph];
+    uint32_t node, off0, stage;
+    decode_try(ix, wr, t, &node, &off0, &stage);
+    ReadView rd{a.seq + o, lut, len, stage == 3 ? 1u : 0u, strand != 0};
+    const uint32_t rlen = stage >= 3 ? len - 1 : len;
+    DfsResult res;
+    res.nrec = 0; res.ntrav = 0;
+    if (mw <= kMaskWordsInline) dfs_masked(ix, node, off0, rd, rlen, mw, stack, mask_ws, depth_cap, &res);
+    else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
+    if (res.nrec == 0) return false;
+    PairOut p = a.pairs[s];
+    p.n_incremented = m - hb + 1;
+    p.rec_count = res.nrec; p.reverse = static_cast<uint8_t>(strand);
+    p.clip_start = stage == 3; p.clip_end = stage == 4; p.stage = static_cast<uint8_t>(stage);
+    a.pairs[s] = p;
+    a.seg_nrec[s] = res.nrec;
+    a.seg_locus[s] = make_uint2(node, off0);
+    a.seg_ntrav[s] = res.ntrav;
+    if (res.ntrav == 1 && mw <= kMaskWordsInline)
+        for (uint32_t wi = 0; wi < mw; wi++) a.seg_mask[static_cast<size_t>(s) * kMaskWordsInline + wi] = res.mask[wi];
+    return true;
+}
+
+__global__ void __launch_bounds__(128, 5) align_walk_kernel(DevIndex ix, RoundArgs ra) {
+    __shared__ uint8_t lut[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = complement_base(static_cast<uint8_t>(i));
+    __syncthreads();
+    const AlignArgs& a = ra.a;
+    const uint32_t n_queue = *ra.n_queue;
+    const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
+    const uint32_t depth_cap = a.max_len + 2;
+    DfsFrame* stack = a.stack_ws + static_cast<size_t>(gthread) * depth_cap;
+    uint32_t* mask_ws = a.mask_ws + static_cast<size_t>(gthread) * depth_cap * kMaskWordsInline;
+    unsigned failed = 0;
+    for (uint32_t q = gthread; q < n_queue; q += total) {
+        const uint32_t s = ra.queue[q];
+        const uint2 cand = ra.cand[s];
+        if (cand.x == kNoCand) continue;                        // try list exhausted: the default (unaligned) result stands
+        const uint32_t hb = a.seg_begin[s];
+        if (!walk_try(ix, a, lut, s, hb, hb + (cand.x >> 1), cand.x & 1u, cand.y, stack, mask_ws, depth_cap)) {
+            ra.cursor[s] = PairCursor{cand.x, cand.y + 1};      // resume just past this try (the screen handles t == T)
+            ra.queue_next[atomicAdd(ra.n_queue_next, 1u)] = s;
+            failed++;
+        }
+    }
+    failed = __reduce_add_sync(0xffffffffu, failed);
+    if ((threadIdx.x & 31) == 0 && failed) atomicAdd(&a.counters[3], static_cast<unsigned long long>(failed));
+}
+
+// Leftovers after the fixed number of rounds (pairs that keep producing tries which pass the filter but yield no
+// path id — low-complexity sequence, 'N' wildcards): ONE WARP PER PAIR runs screen steps and lets lane 0 walk each
+// survivor, in order, until one aligns or the list is exhausted.
+__global__ void __launch_bounds__(128, 5) align_finish_kernel(DevIndex ix, RoundArgs ra) {
+    __shared__ uint8_t lut[256];
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = complement_base(static_cast<uint8_t>(i));
+    __syncthreads();
+    const AlignArgs& a = ra.a;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_queue = *ra.n_queue, n_segs = *a.n_segs_ptr, n_hits = *a.n_hits_ptr;
+    const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gwarp = gthread >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t depth_cap = a.max_len + 2;
+    DfsFrame* stack = a.stack_ws + static_cast<size_t>(gthread) * depth_cap;
+    uint32_t* mask_ws = a.mask_ws + static_cast<size_t>(gthread) * depth_cap * kMaskWordsInline;
+    for (uint32_t q = gwarp; q < n_queue; q += total_warps) {
+        const uint32_t s = ra.queue[q];
+        const uint32_t hb = a.seg_begin[s];
+        const uint32_t he = (s + 1 < n_segs) ? a.seg_begin[s + 1] : n_hits;
+        const uint32_t r = a.hit_read[hb];
+        const uint32_t o = a.off[r], len = a.off[r + 1] - o;
+        const uint8_t* rp = a.seq + o;
+        const PairCursor cur = ra.cursor[s];
+        uint32_t m = hb + (cur.m_strand >> 1), strand = cur.m_strand & 1u, t0 = cur.t;
+        bool done = false;
+        while (m < he && !done) {
+            const WinRec wr = ix.wins[a.hits[m]];
+            const NodeRec sn = ix.nodes[wr.node];
+            const uint32_t T = tries_per_strand(wr);
+            uint32_t pk[2], bad[2];
+            warp_pack_read_prefix(rp, len, strand != 0, lane, pk, bad);
+            for (uint32_t base = t0 & ~31u; base < T && !done; base += 32) {
+                const uint32_t t = base + lane;
+                bool ok = false;
+                if (t >= t0 && t < T) {
+                    uint32_t node, off0, stage;
+                    decode_try(ix, wr, t, &node, &off0, &stage);
+                    uint32_t seq_off = sn.seq_off, seq_len = sn.seq_len;
+                    if (stage == 2) { const NodeRec cn = ix.nodes[node]; seq_off = cn.seq_off; seq_len = cn.seq_len; }
+                    if (off0 < seq_len) {
+                        const uint32_t v = stage == 3 ? 1u : 0u;
+                        ok = prefix_pass(ix, seq_off + off0, pk[v], bad[v], stage >= 3 ? len - 1 : len);
+                    }
+                }
+                uint32_t ball = __ballot_sync(0xffffffffu, ok);
+                while (ball && !done) {                                     // survivors of this chunk, in order
+                    const uint32_t t_c = base + (__ffs(ball) - 1);
+                    ball &= ball - 1;
+                    uint32_t okw = 0;
+                    if (lane == 0) okw = walk_try(ix, a, lut, s, hb, m, strand, t_c, stack, mask_ws, depth_cap) ? 1u : 0u;
+                    done = __shfl_sync(0xffffffffu, okw, 0) != 0;
+                }
+            }
+            if (done) break;
+            t0 = 0;
+            if (strand == 0) {
+                strand = 1;                                                 // graphminion.go:94 RevComplement: Go panics for a byte > 'T'
+                bool badb = false;
+                for (uint32_t i = lane; i < len; i += 32) badb |= rp[i] > 'T';
+                if (__any_sync(0xffffffffu, badb) && lane == 0) { if (atomicCAS(a.error, 0, -6) == 0) a.error[1] = static_cast<int>(r); }
+            } else { strand = 0; m++; }
+        }
+    }
 }
 
 struct EmitArgs {
@@ -334,36 +564,40 @@ struct EmitArgs {
     uint32_t max_len;
 };
 
-// One thread per pair: write the pair's records at the scanned offset. The common case (exactly one
-// traversal with ids, <= 256 paths in the graph) expands the stored bitset; otherwise the DFS is re-run.
-__global__ void __launch_bounds__(128) align_emit_kernel(DevIndex ix, EmitArgs a) {
+// ONE WARP PER PAIR: write the pair's records at the scanned offset. The common case (exactly one traversal with
+// ids, <= 256 paths in the graph) expands the stored bitset with the lanes striding over the start node's path
+// list (path ids ascending == record order); otherwise lane 0 re-runs the DFS in emit mode.
+__global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a) {
     const uint32_t n_segs = *a.n_segs_ptr;
-    const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t gwarp = gthread >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t depth_cap = a.max_len + 2;
     DfsFrame* stack = a.stack_ws + static_cast<size_t>(gthread) * depth_cap;
-    for (uint32_t s = gthread; s < n_segs; s += total) {
-        PairOut p = a.pairs[s];
+    for (uint32_t s = gwarp; s < n_segs; s += total_warps) {
+        const PairOut p = a.pairs[s];
         const uint32_t rb = a.rec_off[s];
-        a.pairs[s].rec_begin = rb;
+        if (lane == 0) a.pairs[s].rec_begin = rb;
         if (p.rec_count == 0) continue;
         const uint2 loc = a.seg_locus[s];
         const uint32_t mw = ix.graph_mask_words[p.graph];
         if (a.seg_ntrav[s] == 1 && mw <= kMaskWordsInline) {
             const NodeRec n0 = ix.nodes[loc.x];
-            uint32_t j = 0, n = 0;
-            for (uint32_t wi = 0; wi < mw; wi++) {
-                uint32_t m = a.seg_mask[static_cast<size_t>(s) * kMaskWordsInline + wi];
-                while (m) {
-                    const uint32_t pid = wi * 32 + (__ffs(m) - 1);
-                    m &= m - 1;
-                    while (j < n0.path_cnt && ix.node_path_id[n0.path_off + j] < pid) j++;
-                    const int32_t pos = (j < n0.path_cnt && ix.node_path_id[n0.path_off + j] == pid) ? ix.node_path_pos[n0.path_off + j] : 0;
-                    a.rec_path[rb + n] = pid;
-                    a.rec_pos[rb + n] = pos + static_cast<int32_t>(loc.y);
-                    n++;
+            const uint32_t* mk = a.seg_mask + static_cast<size_t>(s) * kMaskWordsInline;
+            uint32_t written = 0;
+            for (uint32_t j0 = 0; j0 < n0.path_cnt; j0 += 32) {
+                const uint32_t j = j0 + lane;
+                uint32_t pid = 0; bool on = false;
+                if (j < n0.path_cnt) { pid = ix.node_path_id[n0.path_off + j]; on = (mk[pid >> 5] >> (pid & 31)) & 1u; }
+                const uint32_t ball = __ballot_sync(0xffffffffu, on);
+                if (on) {
+                    const uint32_t slot = rb + written + __popc(ball & ((1u << lane) - 1u));
+                    a.rec_path[slot] = pid;
+                    a.rec_pos[slot] = ix.node_path_pos[n0.path_off + j] + static_cast<int32_t>(loc.y);   // alignment.go:296
                 }
+                written += __popc(ball);
             }
-        } else {
+        } else if (lane == 0) {
             const uint32_t o = a.off[p.read], len = a.off[p.read + 1] - o;
             GlobalRead rd{a.seq + o, len, p.clip_start ? 1u : 0u, p.reverse != 0};
             const uint32_t rlen = len - p.clip_start - p.clip_end;

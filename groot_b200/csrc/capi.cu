@@ -85,7 +85,9 @@ T* upload(const std::vector<T>& v, std::vector<void*>& owned) {
 
 MultTable make_mult(uint32_t k) {
     MultTable m;
-    for (uint64_t i = 0; i < 32; i++) m.c[i] = i ^ (static_cast<uint64_t>(k) * GROOT_MULTI_SEED);
+    const uint64_t C = static_cast<uint64_t>(k) * GROOT_MULTI_SEED;
+    for (uint64_t i = 0; i < 32; i++) { m.c[i] = i ^ C; m.low[i] = static_cast<uint32_t>((C & 31u) ^ i); }
+    m.c0 = C & ~31ull; m.m32 = 32; m.pad = 0;
     return m;
 }
 
@@ -163,7 +165,7 @@ struct grootgpu_index {
     // per (q, threshold) parameter cache
     std::map<std::pair<uint32_t, double>, LenParam> param_cache;
     // workspaces
-    DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_cand, seg_mask, seg_ntrav,
+    DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
         rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error;
     HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_scal;
     std::vector<LenParam> h_len_params;
@@ -195,6 +197,11 @@ void index_to_device(grootgpu_index* ix) {
     d.cn_node = upload(h.cn_node, ix->owned);
     d.sketches = upload(h.sketches, ix->owned);
     d.graph_mask_words = upload(h.graph_mask_words, ix->owned);
+    {
+        std::vector<uint32_t> pfx_off; std::vector<uint64_t> pfx;
+        build_prefix_table(h, pfx_off, pfx);
+        d.pfx_off = upload(pfx_off, ix->owned); d.pfx = upload(pfx, ix->owned);
+    }
     d.k = h.p.k; d.S = h.p.S; d.max_k = h.p.max_k; d.n_bands = h.p.S / h.p.max_k; d.n_wins = static_cast<uint32_t>(h.wins.size());
     ix->h_tables.assign(static_cast<size_t>(h.p.max_k) * d.n_bands, LshTable{nullptr, nullptr, 0, 0});
     void* dt = nullptr;
@@ -424,33 +431,51 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         CK(cudaMemcpyAsync(&n_segs, d_nsegs, 4, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
 
-        // ---- K3: screen (warp per pair) -> verify (thread per pair) -> scan -> emit ----
+        // ---- K3: align (thread per pair) -> scan -> emit ----
         ix->pairs.need(sizeof(PairOut) * static_cast<size_t>(n_segs)); ix->seg_nrec.need(4ull * n_segs); ix->seg_locus.need(8ull * n_segs);
-        ix->rec_off.need(4ull * (n_segs + 1)); ix->seg_cand.need(8ull * n_segs); ix->seg_ntrav.need(4ull * n_segs);
+        ix->rec_off.need(4ull * (n_segs + 1)); ix->seg_ntrav.need(4ull * n_segs);
         ix->seg_mask.need(4ull * kMaskWordsInline * n_segs);
-        const uint32_t stride = (max_len + 16) & ~15u;
-        const size_t align_smem = static_cast<size_t>(kAlignWarps) * 2 * stride;
-        if (align_smem > 200 * 1024) throw std::runtime_error("read too long for the align kernel's shared-memory staging (documented limit)");
-        int screen_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + kAlignWarps - 1) / kAlignWarps, static_cast<uint64_t>(sms) * 8));
-        screen_blocks = std::max(screen_blocks, 1);
         const int vthreads = 128;
         int verify_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + vthreads - 1) / vthreads, static_cast<uint64_t>(sms) * 8));
         verify_blocks = std::max(verify_blocks, 1);
         ix->stack_ws.need(static_cast<size_t>(verify_blocks) * vthreads * (max_len + 2) * sizeof(DfsFrame));
+        ix->mask_ws.need(static_cast<size_t>(verify_blocks) * vthreads * (max_len + 2) * kMaskWordsInline * 4);
         AlignArgs aa{};
         aa.seq = d_seq; aa.off = d_off; aa.hits = ix->hits.as<uint32_t>(); aa.hit_read = ix->hit_read.as<uint32_t>();
         aa.seg_begin = ix->seg_begin.as<uint32_t>(); aa.n_segs_ptr = d_nsegs; aa.n_hits_ptr = ix->hit_off.as<uint32_t>() + n;
-        aa.seg_cand = ix->seg_cand.as<uint2>();
         aa.pairs = ix->pairs.as<PairOut>(); aa.seg_nrec = ix->seg_nrec.as<uint32_t>(); aa.seg_locus = ix->seg_locus.as<uint2>();
         aa.seg_mask = ix->seg_mask.as<uint32_t>(); aa.seg_ntrav = ix->seg_ntrav.as<uint32_t>();
-        aa.stack_ws = ix->stack_ws.as<DfsFrame>(); aa.max_len = max_len; aa.no_align = prm->no_align; aa.error = ix->error.as<int>();
+        aa.stack_ws = ix->stack_ws.as<DfsFrame>(); aa.mask_ws = ix->mask_ws.as<uint32_t>();
+        aa.max_len = max_len; aa.no_align = prm->no_align; aa.error = ix->error.as<int>();
         aa.counters = d_counters;
-        CK(cudaFuncSetAttribute(align_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(align_smem)));
+        // screen/walk rounds over a shrinking, compacted queue; the queue counts stay on the device
+        ix->cursor.need(8ull * n_segs); ix->cand.need(8ull * n_segs); ix->queue_a.need(4ull * n_segs); ix->queue_b.need(4ull * n_segs);
+        ix->qcount.need(64);
+        CK(cudaMemsetAsync(ix->qcount.p, 0, 64, st));
+        uint32_t* qc = ix->qcount.as<uint32_t>();
         CK(cudaEventRecord(ix->ev[2], st));
-        align_screen_kernel<<<screen_blocks, kAlignWarps * 32, align_smem, st>>>(ix->d, aa); launches++;
+        align_init_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ix->d, aa, ix->cursor.as<PairCursor>(), ix->queue_a.as<uint32_t>(), qc); launches++;
         CK(cudaGetLastError());
-        align_verify_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, aa); launches++;
-        CK(cudaGetLastError());
+        int screen_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8));
+        screen_blocks = std::max(screen_blocks, 1);
+        const int kRounds = 6;
+        RoundArgs ra{};
+        ra.a = aa; ra.cursor = ix->cursor.as<PairCursor>(); ra.cand = ix->cand.as<uint2>();
+        for (int round = 0; round < kRounds; round++) {
+            uint32_t* qa = (round & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
+            uint32_t* qb = (round & 1) ? ix->queue_a.as<uint32_t>() : ix->queue_b.as<uint32_t>();
+            ra.queue = qa; ra.queue_next = qb; ra.n_queue = qc + (round & 1); ra.n_queue_next = qc + ((round + 1) & 1);
+            align_screen_kernel<<<screen_blocks, 256, 0, st>>>(ix->d, ra); launches++;
+            align_walk_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++;
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(qc + (round & 1), 0, 4, st));   // this round's count becomes the next round's "next"
+        }
+        {
+            uint32_t* qa = (kRounds & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
+            ra.queue = qa; ra.queue_next = nullptr; ra.n_queue = qc + (kRounds & 1); ra.n_queue_next = nullptr;
+            align_finish_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++;
+            CK(cudaGetLastError());
+        }
         CK(cudaEventRecord(ix->ev[3], st));
         // ---- scan record counts, emit ----
         size_t scan2 = 0;
@@ -473,7 +498,12 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         ea.seg_locus = ix->seg_locus.as<uint2>(); ea.seg_mask = ix->seg_mask.as<uint32_t>(); ea.seg_ntrav = ix->seg_ntrav.as<uint32_t>();
         ea.rec_path = ix->rec_path.as<uint32_t>(); ea.rec_pos = ix->rec_pos.as<int32_t>();
         ea.stack_ws = ix->stack_ws.as<DfsFrame>(); ea.max_len = max_len;
-        align_emit_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ea); launches++;
+        {
+            int emit_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8));
+            // stack_ws holds verify_blocks*128 thread stacks; the emit grid (256-thread blocks) must not exceed that
+            emit_blocks = std::max(1, std::min(emit_blocks, verify_blocks / 2));
+            align_emit_kernel<<<emit_blocks, 256, 0, st>>>(ix->d, ea); launches++;
+        }
         CK(cudaGetLastError());
     } else {
         CK(cudaEventRecord(ix->ev[2], st));

@@ -60,11 +60,21 @@ struct DevIndex {
     const uint64_t* sketches;
     const uint32_t* graph_mask_words;
     const LshTable* tables;  // [(K-1)*n_bands + band]; slots == nullptr when not built yet
+    const uint32_t* pfx_off; // [node_seq bytes + 1] prefix-table CSR (host/prefix_table.cpp), position = NodeRec::seq_off + offset
+    const uint64_t* pfx;
     uint32_t k, S, max_k, n_bands, n_wins;
 };
 
-// multi-hash multipliers i ^ (k * multiSeed), passed by value => they live in the constant bank
-struct MultTable { uint64_t c[32]; };
+// multi-hash multipliers c_i = i ^ (k * multiSeed), passed by value => they live in the constant bank.
+// For i < 32 the xor only touches the low 5 bits: c_i = c0 + low[i] with c0 = C & ~31, low[i] = (C & 31) ^ i,
+// so h * c_i = h * c0 + h * low[i]: one 64-bit product per k-mer plus a 32x32->64 multiply-add per hash.
+struct MultTable {
+    uint64_t c[32];
+    uint64_t c0;
+    uint32_t low[32];
+    uint32_t m32;  // == 32, kept as a runtime value so that >>27 can be issued as multiplies (FMA pipe) instead of shifts (ALU pipe)
+    uint32_t pad;
+};
 
 enum : int { HSTAGE = 4 };  // hits per read staged by the seed kernel before the exact-size fill
 

@@ -59,15 +59,43 @@ __device__ inline void build_seed_tabs(SeedTabs* T, unsigned k) {
 }
 
 // ---- the sketch: registers only -------------------------------------------------------------
+#ifndef GROOT_KHF_VARIANT
+#define GROOT_KHF_VARIANT 0
+#endif
 template <int S>
 __device__ __forceinline__ void khf_update(uint64_t h, const MultTable& M, uint64_t (&sk)[S]) {
     sk[0] = h < sk[0] ? h : sk[0];
+#if GROOT_KHF_VARIANT == 0
 #pragma unroll
     for (int i = 1; i < S; i++) {
         uint64_t x = h * M.c[i];
         x ^= x >> GROOT_MULTI_SHIFT;
         sk[i] = x < sk[i] ? x : sk[i];
     }
+#else
+    // x_i = h*c0 + h*low_i  (exact mod 2^64, see MultTable)
+    const uint32_t h_lo = static_cast<uint32_t>(h), h_hi = static_cast<uint32_t>(h >> 32);
+    const uint64_t A = h * M.c0;
+#pragma unroll
+    for (int i = 1; i < S; i++) {
+        uint32_t x_lo, x_hi;
+        asm("{\n .reg .u64 w;\n mad.wide.u32 w, %2, %3, %4;\n mov.b64 {%0, %1}, w;\n}" : "=r"(x_lo), "=r"(x_hi) : "r"(h_lo), "r"(M.low[i]), "l"(A));
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x_hi) : "r"(h_hi), "r"(M.low[i]));
+        uint64_t x;
+#if GROOT_KHF_VARIANT == 1
+        x = (static_cast<uint64_t>(x_hi) << 32) | x_lo;
+        x ^= x >> GROOT_MULTI_SHIFT;
+#else
+        // x >> 27 through the FMA pipe: (x_lo >> 27) = mulhi(x_lo, 32); (x_hi << 5) = x_hi * 32; (x_hi >> 27) = mulhi(x_hi, 32)
+        const uint32_t a = __umulhi(x_lo, M.m32);
+        uint32_t t_lo;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t_lo) : "r"(x_hi), "r"(M.m32), "r"(a));
+        const uint32_t t_hi = __umulhi(x_hi, M.m32);
+        x = (static_cast<uint64_t>(x_hi ^ t_hi) << 32) | (x_lo ^ t_lo);
+#endif
+        sk[i] = x < sk[i] ? x : sk[i];
+    }
+#endif
 }
 
 // p: read bases (shared or global), len >= k

@@ -141,10 +141,10 @@ typedef struct {
     /* theBoss counters (boss.go:22-27): received, mapped (>=1 graph), multimapped (>1 graph), alignment records */
     uint64_t received, mapped, multimapped, alignments;
     /* device time of the batch in ms, CUDA events on the library's stream: [0] whole batch incl. copies,
-     * [1] seed kernel (sketch+probe+verify), [2] align screen+verify kernels, [3] everything else on the device */
+     * [1] seed kernel (sketch+probe+verify), [2] align kernel (all pairs), [3] everything else on the device */
     float ms[4];
     uint32_t kernel_launches;  /* number of this library's own kernels launched for the batch (CUB scans/selects not counted) */
-    uint64_t slow_path_pairs;  /* diagnostic: pairs whose screened start failed the full DFS (sequential continuation taken) */
+    uint64_t slow_path_pairs;  /* diagnostic: full DFS walks that yielded no path id (filter false positives) */
     /* device copies of the arrays above (same layouts), valid until the next align call on the handle */
     const uint32_t* d_hit_off;
     const uint32_t* d_hits;
