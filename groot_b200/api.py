@@ -90,6 +90,7 @@ def lib():
         L.grootgpu_index_dump_hash.argtypes = [vp, C.POINTER(C.c_uint64)]
         L.grootgpu_index_ref.argtypes = [vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_char_p), C.POINTER(C.c_int32)]
         L.grootgpu_index_query_params.argtypes = [vp, C.c_uint32, C.c_double, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.grootgpu_query_params_host.argtypes = [C.POINTER(IndexParams), C.c_uint32, C.c_double, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.grootgpu_align_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(AlignParams), C.POINTER(BatchResultC)]
         L.grootgpu_align_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(AlignParams), vp, C.POINTER(BatchResultC)]
         L.grootgpu_project_batch.argtypes = [vp, C.POINTER(BatchResultC), vp]
@@ -105,7 +106,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "grootgpu_index_build", "grootgpu_index_build_dir", "grootgpu_index_save", "grootgpu_index_load", "grootgpu_index_destroy",
     "grootgpu_index_get_info", "grootgpu_graphs_dump", "grootgpu_index_dump_file", "grootgpu_index_dump_hash", "grootgpu_index_ref",
-    "grootgpu_index_query_params", "grootgpu_align_batch", "grootgpu_align_batch_device", "grootgpu_project_batch",
+    "grootgpu_index_query_params", "grootgpu_query_params_host", "grootgpu_align_batch", "grootgpu_align_batch_device", "grootgpu_project_batch",
     "grootgpu_weights", "grootgpu_reset_weights", "grootgpu_sketch_batch", "grootgpu_prune", "grootgpu_graph_save_gfa",
     "grootgpu_host_alloc", "grootgpu_host_free", "grootgpu_device_count", "grootgpu_last_error", "grootgpu_version",
 ]
@@ -305,6 +306,14 @@ def graphs_dump(msa_files, dump_path=None, k=31, S=21, w=100, num_part=8, max_k=
     h = C.c_uint64()
     _check(lib().grootgpu_graphs_dump(arr, len(msa_files), C.byref(p), dump_path.encode() if dump_path else None, C.byref(h)))
     return h.value
+
+
+def query_params_host(query_kmers, threshold, k=31, S=21, w=100, num_part=8, max_k=4):
+    """(K, L, eq_min) the LSH Ensemble optimiser / containment threshold give for a query of that many k-mers."""
+    p = IndexParams(k, S, w, num_part, max_k)
+    K, L, e = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    _check(lib().grootgpu_query_params_host(C.byref(p), query_kmers, threshold, C.byref(K), C.byref(L), C.byref(e)))
+    return K.value, L.value, e.value
 
 
 def sketch_batch(seqs, off, k, S, device=0):

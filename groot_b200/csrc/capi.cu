@@ -713,6 +713,17 @@ int grootgpu_index_query_params(grootgpu_index* idx, uint32_t q, double t, uint3
     return GROOTGPU_OK;
 }
 
+int grootgpu_query_params_host(const grootgpu_index_params* p, uint32_t q, double t, uint32_t* K, uint32_t* L, uint32_t* eq_min) {
+    if (!p || q == 0 || p->max_k == 0 || p->sketch_size < p->max_k || p->window_size < p->kmer_size) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    int k = 0, l = 0;
+    const int x = static_cast<int>(p->window_size - p->kmer_size + 1);
+    optimal_kl(static_cast<int>(p->max_k), static_cast<int>(p->sketch_size / p->max_k), x, static_cast<int>(q), t, &k, &l);
+    if (K) *K = static_cast<uint32_t>(k);
+    if (L) *L = static_cast<uint32_t>(l);
+    if (eq_min) *eq_min = static_cast<uint32_t>(eq_min_for(static_cast<int>(p->sketch_size), static_cast<int>(q), x, t));
+    return GROOTGPU_OK;
+}
+
 int grootgpu_align_batch_device(grootgpu_index* idx, const uint8_t* d_seq, const uint32_t* d_seq_off, uint32_t n_reads, uint32_t min_len,
                                 uint32_t max_len, const grootgpu_align_params* params, void* stream, grootgpu_batch_result* out) {
     if (!idx || !d_seq || !d_seq_off || !params || n_reads == 0 || max_len < min_len) return fail(GROOTGPU_ERR_ARG, "bad argument");

@@ -99,6 +99,10 @@ int grootgpu_index_ref(const grootgpu_index* idx, uint32_t graph_id, uint32_t pa
  * lshensemble.Containment(...) > threshold, for a query of `query_kmers` k-mers (lshe.go:153-171). */
 int grootgpu_index_query_params(grootgpu_index* idx, uint32_t query_kmers, double threshold, uint32_t* K, uint32_t* L, uint32_t* eq_min);
 
+/* Same computation from the index parameters alone (host only, no device, no handle). */
+int grootgpu_query_params_host(const grootgpu_index_params* params, uint32_t query_kmers, double threshold,
+                               uint32_t* K, uint32_t* L, uint32_t* eq_min);
+
 /* ---- the hot path --------------------------------------------------------------------------- */
 
 typedef struct {

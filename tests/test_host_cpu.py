@@ -1,0 +1,83 @@
+"""CPU-only tests (no GPU): the C-ABI library loads and exports every symbol include/grootgpu.h declares, the
+host-side logic (MSA -> graph builder, LSH parameter optimiser, synthetic reads, multi-rank gather/merge) agrees
+with the oracle, and compute entry points fail loudly without a device (no CPU fallback)."""
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+from groot_b200 import api, synth
+from oracle import pyoracle as po
+
+
+def test_library_exports_every_header_symbol(root):
+    header = open(os.path.join(root, "include", "grootgpu.h")).read()
+    declared = sorted(set(re.findall(r"\b(grootgpu_[a-z_]+)\s*\(", header)))
+    assert len(declared) >= 20
+    lib = api.lib()
+    for sym in declared:
+        assert hasattr(lib, sym), "libgrootgpu.so does not export " + sym
+    assert sorted(api.EXPORTED_SYMBOLS) == declared
+    assert b"sm_100a" in lib.grootgpu_version()
+
+
+def test_no_cpu_fallback_without_device(root):
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.GrootGpuError) as e:
+        api.Index.build(msa_files=[os.path.join(root, "data", "graph", "test-genes.msa")], k=51, S=30, w=100)
+    assert e.value.code == -2
+    with pytest.raises(api.GrootGpuError) as e:
+        api.sketch_batch(np.frombuffer(b"ACGTACGTACGT", dtype=np.uint8), np.array([0, 12], dtype=np.uint64), 7, 10)
+    assert e.value.code == -2
+
+
+def test_graph_builder_matches_oracle(db_dirs, root, tmp_path):
+    """Product MSA->graph builder (groot_b200/csrc/host/graph_build.cpp) vs the oracle's restatement of
+    gfa.MSA2GFA + graph.CreateGrootGraph on every cluster of arg-annot.90 and on the OXA test cluster."""
+    for files, params in ((sorted(glob.glob(os.path.join(db_dirs["arg-annot.90"], "cluster*.msa"))), dict(k=31, S=21, w=100)),
+                          ([os.path.join(root, "data", "graph", "test-genes.msa")], dict(k=51, S=30, w=100))):
+        api.graphs_dump(files, str(tmp_path / "g.txt"), **params)
+        o = po.Index(msa_files=files, **params)
+        o.dump_file(str(tmp_path / "o.txt"))
+        mine = [ln for ln in open(tmp_path / "g.txt") if ln[0] in "GPN"]
+        ref = [ln for ln in open(tmp_path / "o.txt") if ln[0] in "GPN"]
+        assert len(mine) > 100 and mine == ref
+
+
+def test_masked_graph_and_errors(db_dirs, tmp_path):
+    files = sorted(glob.glob(os.path.join(db_dirs["card.90"], "cluster*.msa")))
+    api.graphs_dump(files, str(tmp_path / "g.txt"), k=31, S=21, w=150)
+    masked = [ln for ln in open(tmp_path / "g.txt") if ln.startswith("G ") and "masked=1" in ln]
+    assert len(masked) >= 1                       # a card.90 cluster holds a sequence < 150 bp (pipeline/index.go:59-65)
+    with pytest.raises(api.GrootGpuError) as e:
+        api.graphs_dump([str(tmp_path / "missing.msa")])
+    assert e.value.code == -3
+    bad = tmp_path / "bad.msa"
+    bad.write_text(">a\nACGT\n>b\nACG\n")
+    with pytest.raises(api.GrootGpuError) as e:
+        api.graphs_dump([str(bad)])
+    assert e.value.code == -4
+
+
+def test_query_params_match_oracle():
+    for q, t in [(70, .99), (60, .99), (80, .99), (70, .97), (70, .95), (20, .99), (1, .99), (50, .9), (69, .99), (71, .99)]:
+        K, L, e = api.query_params_host(q, t)
+        assert (K, L) == po.optimal_kl(4, 5, 70, q, t)
+        assert e == po.eq_min(21, q, 70, t)
+    assert api.query_params_host(120, .99, w=150)[:2] == (4, 1)
+    assert api.query_params_host(50, .99, k=51, S=30, w=100) == po.optimal_kl(4, 7, 50, 50, .99) + (po.eq_min(30, 50, 50, .99),)
+
+
+def test_synth_reads_deterministic_and_composed(db_dirs):
+    seqs = synth.db_sequences(db_dirs["arg-annot.90"])
+    assert len(seqs) == 1749
+    b1, o1 = synth.synth_reads(5000, 100, seqs, seed=42)
+    b2, o2 = synth.synth_reads(5000, 100, seqs, seed=42)
+    assert np.array_equal(b1, b2) and np.array_equal(o1, o2)
+    assert not np.array_equal(b1, synth.synth_reads(5000, 100, seqs, seed=43)[0])
+    assert set(np.unique(b1)) <= set(b"ACGTN")
+    res = po.Index(msa_dir=db_dirs["arg-annot.90"]).map_reads(b1[:100 * 1000], o1[:1001], 0.99, threads=4)
+    assert 0.4 < res.counts["mapped"] / 1000 < 0.6         # ~50 % exact substrings seed, the rest never does
