@@ -9,6 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgrootgpu.so")
+CLI = os.path.join(HERE, "groot-b200")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU = ["capi.cu"]
@@ -32,7 +33,18 @@ def build(force=False, verbose=False, out=OUT, defines=()):
         cmd += ["-Xptxas", "-v"]
     cmd += [os.path.join(CSRC, f) for f in CU + CPP]
     subprocess.check_call(cmd)
+    if out == OUT:
+        build_cli()
     return out
+
+
+def build_cli():
+    """groot-b200: the C++ host driver (pipeline mirror + CLI) linked against libgrootgpu.so."""
+    host = os.path.join(CSRC, "host")
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-pthread", "-o", CLI, os.path.join(host, "main.cpp"), os.path.join(host, "pipeline.cpp"),
+           "-L" + HERE, "-lgrootgpu", "-lz", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd)
+    return CLI
 
 
 if __name__ == "__main__":

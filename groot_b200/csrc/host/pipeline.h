@@ -1,0 +1,118 @@
+// Host-side mirror of the reference's `groot align` pipeline (src/pipeline), in C++ because this image has no Go
+// toolchain (INTEGRATION.md shows the cgo stub for the Go host). Same stage names, argument meaning and error
+// behaviour as the reference:
+//
+//   DataStreamer   src/pipeline/sketch.go:24-77     lines from FASTQ/FASTA files (.gz by extension) or STDIN
+//   FastqHandler   src/pipeline/sketch.go:153-238   4 lines -> FASTQread (header must start with '@'); --fasta mode
+//   FastqChecker   src/pipeline/sketch.go:241-282   read count / mean length; "no fastq reads received" is fatal
+//   ReadMapper     src/pipeline/sketch.go:285-351   theBoss.mapReads: sketch -> query -> align -> BAM + graph weights
+//   GraphPruner    src/pipeline/sketch.go:354-430   Prune(minKmerCoverage) per graph, surviving paths
+//
+// The reference connects stages with chan-of-one-item; here the first three stages are fused into a batching reader
+// that hands ReadMapper struct-of-arrays batches (bases / qualities / names back to back + offsets), which is what
+// crosses the C ABI (grootgpu_align_batch). Nothing in this file computes sketches, queries or alignments.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../../include/grootgpu.h"
+
+namespace groot_host {
+
+// src/pipeline/runtime.go:15-56 (the fields `groot align` uses)
+struct Info {
+    std::string Version = GROOTGPU_REFERENCE_VERSION;
+    int NumProc = 1;
+    double ContainmentThreshold = 0.99;     // -t
+    std::string IndexDir;
+    struct AlignCmd {
+        bool Fasta = false;                 // --fasta
+        double MinKmerCoverage = 1.0;       // -c
+        std::string BAMout;                 // "" == STDOUT
+        bool NoExactAlign = false;          // --noAlign
+    } Sketch;
+    std::string GraphDir = "./groot-graphs";  // -g
+    uint32_t BatchReads = 1u << 20;           // reads per device batch (no counterpart: the reference streams single reads)
+    int Device = 0;
+};
+
+// seqio.FASTQread for a whole batch (src/seqio/seqio.go:26-37), struct-of-arrays
+struct ReadBatch {
+    std::vector<uint8_t> id, seq, qual;        // ID lines incl. the leading '@' / bases / raw ASCII qualities
+    std::vector<uint64_t> id_off, seq_off, qual_off;
+    uint32_t size() const { return seq_off.empty() ? 0 : static_cast<uint32_t>(seq_off.size() - 1); }
+    void clear();
+};
+
+// DataStreamer + FastqHandler + FastqChecker
+class FastqStream {
+  public:
+    FastqStream(const std::vector<std::string>& files, bool fasta);
+    ~FastqStream();
+    // fills `b` with up to max_reads reads; false when the input is exhausted and b is empty
+    bool next(ReadBatch& b, uint32_t max_reads);
+    uint64_t rawCount() const { return raw_count_; }
+    uint64_t lengthTotal() const { return length_total_; }
+
+  private:
+    bool getline(std::string& line);
+    bool open_next();
+    std::vector<std::string> files_;
+    size_t file_i_ = 0;
+    void* gz_ = nullptr;  // gzFile: zlib reads plain files transparently
+    bool fasta_;
+    bool use_stdin_ = false, stdin_done_ = false;
+    std::string pending_header_;
+    uint64_t raw_count_ = 0, length_total_ = 0;
+};
+
+// Minimal BAM writer (what the reference gets from biogo/hts: bam.NewWriter + Write + Close, boss.go:45-105,225-241)
+class BamWriter {
+  public:
+    BamWriter(FILE* out, const std::string& sam_header_text, const std::vector<std::pair<std::string, int32_t>>& refs);
+    ~BamWriter();
+    // one sam.Record as AlignRead builds it (src/graph/alignment.go:114-156)
+    void write(const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag, uint32_t clip_start, uint32_t match_len,
+               uint32_t clip_end, const uint8_t* seq, const uint8_t* qual);
+    void close();  // flushes and appends the BGZF EOF block
+  private:
+    void flush_block();
+    FILE* out_;
+    std::vector<uint8_t> buf_;
+    bool closed_ = false;
+};
+
+class ReadMapper {
+  public:
+    ReadMapper(Info* info, grootgpu_index* index);
+    // theBoss.mapReads: drains the stream; BAM to info->Sketch.BAMout or STDOUT; returns 0 or a GROOTGPU_ERR_* code
+    int Run(FastqStream& reads);
+    // corresponds to num. reads, total num. mapped, num. multimapped, total k-mers (sketch.go:289,302-305)
+    const uint64_t* CollectReadStats() const { return read_stats_; }
+    uint64_t alignmentCount() const { return alignment_count_; }
+    const std::string& error() const { return err_; }
+
+  private:
+    Info* info_;
+    grootgpu_index* index_;
+    uint64_t read_stats_[4] = {0, 0, 0, 0};
+    uint64_t alignment_count_ = 0;
+    std::string err_;
+};
+
+class GraphPruner {
+  public:
+    GraphPruner(Info* info, grootgpu_index* index) : info_(info), index_(index) {}
+    int Run();
+    const std::vector<std::string>& CollectOutput() const { return found_paths_; }
+    const std::vector<uint8_t>& kept() const { return kept_; }
+  private:
+    Info* info_;
+    grootgpu_index* index_;
+    std::vector<std::string> found_paths_;
+    std::vector<uint8_t> kept_;
+};
+
+}  // namespace groot_host

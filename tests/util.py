@@ -64,3 +64,53 @@ def report(records, ref_len, cutoff):
         if (cov > 0).sum() / n >= cutoff:
             out[name[1:] if name.startswith("*") else name] = (len(recs), n)
     return out
+
+
+def read_bam(path):
+    """Minimal BAM decoder (BGZF == concatenated gzip members). Returns (header text, [(ref name, length)], records)
+    with records = list of dicts(name, ref, pos, mapq, flag, cigar, seq, qual, next_ref, next_pos, tlen)."""
+    import struct
+    raw = gzip.decompress(open(path, "rb").read())
+    assert raw[:4] == b"BAM\x01"
+    p = 4
+    l_text, = struct.unpack_from("<i", raw, p); p += 4
+    text = raw[p:p + l_text].decode(); p += l_text
+    n_ref, = struct.unpack_from("<i", raw, p); p += 4
+    refs = []
+    for _ in range(n_ref):
+        l_name, = struct.unpack_from("<i", raw, p); p += 4
+        name = raw[p:p + l_name - 1].decode(); p += l_name
+        l_ref, = struct.unpack_from("<i", raw, p); p += 4
+        refs.append((name, l_ref))
+    recs = []
+    codes = "=ACMGRSVTWYHKDBN"
+    while p < len(raw):
+        block, = struct.unpack_from("<i", raw, p); p += 4
+        ref_id, pos, l_name, mapq, _bin, n_cig, flag, l_seq, nref, npos, tlen = struct.unpack_from("<iiBBHHHiiii", raw, p)
+        q = p + 32
+        name = raw[q:q + l_name - 1].decode(); q += l_name
+        cig = ""
+        for _ in range(n_cig):
+            c, = struct.unpack_from("<I", raw, q); q += 4
+            cig += "%d%s" % (c >> 4, "MIDNSHP=X"[c & 15])
+        sb = raw[q:q + (l_seq + 1) // 2]; q += (l_seq + 1) // 2
+        seq = "".join(codes[(sb[i // 2] >> (4 if i % 2 == 0 else 0)) & 15] for i in range(l_seq))
+        qual = raw[q:q + l_seq]; q += l_seq
+        recs.append(dict(name=name, ref=refs[ref_id][0], pos=pos, mapq=mapq, flag=flag, cigar=cig, seq=seq, qual=qual,
+                         next_ref=nref, next_pos=npos, tlen=tlen))
+        p += block
+    return text, refs, recs
+
+
+def canonical_records_from_oracle(idx, res, names, seqs, quals):
+    """What AlignRead puts into sam.Record for every oracle record (src/graph/alignment.go:114-156), as sortable tuples
+    (name, ref, pos, cigar, flag, seq, qual)."""
+    out = []
+    for r in res.records:
+        ri, g, path, pos, flag, sclip, eclip, mlen = [int(x) for x in r]
+        s, q = seqs[ri], quals[ri]
+        if flag & 0x10:
+            s, q = revcomp(s), q[::-1]
+        cigar = ("%dH" % sclip if sclip else "") + "%dM" % mlen + ("%dH" % eclip if eclip else "")
+        out.append((names[ri][1:].decode(), idx.ref_name(g, path)[0], pos, cigar, flag, s[:mlen].decode(), bytes(q[:mlen])))
+    return sorted(out)
