@@ -207,14 +207,18 @@ def run_ours(args):
     stream = torch.cuda.current_stream().cuda_stream
 
     def step_device():
-        raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, THRESHOLD, stream=stream)
+        raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, THRESHOLD, stream=stream, project_on_device=True)
         if world > 1:   # the one collective of the path: gather every rank's records to rank 0 over NVLink
             gd.gather_results(gd.result_tensors_from_raw(raw, dev), dst=0)
         return raw
 
+    e2e_parts = {"align_batch_ms": 0.0, "device_ms": 0.0}
+
     def step_e2e():
-        raw = idx.map_reads_raw(h_seq.data_ptr(), h_off.data_ptr(), n, THRESHOLD)
-        idx.project(raw, off)
+        t0 = time.perf_counter()
+        raw = idx.map_reads_raw(h_seq.data_ptr(), h_off.data_ptr(), n, THRESHOLD, project_on_device=True)
+        e2e_parts["align_batch_ms"] += (time.perf_counter() - t0) * 1e3
+        e2e_parts["device_ms"] = e2e_parts.get("device_ms", 0.0) + raw.ms[1] + raw.ms[2] + raw.ms[3]
         return raw
 
     # ---- value: inputs resident in HBM ----
@@ -225,12 +229,15 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    seed_ms, align_ms, launches = [], [], 0
+    fam_ms = {k: [] for k in api.KERNEL_FAMILIES}
+    launches = 0
     torch.cuda.synchronize(); barrier()
     e0.record()
     for _ in range(args.steps):
         raw = step_device()
-        seed_ms.append(raw.ms[1]); align_ms.append(raw.ms[2]); launches += raw.kernel_launches
+        for k, v in zip(api.KERNEL_FAMILIES, list(raw.kernel_ms)[:7]):
+            fam_ms[k].append(v)
+        launches += raw.kernel_launches
     e1.record()
     torch.cuda.synchronize(); barrier()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
@@ -243,32 +250,49 @@ def run_ours(args):
     for _ in range(max(1, args.warmup // 2)):
         raw = step_e2e()
     torch.cuda.synchronize(); barrier()
+    e2e_parts.update(align_batch_ms=0.0, device_ms=0.0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         raw = step_e2e()
     torch.cuda.synchronize()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_parts = {k: v / args.steps for k, v in e2e_parts.items()}
     barrier()
     e2e_value = total_reads * args.steps / e2e_s
     h2d = n * L + 4 * (n + 1)
     d2h = 4 * (n + 1) + 4 * raw.n_hits + 32 * raw.n_pairs + 8 * raw.n_records
 
-    # ---- roofline of the dominant kernel (seed: sketch + probe + verify) ----
+    # ---- roofline of the dominant kernel (largest share of the step), algorithmic bytes per DESIGN.md "Rooflines" ----
     peak, peak_src = measured_peaks()
-    seed_b, full_b = algorithmic_bytes_per_read(L, info["S"], stats["hits"], stats["pairs"], stats["records"])
-    seed_avg_ms = sum(seed_ms) / len(seed_ms)
-    achieved = seed_b * n / (seed_avg_ms / 1000.0) / 1e9
+    S = info["S"]
+    fam_avg = {k: sum(v) / len(v) for k, v in fam_ms.items()}
+    fam_bytes = {   # per launch family, for n reads
+        "seed": n * (L + 8 + 32 + 4) + raw.n_hits * (8 * S + 8),                # L + 8 + 32 + 8*S*c + 4 + 8*h with c := h
+        "fill": 4 * n + raw.n_hits * 13,                                         # hit counts in, hits + owner + segment flag out
+        "align_screen": raw.n_pairs * (L + 16 + 8) + raw.n_hits * 32,            # read + pair bookkeeping + window records
+        "align_walk": raw.n_pairs * (L + 16 + 32 + 8 + 32),                      # re-read read + window meta + pair out + locus + path bitset
+        "align_finish": 0,
+        "align_emit": raw.n_pairs * (32 + 8 + 32) + raw.n_records * 8,           # pair + locus + bitset in, 8-byte records out
+        "project": raw.n_pairs * 40,                                             # pair in; the (node, f64) items are internal traffic
+    }
+    dom = max(fam_avg, key=fam_avg.get)
+    achieved = fam_bytes[dom] / (fam_avg[dom] / 1000.0) / 1e9
     traffic = None
-    prof = os.path.join(ROOT, "profiles", "seed_kernel_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            tj = json.load(open(prof))
+            traffic = tj.get(dom, {}).get("dram_bytes_per_read", None)
+            if traffic is not None:
+                traffic = traffic * n
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "seed_kernel<21,4>", "algorithmic_bytes_per_read": seed_b, "kernel_ms": seed_avg_ms, "peak_source": peak_src,
-                "int_ops_per_read": (L - info["k"] + 1) * ((info["S"] - 1) * 12 + 20),
-                "note": "integer-ALU bound kernel: the HBM fraction is small by construction (DESIGN.md Rooflines)"}
+                "kernel": dom, "kernel_ms": fam_avg[dom], "algorithmic_bytes_per_launch": fam_bytes[dom], "peak_source": peak_src,
+                "note": "integer / pointer-chasing kernels: the HBM fraction is small by construction (DESIGN.md Rooflines); "
+                        "seed_kernel is INT-ALU bound (%d integer ops per read)" % ((L - info["k"] + 1) * ((S - 1) * 12 + 20)),
+                "all_kernels": {k: {"ms": fam_avg[k], "algorithmic_GBps": (fam_bytes[k] / (fam_avg[k] / 1000.0) / 1e9) if fam_avg[k] > 0 else 0.0}
+                                for k in api.KERNEL_FAMILIES}}
 
     # ---- CPU baseline (rank 0, N == 1): the oracle port on all host threads, bounded sample ----
     cpu = None
@@ -295,9 +319,10 @@ def run_ours(args):
                        "parallelism": "reads sharded over %d GPU(s), index replicated%s" % (world, ", one NCCL gather of results to rank 0 per step" if world > 1 else ""),
                        "per_read": stats, "index_build_s": t_index},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "includes": "pinned host buffers -> grootgpu_align_batch (H2D, kernels, D2H) -> grootgpu_project_batch (ordered f64 weight replay)"},
+                    "includes": "pinned host buffers -> grootgpu_align_batch (H2D, sketch+query+align+ordered graph weighting kernels, D2H of hits/pairs/records)",
+                    "per_step_ms": e2e_parts},
             "gpu_launches": launches,
-            "kernel_ms": {"seed": seed_avg_ms, "align_search": sum(align_ms) / len(align_ms)},
+            "kernel_ms": fam_avg,
             "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
         print(json.dumps(line))

@@ -37,7 +37,7 @@ class IndexInfo(C.Structure):
 
 class AlignParams(C.Structure):
     _fields_ = [("containment_threshold", C.c_double), ("no_align", C.c_int32), ("keep_sketches", C.c_int32),
-                ("results_on_device", C.c_int32)]
+                ("project_on_device", C.c_int32), ("results_on_device", C.c_int32)]
 
 
 class Pair(C.Structure):
@@ -57,10 +57,12 @@ class BatchResultC(C.Structure):
                 ("hit_off", C.POINTER(C.c_uint32)), ("hits", C.POINTER(C.c_uint32)), ("pairs", C.POINTER(Pair)),
                 ("rec_path", C.POINTER(C.c_uint32)), ("rec_pos", C.POINTER(C.c_int32)), ("sketches", C.POINTER(C.c_uint64)),
                 ("received", C.c_uint64), ("mapped", C.c_uint64), ("multimapped", C.c_uint64), ("alignments", C.c_uint64),
-                ("ms", C.c_float * 4), ("kernel_launches", C.c_uint32), ("slow_path_pairs", C.c_uint64),
+                ("ms", C.c_float * 4), ("kernel_ms", C.c_float * 8), ("kernel_launches", C.c_uint32), ("slow_path_pairs", C.c_uint64),
                 ("d_hit_off", C.c_void_p), ("d_hits", C.c_void_p), ("d_pairs", C.c_void_p), ("d_rec_path", C.c_void_p),
                 ("d_rec_pos", C.c_void_p)]
 
+
+KERNEL_FAMILIES = ("seed", "fill", "align_screen", "align_walk", "align_finish", "align_emit", "project")
 
 _lib = None
 
@@ -141,6 +143,7 @@ class BatchResult:
                            alignments=int(raw.alignments))
         self.ms = dict(total=raw.ms[0], seed=raw.ms[1], align=raw.ms[2], other=raw.ms[3])
         self.kernel_launches = raw.kernel_launches
+        self.kernel_ms = dict(zip(KERNEL_FAMILIES, list(raw.kernel_ms)[:7]))
         self.slow_path_pairs = int(raw.slow_path_pairs)
         if copied:
             self.hit_off = _np(raw.hit_off, raw.n_reads + 1, np.uint32)
@@ -245,11 +248,11 @@ class Index:
         return K.value, L.value, e.value
 
     # -- the hot path -----------------------------------------------------------------------------
-    def map_reads(self, seqs, off, threshold=0.99, no_align=False, keep_sketches=False, project=False):
+    def map_reads(self, seqs, off, threshold=0.99, no_align=False, keep_sketches=False, project=False, project_on_device=False):
         """theBoss.mapReads for one batch (src/pipeline/boss.go:108-242): host buffers in, host result out."""
         seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint64)
-        prm = AlignParams(threshold, int(no_align), int(keep_sketches), 0)
+        prm = AlignParams(threshold, int(no_align), int(keep_sketches), int(project_on_device), 0)
         raw = BatchResultC()
         _check(lib().grootgpu_align_batch(self.h, seqs.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(prm), C.byref(raw)))
         res = BatchResult(raw, self.info()["S"], True)
@@ -257,16 +260,17 @@ class Index:
             self.project(res, off)
         return res
 
-    def map_reads_raw(self, seq_ptr, off_ptr, n_reads, threshold=0.99, no_align=False):
+    def map_reads_raw(self, seq_ptr, off_ptr, n_reads, threshold=0.99, no_align=False, project_on_device=False):
         """Same call on raw host pointers (pinned buffers), returning only the C struct: what bench.py times."""
-        prm = AlignParams(threshold, int(no_align), 0, 0)
+        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), 0)
         raw = BatchResultC()
         _check(lib().grootgpu_align_batch(self.h, seq_ptr, off_ptr, n_reads, C.byref(prm), C.byref(raw)))
         return raw
 
-    def map_reads_device(self, d_seq_ptr, d_off_ptr, n_reads, min_len, max_len, threshold=0.99, no_align=False, stream=None, copy_back=False):
+    def map_reads_device(self, d_seq_ptr, d_off_ptr, n_reads, min_len, max_len, threshold=0.99, no_align=False, stream=None, copy_back=False,
+                         project_on_device=False):
         """Reads already resident in HBM (device pointers as ints)."""
-        prm = AlignParams(threshold, int(no_align), 0, 0 if copy_back else 1)
+        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), 0 if copy_back else 1)
         raw = BatchResultC()
         _check(lib().grootgpu_align_batch_device(self.h, d_seq_ptr, d_off_ptr, n_reads, min_len, max_len, C.byref(prm), stream,
                                                  C.byref(raw)))

@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -26,6 +27,7 @@
 #include "align_kernels.cuh"
 #include "device_types.cuh"
 #include "flat_index.h"
+#include "project_kernels.cuh"
 #include "seed_kernels.cuh"
 
 using namespace groot;
@@ -158,6 +160,9 @@ struct grootgpu_index {
     std::vector<void*> owned;          // device allocations freed on destroy
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t kev[64] = {};          // per-launch timing: pairs (begin, end) tagged with a category
+    int kev_cat[32] = {};
+    int kev_n = 0;
     // LSH tables, built lazily per K (all bands)
     std::vector<LshTable> h_tables;    // [(K-1)*n_bands + band]
     LshTable* d_tables = nullptr;
@@ -168,12 +173,19 @@ struct grootgpu_index {
     DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
         rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error;
     HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_scal;
+    // graph weights live on the device once a batch was projected there; the host copy is refreshed lazily
+    double* d_kmer_freq = nullptr;
+    unsigned long long* d_kmer_total = nullptr;
+    const uint32_t* d_cn_count = nullptr;
+    bool weights_on_device = false;
+    DBuf item_cnt, item_off, pkeys, pkeys2, pvals, pvals2;
     std::vector<LenParam> h_len_params;
     double lp_threshold = -1; uint32_t lp_min = 1, lp_max = 0;
 
     ~grootgpu_index() {
         for (void* p : owned) cudaFree(p);
         for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : kev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -197,6 +209,7 @@ void index_to_device(grootgpu_index* ix) {
     d.cn_node = upload(h.cn_node, ix->owned);
     d.sketches = upload(h.sketches, ix->owned);
     d.graph_mask_words = upload(h.graph_mask_words, ix->owned);
+    ix->d_cn_count = upload(h.cn_count, ix->owned);
     {
         std::vector<uint32_t> pfx_off; std::vector<uint64_t> pfx;
         build_prefix_table(h, pfx_off, pfx);
@@ -212,9 +225,15 @@ void index_to_device(grootgpu_index* ix) {
     d.tables = ix->d_tables;
     CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     for (auto& e : ix->ev) CK(cudaEventCreate(&e));
+    for (auto& e : ix->kev) CK(cudaEventCreate(&e));
     if (h.kmer_freq.size() != h.nodes.size()) h.kmer_freq.assign(h.nodes.size(), 0.0);
     if (h.kmer_total.size() != h.n_graphs) h.kmer_total.assign(h.n_graphs, 0);
     if (h.node_marked.size() != h.nodes.size()) h.node_marked.assign(h.nodes.size(), 0);
+    ix->d_kmer_freq = upload(h.kmer_freq, ix->owned);
+    {
+        std::vector<unsigned long long> kt(h.kmer_total.begin(), h.kmer_total.end());
+        ix->d_kmer_total = upload(kt, ix->owned);
+    }
 }
 
 // Flattened CSR of the lshensemble index for prefix length K: for every band, group the windows by the
@@ -352,6 +371,64 @@ int g_num_sms(int device) {
     return n;
 }
 
+// keep the host copy of the weights authoritative before anything on the host touches them
+void sync_weights_to_host(grootgpu_index* ix) {
+    if (!ix->weights_on_device) return;
+    FlatIndex& h = ix->h;
+    CK(cudaMemcpy(h.kmer_freq.data(), ix->d_kmer_freq, h.kmer_freq.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    std::vector<unsigned long long> kt(h.kmer_total.size());
+    CK(cudaMemcpy(kt.data(), ix->d_kmer_total, kt.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < kt.size(); i++) h.kmer_total[i] = kt[i];
+    ix->weights_on_device = false;
+}
+void push_weights_to_device(grootgpu_index* ix) {
+    if (ix->weights_on_device) return;
+    FlatIndex& h = ix->h;
+    CK(cudaMemcpy(ix->d_kmer_freq, h.kmer_freq.data(), h.kmer_freq.size() * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<unsigned long long> kt(h.kmer_total.begin(), h.kmer_total.end());
+    CK(cudaMemcpy(ix->d_kmer_total, kt.data(), kt.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    ix->weights_on_device = true;
+}
+
+template <class KB, class KE>
+void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n_segs, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
+    push_weights_to_device(ix);
+    ix->item_cnt.need(4ull * n_segs); ix->item_off.need(4ull * (n_segs + 1));
+    ProjectArgs pa{};
+    pa.off = d_off; pa.hits = ix->hits.as<uint32_t>(); pa.pairs = ix->pairs.as<PairOut>(); pa.n_segs_ptr = ix->scalars.as<uint32_t>();
+    pa.cn_count = ix->d_cn_count; pa.item_cnt = ix->item_cnt.as<uint32_t>(); pa.item_off = ix->item_off.as<uint32_t>();
+    pa.kmer_total = ix->d_kmer_total; pa.k = ix->h.p.k;
+    const int blocks = std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8));
+    kbegin(6); project_count_kernel<<<blocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
+    size_t tmp = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(n_segs), st);
+    ix->cub_tmp.need(tmp + 16);
+    cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(n_segs), st);
+    uint32_t lo = 0, lc = 0;
+    CK(cudaMemcpyAsync(&lo, ix->item_off.as<uint32_t>() + (n_segs - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(&lc, ix->item_cnt.as<uint32_t>() + (n_segs - 1), 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const uint64_t n_items = static_cast<uint64_t>(lo) + lc;
+    if (n_items == 0) return;
+    if (n_items >= (1ull << 31)) throw std::length_error("too many weight increments in one batch: use smaller batches");
+    ix->pkeys.need(4 * n_items); ix->pkeys2.need(4 * n_items); ix->pvals.need(8 * n_items); ix->pvals2.need(8 * n_items);
+    pa.keys = ix->pkeys.as<uint32_t>(); pa.vals = ix->pvals.as<double>();
+    kbegin(6); project_expand_kernel<<<blocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
+    int end_bit = 1;
+    while ((1ull << end_bit) < ix->h.nodes.size()) end_bit++;
+    size_t sort_tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, ix->pkeys.as<uint32_t>(), ix->pkeys2.as<uint32_t>(), ix->pvals.as<double>(), ix->pvals2.as<double>(),
+                                    static_cast<int>(n_items), 0, end_bit, st);
+    ix->cub_tmp.need(sort_tmp + 16);
+    cub::DeviceRadixSort::SortPairs(ix->cub_tmp.p, sort_tmp, ix->pkeys.as<uint32_t>(), ix->pkeys2.as<uint32_t>(), ix->pvals.as<double>(), ix->pvals2.as<double>(),
+                                    static_cast<int>(n_items), 0, end_bit, st);
+    const uint32_t n32 = static_cast<uint32_t>(n_items);
+    CK(cudaMemcpyAsync(ix->item_off.as<uint32_t>() + n_segs, &n32, 4, cudaMemcpyHostToDevice, st));
+    const int ablocks = std::max(1, std::min<int>(static_cast<int>((n_items + 255) / 256), sms * 16));
+    kbegin(6); project_accumulate_kernel<<<ablocks, 256, 0, st>>>(ix->pkeys2.as<uint32_t>(), ix->pvals2.as<double>(), ix->item_off.as<uint32_t>() + n_segs, ix->d_kmer_freq); launches++; kend();
+    CK(cudaGetLastError());
+}
+
 // The batch pipeline on the device. d_seq / d_off already resident.
 void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, uint32_t n, uint32_t min_len, uint32_t max_len,
                const grootgpu_align_params* prm, cudaStream_t st, grootgpu_batch_result* out) {
@@ -363,6 +440,9 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
     prepare_params(ix, std::max(min_len, 1u), max_len, prm->containment_threshold);
     const int sms = g_num_sms(ix->device);
     uint32_t launches = 0;
+    ix->kev_n = 0;
+    auto kbegin = [&](int cat) { if (ix->kev_n < 32) { ix->kev_cat[ix->kev_n] = cat; cudaEventRecord(ix->kev[2 * ix->kev_n], st); } };
+    auto kend = [&]() { if (ix->kev_n < 32) { cudaEventRecord(ix->kev[2 * ix->kev_n + 1], st); ix->kev_n++; } };
 
     ix->n_hits.need(4ull * n); ix->hit_off.need(4ull * (n + 1)); ix->stage.need(4ull * HSTAGE * n);
     ix->scalars.need(64); ix->tile_counter.need(16); ix->error.need(16);
@@ -389,7 +469,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
     const uint32_t n_tiles = (n + kTileReads - 1) / kTileReads;
     int seed_blocks = static_cast<int>(std::min<uint64_t>((n_tiles + kSeedThreads / 32 - 1) / (kSeedThreads / 32), static_cast<uint64_t>(sms) * occ));
     CK(cudaEventRecord(ix->ev[0], st));
-    seed_dispatch(S, ix->d, sa, k, seed_smem, std::max(seed_blocks, 1), st); launches++;
+    kbegin(0); seed_dispatch(S, ix->d, sa, k, seed_smem, std::max(seed_blocks, 1), st); launches++; kend();
     CK(cudaGetLastError());
     CK(cudaEventRecord(ix->ev[1], st));
 
@@ -420,7 +500,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         fa.hit_off = ix->hit_off.as<uint32_t>(); fa.stage = ix->stage.as<uint32_t>(); fa.hits = ix->hits.as<uint32_t>();
         fa.hit_read = ix->hit_read.as<uint32_t>(); fa.seg_flag = ix->seg_flag.as<uint8_t>(); fa.counters = d_counters;
         int fill_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
-        fill_dispatch(S, ix->d, fa, k, fill_blocks, st); launches++;
+        kbegin(1); fill_dispatch(S, ix->d, fa, k, fill_blocks, st); launches++; kend();
         CK(cudaGetLastError());
         // ---- (read, graph) segment starts ----
         thrust::counting_iterator<uint32_t> counting(0);
@@ -454,7 +534,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         CK(cudaMemsetAsync(ix->qcount.p, 0, 64, st));
         uint32_t* qc = ix->qcount.as<uint32_t>();
         CK(cudaEventRecord(ix->ev[2], st));
-        align_init_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ix->d, aa, ix->cursor.as<PairCursor>(), ix->queue_a.as<uint32_t>(), qc); launches++;
+        kbegin(2); align_init_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ix->d, aa, ix->cursor.as<PairCursor>(), ix->queue_a.as<uint32_t>(), qc); launches++; kend();
         CK(cudaGetLastError());
         int screen_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8));
         screen_blocks = std::max(screen_blocks, 1);
@@ -465,15 +545,15 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
             uint32_t* qa = (round & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
             uint32_t* qb = (round & 1) ? ix->queue_a.as<uint32_t>() : ix->queue_b.as<uint32_t>();
             ra.queue = qa; ra.queue_next = qb; ra.n_queue = qc + (round & 1); ra.n_queue_next = qc + ((round + 1) & 1);
-            align_screen_kernel<<<screen_blocks, 256, 0, st>>>(ix->d, ra); launches++;
-            align_walk_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++;
+            kbegin(2); align_screen_kernel<<<screen_blocks, 256, 0, st>>>(ix->d, ra); launches++; kend();
+            kbegin(3); align_walk_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++; kend();
             CK(cudaGetLastError());
             CK(cudaMemsetAsync(qc + (round & 1), 0, 4, st));   // this round's count becomes the next round's "next"
         }
         {
             uint32_t* qa = (kRounds & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
             ra.queue = qa; ra.queue_next = nullptr; ra.n_queue = qc + (kRounds & 1); ra.n_queue_next = nullptr;
-            align_finish_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++;
+            kbegin(4); align_finish_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++; kend();
             CK(cudaGetLastError());
         }
         CK(cudaEventRecord(ix->ev[3], st));
@@ -502,13 +582,15 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
             int emit_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8));
             // stack_ws holds verify_blocks*128 thread stacks; the emit grid (256-thread blocks) must not exceed that
             emit_blocks = std::max(1, std::min(emit_blocks, verify_blocks / 2));
-            align_emit_kernel<<<emit_blocks, 256, 0, st>>>(ix->d, ea); launches++;
+            kbegin(5); align_emit_kernel<<<emit_blocks, 256, 0, st>>>(ix->d, ea); launches++; kend();
         }
         CK(cudaGetLastError());
     } else {
         CK(cudaEventRecord(ix->ev[2], st));
         CK(cudaEventRecord(ix->ev[3], st));
     }
+    // ---- a10: ordered graph weighting on the device (optional) ----
+    if (prm->project_on_device && n_segs > 0) project_on_device(ix, d_off, n_segs, sms, st, kbegin, kend, launches);
     CK(cudaEventRecord(ix->ev[4], st));
 
     // ---- results ----
@@ -545,6 +627,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         cudaEventElapsedTime(&all_ms, ix->ev[0], ix->ev[5]);
         out->ms[0] = all_ms; out->ms[1] = seed_ms; out->ms[2] = align_ms; out->ms[3] = dev_ms - seed_ms - align_ms;
         out->kernel_launches = launches;
+        for (int i = 0; i < ix->kev_n; i++) { float ms = 0; cudaEventElapsedTime(&ms, ix->kev[2 * i], ix->kev[2 * i + 1]); out->kernel_ms[ix->kev_cat[i]] += ms; }
         out->slow_path_pairs = counters[3];
         out->d_hit_off = ix->hit_off.as<uint32_t>(); out->d_hits = ix->hits.as<uint32_t>();
         out->d_pairs = reinterpret_cast<const grootgpu_pair*>(ix->pairs.p);
@@ -651,6 +734,7 @@ int grootgpu_graphs_dump(const char* const* msa_paths, uint32_t n_msa, const gro
 
 int grootgpu_index_save(const grootgpu_index* idx, const char* path) {
     if (!idx || !path) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    { grootgpu_index* mi = const_cast<grootgpu_index*>(idx); int rc = guarded([&] { if (mi->weights_on_device) { pick_device(mi->device); sync_weights_to_host(mi); } }); if (rc) return rc; }
     try { save_index(idx->h, path); } catch (std::exception& e) { return fail(GROOTGPU_ERR_IO, e.what()); }
     return GROOTGPU_OK;
 }
@@ -758,6 +842,8 @@ int grootgpu_project_batch(grootgpu_index* idx, const grootgpu_batch_result* res
     if (!idx || !res || !seq_off) return fail(GROOTGPU_ERR_ARG, "bad argument");
     if (res->n_pairs && (!res->pairs || !res->hits)) return fail(GROOTGPU_ERR_ARG, "result holds no host arrays");
     return guarded([&] {
+        pick_device(idx->device);
+        sync_weights_to_host(idx);
         FlatIndex& h = idx->h;
         // pairs are ordered by (read, graph): bucketing by graph keeps read order inside every graph,
         // which is the only order the f64 accumulation of a graph depends on (one minion per graph).
@@ -787,14 +873,18 @@ int grootgpu_project_batch(grootgpu_index* idx, const grootgpu_batch_result* res
     });
 }
 
-int grootgpu_weights(const grootgpu_index* idx, double* kmer_freq, uint64_t* kmer_total) {
-    if (!idx) return fail(GROOTGPU_ERR_ARG, "bad argument");
+int grootgpu_weights(const grootgpu_index* idx_c, double* kmer_freq, uint64_t* kmer_total) {
+    if (!idx_c) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    grootgpu_index* idx = const_cast<grootgpu_index*>(idx_c);
+    int rc = guarded([&] { pick_device(idx->device); sync_weights_to_host(idx); });
+    if (rc) return rc;
     if (kmer_freq) memcpy(kmer_freq, idx->h.kmer_freq.data(), idx->h.kmer_freq.size() * sizeof(double));
     if (kmer_total) memcpy(kmer_total, idx->h.kmer_total.data(), idx->h.kmer_total.size() * sizeof(uint64_t));
     return GROOTGPU_OK;
 }
 int grootgpu_reset_weights(grootgpu_index* idx) {
     if (!idx) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    idx->weights_on_device = false;   // the host copy (zeroed below) becomes authoritative
     std::fill(idx->h.kmer_freq.begin(), idx->h.kmer_freq.end(), 0.0);
     std::fill(idx->h.kmer_total.begin(), idx->h.kmer_total.end(), 0);
     return GROOTGPU_OK;
@@ -815,10 +905,11 @@ int grootgpu_sketch_batch(int device, const uint8_t* seq, const uint64_t* seq_of
 
 int grootgpu_prune(grootgpu_index* idx, double min_cov, uint8_t* kept) {
     if (!idx) return fail(GROOTGPU_ERR_ARG, "bad argument");
-    return guarded([&] { for (uint32_t g = 0; g < idx->h.n_graphs; g++) { bool k = prune_graph(idx->h, g, min_cov); if (kept) kept[g] = k ? 1 : 0; } });
+    return guarded([&] { pick_device(idx->device); sync_weights_to_host(idx); for (uint32_t g = 0; g < idx->h.n_graphs; g++) { bool k = prune_graph(idx->h, g, min_cov); if (kept) kept[g] = k ? 1 : 0; } });
 }
 int grootgpu_graph_save_gfa(const grootgpu_index* idx, uint32_t g, const char* path, int64_t total_kmers, int* written) {
     if (!idx || !path || g >= idx->h.n_graphs) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    { grootgpu_index* mi = const_cast<grootgpu_index*>(idx); int rc = guarded([&] { pick_device(mi->device); sync_weights_to_host(mi); }); if (rc) return rc; }
     std::string s = graph_to_gfa(idx->h, g, total_kmers);
     if (written) *written = s.empty() ? 0 : 1;
     if (s.empty()) return GROOTGPU_OK;

@@ -109,6 +109,8 @@ typedef struct {
     double containment_threshold; /* -t / --contThresh, default 0.99 (cmd/align.go:47) */
     int32_t no_align;             /* --noAlign (cmd/align.go:46): weight graphs from seeds only */
     int32_t keep_sketches;        /* also return the per-read KHF sketches (tests / debugging) */
+    int32_t project_on_device;    /* 1: also run the ordered graph weighting (IncrementSubPath, graph.go:401-451) on the device,
+                                     bit-identical to grootgpu_project_batch; do NOT call grootgpu_project_batch for that batch */
     int32_t results_on_device;    /* 1: skip the device->host copy of the result arrays; the d_* pointers of the
                                      result are set instead (multi-GPU gather, kernel-side timing) */
 } grootgpu_align_params;
@@ -147,6 +149,10 @@ typedef struct {
     /* device time of the batch in ms, CUDA events on the library's stream: [0] whole batch incl. copies,
      * [1] seed kernel (sketch+probe+verify), [2] align kernel (all pairs), [3] everything else on the device */
     float ms[4];
+    /* device time per kernel family, summed over its launches (CUDA events around every launch):
+     * [0] seed_kernel, [1] fill_kernel, [2] align_init + align_screen, [3] align_walk, [4] align_finish, [5] align_emit,
+     * [6] project_count + project_expand + project_accumulate */
+    float kernel_ms[8];
     uint32_t kernel_launches;  /* number of this library's own kernels launched for the batch (CUB scans/selects not counted) */
     uint64_t slow_path_pairs;  /* diagnostic: full DFS walks that yielded no path id (filter false positives) */
     /* device copies of the arrays above (same layouts), valid until the next align call on the handle */

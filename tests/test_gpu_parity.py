@@ -194,6 +194,23 @@ def test_align_parity_variable_length_and_thresholds(argannot, root):
         assert np.array_equal(g.weights()[0], o.weights()[0])
 
 
+def test_device_projection_is_bit_exact(argannot, db_dirs):
+    """The on-device ordered graph weighting (project_*_kernel + stable radix sort) must equal the oracle's sequential
+    f64 accumulation bit for bit, across several batches (KmerFreq carries over) and mixed with the host replay."""
+    g, o = argannot
+    g.reset_weights(); o.reset_weights()
+    for seed in (1, 2, 3):
+        blob, off = _c1_reads(db_dirs["arg-annot.90"], 20000, 100, seed=seed)
+        if seed == 2:
+            g.map_reads(blob, off, 0.99, project=True)                  # host replay in the middle
+        else:
+            g.map_reads(blob, off, 0.99, project_on_device=True)
+        o.map_reads(blob, off, 0.99, threads=8)
+        gw, gt = g.weights(); ow, ot = o.weights()
+        assert np.array_equal(gw, ow) and np.array_equal(gt, ot)
+    assert (g.weights()[0] > 0).sum() > 1000
+
+
 def test_align_no_align_mode(argannot, db_dirs):
     g, o = argannot
     blob, off = _c1_reads(db_dirs["arg-annot.90"], 2000, 100, seed=7)
