@@ -219,6 +219,7 @@ int ReadMapper::Run(FastqStream& reads) {
     grootgpu_align_params prm{};
     prm.containment_threshold = info_->ContainmentThreshold;
     prm.no_align = info_->Sketch.NoExactAlign ? 1 : 0;
+    prm.project_on_device = 1;   // graphminion.go:67 IncrementSubPath: ordered f64 weighting on the GPU, bit-identical to the host replay
     ReadBatch b;
     std::vector<uint8_t> rc_seq, rc_qual;
     uint8_t ctab[256];                     // complementBases (seqio.go:17-23): everything else maps to 0
@@ -227,8 +228,6 @@ int ReadMapper::Run(FastqStream& reads) {
     while (reads.next(b, info_->BatchReads)) {
         grootgpu_batch_result res;
         rc = grootgpu_align_batch(index_, b.seq.data(), b.seq_off.data(), b.size(), &prm, &res);
-        if (rc) { err_ = grootgpu_last_error(); return rc; }
-        rc = grootgpu_project_batch(index_, &res, b.seq_off.data());   // graphminion.go:67 IncrementSubPath, replayed in read order
         if (rc) { err_ = grootgpu_last_error(); return rc; }
         read_stats_[0] += res.received; read_stats_[1] += res.mapped; read_stats_[2] += res.multimapped;
         alignment_count_ += res.alignments;
