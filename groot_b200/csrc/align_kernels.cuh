@@ -178,6 +178,9 @@ struct AlignArgs {
     int no_align;
     int* error;
     unsigned long long* counters;  // [3] += pairs that needed the sequential continuation (diagnostic)
+    const uint32_t* reads2;        // 2-bit copies of the seeded reads, both orientations (seed_kernels.cuh, pack_read2)
+    const uint8_t* read_ok2;       // [n_reads] 1 when reads2 holds the read
+    uint32_t nw32;                 // words per orientation; 0 = no packed copies
 };
 
 // Read view of one thread: forward or reverse complement (computed on the fly through a shared LUT),
@@ -280,6 +283,81 @@ __device__ void dfs_masked(const DevIndex& ix, uint32_t node0, uint32_t off0, RD
             }
             depth--;
         }
+    }
+    res->nrec = nrec; res->ntrav = ntrav;
+}
+
+// ---- packed walk ----------------------------------------------------------------------------------------
+// The same DFS as dfs_masked for the common case — read of upper-case ACGT only that fits the packed copy, graph
+// of <= 256 paths — on 2-bit data: 16 bases are compared with one XOR (node_seq2 against the
+// oriented packed read; two aligned loads + a funnel shift each), and the stack holds BRANCH nodes only, each frame
+// carrying its own cursor into edges[] (a linear chain needs no frame, and backtracking never reloads a node: in
+// the byte-wise walk the unwind loop over one frame per visited node ran with 2 active lanes and was the hot spot
+// of the whole path, profiles/r01_ncu_summary.md).
+// Frame fields are reused: node = index into edges[] of the next untried edge, edge_i = edges left, dist as before.
+__device__ __forceinline__ uint32_t extract16(const uint32_t* __restrict__ w, uint32_t pos) {
+    const uint32_t wi = pos >> 4;
+    return __funnelshift_r(w[wi], w[wi + 1], (pos & 15u) * 2u);
+}
+
+__device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, uint32_t off0, const uint32_t* __restrict__ rd2, uint32_t base0,
+                                           uint32_t rlen, uint32_t mw, bool has_n, DfsFrame* __restrict__ stack, uint32_t* __restrict__ mask_ws,
+                                           uint32_t max_depth, DfsResult* res) {
+    uint32_t nrec = 0, ntrav = 0, depth = 0;
+    uint32_t cur = node0, off = off0, dist = 0;
+    uint32_t cm[kMaskWordsInline];
+#pragma unroll
+    for (int wi = 0; wi < kMaskWordsInline; wi++) cm[wi] = 0xffffffffu;
+    NodeRec nd = ix.nodes[cur];
+    if (off >= nd.seq_len || rlen == 0) { res->nrec = 0; res->ntrav = 0; return; }   // alignment.go:199-201
+    while (true) {
+        // ---- up to 16 bases of the current node ----
+        const uint32_t left_node = nd.seq_len - off, left_read = rlen - dist;
+        uint32_t n = left_node < left_read ? left_node : left_read;
+        n = n < 16u ? n : 16u;
+        const uint32_t x = extract16(ix.node_seq2, nd.seq_off + off) ^ extract16(rd2, base0 + dist);
+        uint32_t mism = (x | (x >> 1)) & 0x55555555u;
+        if (has_n) mism &= ~extract16(ix.node_n2, nd.seq_off + off);   // a reference 'N' matches any read base (alignment.go:212-215)
+        if (n < 16u) mism &= (1u << (2u * n)) - 1u;
+        if (left_node == 0u) mism = 1u;                           // empty node: dfsRecursive fails on entry
+        off += n; dist += n;
+        if (mism == 0u && off != nd.seq_len && dist != rlen) continue;
+        // ---- node finished (or mismatch): membership, success, descend / backtrack ----
+        bool descend = false;
+        if (mism == 0u) {
+            uint32_t any = 0;
+#pragma unroll
+            for (int wi = 0; wi < kMaskWordsInline; wi++)
+                if (wi < mw) { cm[wi] &= ix.node_mask[nd.mask_off + wi]; any |= cm[wi]; }
+            if (any != 0u) {
+                if (dist == rlen || nd.edge_cnt == 0) {           // alignment.go:229: full read matched OR sink node
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) { c += __popc(cm[wi]); res->mask[wi] = cm[wi]; }
+                    nrec += c; ntrav++;
+                } else if (nd.edge_cnt == 1) {
+                    cur = ix.edges[nd.edge_off]; descend = true;
+                } else if (depth < max_depth) {
+                    stack[depth].node = nd.edge_off + 1; stack[depth].edge_i = static_cast<uint16_t>(nd.edge_cnt - 1);
+                    stack[depth].dist = static_cast<uint16_t>(dist);
+#pragma unroll
+                    for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) mask_ws[depth * kMaskWordsInline + wi] = cm[wi];
+                    depth++;
+                    cur = ix.edges[nd.edge_off]; descend = true;
+                }
+            }
+        }
+        if (!descend) {
+            if (depth == 0) break;
+            DfsFrame& top = stack[depth - 1];
+            cur = ix.edges[top.node]; dist = top.dist;
+#pragma unroll
+            for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) cm[wi] = mask_ws[(depth - 1) * kMaskWordsInline + wi];
+            top.node++;
+            if (--top.edge_i == 0) depth--;
+        }
+        nd = ix.nodes[cur];
+        off = 0;
     }
     res->nrec = nrec; res->ntrav = ntrav;
 }
@@ -442,7 +520,11 @@ __device__ __forceinline__ bool walk_try(const DevIndex& ix, const AlignArgs& a,
     const uint32_t rlen = stage >= 3 ? len - 1 : len;
     DfsResult res;
     res.nrec = 0; res.ntrav = 0;
-    if (mw <= kMaskWordsInline) dfs_masked(ix, node, off0, rd, rlen, mw, stack, mask_ws, depth_cap, &res);
+    if (a.nw32 && mw <= kMaskWordsInline && a.read_ok2[r]) {
+        const uint32_t* rd2 = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32 + (strand ? a.nw32 : 0u);
+        const uint32_t base0 = (strand ? a.nw32 * 16u - len : 0u) + (stage == 3 ? 1u : 0u);
+        dfs_packed(ix, node, off0, rd2, base0, rlen, mw, ix.graph_has_n[wr.graph] != 0, stack, mask_ws, depth_cap, &res);
+    } else if (mw <= kMaskWordsInline) dfs_masked(ix, node, off0, rd, rlen, mw, stack, mask_ws, depth_cap, &res);
     else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
     if (res.nrec == 0) return false;
     PairOut p = a.pairs[s];

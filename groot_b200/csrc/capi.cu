@@ -171,7 +171,7 @@ struct grootgpu_index {
     std::map<std::pair<uint32_t, double>, LenParam> param_cache;
     // workspaces
     DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
-        rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error;
+        rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error, reads2, read_ok2;
     HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_scal;
     // graph weights live on the device once a batch was projected there; the host copy is refreshed lazily
     double* d_kmer_freq = nullptr;
@@ -214,6 +214,23 @@ void index_to_device(grootgpu_index* ix) {
         std::vector<uint32_t> pfx_off; std::vector<uint64_t> pfx;
         build_prefix_table(h, pfx_off, pfx);
         d.pfx_off = upload(pfx_off, ix->owned); d.pfx = upload(pfx, ix->owned);
+    }
+    {   // 2-bit copy of the node sequences + per-graph 'N' flag for the packed walk (align_kernels.cuh, dfs_packed)
+        std::vector<uint32_t> seq2((h.node_seq.size() + 15) / 16 + 2, 0u);
+        std::vector<uint32_t> n2(seq2.size(), 0u);
+        for (size_t i = 0; i < h.node_seq.size(); i++) {
+            const uint8_t b = h.node_seq[i];
+            seq2[i >> 4] |= pack_base2(b) << (2 * (i & 15));
+            if (b != 'A' && b != 'C' && b != 'G' && b != 'T') n2[i >> 4] |= 1u << (2 * (i & 15));
+        }
+        std::vector<uint8_t> has_n(std::max<uint32_t>(h.n_graphs, 1), 0);
+        for (uint32_t g = 0; g < h.n_graphs; g++)
+            for (uint32_t n = h.graph_node_base[g]; n < h.graph_node_base[g + 1] && !has_n[g]; n++)
+                for (uint32_t i = 0; i < h.nodes[n].seq_len; i++) {
+                    const uint8_t b = h.node_seq[h.nodes[n].seq_off + i];
+                    if (b != 'A' && b != 'C' && b != 'G' && b != 'T') { has_n[g] = 1; break; }
+                }
+        d.node_seq2 = upload(seq2, ix->owned); d.node_n2 = upload(n2, ix->owned); d.graph_has_n = upload(has_n, ix->owned);
     }
     d.k = h.p.k; d.S = h.p.S; d.max_k = h.p.max_k; d.n_bands = h.p.S / h.p.max_k; d.n_wins = static_cast<uint32_t>(h.wins.size());
     ix->h_tables.assign(static_cast<size_t>(h.p.max_k) * d.n_bands, LshTable{nullptr, nullptr, 0, 0});
@@ -424,8 +441,9 @@ void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n_seg
                                     static_cast<int>(n_items), 0, end_bit, st);
     const uint32_t n32 = static_cast<uint32_t>(n_items);
     CK(cudaMemcpyAsync(ix->item_off.as<uint32_t>() + n_segs, &n32, 4, cudaMemcpyHostToDevice, st));
-    const int ablocks = std::max(1, std::min<int>(static_cast<int>((n_items + 255) / 256), sms * 16));
-    kbegin(6); project_accumulate_kernel<<<ablocks, 256, 0, st>>>(ix->pkeys2.as<uint32_t>(), ix->pvals2.as<double>(), ix->item_off.as<uint32_t>() + n_segs, ix->d_kmer_freq); launches++; kend();
+    const uint32_t n_nodes = static_cast<uint32_t>(ix->h.nodes.size());
+    const int ablocks = std::max(1, std::min<int>(static_cast<int>((n_nodes + 7) / 8), sms * 8));
+    kbegin(6); project_accumulate_kernel<<<ablocks, 256, 0, st>>>(ix->pkeys2.as<uint32_t>(), ix->pvals2.as<double>(), ix->item_off.as<uint32_t>() + n_segs, n_nodes, ix->d_kmer_freq); launches++; kend();
     CK(cudaGetLastError());
 }
 
@@ -499,6 +517,10 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         fa.seq = d_seq; fa.off = d_off; fa.n_reads = n; fa.len_params = ix->len_params.as<LenParam>(); fa.n_hits = ix->n_hits.as<uint32_t>();
         fa.hit_off = ix->hit_off.as<uint32_t>(); fa.stage = ix->stage.as<uint32_t>(); fa.hits = ix->hits.as<uint32_t>();
         fa.hit_read = ix->hit_read.as<uint32_t>(); fa.seg_flag = ix->seg_flag.as<uint8_t>(); fa.counters = d_counters;
+        // 2-bit copies of the seeded reads (both orientations) for the packed walk; reads longer than 256 bases go byte-wise
+        const uint32_t nw32 = prm->no_align ? 0u : (max_len <= 128 ? 8u : max_len <= 256 ? 16u : 0u);
+        if (nw32) { ix->reads2.need(8ull * nw32 * n + 64); ix->read_ok2.need(n); }
+        fa.reads2 = ix->reads2.as<uint32_t>(); fa.read_ok2 = ix->read_ok2.as<uint8_t>(); fa.nw32 = nw32;
         int fill_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
         kbegin(1); fill_dispatch(S, ix->d, fa, k, fill_blocks, st); launches++; kend();
         CK(cudaGetLastError());
@@ -528,6 +550,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         aa.stack_ws = ix->stack_ws.as<DfsFrame>(); aa.mask_ws = ix->mask_ws.as<uint32_t>();
         aa.max_len = max_len; aa.no_align = prm->no_align; aa.error = ix->error.as<int>();
         aa.counters = d_counters;
+        aa.reads2 = ix->reads2.as<uint32_t>(); aa.read_ok2 = ix->read_ok2.as<uint8_t>(); aa.nw32 = nw32;
         // screen/walk rounds over a shrinking, compacted queue; the queue counts stay on the device
         ix->cursor.need(8ull * n_segs); ix->cand.need(8ull * n_segs); ix->queue_a.need(4ull * n_segs); ix->queue_b.need(4ull * n_segs);
         ix->qcount.need(64);

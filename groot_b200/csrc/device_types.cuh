@@ -62,8 +62,14 @@ struct DevIndex {
     const LshTable* tables;  // [(K-1)*n_bands + band]; slots == nullptr when not built yet
     const uint32_t* pfx_off; // [node_seq bytes + 1] prefix-table CSR (host/prefix_table.cpp), position = NodeRec::seq_off + offset
     const uint64_t* pfx;
+    const uint32_t* node_seq2;    // node_seq packed 2 bits per base (pack_base2), 16 bases per word, same positions as node_seq
+    const uint32_t* node_n2;      // same layout: bit 2i of a word set when base i is an 'N' wildcard (alignment.go:212-215)
+    const uint8_t* graph_has_n;   // [G] 1 when a node of the graph holds an 'N' (only then node_n2 is consulted)
     uint32_t k, S, max_k, n_bands, n_wins;
 };
+
+// 2-bit code of an upper-case base: A0 C1 T2 G3, so that the complement (seqio.go:17-23) is code ^ 2
+__host__ __device__ inline uint32_t pack_base2(uint8_t b) { return (b >> 1) & 3u; }
 
 // multi-hash multipliers c_i = i ^ (k * multiSeed), passed by value => they live in the constant bank.
 // For i < 32 the xor only touches the low 5 bits: c_i = c0 + low[i] with c0 = C & ~31, low[i] = (C & 31) ^ i,

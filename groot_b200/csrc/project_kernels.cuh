@@ -8,8 +8,8 @@
 //      increment is computed with IEEE-754 round-to-nearest double intrinsics in the reference's expression
 //      order ((segLen/total)*numKmers)*count, so every addend equals the host's bit for bit.
 //   2. cub::DeviceRadixSort::SortPairs by node id — a STABLE sort, so each node's items stay in read order.
-//   3. project_accumulate  one thread per node segment adds its items to KmerFreq one after the other (the
-//      dependent DADD chain IS the reference's order); KmerTotal is an integer sum (atomics are exact).
+//   3. project_accumulate  one warp per node adds the node's items to KmerFreq one after the other (the dependent
+//      DADD chain IS the reference's order); KmerTotal is an integer sum (atomics are exact).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -71,30 +71,39 @@ __global__ void __launch_bounds__(256) project_expand_kernel(DevIndex ix, Projec
     }
 }
 
-// keys sorted (stable): thread i owns the segment that starts at i, if any. The additions of one node form a
-// dependent DADD chain by definition (that IS the reference's order); everything around it is taken off the chain:
-// the segment end comes from a galloping + binary search, and the addends are loaded eight at a time ahead of use.
+// keys sorted (stable): ONE WARP PER NODE. The additions of one node form a dependent DADD chain by definition (that IS
+// the reference's order), and the hottest node's chain is the critical path of the whole kernel — so everything else
+// is taken off it: lanes 0/1 find the node's segment [lower_bound(node), lower_bound(node + 1)) by binary search, the
+// 32 lanes load 32 addends at a time (coalesced, the next 32 prefetched while the current ones are added) and every
+// lane runs the same chain, fetching addend l from lane l by shuffle (shuffles do not depend on the accumulator, so
+// they pipeline under the DADD latency). One thread per segment with loads ahead of use took ~90 cycles per addend
+// (profiles/r01_ncu_summary.md); this form is bounded by the DADD latency alone.
 __global__ void __launch_bounds__(256) project_accumulate_kernel(const uint32_t* __restrict__ keys, const double* __restrict__ vals,
-                                                                 const uint32_t* __restrict__ n_items_ptr, double* __restrict__ kmer_freq) {
+                                                                 const uint32_t* __restrict__ n_items_ptr, uint32_t n_nodes,
+                                                                 double* __restrict__ kmer_freq) {
     const uint32_t n = *n_items_ptr;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t key = keys[i];
-        if (i > 0 && keys[i - 1] == key) continue;
-        uint32_t lo = i, step = 1;                         // keys[lo] == key
-        while (lo + step < n && keys[lo + step] == key) { lo += step; step <<= 1; }
-        uint32_t hi = lo + step < n ? lo + step : n;       // keys[hi] != key or hi == n
-        while (hi - lo > 1) { const uint32_t mid = lo + (hi - lo) / 2; if (keys[mid] == key) lo = mid; else hi = mid; }
-        const uint32_t end = hi;
-        double acc = kmer_freq[key];
-        uint32_t j = i;
-        for (; j + 8 <= end; j += 8) {
-            const double v0 = vals[j], v1 = vals[j + 1], v2 = vals[j + 2], v3 = vals[j + 3];
-            const double v4 = vals[j + 4], v5 = vals[j + 5], v6 = vals[j + 6], v7 = vals[j + 7];
-            acc = __dadd_rn(acc, v0); acc = __dadd_rn(acc, v1); acc = __dadd_rn(acc, v2); acc = __dadd_rn(acc, v3);   // node.go:25-28, in read order
-            acc = __dadd_rn(acc, v4); acc = __dadd_rn(acc, v5); acc = __dadd_rn(acc, v6); acc = __dadd_rn(acc, v7);
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t node = gwarp; node < n_nodes; node += total_warps) {
+        uint32_t lo = 0, hi = n;                              // lower_bound(node + (lane & 1))
+        const uint32_t want = node + (lane & 1u);
+        while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (keys[mid] < want) lo = mid + 1; else hi = mid; }
+        const uint32_t start = __shfl_sync(0xffffffffu, lo, 0), end = __shfl_sync(0xffffffffu, lo, 1);
+        if (start >= end) continue;
+        double acc = kmer_freq[node];
+        double v = start + lane < end ? vals[start + lane] : 0.0;
+        for (uint32_t base = start; base < end; base += 32) {
+            const uint32_t nxt = base + 32 + lane;
+            const double vn = nxt < end ? vals[nxt] : 0.0;
+            const uint32_t cnt = end - base < 32u ? end - base : 32u;
+#pragma unroll
+            for (uint32_t l = 0; l < 32; l++) {
+                const double x = __shfl_sync(0xffffffffu, v, l);
+                if (l < cnt) acc = __dadd_rn(acc, x);        // node.go:25-28, in read order
+            }
+            v = vn;
         }
-        for (; j < end; j++) acc = __dadd_rn(acc, vals[j]);
-        kmer_freq[key] = acc;
+        if (lane == 0) kmer_freq[node] = acc;
     }
 }
 

@@ -162,6 +162,108 @@ __device__ __forceinline__ void lsh_probe(const DevIndex& ix, const uint64_t (&s
     }
 }
 
+// Warp-cooperative form of lsh_probe for 32 reads at once (lane == read). Every lane looks up its own band
+// slot; the buckets found are then POOLED: an inclusive scan of the bucket sizes turns them into one list of
+// (owner lane, candidate) items which the 32 lanes verify 32 at a time, fetching the owner's sketch slots by
+// shuffle. (With one thread walking its own bucket, a warp ran the candidate loop with ~2 active lanes: the
+// ~11 candidates of a seeded read — neighbouring windows share their first K minima — against 0 for the
+// other half of the reads; 35 % of the kernel's issue slots, profiles/r01_ncu_summary.md.)
+// stage_tile = stage slots of lane 0's read; returns this lane's hit count. Same hits as lsh_probe, in
+// the same order (band, then window id ascending).
+template <int S, int MAXK>
+__device__ __forceinline__ uint32_t warp_probe(const DevIndex& ix, const uint64_t (&sk)[S], LenParam lp, bool valid, uint32_t lane,
+                                               uint32_t* __restrict__ stage_tile) {
+    constexpr int NB = S / MAXK;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const bool probing = valid && lp.eq_min <= S && lp.K != 0;
+    const uint32_t myL = probing ? lp.L : 0u;
+    const uint32_t maxL = __reduce_max_sync(FULL, myL);
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t nh = 0;
+#pragma unroll 1
+    for (uint32_t b = 0; b < maxL && b < NB; b++) {
+        // (1) every lane: its band slot -> bucket [start, start + count)
+        uint32_t start = 0, count = 0;
+        if (b < myL) {
+            uint32_t key[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int bb = 0; bb < NB; bb++) {
+                if (bb == static_cast<int>(b)) {
+#pragma unroll
+                    for (int j = 0; j < MAXK; j++) key[j] = j < lp.K ? static_cast<uint32_t>(sk[bb * MAXK + j]) : 0u;
+                }
+            }
+            const LshTable tab = ix.tables[(lp.K - 1) * NB + b];
+            uint32_t h = band_key_hash(key) & tab.mask;
+            while (true) {
+                const uint4* sp = reinterpret_cast<const uint4*>(tab.slots + h);
+                const uint4 kq = __ldg(sp), rest = __ldg(sp + 1);
+                if (rest.y == 0) break;  // empty
+                if (kq.x == key[0] && kq.y == key[1] && kq.z == key[2] && kq.w == key[3]) { start = rest.x; count = rest.y; break; }
+                h = (h + 1) & tab.mask;
+            }
+        }
+        __syncwarp();
+        // (2) pool the buckets
+        uint32_t incl = count;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); if (lane >= static_cast<uint32_t>(d)) incl += v; }
+        const uint32_t excl = incl - count;
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        // (3) verify 32 (owner, candidate) items per step
+        for (uint32_t base = 0; base < total; base += 32) {
+            const uint32_t item = base + lane;
+            const bool live = item < total;
+            uint32_t o = 0;  // owner = first lane whose inclusive sum exceeds item
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t v = __shfl_sync(FULL, incl, (o + step - 1) & 31u);
+                if (v <= item) o += step;
+            }
+            o &= 31u;
+            const uint32_t o_excl = __shfl_sync(FULL, excl, o), o_incl = __shfl_sync(FULL, incl, o);
+            const uint32_t o_start = __shfl_sync(FULL, start, o);
+            const uint32_t o_K = __shfl_sync(FULL, static_cast<uint32_t>(lp.K), o), o_eqmin = __shfl_sync(FULL, static_cast<uint32_t>(lp.eq_min), o);
+            const uint32_t o_nh = __shfl_sync(FULL, nh, o);
+            uint32_t w = 0;
+            const uint64_t* ws = ix.sketches;
+            if (live) {
+                w = __ldg(ix.tables[(o_K - 1) * NB + b].wins + o_start + (item - o_excl));
+                ws += static_cast<size_t>(w) * S;
+            }
+            uint32_t eq = 0, low = 0;
+#pragma unroll
+            for (int i = 0; i < S; i++) {
+                const uint64_t mine = __shfl_sync(FULL, sk[i], o);
+                const uint64_t v = live ? __ldg(ws + i) : 0ULL;
+                eq += (v == mine);
+                low |= static_cast<uint32_t>(static_cast<uint32_t>(v) == static_cast<uint32_t>(mine)) << i;
+            }
+            const uint32_t kmask = (1u << o_K) - 1u;
+            bool dup = false;  // already reported through an earlier band (lshensemble de-duplicates per forest query)
+#pragma unroll
+            for (int b2 = 0; b2 < NB; b2++)
+                if (b2 < static_cast<int>(b) && ((low >> (b2 * MAXK)) & kmask) == kmask) dup = true;
+            const bool pass = live && eq >= o_eqmin && !dup;
+            const uint32_t pass_mask = __ballot_sync(FULL, pass);
+            // lanes of this step that hold items of owner x: [max(excl_x, base), min(incl_x, base + 32)) - base
+            auto range_mask = [&](uint32_t ex, uint32_t in) {
+                const uint32_t lo = (ex > base ? ex : base) - base;
+                const uint32_t hi = (in < base + 32 ? in : base + 32);
+                if (hi <= base + lo) return 0u;
+                const uint32_t n = hi - base - lo;
+                return (n >= 32 ? FULL : ((1u << n) - 1u)) << lo;
+            };
+            if (pass) {
+                const uint32_t slot = o_nh + __popc(pass_mask & range_mask(o_excl, o_incl) & lt_mask);
+                if (slot < HSTAGE) stage_tile[o * HSTAGE + slot] = w;
+            }
+            if (incl > base && excl < base + 32) nh += __popc(pass_mask & range_mask(excl, incl));
+        }
+    }
+    return nh;
+}
+
 struct SeedArgs {
     const uint8_t* seq;        // read bases, readable 64 bytes past the end
     const uint32_t* off;       // [n+1]
@@ -210,7 +312,6 @@ constexpr int kTileReads = 32;
 template <int S, int MAXK>
 __global__ void __launch_bounds__(kSeedThreads, GROOT_SEED_MIN_BLOCKS) seed_kernel(DevIndex ix, SeedArgs a, MultTable M) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    constexpr int kWarps = kSeedThreads / 32;
     SeedTabs* T = reinterpret_cast<SeedTabs*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(SeedTabs));  // 2 mbarriers per warp
     uint8_t* bufs_all = smem_raw + sizeof(SeedTabs) + 64;
@@ -243,19 +344,6 @@ __global__ void __launch_bounds__(kSeedThreads, GROOT_SEED_MIN_BLOCKS) seed_kern
         if (lane == 0) t = atomicAdd(a.tile_counter, 1u);
         return __shfl_sync(0xffffffffu, t, 0);
     };
-    auto process = [&](const uint8_t* p, uint32_t r, uint32_t len) {
-        uint32_t nh = 0;
-        uint64_t sk[S];
-        khf_sketch<S>(p, len, ix.k, *T, M, sk);
-        if (a.sketches_out) {
-#pragma unroll
-            for (int i = 0; i < S; i++) a.sketches_out[static_cast<size_t>(r) * S + i] = sk[i];
-        }
-        uint32_t* st = a.stage + static_cast<size_t>(r) * HSTAGE;
-        lsh_probe<S, MAXK>(ix, sk, a.len_params[len], [&](uint32_t w) { if (nh < HSTAGE) st[nh] = w; nh++; });
-        return nh;
-    };
-
     unsigned phase[2] = {0, 0};
     int cur = 0;
     uint32_t tile = next_tile();
@@ -274,18 +362,29 @@ __global__ void __launch_bounds__(kSeedThreads, GROOT_SEED_MIN_BLOCKS) seed_kern
             const uint32_t b1 = (a.off[r1] + 15u) & ~15u;
             in_smem = (b1 - b0) <= a.tile_bytes;
         }
+        // ---- sketch: one thread per read, registers only ----
+        uint64_t sk[S];
+        LenParam lp{0, 0, 0xffff};
+        bool valid = false;
         if (r < a.n_reads) {
             const uint32_t o = a.off[r], len = a.off[r + 1] - o;
-            uint32_t nh = 0;
             if (len < ix.k || len > a.max_len) {
                 set_error(a.error, len < ix.k ? -5 : -7, r);  // GROOTGPU_ERR_SHORT_READ / _CAPACITY
-            } else if (in_smem) {
-                nh = process(bufs + static_cast<size_t>(cur) * a.tile_bytes + (o - b0), r, len);   // LDS path
             } else {
-                nh = process(a.seq + o, r, len);                                                   // LDG path
+                if (in_smem) khf_sketch<S>(bufs + static_cast<size_t>(cur) * a.tile_bytes + (o - b0), len, ix.k, *T, M, sk);   // LDS path
+                else khf_sketch<S>(a.seq + o, len, ix.k, *T, M, sk);                                                          // LDG path
+                lp = a.len_params[len];
+                valid = true;
+                if (a.sketches_out) {
+#pragma unroll
+                    for (int i = 0; i < S; i++) a.sketches_out[static_cast<size_t>(r) * S + i] = sk[i];
+                }
             }
-            a.n_hits[r] = nh;
         }
+        __syncwarp();
+        // ---- probe + containment check: the warp's 32 reads pool their candidates (warp_probe) ----
+        const uint32_t nh = warp_probe<S, MAXK>(ix, sk, lp, valid, lane, a.stage + static_cast<size_t>(r0) * HSTAGE);
+        if (r < a.n_reads) a.n_hits[r] = nh;
         __syncwarp();  // every lane is done with buffer `cur`
         cur ^= 1;
         tile = tnext;
@@ -326,7 +425,54 @@ struct FillArgs {
     uint32_t* hit_read;
     uint8_t* seg_flag;
     unsigned long long* counters;  // [0]=mapped reads, [1]=multimapped reads
+    uint32_t* reads2;              // [n * 2 * nw32 + 1] packed copies of the seeded reads (pack_read2), or nullptr
+    uint8_t* read_ok2;             // [n] 1 when reads2 holds the read
+    uint32_t nw32;                 // words per orientation (16 bases each); 0 = packing off
 };
+
+// reverse the order of the sixteen 2-bit groups of a word
+__device__ __forceinline__ uint32_t rev_pairs16(uint32_t x) {
+    const uint32_t r = __brev(x);
+    return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+}
+
+// 2-bit copies of one read for the align kernels: out[0, nw32) = the read (base i in word i >> 4 at bits 2*(i & 15),
+// code pack_base2), out[nw32, 2*nw32) = its reverse complement shifted up by pad = 16*nw32 - len bases (base i of the
+// reverse complement sits at position i + pad). Returns false, writing nothing useful, when the read does not fit
+// or holds anything but upper-case ACGT — such reads take the byte-wise path, which reproduces the reference's
+// handling of 'N' and of bytes RevComplement cannot map (seqio.go:17-23,120-133).
+// Reads aligned 32-bit words: seq must be readable a few bytes past the read (the API asks for 64).
+__device__ inline bool pack_read2(const uint8_t* __restrict__ seq, uint32_t o, uint32_t len, uint32_t nw32, uint32_t* __restrict__ out) {
+    if (len > nw32 * 16u) return false;
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(seq + (o & ~3u));
+    const uint32_t sh = (o & 3u) * 8u;
+    uint32_t prev = __ldg(wp);
+    bool ok = true;
+    for (uint32_t j = 0; j < nw32; j++) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (uint32_t t = 0; t < 4; t++) {
+            const uint32_t bi = 16u * j + 4u * t;   // first base of this byte word
+            if (bi < len) {
+                const uint32_t next = __ldg(wp + 4u * j + t + 1u);
+                const uint32_t w = __funnelshift_r(prev, next, sh);
+                prev = next;
+                const uint32_t nb = len - bi;
+                const uint32_t bytemask = nb >= 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
+                uint32_t c = (w >> 1) & 0x03030303u;
+                const uint32_t m0 = c & 0x01010101u, m1 = (c >> 1) & 0x01010101u;
+                // the byte each code stands for: A 0x41, C 0x43, T 0x54, G 0x47
+                const uint32_t expect = 0x41414141u ^ (m0 << 1) ^ ((m0 & m1) << 2) ^ ((m1 & ~m0) * 0x15u);
+                ok = ok && ((expect ^ w) & bytemask) == 0u;
+                c &= bytemask;
+                acc |= ((c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu) << (8u * t);
+            }
+        }
+        out[j] = acc;
+        out[nw32 + (nw32 - 1u - j)] = rev_pairs16(acc) ^ 0xAAAAAAAAu;
+    }
+    return ok;
+}
 
 template <int S, int MAXK>
 __global__ void __launch_bounds__(kSeedThreads) fill_kernel(DevIndex ix, FillArgs a, MultTable M) {
@@ -338,6 +484,10 @@ __global__ void __launch_bounds__(kSeedThreads) fill_kernel(DevIndex ix, FillArg
         const uint32_t nh = a.n_hits[r];
         if (nh == 0) continue;
         const uint32_t base = a.hit_off[r];
+        if (a.nw32) {
+            const uint32_t o = a.off[r];
+            a.read_ok2[r] = pack_read2(a.seq, o, a.off[r + 1] - o, a.nw32, a.reads2 + static_cast<size_t>(r) * 2u * a.nw32) ? 1 : 0;
+        }
         if (nh <= HSTAGE) {
             for (uint32_t i = 0; i < nh; i++) a.hits[base + i] = a.stage[static_cast<size_t>(r) * HSTAGE + i];
         } else {
