@@ -300,10 +300,14 @@ __device__ __forceinline__ uint32_t extract16(const uint32_t* __restrict__ w, ui
     return __funnelshift_r(w[wi], w[wi + 1], (pos & 15u) * 2u);
 }
 
+// EMIT: additionally writes the (path, pos) records of every successful traversal, traversals in DFS order, path ids
+// ascending inside one (processTraversal, alignment.go:263-317).
+template <bool EMIT>
 __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, uint32_t off0, const uint32_t* __restrict__ rd2, uint32_t base0,
                                            uint32_t rlen, uint32_t mw, bool has_n, DfsFrame* __restrict__ stack, uint32_t* __restrict__ mask_ws,
-                                           uint32_t max_depth, DfsResult* res) {
+                                           uint32_t max_depth, DfsResult* res, uint32_t* __restrict__ out_path = nullptr, int32_t* __restrict__ out_pos = nullptr) {
     uint32_t nrec = 0, ntrav = 0, depth = 0;
+    const uint32_t p0_off = ix.nodes[node0].path_off, p0_cnt = ix.nodes[node0].path_cnt;
     uint32_t cur = node0, off = off0, dist = 0;
     uint32_t cm[kMaskWordsInline];
 #pragma unroll
@@ -331,10 +335,28 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
                 if (wi < mw) { cm[wi] &= ix.node_mask[nd.mask_off + wi]; any |= cm[wi]; }
             if (any != 0u) {
                 if (dist == rlen || nd.edge_cnt == 0) {           // alignment.go:229: full read matched OR sink node
-                    uint32_t c = 0;
+                    if (EMIT) {
+                        uint32_t j = 0;                           // walks the start node's path list: both ascending
 #pragma unroll
-                    for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) { c += __popc(cm[wi]); res->mask[wi] = cm[wi]; }
-                    nrec += c; ntrav++;
+                        for (int wi = 0; wi < kMaskWordsInline; wi++) {
+                            uint32_t m = wi < mw ? cm[wi] : 0u;
+                            while (m) {
+                                const uint32_t pid = wi * 32 + (__ffs(m) - 1);
+                                m &= m - 1;
+                                while (j < p0_cnt && ix.node_path_id[p0_off + j] < pid) j++;
+                                const int32_t pos = (j < p0_cnt && ix.node_path_id[p0_off + j] == pid) ? ix.node_path_pos[p0_off + j] : 0;
+                                out_path[nrec] = pid;
+                                out_pos[nrec] = pos + static_cast<int32_t>(off0);   // alignment.go:296
+                                nrec++;
+                            }
+                        }
+                    } else {
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) { c += __popc(cm[wi]); res->mask[wi] = cm[wi]; }
+                        nrec += c;
+                    }
+                    ntrav++;
                 } else if (nd.edge_cnt == 1) {
                     cur = ix.edges[nd.edge_off]; descend = true;
                 } else if (depth < max_depth) {
@@ -363,30 +385,28 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
 }
 
 constexpr uint32_t kPrefixBases = 8;  // == kPfxLen of host/prefix_table.cpp
-// 2-bit pack of read bases [v, v+8) of the oriented read for v = 0, 1; bad = positions that are not ACGT
-__device__ __forceinline__ void pack_read_prefix(const uint8_t* __restrict__ rp, const uint8_t* lut, uint32_t len, bool rc, uint32_t (&pk)[2], uint32_t (&bad)[2]) {
-    uint32_t p = 0, b = 0;
-    for (uint32_t i = 0; i < kPrefixBases + 1 && i < len; i++) {
-        const uint8_t c = rc ? lut[rp[len - 1 - i]] : rp[i];
-        const uint32_t code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
-        if (code > 3u) b |= 1u << i;
-        p |= (code & 3u) << (2 * i);
-    }
-    constexpr uint32_t m2 = (1u << (2 * kPrefixBases)) - 1u, m1 = (1u << kPrefixBases) - 1u;
-    pk[0] = p & m2; pk[1] = (p >> 2) & m2;
-    bad[0] = b & m1; bad[1] = (b >> 1) & m1;
+// true unless NO traversal starting at graph position `pos` can spell the read's first min(8, rlen) bases.
+// rpk = the read bases 2 bits each (pack_base2), rbad = positions that are not upper-case ACGT. Layouts: host/prefix_table.cpp.
+__device__ __forceinline__ uint32_t spread8(uint32_t x) {   // bit i -> bits 2i and 2i+1
+    x = (x | (x << 4)) & 0x0f0fu; x = (x | (x << 2)) & 0x3333u; x = (x | (x << 1)) & 0x5555u;
+    return x | (x << 1);
 }
-// true unless NO traversal starting at graph position `pos` can spell the read's first min(8, rlen) bases
+__device__ __forceinline__ bool prefix_differs(uint32_t bases, uint32_t L, uint32_t nmask, uint32_t rpk, uint32_t rbad, uint32_t rlen) {
+    L = L < rlen ? L : rlen;                                          // L <= kPrefixBases
+    uint32_t diff = (bases ^ rpk) & ((1u << (2 * L)) - 1u), badm = rbad & ((1u << L) - 1u);
+    if (nmask) { diff &= ~spread8(nmask); badm &= ~nmask; }           // a reference 'N' matches any read byte (alignment.go:212-215)
+    return (diff | badm) != 0;
+}
 __device__ __forceinline__ bool prefix_pass(const DevIndex& ix, uint32_t pos, uint32_t rpk, uint32_t rbad, uint32_t rlen) {
+    const uint32_t e1 = __ldg(ix.pfx1 + pos);
+    if (prefix_differs(e1, (e1 >> 16) & 15u, (e1 >> 20) & 0xffu, rpk, rbad, rlen)) return false;
+    if (!(e1 >> 31)) return true;                                     // the position's only prefix
     const uint32_t b = ix.pfx_off[pos], e = ix.pfx_off[pos + 1];
     for (uint32_t i = b; i < e; i++) {
         const uint64_t ent = ix.pfx[i];
-        if (ent >> 40) return true;                                  // holds an 'N' / too many prefixes: let the DFS decide
-        uint32_t L = static_cast<uint32_t>(ent >> 32) & 31u;
-        L = L < rlen ? L : rlen;
-        const uint32_t m2 = (1u << (2 * L)) - 1u;                    // L <= kPrefixBases
-        const uint32_t m1 = (1u << L) - 1u;
-        if (((static_cast<uint32_t>(ent) ^ rpk) & m2) == 0 && (rbad & m1) == 0) return true;
+        const uint32_t hi = static_cast<uint32_t>(ent >> 32);
+        if (hi & 0x100u) return true;                                 // too many prefixes here: let the DFS decide
+        if (!prefix_differs(static_cast<uint32_t>(ent), hi & 31u, (hi >> 16) & 0xffu, rpk, rbad, rlen)) return true;
     }
     return false;
 }
@@ -422,7 +442,7 @@ struct RoundArgs {
     uint32_t* n_queue_next;    // device scalar (atomic)
 };
 
-__global__ void __launch_bounds__(256) align_init_kernel(DevIndex ix, AlignArgs a, PairCursor* cursor, uint32_t* queue, uint32_t* n_queue) {
+__global__ void __launch_bounds__(256) align_init_kernel(DevIndex ix, AlignArgs a, PairCursor* cursor, uint32_t* queue, uint32_t* qkey, uint32_t* n_queue) {
     const uint32_t n_segs = *a.n_segs_ptr, n_hits = *a.n_hits_ptr;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_segs; s += gridDim.x * blockDim.x) {
         const uint32_t hb = a.seg_begin[s];                             // segments tile hits[]
@@ -435,26 +455,103 @@ __global__ void __launch_bounds__(256) align_init_kernel(DevIndex ix, AlignArgs 
         a.seg_nrec[s] = 0; a.seg_ntrav[s] = 0; a.seg_locus[s] = make_uint2(0, 0);
         cursor[s] = PairCursor{0u, 0u};
         queue[s] = s;
+        qkey[s] = a.hits[hb];                       // first mapping's window: the queue is sorted by it (pairs of one warp walk the same graph region)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *n_queue = a.no_align ? 0u : n_segs;   // graphminion.go:70-72 (--noAlign)
 }
 
-// pack the first kPrefixBases+1 oriented read bases with the whole warp (lane i handles base i)
-__device__ __forceinline__ void warp_pack_read_prefix(const uint8_t* __restrict__ rp, uint32_t len, bool rc, uint32_t lane,
-                                                      uint32_t (&pk)[2], uint32_t (&bad)[2]) {
+// the first kPrefixBases + 1 oriented read bases, 2 bits each, as the two 8-base views the screen needs (v = 0: from
+// base 0; v = 1: from base 1, for the start clip). From the packed copy when there is one, else byte-wise with the
+// whole warp (lane i handles base i).
+__device__ __forceinline__ void warp_read_prefix(const AlignArgs& a, uint32_t r, const uint8_t* __restrict__ rp, uint32_t len, bool rc, uint32_t lane,
+                                                 uint32_t (&pk)[2], uint32_t (&bad)[2]) {
+    constexpr uint32_t m2 = (1u << (2 * kPrefixBases)) - 1u, m1 = (1u << kPrefixBases) - 1u;
+    if (a.nw32 && a.read_ok2[r]) {
+        const uint32_t* rd2 = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32 + (rc ? a.nw32 : 0u);
+        const uint32_t base0 = rc ? a.nw32 * 16u - len : 0u;
+        pk[0] = extract16(rd2, base0) & m2; pk[1] = extract16(rd2, base0 + 1) & m2;   // prefix_pass never looks past the read's end
+        bad[0] = 0; bad[1] = 0;
+        return;
+    }
     uint32_t code = 4;
     if (lane <= kPrefixBases && lane < len) {
         const uint8_t c = rc ? complement_base(rp[len - 1 - lane]) : rp[lane];
-        code = c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 4u;
+        code = (c == 'A' || c == 'C' || c == 'G' || c == 'T') ? pack_base2(c) : 4u;
     }
     const uint32_t b0 = __ballot_sync(0xffffffffu, code & 1u), b1 = __ballot_sync(0xffffffffu, (code >> 1) & 1u);
     const uint32_t bb = __ballot_sync(0xffffffffu, code > 3u && lane < len);
     uint32_t p = 0;
 #pragma unroll
     for (uint32_t i = 0; i <= kPrefixBases; i++) p |= (((b0 >> i) & 1u) | (((b1 >> i) & 1u) << 1)) << (2 * i);
-    constexpr uint32_t m2 = (1u << (2 * kPrefixBases)) - 1u, m1 = (1u << kPrefixBases) - 1u;
     pk[0] = p & m2; pk[1] = (p >> 2) & m2;
     bad[0] = bb & m1; bad[1] = (bb >> 1) & m1;
+}
+
+// Warp-cooperative screen of one (mapping, strand): the lowest try index t >= t0 whose start position passes the
+// prefix filter, or kNoCand. Tries that dfsRecursive rejects on entry (offset beyond the node, alignment.go:199-201)
+// are never enumerated: stage 1 covers only the offsets that exist on the seed node, stage 2 pools the existing
+// offsets 0..10 of up to 32 contained nodes at a time (inclusive scan + owner search, as in warp_probe); the try
+// NUMBERING stays the reference's (decode_try), so cursors and results are unchanged. wr, sn, t0, len are uniform.
+__device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinRec& wr, const NodeRec& sn, uint32_t t0, const uint32_t (&pk)[2],
+                                                  const uint32_t (&bad)[2], uint32_t len, uint32_t lane) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t T1 = wr.merge_span + wr.win_size + 1u;
+    // stage 1: offsets OffSet + t on the seed node
+    const uint32_t room = sn.seq_len > wr.offset ? sn.seq_len - wr.offset : 0u;
+    const uint32_t n1 = T1 < room ? T1 : room;
+    for (uint32_t base = t0 & ~31u; base < n1; base += 32) {
+        const uint32_t t = base + lane;
+        const bool ok = t >= t0 && t < n1 && prefix_pass(ix, sn.seq_off + wr.offset + t, pk[0], bad[0], len);
+        const uint32_t ball = __ballot_sync(FULL, ok);
+        if (ball) return base + (__ffs(ball) - 1);
+    }
+    // stage 2: offsets 0..10 on every contained node
+    const uint32_t ci0 = t0 > T1 ? (t0 - T1) / 11u : 0u;
+    for (uint32_t cb = ci0 & ~31u; cb < wr.cn_cnt; cb += 32) {
+        const uint32_t ci = cb + lane;
+        uint32_t cnt = 0, so = 0;
+        if (ci < wr.cn_cnt) {
+            const NodeRec cn = ix.nodes[ix.cn_node[wr.cn_off + ci]];
+            so = cn.seq_off; cnt = cn.seq_len < 11u ? cn.seq_len : 11u;
+        }
+        uint32_t incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(FULL, incl, d); if (lane >= static_cast<uint32_t>(d)) incl += v; }
+        const uint32_t excl = incl - cnt, total = __shfl_sync(FULL, incl, 31);
+        for (uint32_t ib = 0; ib < total; ib += 32) {
+            const uint32_t item = ib + lane;
+            uint32_t o = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t v = __shfl_sync(FULL, incl, (o + step - 1) & 31u);
+                if (v <= item) o += step;
+            }
+            o &= 31u;
+            const uint32_t off0 = item - __shfl_sync(FULL, excl, o);
+            const uint32_t pos = __shfl_sync(FULL, so, o) + off0;
+            const uint32_t t = T1 + 11u * (cb + o) + off0;
+            const bool ok = item < total && t >= t0 && prefix_pass(ix, pos, pk[0], bad[0], len);
+            const uint32_t ball = __ballot_sync(FULL, ok);
+            if (ball) return __shfl_sync(FULL, t, __ffs(ball) - 1);
+        }
+    }
+    // stage 3 (1-base start clip: read[1:]) and stage 4 (1-base end clip: read[:len-1]) at the seed position (alignment.go:73-103)
+    const uint32_t tA = T1 + 11u * wr.cn_cnt;
+    {
+        const uint32_t t = tA + lane;
+        const bool ok = lane < 2 && t >= t0 && room > 0 && prefix_pass(ix, sn.seq_off + wr.offset, pk[lane == 0 ? 1 : 0], bad[lane == 0 ? 1 : 0], len - 1);
+        const uint32_t ball = __ballot_sync(FULL, ok);
+        if (ball) return tA + (__ffs(ball) - 1);
+    }
+    return kNoCand;
+}
+
+// graphminion.go:94: the read is reverse complemented for the second strand; Go panics for a byte > 'T' (seqio.go:122)
+__device__ __forceinline__ void check_revcomp_bytes(const AlignArgs& a, uint32_t r, const uint8_t* __restrict__ rp, uint32_t len, uint32_t lane) {
+    if (a.nw32 && a.read_ok2[r]) return;   // upper-case ACGT only
+    bool badb = false;
+    for (uint32_t i = lane; i < len; i += 32) badb |= rp[i] > 'T';
+    if (__any_sync(0xffffffffu, badb) && lane == 0) { if (atomicCAS(a.error, 0, -6) == 0) a.error[1] = static_cast<int>(r); }
 }
 
 __global__ void __launch_bounds__(256) align_screen_kernel(DevIndex ix, RoundArgs ra) {
@@ -472,40 +569,21 @@ __global__ void __launch_bounds__(256) align_screen_kernel(DevIndex ix, RoundArg
         const PairCursor cur = ra.cursor[s];
         uint32_t m = hb + (cur.m_strand >> 1), strand = cur.m_strand & 1u, t0 = cur.t;
         uint2 cand = make_uint2(kNoCand, 0u);
-        while (m < he && cand.x == kNoCand) {
+        while (m < he) {
             const WinRec wr = ix.wins[a.hits[m]];
             const NodeRec sn = ix.nodes[wr.node];
-            const uint32_t T = tries_per_strand(wr);
             uint32_t pk[2], bad[2];
-            warp_pack_read_prefix(rp, len, strand != 0, lane, pk, bad);
-            for (uint32_t base = t0 & ~31u; base < T && cand.x == kNoCand; base += 32) {
-                const uint32_t t = base + lane;
-                bool ok = false;
-                if (t >= t0 && t < T) {
-                    uint32_t node, off0, stage;
-                    decode_try(ix, wr, t, &node, &off0, &stage);
-                    uint32_t seq_off = sn.seq_off, seq_len = sn.seq_len;
-                    if (stage == 2) { const NodeRec cn = ix.nodes[node]; seq_off = cn.seq_off; seq_len = cn.seq_len; }
-                    if (off0 < seq_len) {                                   // else dfsRecursive fails on entry (alignment.go:199-201)
-                        const uint32_t v = stage == 3 ? 1u : 0u;            // the start clip compares from read base 1
-                        ok = prefix_pass(ix, seq_off + off0, pk[v], bad[v], stage >= 3 ? len - 1 : len);
-                    }
-                }
-                const uint32_t ball = __ballot_sync(0xffffffffu, ok);
-                if (ball) cand = make_uint2(((m - hb) << 1) | strand, base + (__ffs(ball) - 1));
-            }
-            if (cand.x != kNoCand) break;
+            warp_read_prefix(a, r, rp, len, strand != 0, lane, pk, bad);
+            const uint32_t t = screen_strand(ix, wr, sn, t0, pk, bad, len, lane);
+            if (t != kNoCand) { cand = make_uint2(((m - hb) << 1) | strand, t); break; }
             t0 = 0;
-            if (strand == 0) {
-                strand = 1;                                                 // graphminion.go:94 RevComplement: Go panics for a byte > 'T'
-                bool badb = false;
-                for (uint32_t i = lane; i < len; i += 32) badb |= rp[i] > 'T';
-                if (__any_sync(0xffffffffu, badb) && lane == 0) { if (atomicCAS(a.error, 0, -6) == 0) a.error[1] = static_cast<int>(r); }
-            } else { strand = 0; m++; }
+            if (strand == 0) { strand = 1; check_revcomp_bytes(a, r, rp, len, lane); }
+            else { strand = 0; m++; }
         }
         if (lane == 0) ra.cand[s] = cand;
     }
 }
+
 
 // walk one try of pair s; on success fills the pair's outputs and returns true
 __device__ __forceinline__ bool walk_try(const DevIndex& ix, const AlignArgs& a, const uint8_t* lut, uint32_t s, uint32_t hb,
@@ -523,7 +601,7 @@ __device__ __forceinline__ bool walk_try(const DevIndex& ix, const AlignArgs& a,
     if (a.nw32 && mw <= kMaskWordsInline && a.read_ok2[r]) {
         const uint32_t* rd2 = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32 + (strand ? a.nw32 : 0u);
         const uint32_t base0 = (strand ? a.nw32 * 16u - len : 0u) + (stage == 3 ? 1u : 0u);
-        dfs_packed(ix, node, off0, rd2, base0, rlen, mw, ix.graph_has_n[wr.graph] != 0, stack, mask_ws, depth_cap, &res);
+        dfs_packed<false>(ix, node, off0, rd2, base0, rlen, mw, ix.graph_has_n[wr.graph] != 0, stack, mask_ws, depth_cap, &res);
     } else if (mw <= kMaskWordsInline) dfs_masked(ix, node, off0, rd, rlen, mw, stack, mask_ws, depth_cap, &res);
     else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
     if (res.nrec == 0) return false;
@@ -567,8 +645,8 @@ __global__ void __launch_bounds__(128, 5) align_walk_kernel(DevIndex ix, RoundAr
 }
 
 // Leftovers after the fixed number of rounds (pairs that keep producing tries which pass the filter but yield no
-// path id — low-complexity sequence, 'N' wildcards): ONE WARP PER PAIR runs screen steps and lets lane 0 walk each
-// survivor, in order, until one aligns or the list is exhausted.
+// path id — low-complexity sequence, 'N' wildcards): ONE WARP PER PAIR alternates screen steps and walks (lane 0)
+// until one aligns or the list is exhausted.
 __global__ void __launch_bounds__(128, 5) align_finish_kernel(DevIndex ix, RoundArgs ra) {
     __shared__ uint8_t lut[256];
     for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = complement_base(static_cast<uint8_t>(i));
@@ -594,42 +672,24 @@ __global__ void __launch_bounds__(128, 5) align_finish_kernel(DevIndex ix, Round
         while (m < he && !done) {
             const WinRec wr = ix.wins[a.hits[m]];
             const NodeRec sn = ix.nodes[wr.node];
-            const uint32_t T = tries_per_strand(wr);
             uint32_t pk[2], bad[2];
-            warp_pack_read_prefix(rp, len, strand != 0, lane, pk, bad);
-            for (uint32_t base = t0 & ~31u; base < T && !done; base += 32) {
-                const uint32_t t = base + lane;
-                bool ok = false;
-                if (t >= t0 && t < T) {
-                    uint32_t node, off0, stage;
-                    decode_try(ix, wr, t, &node, &off0, &stage);
-                    uint32_t seq_off = sn.seq_off, seq_len = sn.seq_len;
-                    if (stage == 2) { const NodeRec cn = ix.nodes[node]; seq_off = cn.seq_off; seq_len = cn.seq_len; }
-                    if (off0 < seq_len) {
-                        const uint32_t v = stage == 3 ? 1u : 0u;
-                        ok = prefix_pass(ix, seq_off + off0, pk[v], bad[v], stage >= 3 ? len - 1 : len);
-                    }
-                }
-                uint32_t ball = __ballot_sync(0xffffffffu, ok);
-                while (ball && !done) {                                     // survivors of this chunk, in order
-                    const uint32_t t_c = base + (__ffs(ball) - 1);
-                    ball &= ball - 1;
-                    uint32_t okw = 0;
-                    if (lane == 0) okw = walk_try(ix, a, lut, s, hb, m, strand, t_c, stack, mask_ws, depth_cap) ? 1u : 0u;
-                    done = __shfl_sync(0xffffffffu, okw, 0) != 0;
-                }
+            warp_read_prefix(a, r, rp, len, strand != 0, lane, pk, bad);
+            while (!done) {
+                const uint32_t t = screen_strand(ix, wr, sn, t0, pk, bad, len, lane);
+                if (t == kNoCand) break;
+                uint32_t okw = 0;
+                if (lane == 0) okw = walk_try(ix, a, lut, s, hb, m, strand, t, stack, mask_ws, depth_cap) ? 1u : 0u;
+                done = __shfl_sync(0xffffffffu, okw, 0) != 0;
+                t0 = t + 1;
             }
             if (done) break;
             t0 = 0;
-            if (strand == 0) {
-                strand = 1;                                                 // graphminion.go:94 RevComplement: Go panics for a byte > 'T'
-                bool badb = false;
-                for (uint32_t i = lane; i < len; i += 32) badb |= rp[i] > 'T';
-                if (__any_sync(0xffffffffu, badb) && lane == 0) { if (atomicCAS(a.error, 0, -6) == 0) a.error[1] = static_cast<int>(r); }
-            } else { strand = 0; m++; }
+            if (strand == 0) { strand = 1; check_revcomp_bytes(a, r, rp, len, lane); }
+            else { strand = 0; m++; }
         }
     }
 }
+
 
 struct EmitArgs {
     const uint8_t* seq;
@@ -643,19 +703,23 @@ struct EmitArgs {
     uint32_t* rec_path;
     int32_t* rec_pos;
     DfsFrame* stack_ws;
+    uint32_t* mask_ws;
     uint32_t max_len;
+    const uint32_t* reads2;
+    const uint8_t* read_ok2;
+    uint32_t nw32;
+    uint32_t* multi_queue;     // pairs whose records need a second DFS (several traversals, > 256 paths)
+    uint32_t* n_multi;         // device scalar, zeroed before align_emit_kernel
 };
 
 // ONE WARP PER PAIR: write the pair's records at the scanned offset. The common case (exactly one traversal with
 // ids, <= 256 paths in the graph) expands the stored bitset with the lanes striding over the start node's path
-// list (path ids ascending == record order); otherwise lane 0 re-runs the DFS in emit mode.
+// list (path ids ascending == record order); every other pair is queued for align_emit_multi_kernel.
 __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a) {
     const uint32_t n_segs = *a.n_segs_ptr;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gwarp = gthread >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t depth_cap = a.max_len + 2;
-    DfsFrame* stack = a.stack_ws + static_cast<size_t>(gthread) * depth_cap;
     for (uint32_t s = gwarp; s < n_segs; s += total_warps) {
         const PairOut p = a.pairs[s];
         const uint32_t rb = a.rec_off[s];
@@ -680,11 +744,36 @@ __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a
                 written += __popc(ball);
             }
         } else if (lane == 0) {
-            const uint32_t o = a.off[p.read], len = a.off[p.read + 1] - o;
+            a.multi_queue[atomicAdd(a.n_multi, 1u)] = s;
+        }
+    }
+}
+
+// ONE THREAD PER QUEUED PAIR: re-runs the DFS from the pair's successful start in emit mode — several traversals
+// spell the read (typically through an 'N' node next to the read's own allele), each contributes its own records.
+__global__ void __launch_bounds__(128) align_emit_multi_kernel(DevIndex ix, EmitArgs a) {
+    const uint32_t n = *a.n_multi;
+    const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
+    const uint32_t depth_cap = a.max_len + 2;
+    DfsFrame* stack = a.stack_ws + static_cast<size_t>(gthread) * depth_cap;
+    uint32_t* mask_ws = a.mask_ws + static_cast<size_t>(gthread) * depth_cap * kMaskWordsInline;
+    for (uint32_t q = gthread; q < n; q += total) {
+        const uint32_t s = a.multi_queue[q];
+        const PairOut p = a.pairs[s];
+        const uint32_t rb = a.rec_off[s];
+        const uint2 loc = a.seg_locus[s];
+        const uint32_t mw = ix.graph_mask_words[p.graph];
+        const uint32_t o = a.off[p.read], len = a.off[p.read + 1] - o;
+        const uint32_t rlen = len - p.clip_start - p.clip_end;
+        DfsResult res;
+        res.nrec = 0; res.ntrav = 0;
+        if (a.nw32 && mw <= kMaskWordsInline && a.read_ok2[p.read]) {
+            const uint32_t* rd2 = a.reads2 + static_cast<size_t>(p.read) * 2u * a.nw32 + (p.reverse ? a.nw32 : 0u);
+            const uint32_t base0 = (p.reverse ? a.nw32 * 16u - len : 0u) + (p.clip_start ? 1u : 0u);
+            dfs_packed<true>(ix, loc.x, loc.y, rd2, base0, rlen, mw, ix.graph_has_n[p.graph] != 0, stack, mask_ws, depth_cap, &res,
+                             a.rec_path + rb, a.rec_pos + rb);
+        } else {
             GlobalRead rd{a.seq + o, len, p.clip_start ? 1u : 0u, p.reverse != 0};
-            const uint32_t rlen = len - p.clip_start - p.clip_end;
-            DfsResult res;
-            res.nrec = 0; res.ntrav = 0;
             dfs_align<DFS_EMIT>(ix, loc.x, loc.y, rd, rlen, mw, stack, depth_cap, &res, a.rec_path + rb, a.rec_pos + rb);
         }
     }

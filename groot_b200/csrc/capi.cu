@@ -171,7 +171,7 @@ struct grootgpu_index {
     std::map<std::pair<uint32_t, double>, LenParam> param_cache;
     // workspaces
     DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
-        rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error, reads2, read_ok2;
+        rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error, reads2, read_ok2, qkey, qkey2;
     HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_scal;
     // graph weights live on the device once a batch was projected there; the host copy is refreshed lazily
     double* d_kmer_freq = nullptr;
@@ -211,9 +211,9 @@ void index_to_device(grootgpu_index* ix) {
     d.graph_mask_words = upload(h.graph_mask_words, ix->owned);
     ix->d_cn_count = upload(h.cn_count, ix->owned);
     {
-        std::vector<uint32_t> pfx_off; std::vector<uint64_t> pfx;
-        build_prefix_table(h, pfx_off, pfx);
-        d.pfx_off = upload(pfx_off, ix->owned); d.pfx = upload(pfx, ix->owned);
+        std::vector<uint32_t> pfx_off, pfx1; std::vector<uint64_t> pfx;
+        build_prefix_table(h, pfx_off, pfx, pfx1);
+        d.pfx_off = upload(pfx_off, ix->owned); d.pfx = upload(pfx, ix->owned); d.pfx1 = upload(pfx1, ix->owned);
     }
     {   // 2-bit copy of the node sequences + per-graph 'N' flag for the packed walk (align_kernels.cuh, dfs_packed)
         std::vector<uint32_t> seq2((h.node_seq.size() + 15) / 16 + 2, 0u);
@@ -557,8 +557,20 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         CK(cudaMemsetAsync(ix->qcount.p, 0, 64, st));
         uint32_t* qc = ix->qcount.as<uint32_t>();
         CK(cudaEventRecord(ix->ev[2], st));
-        kbegin(2); align_init_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ix->d, aa, ix->cursor.as<PairCursor>(), ix->queue_a.as<uint32_t>(), qc); launches++; kend();
+        ix->qkey.need(4ull * n_segs); ix->qkey2.need(4ull * n_segs);
+        kbegin(2); align_init_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ix->d, aa, ix->cursor.as<PairCursor>(), ix->queue_b.as<uint32_t>(), ix->qkey.as<uint32_t>(), qc); launches++; kend();
         CK(cudaGetLastError());
+        {   // queue ordered by window id: the 32 pairs a warp walks together sit on the same graph region (same nodes, same
+            // branch pattern), instead of 32 unrelated walks of very different lengths idling on each other
+            int wbits = 1;
+            while ((1ull << wbits) < ix->h.wins.size()) wbits++;
+            size_t qs = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, qs, ix->qkey.as<uint32_t>(), ix->qkey2.as<uint32_t>(), ix->queue_b.as<uint32_t>(), ix->queue_a.as<uint32_t>(),
+                                            static_cast<int>(n_segs), 0, wbits, st);
+            ix->cub_tmp.need(qs + 16);
+            cub::DeviceRadixSort::SortPairs(ix->cub_tmp.p, qs, ix->qkey.as<uint32_t>(), ix->qkey2.as<uint32_t>(), ix->queue_b.as<uint32_t>(), ix->queue_a.as<uint32_t>(),
+                                            static_cast<int>(n_segs), 0, wbits, st);
+        }
         int screen_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8));
         screen_blocks = std::max(screen_blocks, 1);
         const int kRounds = 6;
@@ -600,12 +612,15 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         ea.seq = d_seq; ea.off = d_off; ea.n_segs_ptr = d_nsegs; ea.pairs = ix->pairs.as<PairOut>(); ea.rec_off = ix->rec_off.as<uint32_t>();
         ea.seg_locus = ix->seg_locus.as<uint2>(); ea.seg_mask = ix->seg_mask.as<uint32_t>(); ea.seg_ntrav = ix->seg_ntrav.as<uint32_t>();
         ea.rec_path = ix->rec_path.as<uint32_t>(); ea.rec_pos = ix->rec_pos.as<int32_t>();
-        ea.stack_ws = ix->stack_ws.as<DfsFrame>(); ea.max_len = max_len;
+        ea.stack_ws = ix->stack_ws.as<DfsFrame>(); ea.mask_ws = ix->mask_ws.as<uint32_t>(); ea.max_len = max_len;
+        ea.reads2 = ix->reads2.as<uint32_t>(); ea.read_ok2 = ix->read_ok2.as<uint8_t>(); ea.nw32 = nw32;
+        ea.multi_queue = ix->queue_a.as<uint32_t>(); ea.n_multi = qc + 2;      // the align queues are free by now
         {
-            int emit_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8));
-            // stack_ws holds verify_blocks*128 thread stacks; the emit grid (256-thread blocks) must not exceed that
-            emit_blocks = std::max(1, std::min(emit_blocks, verify_blocks / 2));
+            CK(cudaMemsetAsync(qc + 2, 0, 4, st));
+            const int emit_blocks = std::max(1, static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8)));
             kbegin(5); align_emit_kernel<<<emit_blocks, 256, 0, st>>>(ix->d, ea); launches++; kend();
+            // thread stacks: stack_ws / mask_ws hold verify_blocks * vthreads of them
+            kbegin(5); align_emit_multi_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ea); launches++; kend();
         }
         CK(cudaGetLastError());
     } else {
