@@ -51,6 +51,9 @@ struct CudaError : std::runtime_error { using std::runtime_error::runtime_error;
 // grow-only device / pinned-host buffers
 struct DBuf {
     void* p = nullptr; size_t cap = 0;
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
     void need(size_t bytes) {
         if (bytes <= cap) return;
         if (p) cudaFree(p);
@@ -64,6 +67,9 @@ struct DBuf {
 };
 struct HBuf {
     void* p = nullptr; size_t cap = 0;
+    HBuf() = default;
+    HBuf(const HBuf&) = delete;
+    HBuf& operator=(const HBuf&) = delete;
     void need(size_t bytes) {
         if (bytes <= cap) return;
         if (p) cudaFreeHost(p);
@@ -91,6 +97,26 @@ MultTable make_mult(uint32_t k) {
     for (uint64_t i = 0; i < 32; i++) { m.c[i] = i ^ C; m.low[i] = static_cast<uint32_t>((C & 31u) ^ i); }
     m.c0 = C & ~31ull; m.m32 = 32; m.pad = 0;
     return m;
+}
+
+// ---- scalar traffic without the copy engines ---------------------------------------------------------------
+// The batch pipeline needs a handful of device scalars on the host (hit / pair / record totals, error flags) and
+// pushes a few back. As cudaMemcpyAsync these 4-byte transfers queue on the DMA engines BEHIND the 200 MB chunk
+// copies of the chunked host path and stall the compute stream for milliseconds; as tiny kernels writing mapped
+// pinned memory (peek) or taking the value as an argument (poke / zero) they depend on the compute stream alone.
+struct PeekArgs { const uint32_t* src[12]; uint32_t n; };
+__global__ void peek_kernel(PeekArgs a, volatile uint32_t* dst) {
+    if (threadIdx.x < a.n) dst[threadIdx.x] = *a.src[threadIdx.x];
+    __threadfence_system();
+}
+struct PokeArgs { uint32_t* dst[8]; uint32_t val[8]; uint32_t n; };
+__global__ void poke_kernel(PokeArgs a) {
+    if (threadIdx.x < a.n) *a.dst[threadIdx.x] = a.val[threadIdx.x];
+}
+struct ZeroArgs { uint32_t* p[6]; uint32_t words[6]; uint32_t n; };
+__global__ void zero_kernel(ZeroArgs a) {
+    for (uint32_t b = 0; b < a.n; b++)
+        for (uint32_t i = threadIdx.x; i < a.words[b]; i += blockDim.x) a.p[b][i] = 0u;
 }
 
 int pick_device(int device) {
@@ -173,6 +199,12 @@ struct grootgpu_index {
     DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
         rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error, reads2, read_ok2, qkey, qkey2;
     HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_scal;
+    // chunked host path (grootgpu_align_batch): input double buffers, the second set of result buffers, copy streams
+    DBuf in_seq[2], in_off64[2], in_off32[2], alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches, len_minmax;
+    cudaStream_t st_in = nullptr, st_out = nullptr;
+    uint32_t* h_peek = nullptr;        // mapped pinned words the device writes scalars into (peek()): no copy engine involved
+    uint32_t* d_peek = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     // graph weights live on the device once a batch was projected there; the host copy is refreshed lazily
     double* d_kmer_freq = nullptr;
     unsigned long long* d_kmer_total = nullptr;
@@ -187,10 +219,40 @@ struct grootgpu_index {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : kev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
+        if (h_peek) cudaFreeHost(h_peek);
+        if (st_in) cudaStreamDestroy(st_in);
+        if (st_out) cudaStreamDestroy(st_out);
+        for (auto& e : ev_in) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_done) if (e) cudaEventDestroy(e);
+        for (auto& e : ev_out) if (e) cudaEventDestroy(e);
+        if (ev_t0) cudaEventDestroy(ev_t0);
+        if (ev_t1) cudaEventDestroy(ev_t1);
     }
 };
 
 namespace {
+
+// peek: device words -> host through mapped memory (returns after synchronising the stream); poke / zero: host values -> device words
+const uint32_t* peek(grootgpu_index* ix, cudaStream_t st, std::initializer_list<const uint32_t*> src) {
+    PeekArgs a{};
+    for (const uint32_t* p : src) a.src[a.n++] = p;
+    peek_kernel<<<1, 32, 0, st>>>(a, ix->d_peek);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    return ix->h_peek;
+}
+void poke(cudaStream_t st, std::initializer_list<std::pair<uint32_t*, uint32_t>> w) {
+    PokeArgs a{};
+    for (auto& x : w) { a.dst[a.n] = x.first; a.val[a.n] = x.second; a.n++; }
+    poke_kernel<<<1, 32, 0, st>>>(a);
+    CK(cudaGetLastError());
+}
+void zero_words(cudaStream_t st, std::initializer_list<std::pair<void*, uint32_t>> bufs) {
+    ZeroArgs a{};
+    for (auto& x : bufs) { a.p[a.n] = static_cast<uint32_t*>(x.first); a.words[a.n] = x.second; a.n++; }
+    zero_kernel<<<1, 64, 0, st>>>(a);
+    CK(cudaGetLastError());
+}
 
 void index_to_device(grootgpu_index* ix) {
     pick_device(ix->device);
@@ -241,6 +303,14 @@ void index_to_device(grootgpu_index* ix) {
     CK(cudaMemcpy(dt, ix->h_tables.data(), ix->h_tables.size() * sizeof(LshTable), cudaMemcpyHostToDevice));
     d.tables = ix->d_tables;
     CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&ix->h_peek), 64 * sizeof(uint32_t), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ix->d_peek), ix->h_peek, 0));
+    CK(cudaStreamCreateWithFlags(&ix->st_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ix->st_out, cudaStreamNonBlocking));
+    for (auto& e : ix->ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ix->ev_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (auto& e : ix->ev_out) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CK(cudaEventCreate(&ix->ev_t0)); CK(cudaEventCreate(&ix->ev_t1));
     for (auto& e : ix->ev) CK(cudaEventCreate(&e));
     for (auto& e : ix->kev) CK(cudaEventCreate(&e));
     if (h.kmer_freq.size() != h.nodes.size()) h.kmer_freq.assign(h.nodes.size(), 0.0);
@@ -421,11 +491,8 @@ void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n_seg
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(n_segs), st);
     ix->cub_tmp.need(tmp + 16);
     cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(n_segs), st);
-    uint32_t lo = 0, lc = 0;
-    CK(cudaMemcpyAsync(&lo, ix->item_off.as<uint32_t>() + (n_segs - 1), 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&lc, ix->item_cnt.as<uint32_t>() + (n_segs - 1), 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    const uint64_t n_items = static_cast<uint64_t>(lo) + lc;
+    const uint32_t* pk = peek(ix, st, {ix->item_off.as<uint32_t>() + (n_segs - 1), ix->item_cnt.as<uint32_t>() + (n_segs - 1)});
+    const uint64_t n_items = static_cast<uint64_t>(pk[0]) + pk[1];
     if (n_items == 0) return;
     if (n_items >= (1ull << 31)) throw std::length_error("too many weight increments in one batch: use smaller batches");
     ix->pkeys.need(4 * n_items); ix->pkeys2.need(4 * n_items); ix->pvals.need(8 * n_items); ix->pvals2.need(8 * n_items);
@@ -440,7 +507,7 @@ void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n_seg
     cub::DeviceRadixSort::SortPairs(ix->cub_tmp.p, sort_tmp, ix->pkeys.as<uint32_t>(), ix->pkeys2.as<uint32_t>(), ix->pvals.as<double>(), ix->pvals2.as<double>(),
                                     static_cast<int>(n_items), 0, end_bit, st);
     const uint32_t n32 = static_cast<uint32_t>(n_items);
-    CK(cudaMemcpyAsync(ix->item_off.as<uint32_t>() + n_segs, &n32, 4, cudaMemcpyHostToDevice, st));
+    poke(st, {{ix->item_off.as<uint32_t>() + n_segs, n32}});
     const uint32_t n_nodes = static_cast<uint32_t>(ix->h.nodes.size());
     const int ablocks = std::max(1, std::min<int>(static_cast<int>((n_nodes + 7) / 8), sms * 8));
     kbegin(6); project_accumulate_kernel<<<ablocks, 256, 0, st>>>(ix->pkeys2.as<uint32_t>(), ix->pvals2.as<double>(), ix->item_off.as<uint32_t>() + n_segs, n_nodes, ix->d_kmer_freq); launches++; kend();
@@ -465,9 +532,8 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
     ix->n_hits.need(4ull * n); ix->hit_off.need(4ull * (n + 1)); ix->stage.need(4ull * HSTAGE * n);
     ix->scalars.need(64); ix->tile_counter.need(16); ix->error.need(16);
     // scalars: [0]=n_segs (u32), counters as u64 at +8: [0]=mapped,[1]=multimapped,[2]=records
-    CK(cudaMemsetAsync(ix->scalars.p, 0, 64, st));
-    CK(cudaMemsetAsync(ix->tile_counter.p, 0, 16, st));
-    CK(cudaMemsetAsync(ix->error.p, 0, 16, st));
+    ix->qcount.need(64);
+    zero_words(st, {{ix->scalars.p, 16}, {ix->tile_counter.p, 4}, {ix->error.p, 4}, {ix->qcount.p, 16}});
     uint32_t* d_nsegs = ix->scalars.as<uint32_t>();
     unsigned long long* d_counters = reinterpret_cast<unsigned long long*>(ix->scalars.as<uint8_t>() + 8);
     uint64_t* d_sk = nullptr;
@@ -496,18 +562,16 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ix->n_hits.as<uint32_t>(), ix->hit_off.as<uint32_t>(), static_cast<int>(n), st);
     ix->cub_tmp.need(tmp_bytes + 16);
     cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, tmp_bytes, ix->n_hits.as<uint32_t>(), ix->hit_off.as<uint32_t>(), static_cast<int>(n), st);
-    uint32_t last_off = 0, last_cnt = 0;
-    CK(cudaMemcpyAsync(&last_off, ix->hit_off.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(&last_cnt, ix->n_hits.as<uint32_t>() + (n - 1), 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    uint32_t H = 0;
     {
-        int err[2];
-        CK(cudaMemcpy(err, ix->error.p, 8, cudaMemcpyDeviceToHost));
-        if (err[0] == GROOTGPU_ERR_SHORT_READ) throw std::invalid_argument("read " + std::to_string(err[1]) + " is shorter than k (the reference panics at boss.go:164-166)");
-        if (err[0] != 0) throw std::length_error("read " + std::to_string(err[1]) + " exceeds the declared maximum length");
+        const uint32_t* pk = peek(ix, st, {ix->hit_off.as<uint32_t>() + (n - 1), ix->n_hits.as<uint32_t>() + (n - 1),
+                                           ix->error.as<uint32_t>(), ix->error.as<uint32_t>() + 1});
+        const int err0 = static_cast<int>(pk[2]), err1 = static_cast<int>(pk[3]);
+        if (err0 == GROOTGPU_ERR_SHORT_READ) throw std::invalid_argument("read " + std::to_string(err1) + " is shorter than k (the reference panics at boss.go:164-166)");
+        if (err0 != 0) throw std::length_error("read " + std::to_string(err1) + " exceeds the declared maximum length");
+        H = pk[0] + pk[1];
     }
-    const uint32_t H = last_off + last_cnt;
-    CK(cudaMemcpyAsync(ix->hit_off.as<uint32_t>() + n, &H, 4, cudaMemcpyHostToDevice, st));
+    poke(st, {{ix->hit_off.as<uint32_t>() + n, H}});
 
     uint32_t n_segs = 0;
     uint64_t R = 0;
@@ -530,8 +594,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         cub::DeviceSelect::Flagged(nullptr, sel_bytes, counting, ix->seg_flag.as<uint8_t>(), ix->seg_begin.as<uint32_t>(), d_nsegs, static_cast<int>(H), st);
         ix->cub_tmp.need(sel_bytes + 16);
         cub::DeviceSelect::Flagged(ix->cub_tmp.p, sel_bytes, counting, ix->seg_flag.as<uint8_t>(), ix->seg_begin.as<uint32_t>(), d_nsegs, static_cast<int>(H), st);
-        CK(cudaMemcpyAsync(&n_segs, d_nsegs, 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        n_segs = peek(ix, st, {d_nsegs})[0];
 
         // ---- K3: align (thread per pair) -> scan -> emit ----
         ix->pairs.need(sizeof(PairOut) * static_cast<size_t>(n_segs)); ix->seg_nrec.need(4ull * n_segs); ix->seg_locus.need(8ull * n_segs);
@@ -553,8 +616,6 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         aa.reads2 = ix->reads2.as<uint32_t>(); aa.read_ok2 = ix->read_ok2.as<uint8_t>(); aa.nw32 = nw32;
         // screen/walk rounds over a shrinking, compacted queue; the queue counts stay on the device
         ix->cursor.need(8ull * n_segs); ix->cand.need(8ull * n_segs); ix->queue_a.need(4ull * n_segs); ix->queue_b.need(4ull * n_segs);
-        ix->qcount.need(64);
-        CK(cudaMemsetAsync(ix->qcount.p, 0, 64, st));
         uint32_t* qc = ix->qcount.as<uint32_t>();
         CK(cudaEventRecord(ix->ev[2], st));
         ix->qkey.need(4ull * n_segs); ix->qkey2.need(4ull * n_segs);
@@ -583,7 +644,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
             kbegin(2); align_screen_kernel<<<screen_blocks, 256, 0, st>>>(ix->d, ra); launches++; kend();
             kbegin(3); align_walk_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++; kend();
             CK(cudaGetLastError());
-            CK(cudaMemsetAsync(qc + (round & 1), 0, 4, st));   // this round's count becomes the next round's "next"
+            poke(st, {{qc + (round & 1), 0u}});   // this round's count becomes the next round's "next"
         }
         {
             uint32_t* qa = (kRounds & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
@@ -598,13 +659,11 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         ix->cub_tmp.need(scan2 + 16);
         cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, scan2, ix->seg_nrec.as<uint32_t>(), ix->rec_off.as<uint32_t>(), static_cast<int>(n_segs), st);
         uint32_t lo = 0, lc = 0;
-        CK(cudaMemcpyAsync(&lo, ix->rec_off.as<uint32_t>() + (n_segs - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&lc, ix->seg_nrec.as<uint32_t>() + (n_segs - 1), 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
         {
-            int err[2];
-            CK(cudaMemcpy(err, ix->error.p, 8, cudaMemcpyDeviceToHost));
-            if (err[0] == GROOTGPU_ERR_BAD_BASE) throw std::domain_error("read " + std::to_string(err[1]) + " holds a base > 'T' and had to be reverse complemented (the reference panics at seqio.go:122)");
+            const uint32_t* pk = peek(ix, st, {ix->rec_off.as<uint32_t>() + (n_segs - 1), ix->seg_nrec.as<uint32_t>() + (n_segs - 1),
+                                               ix->error.as<uint32_t>(), ix->error.as<uint32_t>() + 1});
+            lo = pk[0]; lc = pk[1];
+            if (static_cast<int>(pk[2]) == GROOTGPU_ERR_BAD_BASE) throw std::domain_error("read " + std::to_string(static_cast<int>(pk[3])) + " holds a base > 'T' and had to be reverse complemented (the reference panics at seqio.go:122)");
         }
         R = static_cast<uint64_t>(lo) + lc;
         ix->rec_path.need(4ull * std::max<uint64_t>(R, 1)); ix->rec_pos.need(4ull * std::max<uint64_t>(R, 1));
@@ -616,7 +675,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         ea.reads2 = ix->reads2.as<uint32_t>(); ea.read_ok2 = ix->read_ok2.as<uint8_t>(); ea.nw32 = nw32;
         ea.multi_queue = ix->queue_a.as<uint32_t>(); ea.n_multi = qc + 2;      // the align queues are free by now
         {
-            CK(cudaMemsetAsync(qc + 2, 0, 4, st));
+            poke(st, {{qc + 2, 0u}});
             const int emit_blocks = std::max(1, static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8)));
             kbegin(5); align_emit_kernel<<<emit_blocks, 256, 0, st>>>(ix->d, ea); launches++; kend();
             // thread stacks: stack_ws / mask_ws hold verify_blocks * vthreads of them
@@ -633,7 +692,6 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
 
     // ---- results ----
     unsigned long long counters[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(counters, d_counters, 32, cudaMemcpyDeviceToHost, st));
     if (copy_back) {
         ix->r_hit_off.need(4ull * (n + 1)); ix->r_hits.need(4ull * std::max<uint32_t>(H, 1)); ix->r_pairs.need(sizeof(PairOut) * std::max<size_t>(n_segs, 1));
         ix->r_rec_path.need(4ull * std::max<uint64_t>(R, 1)); ix->r_rec_pos.need(4ull * std::max<uint64_t>(R, 1));
@@ -647,7 +705,11 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         if (prm->keep_sketches) { ix->r_sketches.need(8ull * S * n); CK(cudaMemcpyAsync(ix->r_sketches.p, ix->sketches.p, 8ull * S * n, cudaMemcpyDeviceToHost, st)); }
     }
     CK(cudaEventRecord(ix->ev[5], st));
-    CK(cudaStreamSynchronize(st));
+    {
+        const uint32_t* c32 = reinterpret_cast<const uint32_t*>(d_counters);
+        const uint32_t* pk = peek(ix, st, {c32, c32 + 1, c32 + 2, c32 + 3, c32 + 4, c32 + 5, c32 + 6, c32 + 7});   // synchronises the stream
+        for (int i = 0; i < 4; i++) counters[i] = static_cast<unsigned long long>(pk[2 * i]) | (static_cast<unsigned long long>(pk[2 * i + 1]) << 32);
+    }
     if (out) {
         memset(out, 0, sizeof *out);
         out->n_reads = n; out->n_hits = H; out->n_pairs = n_segs; out->n_records = R;
@@ -671,6 +733,162 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         out->d_pairs = reinterpret_cast<const grootgpu_pair*>(ix->pairs.p);
         out->d_rec_path = ix->rec_path.as<uint32_t>(); out->d_rec_pos = ix->rec_pos.as<int32_t>();
     }
+}
+
+
+// ---- chunked host path --------------------------------------------------------------------------------------
+// u64 host offsets of one chunk -> u32 offsets relative to the chunk's first base, plus min / max read length
+__global__ void __launch_bounds__(256) chunk_offsets_kernel(const uint64_t* __restrict__ off64, uint32_t n, uint32_t* __restrict__ off32,
+                                                            uint32_t* __restrict__ minmax) {
+    const uint64_t base = off64[0];
+    uint32_t mn = 0xffffffffu, mx = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+        const uint64_t o = off64[i];
+        off32[i] = static_cast<uint32_t>(o - base);
+        if (i < n) {
+            const uint64_t l = off64[i + 1] - o;
+            const uint32_t l32 = l > 0xffffffffull ? 0xffffffffu : static_cast<uint32_t>(l);
+            mn = min(mn, l32); mx = max(mx, l32);
+        }
+    }
+    mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&minmax[0], mn); atomicMax(&minmax[1], mx); }
+}
+
+// chunk-local indices -> batch-global ones, before the chunk's arrays are copied to their place in the host result
+__global__ void __launch_bounds__(256) chunk_rebase_kernel(PairOut* __restrict__ pairs, uint32_t n_pairs, uint32_t* __restrict__ hit_off, uint32_t n_off,
+                                                           uint32_t read_base, uint32_t hit_base, uint32_t rec_base) {
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t i = i0; i < n_pairs; i += stride) {
+        pairs[i].read += read_base; pairs[i].hit_begin += hit_base; pairs[i].rec_begin += rec_base;
+    }
+    for (uint32_t i = i0; i < n_off; i += stride) hit_off[i] += hit_base;
+}
+
+// grow a pinned result buffer to `need` bytes keeping its first `used` bytes (pending copies into it are drained first)
+void grow_keep(HBuf& b, size_t need, size_t used, cudaStream_t drain) {
+    if (need <= b.cap) return;
+    CK(cudaStreamSynchronize(drain));
+    HBuf nb;
+    nb.need(need);
+    if (used) memcpy(nb.p, b.p, used);
+    std::swap(b.p, nb.p); std::swap(b.cap, nb.cap);
+}
+
+uint32_t chunk_reads_setting() {   // reads per pipeline chunk; GROOTGPU_CHUNK_READS overrides (tests force many small chunks)
+    const char* e = getenv("GROOTGPU_CHUNK_READS");
+    const long x = e ? atol(e) : 0;
+    return static_cast<uint32_t>(x > 0 ? x : 2500000l);
+}
+
+// Host buffers in, host results out, as a 3-stage pipeline over chunks of reads: while chunk i runs on the compute
+// stream, chunk i+1's bases and offsets are copied in (st_in) and chunk i-1's result arrays are copied out (st_out)
+// from the other set of result buffers, straight to their final place in the batch-wide host arrays. The chunks are
+// processed in read order on one stream, so the ordered graph weighting sees the same sequence as a single batch.
+void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* seq_off, uint32_t n, const grootgpu_align_params* prm,
+                       grootgpu_batch_result* out) {
+    cudaStream_t st = ix->stream, st_in = ix->st_in, st_out = ix->st_out;
+    const uint32_t S = ix->h.p.S;
+    // chunk boundaries: ~chunk_reads_setting() reads and always < 4 GiB of bases; the first and the last chunk are a
+    // quarter of that, because the first copy-in and the last copy-out are the two transfers nothing overlaps
+    std::vector<uint32_t> cb{0};
+    {
+        const uint32_t target = chunk_reads_setting(), edge = std::max(1u, target / 4);
+        const uint64_t max_bytes = (1ull << 32) - 4096;
+        while (cb.back() < n) {
+            const uint32_t r0 = cb.back(), left = n - r0;
+            uint32_t want = r0 == 0 ? edge : target;
+            if (left > edge && left - edge < want) want = left - edge;   // leave a last chunk of `edge` reads
+            uint32_t r1 = r0 + std::min(left, want);
+            while (r1 > r0 + 1 && seq_off[r1] - seq_off[r0] >= max_bytes) r1 = r0 + (r1 - r0) / 2;
+            if (seq_off[r1] - seq_off[r0] >= max_bytes) throw std::length_error("a read of 4 GiB or more");
+            cb.push_back(r1);
+        }
+    }
+    const uint32_t C = static_cast<uint32_t>(cb.size()) - 1;
+    struct Drain {   // nothing may still be copying from / into caller or handle memory when we leave, also on errors
+        grootgpu_index* ix;
+        ~Drain() { cudaStreamSynchronize(ix->st_in); cudaStreamSynchronize(ix->stream); cudaStreamSynchronize(ix->st_out); }
+    } drain{ix};
+    auto issue_input = [&](uint32_t c) {
+        const uint32_t r0 = cb[c], nc = cb[c + 1] - r0, b = c & 1;
+        const uint64_t bytes = seq_off[cb[c + 1]] - seq_off[r0];
+        ix->in_seq[b].need(bytes + 64); ix->in_off64[b].need(8ull * (nc + 1)); ix->in_off32[b].need(4ull * (nc + 1));
+        CK(cudaMemcpyAsync(ix->in_seq[b].p, seq + seq_off[r0], bytes, cudaMemcpyHostToDevice, st_in));
+        CK(cudaMemsetAsync(ix->in_seq[b].as<uint8_t>() + bytes, 0, 64, st_in));
+        CK(cudaMemcpyAsync(ix->in_off64[b].p, seq_off + r0, 8ull * (nc + 1), cudaMemcpyHostToDevice, st_in));
+        CK(cudaEventRecord(ix->ev_in[b], st_in));
+    };
+    auto swap_buf = [](DBuf& x, DBuf& y) { std::swap(x.p, y.p); std::swap(x.cap, y.cap); };   // DBuf owns its pointer: swap fields, not objects
+    auto swap_result_sets = [&] {
+        swap_buf(ix->hits, ix->alt_hits); swap_buf(ix->pairs, ix->alt_pairs); swap_buf(ix->rec_path, ix->alt_rec_path);
+        swap_buf(ix->rec_pos, ix->alt_rec_pos); swap_buf(ix->hit_off, ix->alt_hit_off); swap_buf(ix->sketches, ix->alt_sketches);
+    };
+    ix->len_minmax.need(16);
+    ix->r_hit_off.need(4ull * (static_cast<size_t>(n) + 1));
+    if (prm->keep_sketches) ix->r_sketches.need(8ull * S * n);
+    grootgpu_align_params cprm = *prm;
+    cprm.results_on_device = 1;
+    uint64_t hit_base = 0, pair_base = 0, rec_base = 0;
+    grootgpu_batch_result total{};
+    CK(cudaEventRecord(ix->ev_t0, st_in));
+    issue_input(0);
+    for (uint32_t c = 0; c < C; c++) {
+        const uint32_t r0 = cb[c], nc = cb[c + 1] - r0, b = c & 1;
+        if (c + 1 < C) issue_input(c + 1);      // its buffers were last read by chunk c-1, which has completed (run_batch returns synchronised)
+        CK(cudaStreamWaitEvent(st, ix->ev_in[b], 0));
+        poke(st, {{ix->len_minmax.as<uint32_t>(), 0xffffffffu}, {ix->len_minmax.as<uint32_t>() + 1, 0u}});
+        chunk_offsets_kernel<<<std::max(1u, std::min<uint32_t>((nc + 256) / 256, 1184u)), 256, 0, st>>>(ix->in_off64[b].as<uint64_t>(), nc, ix->in_off32[b].as<uint32_t>(),
+                                                                                                     ix->len_minmax.as<uint32_t>());
+        uint32_t mm[2] = {0, 0};
+        { const uint32_t* pk = peek(ix, st, {ix->len_minmax.as<uint32_t>(), ix->len_minmax.as<uint32_t>() + 1}); mm[0] = pk[0]; mm[1] = pk[1]; }
+        if (mm[0] < ix->h.p.k) throw std::invalid_argument("a read is shorter than k (the reference panics at boss.go:164-166)");
+        swap_result_sets();                      // this chunk writes the set the copy-out of chunk c-2 has released
+        if (c >= 2) CK(cudaStreamWaitEvent(st, ix->ev_out[b], 0));
+        grootgpu_batch_result r{};
+        run_batch(ix, ix->in_seq[b].as<uint8_t>(), ix->in_off32[b].as<uint32_t>(), nc, mm[0], mm[1], &cprm, st, &r);
+        if (hit_base + r.n_hits >= (1ull << 32) || rec_base + r.n_records >= (1ull << 32))
+            throw std::length_error("more than 2^32 hits or records in one batch: use smaller batches");
+        const uint32_t n_off = nc + (c + 1 == C ? 1u : 0u);
+        const uint32_t np = static_cast<uint32_t>(r.n_pairs);
+        chunk_rebase_kernel<<<std::max(1u, std::min<uint32_t>((std::max(np, n_off) + 255) / 256, 1184u)), 256, 0, st>>>(
+            ix->pairs.as<PairOut>(), np, ix->hit_off.as<uint32_t>(), n_off, r0, static_cast<uint32_t>(hit_base), static_cast<uint32_t>(rec_base));
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(ix->ev_done[b], st));
+        // copy-out, straight to the final place; the pinned arrays grow by extrapolating this chunk's yield
+        const double scale = 1.15 * static_cast<double>(n) / static_cast<double>(cb[c + 1]);
+        auto want = [&](uint64_t used_after, size_t elem) { return static_cast<size_t>(static_cast<double>(used_after) * scale) * elem + 4096; };
+        if ((hit_base + r.n_hits) * 4 > ix->r_hits.cap) grow_keep(ix->r_hits, want(hit_base + r.n_hits, 4), hit_base * 4, st_out);
+        if ((pair_base + r.n_pairs) * sizeof(PairOut) > ix->r_pairs.cap) grow_keep(ix->r_pairs, want(pair_base + r.n_pairs, sizeof(PairOut)), pair_base * sizeof(PairOut), st_out);
+        if ((rec_base + r.n_records) * 4 > ix->r_rec_path.cap) grow_keep(ix->r_rec_path, want(rec_base + r.n_records, 4), rec_base * 4, st_out);
+        if ((rec_base + r.n_records) * 4 > ix->r_rec_pos.cap) grow_keep(ix->r_rec_pos, want(rec_base + r.n_records, 4), rec_base * 4, st_out);
+        CK(cudaStreamWaitEvent(st_out, ix->ev_done[b], 0));
+        CK(cudaMemcpyAsync(ix->r_hit_off.as<uint32_t>() + r0, ix->hit_off.p, 4ull * n_off, cudaMemcpyDeviceToHost, st_out));
+        if (r.n_hits) CK(cudaMemcpyAsync(ix->r_hits.as<uint32_t>() + hit_base, ix->hits.p, 4ull * r.n_hits, cudaMemcpyDeviceToHost, st_out));
+        if (r.n_pairs) CK(cudaMemcpyAsync(ix->r_pairs.as<PairOut>() + pair_base, ix->pairs.p, sizeof(PairOut) * r.n_pairs, cudaMemcpyDeviceToHost, st_out));
+        if (r.n_records) {
+            CK(cudaMemcpyAsync(ix->r_rec_path.as<uint32_t>() + rec_base, ix->rec_path.p, 4ull * r.n_records, cudaMemcpyDeviceToHost, st_out));
+            CK(cudaMemcpyAsync(ix->r_rec_pos.as<int32_t>() + rec_base, ix->rec_pos.p, 4ull * r.n_records, cudaMemcpyDeviceToHost, st_out));
+        }
+        if (prm->keep_sketches) CK(cudaMemcpyAsync(ix->r_sketches.as<uint64_t>() + static_cast<size_t>(r0) * S, ix->sketches.p, 8ull * S * nc, cudaMemcpyDeviceToHost, st_out));
+        CK(cudaEventRecord(ix->ev_out[b], st_out));
+        hit_base += r.n_hits; pair_base += r.n_pairs; rec_base += r.n_records;
+        total.mapped += r.mapped; total.multimapped += r.multimapped; total.slow_path_pairs += r.slow_path_pairs;
+        total.kernel_launches += r.kernel_launches + 2;
+        for (int i = 1; i < 4; i++) total.ms[i] += r.ms[i];
+        for (int i = 0; i < 8; i++) total.kernel_ms[i] += r.kernel_ms[i];
+    }
+    CK(cudaEventRecord(ix->ev_t1, st_out));
+    CK(cudaStreamSynchronize(st_out));
+    memset(out, 0, sizeof *out);
+    *out = total;
+    out->n_reads = n; out->n_hits = hit_base; out->n_pairs = pair_base; out->n_records = rec_base;
+    out->hit_off = ix->r_hit_off.as<uint32_t>(); out->hits = ix->r_hits.as<uint32_t>();
+    out->pairs = reinterpret_cast<const grootgpu_pair*>(ix->r_pairs.p);
+    out->rec_path = ix->r_rec_path.as<uint32_t>(); out->rec_pos = ix->r_rec_pos.as<int32_t>();
+    out->sketches = prm->keep_sketches ? ix->r_sketches.as<uint64_t>() : nullptr;
+    out->received = n; out->alignments = rec_base;
+    cudaEventElapsedTime(&out->ms[0], ix->ev_t0, ix->ev_t1);
 }
 
 void fnv_sink(void* ctx, const char* d, size_t n) { uint64_t& hsh = *static_cast<uint64_t*>(ctx); for (size_t i = 0; i < n; i++) { hsh ^= static_cast<uint8_t>(d[i]); hsh *= 1099511628211ULL; } }
@@ -858,10 +1076,12 @@ int grootgpu_align_batch_device(grootgpu_index* idx, const uint8_t* d_seq, const
 int grootgpu_align_batch(grootgpu_index* idx, const uint8_t* seq, const uint64_t* seq_off, uint32_t n_reads, const grootgpu_align_params* params,
                          grootgpu_batch_result* out) {
     if (!idx || !seq || !seq_off || !params || !out || n_reads == 0) return fail(GROOTGPU_ERR_ARG, "bad argument");
-    const uint64_t total = seq_off[n_reads] - seq_off[0];
-    if (total >= (1ull << 32) - 64) return fail(GROOTGPU_ERR_CAPACITY, "a batch holds at most 4 GiB of bases: split it");
     return guarded([&] {
         pick_device(idx->device);
+        if (!params->results_on_device) { run_batch_chunked(idx, seq, seq_off, n_reads, params, out); return; }
+        // results stay on the device: one shot (the d_* pointers of the result must cover the whole batch)
+        const uint64_t total = seq_off[n_reads] - seq_off[0];
+        if (total >= (1ull << 32) - 64) throw std::length_error("a batch whose results stay on the device holds at most 4 GiB of bases: split it");
         cudaStream_t st = idx->stream;
         std::vector<uint32_t> off32(n_reads + 1);
         uint32_t mn = 0xffffffffu, mx = 0;

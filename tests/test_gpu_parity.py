@@ -211,6 +211,26 @@ def test_device_projection_is_bit_exact(argannot, db_dirs):
     assert (g.weights()[0] > 0).sum() > 1000
 
 
+def test_align_chunked_pipeline_matches_single_shot(argannot, db_dirs, root, monkeypatch):
+    """grootgpu_align_batch streams the batch through the device in chunks (copy-in / kernels / copy-out overlapped,
+    results rebased to batch-wide indices). Forcing many ragged chunks must not change a single output word, nor the
+    order-dependent f64 graph weights, with the weighting done on the device or replayed on the host."""
+    g, o = argannot
+    names, seqs, quals = load_fastq(os.path.join(root, "data", "reads", "full-argannot-perfect-reads-small-variable-rl.fq.gz"))
+    blob_v, off_v = pack_reads([s for s in seqs if len(s) >= 31])
+    for (blob, off), chunk in ((_c1_reads(db_dirs["arg-annot.90"], 5003, 100), "257"), ((blob_v, off_v), "64"), (_c1_reads(db_dirs["arg-annot.90"], 300, 100), "1")):
+        monkeypatch.setenv("GROOTGPU_CHUNK_READS", chunk)
+        for on_device in (True, False):
+            g.reset_weights(); o.reset_weights()
+            gr = g.map_reads(blob, off, 0.99, project=not on_device, project_on_device=on_device, keep_sketches=True)
+            orr = o.map_reads(blob, off, 0.99, threads=8, keep_sketches=True)
+            assert_same_result(gr, orr)
+            assert np.array_equal(gr.sketches, orr.sketches)
+            assert np.array_equal(g.weights()[0], o.weights()[0])
+            assert np.array_equal(g.weights()[1], o.weights()[1])
+    monkeypatch.delenv("GROOTGPU_CHUNK_READS")
+
+
 def test_align_no_align_mode(argannot, db_dirs):
     g, o = argannot
     blob, off = _c1_reads(db_dirs["arg-annot.90"], 2000, 100, seed=7)

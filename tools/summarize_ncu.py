@@ -13,7 +13,8 @@ out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
 FAMILY = [("seed_kernel", "seed"), ("fill_kernel", "fill"), ("align_init", "align_screen"), ("align_screen", "align_screen"),
-          ("align_walk", "align_walk"), ("align_finish", "align_finish"), ("align_emit", "align_emit"), ("project_", "project"),
+          ("align_walk", "align_walk"), ("align_finish", "align_finish"), ("align_emit", "align_emit"), ("project_", "project"), ("peek_kernel", "scalars"), ("poke_kernel", "scalars"), ("zero_kernel", "scalars"),
+          ("chunk_", "chunk glue"),
           ("sketch_kernel", "sketch(index)")]
 
 
