@@ -385,30 +385,19 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
 }
 
 constexpr uint32_t kPrefixBases = 8;  // == kPfxLen of host/prefix_table.cpp
-// true unless NO traversal starting at graph position `pos` can spell the read's first min(8, rlen) bases.
-// rpk = the read bases 2 bits each (pack_base2), rbad = positions that are not upper-case ACGT. Layouts: host/prefix_table.cpp.
-__device__ __forceinline__ uint32_t spread8(uint32_t x) {   // bit i -> bits 2i and 2i+1
-    x = (x | (x << 4)) & 0x0f0fu; x = (x | (x << 2)) & 0x3333u; x = (x | (x << 1)) & 0x5555u;
-    return x | (x << 1);
+// true unless NO traversal starting at graph position `pos` can spell the read's first min(8, rlen) bases: every base
+// must lie in the allele set of its step (host/prefix_table.cpp). oh = the read's bases one-hot, 4 bits per base
+// (read_onehot); a read byte that is not upper-case ACGT has an empty nibble and passes (the DFS decides).
+__device__ __forceinline__ bool prefix_pass(const DevIndex& ix, uint32_t pos, uint32_t oh, uint32_t rlen) {
+    const uint32_t lim = rlen >= kPrefixBases ? 0xffffffffu : (1u << (4 * rlen)) - 1u;
+    return (oh & ~__ldg(ix.pfxset + pos) & lim) == 0;
 }
-__device__ __forceinline__ bool prefix_differs(uint32_t bases, uint32_t L, uint32_t nmask, uint32_t rpk, uint32_t rbad, uint32_t rlen) {
-    L = L < rlen ? L : rlen;                                          // L <= kPrefixBases
-    uint32_t diff = (bases ^ rpk) & ((1u << (2 * L)) - 1u), badm = rbad & ((1u << L) - 1u);
-    if (nmask) { diff &= ~spread8(nmask); badm &= ~nmask; }           // a reference 'N' matches any read byte (alignment.go:212-215)
-    return (diff | badm) != 0;
-}
-__device__ __forceinline__ bool prefix_pass(const DevIndex& ix, uint32_t pos, uint32_t rpk, uint32_t rbad, uint32_t rlen) {
-    const uint32_t e1 = __ldg(ix.pfx1 + pos);
-    if (prefix_differs(e1, (e1 >> 16) & 15u, (e1 >> 20) & 0xffu, rpk, rbad, rlen)) return false;
-    if (!(e1 >> 31)) return true;                                     // the position's only prefix
-    const uint32_t b = ix.pfx_off[pos], e = ix.pfx_off[pos + 1];
-    for (uint32_t i = b; i < e; i++) {
-        const uint64_t ent = ix.pfx[i];
-        const uint32_t hi = static_cast<uint32_t>(ent >> 32);
-        if (hi & 0x100u) return true;                                 // too many prefixes here: let the DFS decide
-        if (!prefix_differs(static_cast<uint32_t>(ent), hi & 31u, (hi >> 16) & 0xffu, rpk, rbad, rlen)) return true;
-    }
-    return false;
+// pk = 8 bases 2 bits each (pack_base2), bad = positions that are not upper-case ACGT
+__device__ __forceinline__ uint32_t read_onehot(uint32_t pk, uint32_t bad) {
+    uint32_t oh = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < kPrefixBases; i++) oh |= (((bad >> i) & 1u) ? 0u : (1u << ((pk >> (2 * i)) & 3u))) << (4 * i);
+    return oh;
 }
 
 // ---- the ordered try list of one (mapping, strand) ---------------------------------------------------
@@ -440,6 +429,8 @@ struct RoundArgs {
     uint32_t* queue_next;      // pairs re-queued for the next round
     const uint32_t* n_queue;   // device scalar
     uint32_t* n_queue_next;    // device scalar (atomic)
+    uint32_t* slow_queue;      // pairs that cannot take the packed walk: align_finish_kernel walks them byte-wise
+    uint32_t* n_slow;          // device scalar (atomic)
 };
 
 __global__ void __launch_bounds__(256) align_init_kernel(DevIndex ix, AlignArgs a, PairCursor* cursor, uint32_t* queue, uint32_t* qkey, uint32_t* n_queue) {
@@ -464,13 +455,12 @@ __global__ void __launch_bounds__(256) align_init_kernel(DevIndex ix, AlignArgs 
 // base 0; v = 1: from base 1, for the start clip). From the packed copy when there is one, else byte-wise with the
 // whole warp (lane i handles base i).
 __device__ __forceinline__ void warp_read_prefix(const AlignArgs& a, uint32_t r, const uint8_t* __restrict__ rp, uint32_t len, bool rc, uint32_t lane,
-                                                 uint32_t (&pk)[2], uint32_t (&bad)[2]) {
+                                                 uint32_t (&oh)[2]) {
     constexpr uint32_t m2 = (1u << (2 * kPrefixBases)) - 1u, m1 = (1u << kPrefixBases) - 1u;
     if (a.nw32 && a.read_ok2[r]) {
         const uint32_t* rd2 = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32 + (rc ? a.nw32 : 0u);
         const uint32_t base0 = rc ? a.nw32 * 16u - len : 0u;
-        pk[0] = extract16(rd2, base0) & m2; pk[1] = extract16(rd2, base0 + 1) & m2;   // prefix_pass never looks past the read's end
-        bad[0] = 0; bad[1] = 0;
+        oh[0] = read_onehot(extract16(rd2, base0) & m2, 0u); oh[1] = read_onehot(extract16(rd2, base0 + 1) & m2, 0u);   // prefix_pass never looks past the read's end
         return;
     }
     uint32_t code = 4;
@@ -483,8 +473,8 @@ __device__ __forceinline__ void warp_read_prefix(const AlignArgs& a, uint32_t r,
     uint32_t p = 0;
 #pragma unroll
     for (uint32_t i = 0; i <= kPrefixBases; i++) p |= (((b0 >> i) & 1u) | (((b1 >> i) & 1u) << 1)) << (2 * i);
-    pk[0] = p & m2; pk[1] = (p >> 2) & m2;
-    bad[0] = bb & m1; bad[1] = (bb >> 1) & m1;
+    oh[0] = read_onehot(p & m2, bb & m1);            // prefix_pass never looks past the read's end
+    oh[1] = read_onehot((p >> 2) & m2, (bb >> 1) & m1);
 }
 
 // Warp-cooperative screen of one (mapping, strand): the lowest try index t >= t0 whose start position passes the
@@ -492,8 +482,8 @@ __device__ __forceinline__ void warp_read_prefix(const AlignArgs& a, uint32_t r,
 // are never enumerated: stage 1 covers only the offsets that exist on the seed node, stage 2 pools the existing
 // offsets 0..10 of up to 32 contained nodes at a time (inclusive scan + owner search, as in warp_probe); the try
 // NUMBERING stays the reference's (decode_try), so cursors and results are unchanged. wr, sn, t0, len are uniform.
-__device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinRec& wr, const NodeRec& sn, uint32_t t0, const uint32_t (&pk)[2],
-                                                  const uint32_t (&bad)[2], uint32_t len, uint32_t lane) {
+__device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinRec& wr, const NodeRec& sn, uint32_t t0, const uint32_t (&oh)[2],
+                                                  uint32_t len, uint32_t lane) {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t T1 = wr.merge_span + wr.win_size + 1u;
     // stage 1: offsets OffSet + t on the seed node
@@ -501,7 +491,7 @@ __device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinR
     const uint32_t n1 = T1 < room ? T1 : room;
     for (uint32_t base = t0 & ~31u; base < n1; base += 32) {
         const uint32_t t = base + lane;
-        const bool ok = t >= t0 && t < n1 && prefix_pass(ix, sn.seq_off + wr.offset + t, pk[0], bad[0], len);
+        const bool ok = t >= t0 && t < n1 && prefix_pass(ix, sn.seq_off + wr.offset + t, oh[0], len);
         const uint32_t ball = __ballot_sync(FULL, ok);
         if (ball) return base + (__ffs(ball) - 1);
     }
@@ -530,7 +520,7 @@ __device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinR
             const uint32_t off0 = item - __shfl_sync(FULL, excl, o);
             const uint32_t pos = __shfl_sync(FULL, so, o) + off0;
             const uint32_t t = T1 + 11u * (cb + o) + off0;
-            const bool ok = item < total && t >= t0 && prefix_pass(ix, pos, pk[0], bad[0], len);
+            const bool ok = item < total && t >= t0 && prefix_pass(ix, pos, oh[0], len);
             const uint32_t ball = __ballot_sync(FULL, ok);
             if (ball) return __shfl_sync(FULL, t, __ffs(ball) - 1);
         }
@@ -539,7 +529,7 @@ __device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinR
     const uint32_t tA = T1 + 11u * wr.cn_cnt;
     {
         const uint32_t t = tA + lane;
-        const bool ok = lane < 2 && t >= t0 && room > 0 && prefix_pass(ix, sn.seq_off + wr.offset, pk[lane == 0 ? 1 : 0], bad[lane == 0 ? 1 : 0], len - 1);
+        const bool ok = lane < 2 && t >= t0 && room > 0 && prefix_pass(ix, sn.seq_off + wr.offset, lane == 0 ? oh[1] : oh[0], len - 1);
         const uint32_t ball = __ballot_sync(FULL, ok);
         if (ball) return tA + (__ffs(ball) - 1);
     }
@@ -572,9 +562,9 @@ __global__ void __launch_bounds__(256) align_screen_kernel(DevIndex ix, RoundArg
         while (m < he) {
             const WinRec wr = ix.wins[a.hits[m]];
             const NodeRec sn = ix.nodes[wr.node];
-            uint32_t pk[2], bad[2];
-            warp_read_prefix(a, r, rp, len, strand != 0, lane, pk, bad);
-            const uint32_t t = screen_strand(ix, wr, sn, t0, pk, bad, len, lane);
+            uint32_t oh[2];
+            warp_read_prefix(a, r, rp, len, strand != 0, lane, oh);
+            const uint32_t t = screen_strand(ix, wr, sn, t0, oh, len, lane);
             if (t != kNoCand) { cand = make_uint2(((m - hb) << 1) | strand, t); break; }
             t0 = 0;
             if (strand == 0) { strand = 1; check_revcomp_bytes(a, r, rp, len, lane); }
@@ -585,16 +575,18 @@ __global__ void __launch_bounds__(256) align_screen_kernel(DevIndex ix, RoundArg
 }
 
 
-// walk one try of pair s; on success fills the pair's outputs and returns true
-__device__ __forceinline__ bool walk_try(const DevIndex& ix, const AlignArgs& a, const uint8_t* lut, uint32_t s, uint32_t hb,
-                                         uint32_t m, uint32_t strand, uint32_t t, DfsFrame* stack, uint32_t* mask_ws, uint32_t depth_cap) {
+// walk one try of pair s: 1 = aligned (the pair's outputs are filled), 0 = no path id from this try, -1 (PACKED_ONLY)
+// = the pair cannot take the packed walk (read with other bytes than ACGT or longer than the packed copy, graph of
+// more than 256 paths) and is left to the byte-wise walk of align_finish_kernel.
+template <bool PACKED_ONLY>
+__device__ __forceinline__ int walk_try(const DevIndex& ix, const AlignArgs& a, const uint8_t* lut, uint32_t s, uint32_t hb,
+                                        uint32_t m, uint32_t strand, uint32_t t, DfsFrame* stack, uint32_t* mask_ws, uint32_t depth_cap) {
     const WinRec wr = ix.wins[a.hits[m]];
     const uint32_t r = a.hit_read[hb];
     const uint32_t o = a.off[r], len = a.off[r + 1] - o;
     const uint32_t mw = ix.graph_mask_words[wr.graph];
     uint32_t node, off0, stage;
     decode_try(ix, wr, t, &node, &off0, &stage);
-    ReadView rd{a.seq + o, lut, len, stage == 3 ? 1u : 0u, strand != 0};
     const uint32_t rlen = stage >= 3 ? len - 1 : len;
     DfsResult res;
     res.nrec = 0; res.ntrav = 0;
@@ -602,9 +594,14 @@ __device__ __forceinline__ bool walk_try(const DevIndex& ix, const AlignArgs& a,
         const uint32_t* rd2 = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32 + (strand ? a.nw32 : 0u);
         const uint32_t base0 = (strand ? a.nw32 * 16u - len : 0u) + (stage == 3 ? 1u : 0u);
         dfs_packed<false>(ix, node, off0, rd2, base0, rlen, mw, ix.graph_has_n[wr.graph] != 0, stack, mask_ws, depth_cap, &res);
-    } else if (mw <= kMaskWordsInline) dfs_masked(ix, node, off0, rd, rlen, mw, stack, mask_ws, depth_cap, &res);
-    else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
-    if (res.nrec == 0) return false;
+    } else if (PACKED_ONLY) {
+        return -1;
+    } else {
+        ReadView rd{a.seq + o, lut, len, stage == 3 ? 1u : 0u, strand != 0};
+        if (mw <= kMaskWordsInline) dfs_masked(ix, node, off0, rd, rlen, mw, stack, mask_ws, depth_cap, &res);
+        else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
+    }
+    if (res.nrec == 0) return 0;
     PairOut p = a.pairs[s];
     p.n_incremented = m - hb + 1;
     p.rec_count = res.nrec; p.reverse = static_cast<uint8_t>(strand);
@@ -615,13 +612,10 @@ __device__ __forceinline__ bool walk_try(const DevIndex& ix, const AlignArgs& a,
     a.seg_ntrav[s] = res.ntrav;
     if (res.ntrav == 1 && mw <= kMaskWordsInline)
         for (uint32_t wi = 0; wi < mw; wi++) a.seg_mask[static_cast<size_t>(s) * kMaskWordsInline + wi] = res.mask[wi];
-    return true;
+    return 1;
 }
 
-__global__ void __launch_bounds__(128, 5) align_walk_kernel(DevIndex ix, RoundArgs ra) {
-    __shared__ uint8_t lut[256];
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = complement_base(static_cast<uint8_t>(i));
-    __syncthreads();
+__global__ void __launch_bounds__(128, 8) align_walk_kernel(DevIndex ix, RoundArgs ra) {
     const AlignArgs& a = ra.a;
     const uint32_t n_queue = *ra.n_queue;
     const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
@@ -634,10 +628,14 @@ __global__ void __launch_bounds__(128, 5) align_walk_kernel(DevIndex ix, RoundAr
         const uint2 cand = ra.cand[s];
         if (cand.x == kNoCand) continue;                        // try list exhausted: the default (unaligned) result stands
         const uint32_t hb = a.seg_begin[s];
-        if (!walk_try(ix, a, lut, s, hb, hb + (cand.x >> 1), cand.x & 1u, cand.y, stack, mask_ws, depth_cap)) {
+        const int rc = walk_try<true>(ix, a, nullptr, s, hb, hb + (cand.x >> 1), cand.x & 1u, cand.y, stack, mask_ws, depth_cap);
+        if (rc == 0) {
             ra.cursor[s] = PairCursor{cand.x, cand.y + 1};      // resume just past this try (the screen handles t == T)
             ra.queue_next[atomicAdd(ra.n_queue_next, 1u)] = s;
             failed++;
+        } else if (rc < 0) {
+            ra.cursor[s] = PairCursor{cand.x, cand.y};          // the byte-wise walk starts from this very try
+            ra.slow_queue[atomicAdd(ra.n_slow, 1u)] = s;
         }
     }
     failed = __reduce_add_sync(0xffffffffu, failed);
@@ -672,13 +670,13 @@ __global__ void __launch_bounds__(128, 5) align_finish_kernel(DevIndex ix, Round
         while (m < he && !done) {
             const WinRec wr = ix.wins[a.hits[m]];
             const NodeRec sn = ix.nodes[wr.node];
-            uint32_t pk[2], bad[2];
-            warp_read_prefix(a, r, rp, len, strand != 0, lane, pk, bad);
+            uint32_t oh[2];
+            warp_read_prefix(a, r, rp, len, strand != 0, lane, oh);
             while (!done) {
-                const uint32_t t = screen_strand(ix, wr, sn, t0, pk, bad, len, lane);
+                const uint32_t t = screen_strand(ix, wr, sn, t0, oh, len, lane);
                 if (t == kNoCand) break;
                 uint32_t okw = 0;
-                if (lane == 0) okw = walk_try(ix, a, lut, s, hb, m, strand, t, stack, mask_ws, depth_cap) ? 1u : 0u;
+                if (lane == 0) okw = walk_try<false>(ix, a, lut, s, hb, m, strand, t, stack, mask_ws, depth_cap) > 0 ? 1u : 0u;
                 done = __shfl_sync(0xffffffffu, okw, 0) != 0;
                 t0 = t + 1;
             }
@@ -708,6 +706,7 @@ struct EmitArgs {
     const uint32_t* reads2;
     const uint8_t* read_ok2;
     uint32_t nw32;
+    const uint32_t* order;     // pair ids sorted by first window (or nullptr)
     uint32_t* multi_queue;     // pairs whose records need a second DFS (several traversals, > 256 paths)
     uint32_t* n_multi;         // device scalar, zeroed before align_emit_kernel
 };
@@ -720,7 +719,8 @@ __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gwarp = gthread >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t s = gwarp; s < n_segs; s += total_warps) {
+    for (uint32_t q = gwarp; q < n_segs; q += total_warps) {
+        const uint32_t s = a.order ? a.order[q] : q;   // window order: neighbouring warps expand the same start nodes
         const PairOut p = a.pairs[s];
         const uint32_t rb = a.rec_off[s];
         if (lane == 0) a.pairs[s].rec_begin = rb;

@@ -197,7 +197,7 @@ struct grootgpu_index {
     std::map<std::pair<uint32_t, double>, LenParam> param_cache;
     // workspaces
     DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
-        rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error, reads2, read_ok2, qkey, qkey2;
+        rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error, reads2, read_ok2, qkey, qkey2, order, slow_q;
     HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_scal;
     // chunked host path (grootgpu_align_batch): input double buffers, the second set of result buffers, copy streams
     DBuf in_seq[2], in_off64[2], in_off32[2], alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches, len_minmax;
@@ -273,9 +273,9 @@ void index_to_device(grootgpu_index* ix) {
     d.graph_mask_words = upload(h.graph_mask_words, ix->owned);
     ix->d_cn_count = upload(h.cn_count, ix->owned);
     {
-        std::vector<uint32_t> pfx_off, pfx1; std::vector<uint64_t> pfx;
-        build_prefix_table(h, pfx_off, pfx, pfx1);
-        d.pfx_off = upload(pfx_off, ix->owned); d.pfx = upload(pfx, ix->owned); d.pfx1 = upload(pfx1, ix->owned);
+        std::vector<uint32_t> pset;
+        build_prefix_sets(h, pset);
+        d.pfxset = upload(pset, ix->owned);
     }
     {   // 2-bit copy of the node sequences + per-graph 'N' flag for the packed walk (align_kernels.cuh, dfs_packed)
         std::vector<uint32_t> seq2((h.node_seq.size() + 15) / 16 + 2, 0u);
@@ -478,13 +478,14 @@ void push_weights_to_device(grootgpu_index* ix) {
 }
 
 template <class KB, class KE>
-void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n_segs, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
+void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n_segs, int sms, bool use_order, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
     push_weights_to_device(ix);
     ix->item_cnt.need(4ull * n_segs); ix->item_off.need(4ull * (n_segs + 1));
     ProjectArgs pa{};
     pa.off = d_off; pa.hits = ix->hits.as<uint32_t>(); pa.pairs = ix->pairs.as<PairOut>(); pa.n_segs_ptr = ix->scalars.as<uint32_t>();
     pa.cn_count = ix->d_cn_count; pa.item_cnt = ix->item_cnt.as<uint32_t>(); pa.item_off = ix->item_off.as<uint32_t>();
     pa.kmer_total = ix->d_kmer_total; pa.k = ix->h.p.k;
+    pa.order = use_order ? ix->order.as<uint32_t>() : nullptr;
     const int blocks = std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8));
     kbegin(6); project_count_kernel<<<blocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
     size_t tmp = 0;
@@ -582,7 +583,8 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         fa.hit_off = ix->hit_off.as<uint32_t>(); fa.stage = ix->stage.as<uint32_t>(); fa.hits = ix->hits.as<uint32_t>();
         fa.hit_read = ix->hit_read.as<uint32_t>(); fa.seg_flag = ix->seg_flag.as<uint8_t>(); fa.counters = d_counters;
         // 2-bit copies of the seeded reads (both orientations) for the packed walk; reads longer than 256 bases go byte-wise
-        const uint32_t nw32 = prm->no_align ? 0u : (max_len <= 128 ? 8u : max_len <= 256 ? 16u : 0u);
+        uint32_t nw32 = 0;   // words of 16 bases per orientation: 8 (<= 128 bases) .. 64 (<= 1024); longer reads go byte-wise
+        if (!prm->no_align && max_len <= 1024) { nw32 = 8; while (nw32 * 16u < max_len) nw32 *= 2; }
         if (nw32) { ix->reads2.need(8ull * nw32 * n + 64); ix->read_ok2.need(n); }
         fa.reads2 = ix->reads2.as<uint32_t>(); fa.read_ok2 = ix->read_ok2.as<uint8_t>(); fa.nw32 = nw32;
         int fill_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
@@ -618,18 +620,19 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         ix->cursor.need(8ull * n_segs); ix->cand.need(8ull * n_segs); ix->queue_a.need(4ull * n_segs); ix->queue_b.need(4ull * n_segs);
         uint32_t* qc = ix->qcount.as<uint32_t>();
         CK(cudaEventRecord(ix->ev[2], st));
-        ix->qkey.need(4ull * n_segs); ix->qkey2.need(4ull * n_segs);
+        ix->qkey.need(4ull * n_segs); ix->qkey2.need(4ull * n_segs); ix->order.need(4ull * n_segs); ix->slow_q.need(4ull * n_segs);
         kbegin(2); align_init_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ix->d, aa, ix->cursor.as<PairCursor>(), ix->queue_b.as<uint32_t>(), ix->qkey.as<uint32_t>(), qc); launches++; kend();
         CK(cudaGetLastError());
-        {   // queue ordered by window id: the 32 pairs a warp walks together sit on the same graph region (same nodes, same
-            // branch pattern), instead of 32 unrelated walks of very different lengths idling on each other
+        {   // pair order by window id: the 32 pairs a warp walks together sit on the same graph region (same nodes, same
+            // branch pattern), instead of 32 unrelated walks of very different lengths idling on each other. The order
+            // is kept for the emit and weighting kernels.
             int wbits = 1;
             while ((1ull << wbits) < ix->h.wins.size()) wbits++;
             size_t qs = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, qs, ix->qkey.as<uint32_t>(), ix->qkey2.as<uint32_t>(), ix->queue_b.as<uint32_t>(), ix->queue_a.as<uint32_t>(),
+            cub::DeviceRadixSort::SortPairs(nullptr, qs, ix->qkey.as<uint32_t>(), ix->qkey2.as<uint32_t>(), ix->queue_b.as<uint32_t>(), ix->order.as<uint32_t>(),
                                             static_cast<int>(n_segs), 0, wbits, st);
             ix->cub_tmp.need(qs + 16);
-            cub::DeviceRadixSort::SortPairs(ix->cub_tmp.p, qs, ix->qkey.as<uint32_t>(), ix->qkey2.as<uint32_t>(), ix->queue_b.as<uint32_t>(), ix->queue_a.as<uint32_t>(),
+            cub::DeviceRadixSort::SortPairs(ix->cub_tmp.p, qs, ix->qkey.as<uint32_t>(), ix->qkey2.as<uint32_t>(), ix->queue_b.as<uint32_t>(), ix->order.as<uint32_t>(),
                                             static_cast<int>(n_segs), 0, wbits, st);
         }
         int screen_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8));
@@ -637,8 +640,9 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         const int kRounds = 6;
         RoundArgs ra{};
         ra.a = aa; ra.cursor = ix->cursor.as<PairCursor>(); ra.cand = ix->cand.as<uint2>();
+        ra.slow_queue = ix->slow_q.as<uint32_t>(); ra.n_slow = qc + 3;
         for (int round = 0; round < kRounds; round++) {
-            uint32_t* qa = (round & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
+            uint32_t* qa = round == 0 ? ix->order.as<uint32_t>() : (round & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
             uint32_t* qb = (round & 1) ? ix->queue_a.as<uint32_t>() : ix->queue_b.as<uint32_t>();
             ra.queue = qa; ra.queue_next = qb; ra.n_queue = qc + (round & 1); ra.n_queue_next = qc + ((round + 1) & 1);
             kbegin(2); align_screen_kernel<<<screen_blocks, 256, 0, st>>>(ix->d, ra); launches++; kend();
@@ -649,6 +653,8 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         {
             uint32_t* qa = (kRounds & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
             ra.queue = qa; ra.queue_next = nullptr; ra.n_queue = qc + (kRounds & 1); ra.n_queue_next = nullptr;
+            kbegin(4); align_finish_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++; kend();
+            ra.queue = ix->slow_q.as<uint32_t>(); ra.n_queue = qc + 3;        // pairs the packed walk could not take
             kbegin(4); align_finish_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++; kend();
             CK(cudaGetLastError());
         }
@@ -674,6 +680,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         ea.stack_ws = ix->stack_ws.as<DfsFrame>(); ea.mask_ws = ix->mask_ws.as<uint32_t>(); ea.max_len = max_len;
         ea.reads2 = ix->reads2.as<uint32_t>(); ea.read_ok2 = ix->read_ok2.as<uint8_t>(); ea.nw32 = nw32;
         ea.multi_queue = ix->queue_a.as<uint32_t>(); ea.n_multi = qc + 2;      // the align queues are free by now
+        ea.order = prm->no_align ? nullptr : ix->order.as<uint32_t>();
         {
             poke(st, {{qc + 2, 0u}});
             const int emit_blocks = std::max(1, static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8)));
@@ -687,7 +694,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         CK(cudaEventRecord(ix->ev[3], st));
     }
     // ---- a10: ordered graph weighting on the device (optional) ----
-    if (prm->project_on_device && n_segs > 0) project_on_device(ix, d_off, n_segs, sms, st, kbegin, kend, launches);
+    if (prm->project_on_device && n_segs > 0) project_on_device(ix, d_off, n_segs, sms, !prm->no_align, st, kbegin, kend, launches);
     CK(cudaEventRecord(ix->ev[4], st));
 
     // ---- results ----

@@ -60,9 +60,7 @@ struct DevIndex {
     const uint64_t* sketches;
     const uint32_t* graph_mask_words;
     const LshTable* tables;  // [(K-1)*n_bands + band]; slots == nullptr when not built yet
-    const uint32_t* pfx_off; // [node_seq bytes + 1] prefix-table CSR (host/prefix_table.cpp), position = NodeRec::seq_off + offset
-    const uint64_t* pfx;
-    const uint32_t* pfx1;    // [node_seq bytes + 1] one-load form: single wildcard-free prefix = packed | len << 16; bit 31 = consult pfx_off/pfx
+    const uint32_t* pfxset;  // [node_seq bytes + 1] allele sets of the first 8 steps from a position (host/prefix_table.cpp), position = NodeRec::seq_off + offset
     const uint32_t* node_seq2;    // node_seq packed 2 bits per base (pack_base2), 16 bases per word, same positions as node_seq
     const uint32_t* node_n2;      // same layout: bit 2i of a word set when base i is an 'N' wildcard (alignment.go:212-215)
     const uint8_t* graph_has_n;   // [G] 1 when a node of the graph holds an 'N' (only then node_n2 is consulted)

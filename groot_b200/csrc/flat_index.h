@@ -95,7 +95,7 @@ void load_index(FlatIndex& idx, const std::string& path);
 void dump_index(const FlatIndex& idx, void (*sink)(void* ctx, const char* data, size_t n), void* ctx);
 
 // derived acceleration structure for the align kernel (host/prefix_table.cpp)
-void build_prefix_table(const FlatIndex& idx, std::vector<uint32_t>& pfx_off, std::vector<uint64_t>& pfx, std::vector<uint32_t>& pfx1);
+void build_prefix_sets(const FlatIndex& idx, std::vector<uint32_t>& pset);
 
 // lshensemble parameter optimiser + containment threshold, exact f64 expressions (host, once per query size)
 void optimal_kl(int max_k, int max_l, int x, int q, double t, int* K, int* L);

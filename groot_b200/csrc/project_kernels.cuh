@@ -32,6 +32,7 @@ struct ProjectArgs {
     double* vals;                 // [n_items]
     unsigned long long* kmer_total;   // [n_graphs]
     uint32_t k;
+    const uint32_t* order;        // pair ids sorted by first window (or nullptr): the pairs a warp expands share their windows
 };
 
 __global__ void __launch_bounds__(256) project_count_kernel(DevIndex ix, ProjectArgs a) {
@@ -46,7 +47,8 @@ __global__ void __launch_bounds__(256) project_count_kernel(DevIndex ix, Project
 
 __global__ void __launch_bounds__(256) project_expand_kernel(DevIndex ix, ProjectArgs a) {
     const uint32_t n_segs = *a.n_segs_ptr;
-    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < n_segs; s += gridDim.x * blockDim.x) {
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < n_segs; q += gridDim.x * blockDim.x) {
+        const uint32_t s = a.order ? a.order[q] : q;
         const PairOut p = a.pairs[s];
         const uint32_t len = a.off[p.read + 1] - a.off[p.read];
         const double kmers = static_cast<double>(static_cast<int>(len) - static_cast<int>(a.k)) + 1.0;   // graphminion.go:60
