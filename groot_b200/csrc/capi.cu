@@ -95,7 +95,7 @@ MultTable make_mult(uint32_t k) {
     MultTable m;
     const uint64_t C = static_cast<uint64_t>(k) * GROOT_MULTI_SEED;
     for (uint64_t i = 0; i < 32; i++) { m.c[i] = i ^ C; m.low[i] = static_cast<uint32_t>((C & 31u) ^ i); }
-    m.c0 = C & ~31ull; m.m32 = 32; m.pad = 0;
+    m.c0 = C & ~31ull; m.m32 = 32; m.one = 1;
     return m;
 }
 

@@ -78,7 +78,7 @@ struct MultTable {
     uint64_t c0;
     uint32_t low[32];
     uint32_t m32;  // == 32, kept as a runtime value so that >>27 can be issued as multiplies (FMA pipe) instead of shifts (ALU pipe)
-    uint32_t pad;
+    uint32_t one;  // == 1, a runtime value for the same reason: the running-minimum update as predicated multiply-adds
 };
 
 enum : int { HSTAGE = 4 };  // hits per read staged by the seed kernel before the exact-size fill

@@ -60,12 +60,35 @@ __device__ inline void build_seed_tabs(SeedTabs* T, unsigned k) {
 
 // ---- the sketch: registers only -------------------------------------------------------------
 #ifndef GROOT_KHF_VARIANT
-#define GROOT_KHF_VARIANT 0
+#define GROOT_KHF_VARIANT 3
 #endif
+// m = min(m, x) with the two conditional moves issued as predicated multiply-adds (x * 1 + 0): they go to the FMA
+// pipe, which has room, instead of the ALU pipe, which is the one that bounds this kernel (2 SEL per hash out of 8 ALU
+// instructions; DESIGN.md "Kernels").
+__device__ __forceinline__ void min_u64_fma(uint64_t& m, uint64_t x, uint32_t one) {
+    uint32_t mlo = static_cast<uint32_t>(m), mhi = static_cast<uint32_t>(m >> 32);
+    const uint32_t xlo = static_cast<uint32_t>(x), xhi = static_cast<uint32_t>(x >> 32);
+    asm("{\n\t.reg .pred p;\n\t.reg .u64 a, b;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%0, %1};\n\tsetp.lt.u64 p, a, b;\n\t"
+        "@p mad.lo.u32 %0, %2, %4, 0;\n\t@p mad.lo.u32 %1, %3, %4, 0;\n\t}"
+        : "+r"(mlo), "+r"(mhi)
+        : "r"(xlo), "r"(xhi), "r"(one));
+    m = (static_cast<uint64_t>(mhi) << 32) | mlo;
+}
+
 template <int S>
 __device__ __forceinline__ void khf_update(uint64_t h, const MultTable& M, uint64_t (&sk)[S]) {
+#if GROOT_KHF_VARIANT == 3
+    min_u64_fma(sk[0], h, M.one);
+#pragma unroll
+    for (int i = 1; i < S; i++) {
+        uint64_t x = h * M.c[i];
+        x ^= x >> GROOT_MULTI_SHIFT;
+        min_u64_fma(sk[i], x, M.one);
+    }
+    return;
+#endif
     sk[0] = h < sk[0] ? h : sk[0];
-#if GROOT_KHF_VARIANT == 0
+#if GROOT_KHF_VARIANT == 0 || GROOT_KHF_VARIANT == 3
 #pragma unroll
     for (int i = 1; i < S; i++) {
         uint64_t x = h * M.c[i];
