@@ -209,6 +209,7 @@ struct grootgpu_index {
     double* d_kmer_freq = nullptr;
     unsigned long long* d_kmer_total = nullptr;
     const uint32_t* d_cn_count = nullptr;
+    const double* d_cn_ratio = nullptr;
     bool weights_on_device = false;
     DBuf item_cnt, item_off, pkeys, pkeys2, pvals, pvals2;
     std::vector<LenParam> h_len_params;
@@ -272,6 +273,15 @@ void index_to_device(grootgpu_index* ix) {
     d.sketches = upload(h.sketches, ix->owned);
     d.graph_mask_words = upload(h.graph_mask_words, ix->owned);
     ix->d_cn_count = upload(h.cn_count, ix->owned);
+    {   // IncrementSubPath's per-node share of a window (graph.go:427-441): segLen / total, both f64, total = sum of integers (exact)
+        std::vector<double> ratio(h.cn_node.size(), 1.0);
+        for (const WinRec& w : h.wins) {
+            double total = 0.0;
+            for (uint32_t j = 0; j < w.cn_cnt; j++) total += static_cast<double>(h.nodes[h.cn_node[w.cn_off + j]].seq_len);
+            for (uint32_t j = 0; j < w.cn_cnt; j++) ratio[w.cn_off + j] = static_cast<double>(h.nodes[h.cn_node[w.cn_off + j]].seq_len) / total;
+        }
+        ix->d_cn_ratio = upload(ratio, ix->owned);
+    }
     {
         std::vector<uint32_t> pset;
         build_prefix_sets(h, pset);
@@ -478,27 +488,28 @@ void push_weights_to_device(grootgpu_index* ix) {
 }
 
 template <class KB, class KE>
-void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n_segs, int sms, bool use_order, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
+void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n, uint32_t n_segs, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
     push_weights_to_device(ix);
-    ix->item_cnt.need(4ull * n_segs); ix->item_off.need(4ull * (n_segs + 1));
+    ix->item_cnt.need(4ull * H); ix->item_off.need(4ull * (H + 1));
     ProjectArgs pa{};
-    pa.off = d_off; pa.hits = ix->hits.as<uint32_t>(); pa.pairs = ix->pairs.as<PairOut>(); pa.n_segs_ptr = ix->scalars.as<uint32_t>();
-    pa.cn_count = ix->d_cn_count; pa.item_cnt = ix->item_cnt.as<uint32_t>(); pa.item_off = ix->item_off.as<uint32_t>();
+    pa.off = d_off; pa.hits = ix->hits.as<uint32_t>(); pa.hit_read = ix->hit_read.as<uint32_t>(); pa.pairs = ix->pairs.as<PairOut>();
+    pa.n_segs_ptr = ix->scalars.as<uint32_t>(); pa.n_hits_ptr = ix->hit_off.as<uint32_t>() + n;
+    pa.cn_count = ix->d_cn_count; pa.cn_ratio = ix->d_cn_ratio; pa.item_cnt = ix->item_cnt.as<uint32_t>(); pa.item_off = ix->item_off.as<uint32_t>();
     pa.kmer_total = ix->d_kmer_total; pa.k = ix->h.p.k;
-    pa.order = use_order ? ix->order.as<uint32_t>() : nullptr;
     const int blocks = std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8));
     kbegin(6); project_count_kernel<<<blocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
     size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(n_segs), st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(H), st);
     ix->cub_tmp.need(tmp + 16);
-    cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(n_segs), st);
-    const uint32_t* pk = peek(ix, st, {ix->item_off.as<uint32_t>() + (n_segs - 1), ix->item_cnt.as<uint32_t>() + (n_segs - 1)});
+    cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(H), st);
+    const uint32_t* pk = peek(ix, st, {ix->item_off.as<uint32_t>() + (H - 1), ix->item_cnt.as<uint32_t>() + (H - 1)});
     const uint64_t n_items = static_cast<uint64_t>(pk[0]) + pk[1];
     if (n_items == 0) return;
     if (n_items >= (1ull << 31)) throw std::length_error("too many weight increments in one batch: use smaller batches");
     ix->pkeys.need(4 * n_items); ix->pkeys2.need(4 * n_items); ix->pvals.need(8 * n_items); ix->pvals2.need(8 * n_items);
     pa.keys = ix->pkeys.as<uint32_t>(); pa.vals = ix->pvals.as<double>();
-    kbegin(6); project_expand_kernel<<<blocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
+    const int eblocks = std::max(1, std::min<int>((H + 255) / 256, sms * 8));
+    kbegin(6); project_expand_kernel<<<eblocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
     int end_bit = 1;
     while ((1ull << end_bit) < ix->h.nodes.size()) end_bit++;
     size_t sort_tmp = 0;
@@ -508,10 +519,10 @@ void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n_seg
     cub::DeviceRadixSort::SortPairs(ix->cub_tmp.p, sort_tmp, ix->pkeys.as<uint32_t>(), ix->pkeys2.as<uint32_t>(), ix->pvals.as<double>(), ix->pvals2.as<double>(),
                                     static_cast<int>(n_items), 0, end_bit, st);
     const uint32_t n32 = static_cast<uint32_t>(n_items);
-    poke(st, {{ix->item_off.as<uint32_t>() + n_segs, n32}});
+    poke(st, {{ix->item_off.as<uint32_t>() + H, n32}});
     const uint32_t n_nodes = static_cast<uint32_t>(ix->h.nodes.size());
     const int ablocks = std::max(1, std::min<int>(static_cast<int>((n_nodes + 7) / 8), sms * 8));
-    kbegin(6); project_accumulate_kernel<<<ablocks, 256, 0, st>>>(ix->pkeys2.as<uint32_t>(), ix->pvals2.as<double>(), ix->item_off.as<uint32_t>() + n_segs, n_nodes, ix->d_kmer_freq); launches++; kend();
+    kbegin(6); project_accumulate_kernel<<<ablocks, 256, 0, st>>>(ix->pkeys2.as<uint32_t>(), ix->pvals2.as<double>(), ix->item_off.as<uint32_t>() + H, n_nodes, ix->d_kmer_freq); launches++; kend();
     CK(cudaGetLastError());
 }
 
@@ -637,7 +648,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         }
         int screen_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8));
         screen_blocks = std::max(screen_blocks, 1);
-        const int kRounds = 6;
+        const int kRounds = 2;   // later rounds hold a handful of stragglers: align_finish_kernel takes them in one launch
         RoundArgs ra{};
         ra.a = aa; ra.cursor = ix->cursor.as<PairCursor>(); ra.cand = ix->cand.as<uint2>();
         ra.slow_queue = ix->slow_q.as<uint32_t>(); ra.n_slow = qc + 3;
@@ -694,7 +705,7 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         CK(cudaEventRecord(ix->ev[3], st));
     }
     // ---- a10: ordered graph weighting on the device (optional) ----
-    if (prm->project_on_device && n_segs > 0) project_on_device(ix, d_off, n_segs, sms, !prm->no_align, st, kbegin, kend, launches);
+    if (prm->project_on_device && n_segs > 0) project_on_device(ix, d_off, n, n_segs, H, sms, st, kbegin, kend, launches);
     CK(cudaEventRecord(ix->ev[4], st));
 
     // ---- results ----
