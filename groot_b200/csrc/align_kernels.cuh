@@ -39,6 +39,7 @@
 namespace groot {
 
 constexpr int kMaskWordsInline = 8; // path bitsets of up to 256 paths travel from verify to emit without a second DFS
+constexpr uint32_t kTravRewalk = 0x80000000u;  // seg_ntrav flag: the traversals' bitsets did not fit seg_mask, the emit walks again
 
 struct DfsFrame {
     uint32_t node;
@@ -178,7 +179,7 @@ struct AlignArgs {
     int no_align;
     int* error;
     unsigned long long* counters;  // [3] += pairs that needed the sequential continuation (diagnostic)
-    const uint32_t* reads2;        // 2-bit copies of the seeded reads, both orientations (seed_kernels.cuh, pack_read2)
+    const uint32_t* reads2;        // 2-bit copies of the seeded reads, both orientations (seed_kernels.cuh, pack_reads_kernel)
     const uint8_t* read_ok2;       // [n_reads] 1 when reads2 holds the read
     uint32_t nw32;                 // words per orientation; 0 = no packed copies
 };
@@ -305,7 +306,8 @@ __device__ __forceinline__ uint32_t extract16(const uint32_t* __restrict__ w, ui
 template <bool EMIT>
 __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, uint32_t off0, const uint32_t* __restrict__ rd2, uint32_t base0,
                                            uint32_t rlen, uint32_t mw, bool has_n, DfsFrame* __restrict__ stack, uint32_t* __restrict__ mask_ws,
-                                           uint32_t max_depth, DfsResult* res, uint32_t* __restrict__ out_path = nullptr, int32_t* __restrict__ out_pos = nullptr) {
+                                           uint32_t max_depth, DfsResult* res, uint32_t* __restrict__ trav_masks,
+                                           uint32_t* __restrict__ out_path = nullptr, int32_t* __restrict__ out_pos = nullptr) {
     uint32_t nrec = 0, ntrav = 0, depth = 0;
     const uint32_t p0_off = ix.nodes[node0].path_off, p0_cnt = ix.nodes[node0].path_cnt;
     uint32_t cur = node0, off = off0, dist = 0;
@@ -351,9 +353,13 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
                             }
                         }
                     } else {
+                        // the path bitsets of the first traversals are kept (as many as fit the pair's kMaskWordsInline
+                        // words): the emit kernel expands them without walking again
+                        const bool keep = (ntrav + 1) * mw <= static_cast<uint32_t>(kMaskWordsInline);
                         uint32_t c = 0;
 #pragma unroll
-                        for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) { c += __popc(cm[wi]); res->mask[wi] = cm[wi]; }
+                        for (int wi = 0; wi < kMaskWordsInline; wi++)
+                            if (wi < mw) { c += __popc(cm[wi]); if (keep) trav_masks[ntrav * mw + wi] = cm[wi]; }
                         nrec += c;
                     }
                     ntrav++;
@@ -590,16 +596,24 @@ __device__ __forceinline__ int walk_try(const DevIndex& ix, const AlignArgs& a, 
     const uint32_t rlen = stage >= 3 ? len - 1 : len;
     DfsResult res;
     res.nrec = 0; res.ntrav = 0;
+    bool inline_masks = false;   // seg_mask holds the path bitset of every traversal
     if (a.nw32 && mw <= kMaskWordsInline && a.read_ok2[r]) {
         const uint32_t* rd2 = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32 + (strand ? a.nw32 : 0u);
         const uint32_t base0 = (strand ? a.nw32 * 16u - len : 0u) + (stage == 3 ? 1u : 0u);
-        dfs_packed<false>(ix, node, off0, rd2, base0, rlen, mw, ix.graph_has_n[wr.graph] != 0, stack, mask_ws, depth_cap, &res);
+        dfs_packed<false>(ix, node, off0, rd2, base0, rlen, mw, ix.graph_has_n[wr.graph] != 0, stack, mask_ws, depth_cap, &res,
+                          a.seg_mask + static_cast<size_t>(s) * kMaskWordsInline);
+        inline_masks = res.ntrav * mw <= static_cast<uint32_t>(kMaskWordsInline);
     } else if (PACKED_ONLY) {
         return -1;
     } else {
         ReadView rd{a.seq + o, lut, len, stage == 3 ? 1u : 0u, strand != 0};
-        if (mw <= kMaskWordsInline) dfs_masked(ix, node, off0, rd, rlen, mw, stack, mask_ws, depth_cap, &res);
-        else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
+        if (mw <= kMaskWordsInline) {
+            dfs_masked(ix, node, off0, rd, rlen, mw, stack, mask_ws, depth_cap, &res);
+            if (res.ntrav == 1) {
+                inline_masks = true;
+                for (uint32_t wi = 0; wi < mw; wi++) a.seg_mask[static_cast<size_t>(s) * kMaskWordsInline + wi] = res.mask[wi];
+            }
+        } else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
     }
     if (res.nrec == 0) return 0;
     PairOut p = a.pairs[s];
@@ -609,9 +623,7 @@ __device__ __forceinline__ int walk_try(const DevIndex& ix, const AlignArgs& a, 
     a.pairs[s] = p;
     a.seg_nrec[s] = res.nrec;
     a.seg_locus[s] = make_uint2(node, off0);
-    a.seg_ntrav[s] = res.ntrav;
-    if (res.ntrav == 1 && mw <= kMaskWordsInline)
-        for (uint32_t wi = 0; wi < mw; wi++) a.seg_mask[static_cast<size_t>(s) * kMaskWordsInline + wi] = res.mask[wi];
+    a.seg_ntrav[s] = inline_masks ? res.ntrav : (res.ntrav | kTravRewalk);
     return 1;
 }
 
@@ -711,41 +723,63 @@ struct EmitArgs {
     uint32_t* n_multi;         // device scalar, zeroed before align_emit_kernel
 };
 
-// ONE WARP PER PAIR: write the pair's records at the scanned offset. The common case (exactly one traversal with
-// ids, <= 256 paths in the graph) expands the stored bitset with the lanes striding over the start node's path
-// list (path ids ascending == record order); every other pair is queued for align_emit_multi_kernel.
+// ONE WARP PER PAIR: write the pair's records at the scanned offset. The walk kept the path bitset of every traversal
+// that fits the pair's kMaskWordsInline words (8 traversals in a graph of <= 32 paths, 1 in a graph of 129..256):
+// each is expanded with the lanes striding over the start node's path list (path ids ascending == record order).
+// Pairs with more traversals than that (kTravRewalk) are left to align_emit_multi_kernel.
 __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a) {
     const uint32_t n_segs = *a.n_segs_ptr;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gwarp = gthread >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t q = gwarp; q < n_segs; q += total_warps) {
-        const uint32_t s = a.order ? a.order[q] : q;   // window order: neighbouring warps expand the same start nodes
+        const uint32_t s = a.order ? a.order[q] : q;   // window order: neighbouring warps expand the same start nodes (L1 hits)
         const PairOut p = a.pairs[s];
         const uint32_t rb = a.rec_off[s];
         if (lane == 0) a.pairs[s].rec_begin = rb;
         if (p.rec_count == 0) continue;
-        const uint2 loc = a.seg_locus[s];
-        const uint32_t mw = ix.graph_mask_words[p.graph];
-        if (a.seg_ntrav[s] == 1 && mw <= kMaskWordsInline) {
+        const uint32_t ntrav = a.seg_ntrav[s];
+        if (!(ntrav & kTravRewalk)) {
+            const uint2 loc = a.seg_locus[s];
+            const uint32_t mw = ix.graph_mask_words[p.graph];
             const NodeRec n0 = ix.nodes[loc.x];
-            const uint32_t* mk = a.seg_mask + static_cast<size_t>(s) * kMaskWordsInline;
             uint32_t written = 0;
-            for (uint32_t j0 = 0; j0 < n0.path_cnt; j0 += 32) {
-                const uint32_t j = j0 + lane;
-                uint32_t pid = 0; bool on = false;
-                if (j < n0.path_cnt) { pid = ix.node_path_id[n0.path_off + j]; on = (mk[pid >> 5] >> (pid & 31)) & 1u; }
-                const uint32_t ball = __ballot_sync(0xffffffffu, on);
-                if (on) {
-                    const uint32_t slot = rb + written + __popc(ball & ((1u << lane) - 1u));
-                    a.rec_path[slot] = pid;
-                    a.rec_pos[slot] = ix.node_path_pos[n0.path_off + j] + static_cast<int32_t>(loc.y);   // alignment.go:296
+            for (uint32_t t = 0; t < ntrav; t++) {                     // traversals in DFS order, path ids ascending inside one
+                const uint32_t* mk = a.seg_mask + static_cast<size_t>(s) * kMaskWordsInline + t * mw;
+                for (uint32_t j0 = 0; j0 < n0.path_cnt; j0 += 32) {
+                    const uint32_t j = j0 + lane;
+                    uint32_t pid = 0; bool on = false;
+                    if (j < n0.path_cnt) { pid = ix.node_path_id[n0.path_off + j]; on = (mk[pid >> 5] >> (pid & 31)) & 1u; }
+                    const uint32_t ball = __ballot_sync(0xffffffffu, on);
+                    if (on) {
+                        const uint32_t slot = rb + written + __popc(ball & ((1u << lane) - 1u));
+                        a.rec_path[slot] = pid;
+                        a.rec_pos[slot] = ix.node_path_pos[n0.path_off + j] + static_cast<int32_t>(loc.y);   // alignment.go:296
+                    }
+                    written += __popc(ball);
                 }
-                written += __popc(ball);
             }
-        } else if (lane == 0) {
-            a.multi_queue[atomicAdd(a.n_multi, 1u)] = s;
         }
+    }
+}
+
+// Pairs whose records need a second DFS (more traversals spell the read than seg_mask can hold — several are common
+// where the MSA places the gaps of two sequences differently — or a graph of more than 256 paths), collected IN WINDOW ORDER so that the 32 walks a
+// warp of align_emit_multi_kernel runs together are walks over the same graph region.
+__global__ void __launch_bounds__(256) align_emit_classify_kernel(EmitArgs a) {
+    const uint32_t n_segs = *a.n_segs_ptr;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (uint32_t qb = i0 - lane; qb < n_segs; qb += stride) {
+        const uint32_t q = qb + lane;
+        uint32_t s = 0; bool multi = false;
+        if (q < n_segs) { s = a.order ? a.order[q] : q; multi = (a.seg_ntrav[s] & kTravRewalk) != 0; }
+        const uint32_t ball = __ballot_sync(0xffffffffu, multi);
+        if (!ball) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.n_multi, static_cast<uint32_t>(__popc(ball)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (multi) a.multi_queue[base + __popc(ball & ((1u << lane) - 1u))] = s;
     }
 }
 
@@ -770,7 +804,7 @@ __global__ void __launch_bounds__(128) align_emit_multi_kernel(DevIndex ix, Emit
         if (a.nw32 && mw <= kMaskWordsInline && a.read_ok2[p.read]) {
             const uint32_t* rd2 = a.reads2 + static_cast<size_t>(p.read) * 2u * a.nw32 + (p.reverse ? a.nw32 : 0u);
             const uint32_t base0 = (p.reverse ? a.nw32 * 16u - len : 0u) + (p.clip_start ? 1u : 0u);
-            dfs_packed<true>(ix, loc.x, loc.y, rd2, base0, rlen, mw, ix.graph_has_n[p.graph] != 0, stack, mask_ws, depth_cap, &res,
+            dfs_packed<true>(ix, loc.x, loc.y, rd2, base0, rlen, mw, ix.graph_has_n[p.graph] != 0, stack, mask_ws, depth_cap, &res, nullptr,
                              a.rec_path + rb, a.rec_pos + rb);
         } else {
             GlobalRead rd{a.seq + o, len, p.clip_start ? 1u : 0u, p.reverse != 0};

@@ -202,6 +202,9 @@ struct grootgpu_index {
     // chunked host path (grootgpu_align_batch): input double buffers, the second set of result buffers, copy streams
     DBuf in_seq[2], in_off64[2], in_off32[2], alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches, len_minmax;
     cudaStream_t st_in = nullptr, st_out = nullptr;
+    cudaStream_t st_side = nullptr;    // the ordered graph weighting runs here, next to the record emit on the main stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    DBuf cub_tmp2;
     uint32_t* h_peek = nullptr;        // mapped pinned words the device writes scalars into (peek()): no copy engine involved
     uint32_t* d_peek = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
@@ -221,6 +224,9 @@ struct grootgpu_index {
         for (auto& e : kev) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
         if (h_peek) cudaFreeHost(h_peek);
+        if (st_side) cudaStreamDestroy(st_side);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         if (st_in) cudaStreamDestroy(st_in);
         if (st_out) cudaStreamDestroy(st_out);
         for (auto& e : ev_in) if (e) cudaEventDestroy(e);
@@ -234,13 +240,13 @@ struct grootgpu_index {
 namespace {
 
 // peek: device words -> host through mapped memory (returns after synchronising the stream); poke / zero: host values -> device words
-const uint32_t* peek(grootgpu_index* ix, cudaStream_t st, std::initializer_list<const uint32_t*> src) {
+const uint32_t* peek(grootgpu_index* ix, cudaStream_t st, std::initializer_list<const uint32_t*> src, int slot = 0) {
     PeekArgs a{};
     for (const uint32_t* p : src) a.src[a.n++] = p;
-    peek_kernel<<<1, 32, 0, st>>>(a, ix->d_peek);
+    peek_kernel<<<1, 32, 0, st>>>(a, ix->d_peek + 16 * slot);     // slot: one per stream that may have a peek in flight
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
-    return ix->h_peek;
+    return ix->h_peek + 16 * slot;
 }
 void poke(cudaStream_t st, std::initializer_list<std::pair<uint32_t*, uint32_t>> w) {
     PokeArgs a{};
@@ -315,6 +321,8 @@ void index_to_device(grootgpu_index* ix) {
     CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     CK(cudaHostAlloc(reinterpret_cast<void**>(&ix->h_peek), 64 * sizeof(uint32_t), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ix->d_peek), ix->h_peek, 0));
+    CK(cudaStreamCreateWithFlags(&ix->st_side, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&ix->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ix->st_out, cudaStreamNonBlocking));
     for (auto& e : ix->ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -423,7 +431,8 @@ struct SeedLaunch {
     }
     template <int S>
     static void fill(const DevIndex& d, const FillArgs& a, uint32_t k, int blocks, cudaStream_t st) {
-        fill_kernel<S, 4><<<blocks, kSeedThreads, 0, st>>>(d, a, make_mult(k));
+        fill_kernel<S, 4, false><<<blocks, kSeedThreads, 0, st>>>(d, a, make_mult(k));
+        fill_kernel<S, 4, true><<<blocks, kSeedThreads, 0, st>>>(d, a, make_mult(k));   // reads with more than HSTAGE hits (rare)
     }
     template <int S>
     static int seed_occupancy(size_t smem) {
@@ -487,22 +496,34 @@ void push_weights_to_device(grootgpu_index* ix) {
     ix->weights_on_device = true;
 }
 
-template <class KB, class KE>
-void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n, uint32_t n_segs, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
-    push_weights_to_device(ix);
-    ix->item_cnt.need(4ull * H); ix->item_off.need(4ull * (H + 1));
+// a10 on the device in two phases, both on the side stream `st` (slot 1 of the peek buffer, its own CUB scratch):
+//   project_begin   per-mapping item counts + their exclusive scan (no host round trip)
+//   project_finish  item total -> host, expand, stable sort by node, one ordered f64 chain per node
+// The caller runs the record emit on the main stream between the two.
+ProjectArgs project_args(grootgpu_index* ix, const uint32_t* d_off, uint32_t n) {
     ProjectArgs pa{};
     pa.off = d_off; pa.hits = ix->hits.as<uint32_t>(); pa.hit_read = ix->hit_read.as<uint32_t>(); pa.pairs = ix->pairs.as<PairOut>();
     pa.n_segs_ptr = ix->scalars.as<uint32_t>(); pa.n_hits_ptr = ix->hit_off.as<uint32_t>() + n;
     pa.cn_count = ix->d_cn_count; pa.cn_ratio = ix->d_cn_ratio; pa.item_cnt = ix->item_cnt.as<uint32_t>(); pa.item_off = ix->item_off.as<uint32_t>();
     pa.kmer_total = ix->d_kmer_total; pa.k = ix->h.p.k;
+    return pa;
+}
+template <class KB, class KE>
+void project_begin(grootgpu_index* ix, const uint32_t* d_off, uint32_t n, uint32_t n_segs, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
+    push_weights_to_device(ix);
+    ix->item_cnt.need(4ull * H); ix->item_off.need(4ull * (H + 1));
+    ProjectArgs pa = project_args(ix, d_off, n);
     const int blocks = std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8));
     kbegin(6); project_count_kernel<<<blocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
     size_t tmp = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(H), st);
-    ix->cub_tmp.need(tmp + 16);
-    cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(H), st);
-    const uint32_t* pk = peek(ix, st, {ix->item_off.as<uint32_t>() + (H - 1), ix->item_cnt.as<uint32_t>() + (H - 1)});
+    ix->cub_tmp2.need(tmp + 16);
+    cub::DeviceScan::ExclusiveSum(ix->cub_tmp2.p, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(H), st);
+}
+template <class KB, class KE>
+void project_finish(grootgpu_index* ix, const uint32_t* d_off, uint32_t n, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
+    ProjectArgs pa = project_args(ix, d_off, n);
+    const uint32_t* pk = peek(ix, st, {ix->item_off.as<uint32_t>() + (H - 1), ix->item_cnt.as<uint32_t>() + (H - 1)}, 1);
     const uint64_t n_items = static_cast<uint64_t>(pk[0]) + pk[1];
     if (n_items == 0) return;
     if (n_items >= (1ull << 31)) throw std::length_error("too many weight increments in one batch: use smaller batches");
@@ -515,8 +536,8 @@ void project_on_device(grootgpu_index* ix, const uint32_t* d_off, uint32_t n, ui
     size_t sort_tmp = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, ix->pkeys.as<uint32_t>(), ix->pkeys2.as<uint32_t>(), ix->pvals.as<double>(), ix->pvals2.as<double>(),
                                     static_cast<int>(n_items), 0, end_bit, st);
-    ix->cub_tmp.need(sort_tmp + 16);
-    cub::DeviceRadixSort::SortPairs(ix->cub_tmp.p, sort_tmp, ix->pkeys.as<uint32_t>(), ix->pkeys2.as<uint32_t>(), ix->pvals.as<double>(), ix->pvals2.as<double>(),
+    ix->cub_tmp2.need(sort_tmp + 16);
+    cub::DeviceRadixSort::SortPairs(ix->cub_tmp2.p, sort_tmp, ix->pkeys.as<uint32_t>(), ix->pkeys2.as<uint32_t>(), ix->pvals.as<double>(), ix->pvals2.as<double>(),
                                     static_cast<int>(n_items), 0, end_bit, st);
     const uint32_t n32 = static_cast<uint32_t>(n_items);
     poke(st, {{ix->item_off.as<uint32_t>() + H, n32}});
@@ -540,6 +561,11 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
     ix->kev_n = 0;
     auto kbegin = [&](int cat) { if (ix->kev_n < 32) { ix->kev_cat[ix->kev_n] = cat; cudaEventRecord(ix->kev[2 * ix->kev_n], st); } };
     auto kend = [&]() { if (ix->kev_n < 32) { cudaEventRecord(ix->kev[2 * ix->kev_n + 1], st); ix->kev_n++; } };
+    cudaStream_t st2 = ix->st_side;
+    auto kbegin2 = [&](int cat) { if (ix->kev_n < 32) { ix->kev_cat[ix->kev_n] = cat; cudaEventRecord(ix->kev[2 * ix->kev_n], st2); } };
+    auto kend2 = [&]() { if (ix->kev_n < 32) { cudaEventRecord(ix->kev[2 * ix->kev_n + 1], st2); ix->kev_n++; } };
+    const bool project = prm->project_on_device != 0;
+    CK(cudaStreamSynchronize(st2));   // idle unless a previous batch failed between fork and join
 
     ix->n_hits.need(4ull * n); ix->hit_off.need(4ull * (n + 1)); ix->stage.need(4ull * HSTAGE * n);
     ix->scalars.need(64); ix->tile_counter.need(16); ix->error.need(16);
@@ -599,7 +625,9 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         if (nw32) { ix->reads2.need(8ull * nw32 * n + 64); ix->read_ok2.need(n); }
         fa.reads2 = ix->reads2.as<uint32_t>(); fa.read_ok2 = ix->read_ok2.as<uint8_t>(); fa.nw32 = nw32;
         int fill_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
-        kbegin(1); fill_dispatch(S, ix->d, fa, k, fill_blocks, st); launches++; kend();
+        kbegin(1); fill_dispatch(S, ix->d, fa, k, fill_blocks, st); launches += 2;
+        if (nw32) { pack_reads_kernel<<<std::max(1, std::min<int>((n + 31) / 32, sms * 8)), 256, 0, st>>>(fa); launches++; }
+        kend();
         CK(cudaGetLastError());
         // ---- (read, graph) segment starts ----
         thrust::counting_iterator<uint32_t> counting(0);
@@ -670,6 +698,12 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
             CK(cudaGetLastError());
         }
         CK(cudaEventRecord(ix->ev[3], st));
+        // ---- a10: the ordered graph weighting starts on the side stream; it needs the pairs, not their records ----
+        if (project) {
+            CK(cudaEventRecord(ix->ev_fork, st));
+            CK(cudaStreamWaitEvent(st2, ix->ev_fork, 0));
+            project_begin(ix, d_off, n, n_segs, H, sms, st2, kbegin2, kend2, launches);
+        }
         // ---- scan record counts, emit ----
         size_t scan2 = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, scan2, ix->seg_nrec.as<uint32_t>(), ix->rec_off.as<uint32_t>(), static_cast<int>(n_segs), st);
@@ -696,16 +730,20 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
             poke(st, {{qc + 2, 0u}});
             const int emit_blocks = std::max(1, static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8)));
             kbegin(5); align_emit_kernel<<<emit_blocks, 256, 0, st>>>(ix->d, ea); launches++; kend();
+            kbegin(5); align_emit_classify_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ea); launches++; kend();
             // thread stacks: stack_ws / mask_ws hold verify_blocks * vthreads of them
             kbegin(5); align_emit_multi_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ea); launches++; kend();
         }
         CK(cudaGetLastError());
+        if (project) {
+            project_finish(ix, d_off, n, H, sms, st2, kbegin2, kend2, launches);
+            CK(cudaEventRecord(ix->ev_join, st2));
+            CK(cudaStreamWaitEvent(st, ix->ev_join, 0));
+        }
     } else {
         CK(cudaEventRecord(ix->ev[2], st));
         CK(cudaEventRecord(ix->ev[3], st));
     }
-    // ---- a10: ordered graph weighting on the device (optional) ----
-    if (prm->project_on_device && n_segs > 0) project_on_device(ix, d_off, n, n_segs, H, sms, st, kbegin, kend, launches);
     CK(cudaEventRecord(ix->ev[4], st));
 
     // ---- results ----

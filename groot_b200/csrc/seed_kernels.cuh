@@ -448,7 +448,7 @@ struct FillArgs {
     uint32_t* hit_read;
     uint8_t* seg_flag;
     unsigned long long* counters;  // [0]=mapped reads, [1]=multimapped reads
-    uint32_t* reads2;              // [n * 2 * nw32 + 1] packed copies of the seeded reads (pack_read2), or nullptr
+    uint32_t* reads2;              // [n * 2 * nw32 + 1] packed copies of the seeded reads (pack_reads_kernel), or nullptr
     uint8_t* read_ok2;             // [n] 1 when reads2 holds the read
     uint32_t nw32;                 // words per orientation (16 bases each); 0 = packing off
 };
@@ -459,59 +459,75 @@ __device__ __forceinline__ uint32_t rev_pairs16(uint32_t x) {
     return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
 }
 
-// 2-bit copies of one read for the align kernels: out[0, nw32) = the read (base i in word i >> 4 at bits 2*(i & 15),
-// code pack_base2), out[nw32, 2*nw32) = its reverse complement shifted up by pad = 16*nw32 - len bases (base i of the
-// reverse complement sits at position i + pad). Returns false, writing nothing useful, when the read does not fit
-// or holds anything but upper-case ACGT — such reads take the byte-wise path, which reproduces the reference's
-// handling of 'N' and of bytes RevComplement cannot map (seqio.go:17-23,120-133).
-// Reads aligned 32-bit words: seq must be readable a few bytes past the read (the API asks for 64).
-__device__ inline bool pack_read2(const uint8_t* __restrict__ seq, uint32_t o, uint32_t len, uint32_t nw32, uint32_t* __restrict__ out) {
-    if (len > nw32 * 16u) return false;
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(seq + (o & ~3u));
-    const uint32_t sh = (o & 3u) * 8u;
-    uint32_t prev = __ldg(wp);
-    bool ok = true;
-    for (uint32_t j = 0; j < nw32; j++) {
-        uint32_t acc = 0;
+// 2-bit copies of the seeded reads for the align kernels, per read r at reads2 + r * 2 * nw32:
+//   words [0, nw32)        the read: base i in word i >> 4 at bits 2 * (i & 15), code pack_base2
+//   words [nw32, 2 * nw32) its reverse complement shifted up by pad = 16 * nw32 - len bases (base i of the reverse
+//                          complement sits at position i + pad)
+// read_ok2[r] = 0 when the read does not fit or holds anything but upper-case ACGT — such reads take the byte-wise
+// path, which reproduces the reference's handling of 'N' and of bytes RevComplement cannot map (seqio.go:17-23,120-133).
+// A GROUP of 8 lanes per read, lane j of the group packing output words j, j + 8, ... (16 bases = four aligned 32-bit
+// loads + realignment each; seq must be readable a few bytes past the read, the API asks for 64), so a warp's loads
+// run along the reads instead of 32 lanes striding through 32 different reads.
+__global__ void __launch_bounds__(256) pack_reads_kernel(FillArgs a) {
+    const uint32_t lane = threadIdx.x & 31, gl = lane & 7u, grp = lane >> 3;
+    const uint32_t gmask = 0xffu << (grp * 8);
+    const uint32_t g0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, gstride = (gridDim.x * blockDim.x) >> 3;
+    const uint32_t n_iter = (a.n_reads + gstride - 1) / gstride;          // same trip count for every group of a warp
+    for (uint32_t it = 0; it < n_iter; it++) {
+        const uint32_t r = g0 + it * gstride;
+        const bool live = r < a.n_reads && a.n_hits[r] != 0;
+        bool ok = true;
+        if (live) {
+            const uint32_t o = a.off[r], len = a.off[r + 1] - o;
+            uint32_t* out = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32;
+            ok = len <= a.nw32 * 16u;
+            for (uint32_t j = gl; j < a.nw32 && ok; j += 8) {
+                const uint32_t b0 = o + 16u * j;                          // first byte of this output word
+                const uint32_t* wp = reinterpret_cast<const uint32_t*>(a.seq + (b0 & ~3u));
+                const uint32_t sh = (b0 & 3u) * 8u;
+                uint32_t acc = 0;
+                if (16u * j < len) {
+                    uint32_t prev = __ldg(wp);
 #pragma unroll
-        for (uint32_t t = 0; t < 4; t++) {
-            const uint32_t bi = 16u * j + 4u * t;   // first base of this byte word
-            if (bi < len) {
-                const uint32_t next = __ldg(wp + 4u * j + t + 1u);
-                const uint32_t w = __funnelshift_r(prev, next, sh);
-                prev = next;
-                const uint32_t nb = len - bi;
-                const uint32_t bytemask = nb >= 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
-                uint32_t c = (w >> 1) & 0x03030303u;
-                const uint32_t m0 = c & 0x01010101u, m1 = (c >> 1) & 0x01010101u;
-                // the byte each code stands for: A 0x41, C 0x43, T 0x54, G 0x47
-                const uint32_t expect = 0x41414141u ^ (m0 << 1) ^ ((m0 & m1) << 2) ^ ((m1 & ~m0) * 0x15u);
-                ok = ok && ((expect ^ w) & bytemask) == 0u;
-                c &= bytemask;
-                acc |= ((c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu) << (8u * t);
+                    for (uint32_t t = 0; t < 4; t++) {
+                        const uint32_t bi = 16u * j + 4u * t;
+                        if (bi < len) {
+                            const uint32_t next = __ldg(wp + t + 1u);
+                            const uint32_t w = __funnelshift_r(prev, next, sh);
+                            prev = next;
+                            const uint32_t nb = len - bi;
+                            const uint32_t bytemask = nb >= 4u ? 0xffffffffu : ((1u << (8u * nb)) - 1u);
+                            uint32_t c = (w >> 1) & 0x03030303u;
+                            const uint32_t m0 = c & 0x01010101u, m1 = (c >> 1) & 0x01010101u;
+                            const uint32_t expect = 0x41414141u ^ (m0 << 1) ^ ((m0 & m1) << 2) ^ ((m1 & ~m0) * 0x15u);   // A 0x41, C 0x43, T 0x54, G 0x47
+                            ok = ok && ((expect ^ w) & bytemask) == 0u;
+                            c &= bytemask;
+                            acc |= ((c | (c >> 6) | (c >> 12) | (c >> 18)) & 0xffu) << (8u * t);
+                        }
+                    }
+                }
+                out[j] = acc;
+                out[a.nw32 + (a.nw32 - 1u - j)] = rev_pairs16(acc) ^ 0xAAAAAAAAu;
             }
         }
-        out[j] = acc;
-        out[nw32 + (nw32 - 1u - j)] = rev_pairs16(acc) ^ 0xAAAAAAAAu;
+        const uint32_t bad = __ballot_sync(0xffffffffu, live && !ok);
+        if (live && gl == 0) a.read_ok2[r] = (bad & gmask) ? 0 : 1;
     }
-    return ok;
 }
 
-template <int S, int MAXK>
+// REFILL = false: the reads whose hits were all staged (the lean, common kernel). REFILL = true: only the rare reads
+// with more than HSTAGE hits, whose probe is redone (kept apart so that its sketch registers do not set the
+// occupancy of the common case).
+template <int S, int MAXK, bool REFILL>
 __global__ void __launch_bounds__(kSeedThreads) fill_kernel(DevIndex ix, FillArgs a, MultTable M) {
     __shared__ SeedTabs T;
-    build_seed_tabs(&T, ix.k);
-    __syncthreads();
+    if (REFILL) { build_seed_tabs(&T, ix.k); __syncthreads(); }
     unsigned mapped = 0, multi = 0;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
         const uint32_t nh = a.n_hits[r];
-        if (nh == 0) continue;
+        if (nh == 0 || (nh > HSTAGE) != REFILL) continue;
         const uint32_t base = a.hit_off[r];
-        if (a.nw32) {
-            const uint32_t o = a.off[r];
-            a.read_ok2[r] = pack_read2(a.seq, o, a.off[r + 1] - o, a.nw32, a.reads2 + static_cast<size_t>(r) * 2u * a.nw32) ? 1 : 0;
-        }
-        if (nh <= HSTAGE) {
+        if (!REFILL) {
             for (uint32_t i = 0; i < nh; i++) a.hits[base + i] = a.stage[static_cast<size_t>(r) * HSTAGE + i];
         } else {
             const uint32_t o = a.off[r], len = a.off[r + 1] - o;
