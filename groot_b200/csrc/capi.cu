@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
@@ -887,10 +888,14 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
     cprm.results_on_device = 1;
     uint64_t hit_base = 0, pair_base = 0, rec_base = 0;
     grootgpu_batch_result total{};
+    const bool trace = getenv("GROOTGPU_TRACE") != nullptr;   // host-side timeline of the chunk pipeline on stderr
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     CK(cudaEventRecord(ix->ev_t0, st_in));
     issue_input(0);
     for (uint32_t c = 0; c < C; c++) {
         const uint32_t r0 = cb[c], nc = cb[c + 1] - r0, b = c & 1;
+        const double t_c0 = now_ms();
         if (c + 1 < C) issue_input(c + 1);      // its buffers were last read by chunk c-1, which has completed (run_batch returns synchronised)
         CK(cudaStreamWaitEvent(st, ix->ev_in[b], 0));
         poke(st, {{ix->len_minmax.as<uint32_t>(), 0xffffffffu}, {ix->len_minmax.as<uint32_t>() + 1, 0u}});
@@ -902,7 +907,9 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
         swap_result_sets();                      // this chunk writes the set the copy-out of chunk c-2 has released
         if (c >= 2) CK(cudaStreamWaitEvent(st, ix->ev_out[b], 0));
         grootgpu_batch_result r{};
+        const double t_c1 = now_ms();
         run_batch(ix, ix->in_seq[b].as<uint8_t>(), ix->in_off32[b].as<uint32_t>(), nc, mm[0], mm[1], &cprm, st, &r);
+        const double t_c2 = now_ms();
         if (hit_base + r.n_hits >= (1ull << 32) || rec_base + r.n_records >= (1ull << 32))
             throw std::length_error("more than 2^32 hits or records in one batch: use smaller batches");
         const uint32_t n_off = nc + (c + 1 == C ? 1u : 0u);
@@ -928,6 +935,8 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
         }
         if (prm->keep_sketches) CK(cudaMemcpyAsync(ix->r_sketches.as<uint64_t>() + static_cast<size_t>(r0) * S, ix->sketches.p, 8ull * S * nc, cudaMemcpyDeviceToHost, st_out));
         CK(cudaEventRecord(ix->ev_out[b], st_out));
+        if (trace) fprintf(stderr, "[grootgpu] chunk %u: %u reads  start %.2f ms  input ready %.2f  kernels done %.2f (device %.2f ms)  copy-out issued %.2f\n",
+                           c, nc, t_c0, t_c1, t_c2, r.ms[1] + r.ms[2] + r.ms[3], now_ms());
         hit_base += r.n_hits; pair_base += r.n_pairs; rec_base += r.n_records;
         total.mapped += r.mapped; total.multimapped += r.multimapped; total.slow_path_pairs += r.slow_path_pairs;
         total.kernel_launches += r.kernel_launches + 2;
@@ -936,6 +945,7 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
     }
     CK(cudaEventRecord(ix->ev_t1, st_out));
     CK(cudaStreamSynchronize(st_out));
+    if (trace) fprintf(stderr, "[grootgpu] batch of %u reads in %u chunks done at %.2f ms\n", n, C, now_ms());
     memset(out, 0, sizeof *out);
     *out = total;
     out->n_reads = n; out->n_hits = hit_base; out->n_pairs = pair_base; out->n_records = rec_base;
