@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <cub/device/device_radix_sort.cuh>
@@ -17,7 +18,9 @@
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
 #include <fstream>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -180,59 +183,83 @@ std::string slurp(const std::string& path) {
 }  // namespace
 
 // =================================================================================================
+// Everything one batch in flight needs besides the (read-only) index: device scratch, result arrays, streams, events.
+// The handle owns two of them ("lanes").
+struct Workspace {
+    cudaStream_t stream = nullptr;     // the lane's compute stream
+    cudaStream_t st_side = nullptr;    // the ordered graph weighting runs here, next to the record emit on the compute stream
+    cudaEvent_t ev[6] = {};
+    cudaEvent_t kev[64] = {};          // per-launch timing: pairs (begin, end) tagged with a category
+    int kev_cat[32] = {};
+    int kev_n = 0;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr, ev_acc = nullptr;
+    cudaEvent_t ev_out[2] = {};        // copy-out of the chunk that last used result set 0 / 1 has completed
+    int rset = 0;                      // result set in use: the lane alternates so that a chunk never waits for the previous copy-out
+    uint32_t* h_peek = nullptr;        // mapped pinned words the device writes scalars into (peek()): no copy engine involved
+    uint32_t* d_peek = nullptr;
+    DBuf seq, off, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
+        rec_path, rec_pos, stack_ws, cub_tmp, cub_tmp2, sketches, tile_counter, error, reads2, read_ok2, qkey, qkey2, order, slow_q, len_minmax,
+        item_cnt, item_off, pkeys, pkeys2, pvals, pvals2;
+    DBuf alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches;   // the other result set of the chunked host path
+    // ordering of the graph weighting across lanes (chunked host path): called around the accumulate of a chunk
+    std::function<void(cudaStream_t)> acc_before, acc_after;
+
+    void swap_result_sets() {          // DBuf owns its pointer: swap fields, not objects
+        auto sw = [](DBuf& x, DBuf& y) { std::swap(x.p, y.p); std::swap(x.cap, y.cap); };
+        sw(hits, alt_hits); sw(pairs, alt_pairs); sw(rec_path, alt_rec_path); sw(rec_pos, alt_rec_pos); sw(hit_off, alt_hit_off); sw(sketches, alt_sketches);
+        rset ^= 1;
+    }
+    void create() {
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&st_side, cudaStreamNonBlocking));
+        for (auto& e : ev) CK(cudaEventCreate(&e));
+        for (auto& e : kev) CK(cudaEventCreate(&e));
+        for (cudaEvent_t* e : {&ev_fork, &ev_join, &ev_done, &ev_acc, &ev_out[0], &ev_out[1]}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&h_peek), 64 * sizeof(uint32_t), cudaHostAllocMapped));
+        CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_peek), h_peek, 0));
+    }
+    ~Workspace() {
+        for (auto& e : ev) if (e) cudaEventDestroy(e);
+        for (auto& e : kev) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {ev_fork, ev_join, ev_done, ev_acc, ev_out[0], ev_out[1]}) if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+        if (st_side) cudaStreamDestroy(st_side);
+        if (h_peek) cudaFreeHost(h_peek);
+    }
+};
+
 struct grootgpu_index {
     FlatIndex h;
     int device = 0;
     DevIndex d{};
     std::vector<void*> owned;          // device allocations freed on destroy
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
-    cudaEvent_t kev[64] = {};          // per-launch timing: pairs (begin, end) tagged with a category
-    int kev_cat[32] = {};
-    int kev_n = 0;
     // LSH tables, built lazily per K (all bands)
     std::vector<LshTable> h_tables;    // [(K-1)*n_bands + band]
     LshTable* d_tables = nullptr;
     bool tables_built[8] = {};
     // per (q, threshold) parameter cache
     std::map<std::pair<uint32_t, double>, LenParam> param_cache;
-    // workspaces
-    DBuf seq, off, len_params, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
-        rec_path, rec_pos, stack_ws, cub_tmp, sketches, tile_counter, error, reads2, read_ok2, qkey, qkey2, order, slow_q;
-    HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_scal;
-    // chunked host path (grootgpu_align_batch): input double buffers, the second set of result buffers, copy streams
-    DBuf in_seq[2], in_off64[2], in_off32[2], alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches, len_minmax;
-    cudaStream_t st_in = nullptr, st_out = nullptr;
-    cudaStream_t st_side = nullptr;    // the ordered graph weighting runs here, next to the record emit on the main stream
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    DBuf cub_tmp2;
-    uint32_t* h_peek = nullptr;        // mapped pinned words the device writes scalars into (peek()): no copy engine involved
-    uint32_t* d_peek = nullptr;
-    cudaEvent_t ev_in[2] = {}, ev_done[2] = {}, ev_out[2] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    DBuf len_params;                   // per read length: (K, L, eq_min), shared by the lanes (prepare_params, under params_mu)
+    std::mutex params_mu;
+    HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches;   // batch-wide host result arrays
+    Workspace ws[2];                   // two lanes: the chunked host path runs consecutive chunks on alternating lanes
+    cudaStream_t st_in = nullptr, st_out = nullptr;   // copy-in / copy-out of the chunked host path
+    DBuf in_seq[4], in_off64[4], in_off32[4];
+    cudaEvent_t ev_in[4] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     // graph weights live on the device once a batch was projected there; the host copy is refreshed lazily
     double* d_kmer_freq = nullptr;
     unsigned long long* d_kmer_total = nullptr;
     const uint32_t* d_cn_count = nullptr;
     const double* d_cn_ratio = nullptr;
     bool weights_on_device = false;
-    DBuf item_cnt, item_off, pkeys, pkeys2, pvals, pvals2;
     std::vector<LenParam> h_len_params;
     double lp_threshold = -1; uint32_t lp_min = 1, lp_max = 0;
 
     ~grootgpu_index() {
         for (void* p : owned) cudaFree(p);
-        for (auto& e : ev) if (e) cudaEventDestroy(e);
-        for (auto& e : kev) if (e) cudaEventDestroy(e);
-        if (stream) cudaStreamDestroy(stream);
-        if (h_peek) cudaFreeHost(h_peek);
-        if (st_side) cudaStreamDestroy(st_side);
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        if (ev_join) cudaEventDestroy(ev_join);
         if (st_in) cudaStreamDestroy(st_in);
         if (st_out) cudaStreamDestroy(st_out);
         for (auto& e : ev_in) if (e) cudaEventDestroy(e);
-        for (auto& e : ev_done) if (e) cudaEventDestroy(e);
-        for (auto& e : ev_out) if (e) cudaEventDestroy(e);
         if (ev_t0) cudaEventDestroy(ev_t0);
         if (ev_t1) cudaEventDestroy(ev_t1);
     }
@@ -241,13 +268,13 @@ struct grootgpu_index {
 namespace {
 
 // peek: device words -> host through mapped memory (returns after synchronising the stream); poke / zero: host values -> device words
-const uint32_t* peek(grootgpu_index* ix, cudaStream_t st, std::initializer_list<const uint32_t*> src, int slot = 0) {
+const uint32_t* peek(Workspace* w, cudaStream_t st, std::initializer_list<const uint32_t*> src, int slot = 0) {
     PeekArgs a{};
     for (const uint32_t* p : src) a.src[a.n++] = p;
-    peek_kernel<<<1, 32, 0, st>>>(a, ix->d_peek + 16 * slot);     // slot: one per stream that may have a peek in flight
+    peek_kernel<<<1, 32, 0, st>>>(a, w->d_peek + 16 * slot);     // slot: one per stream that may have a peek in flight
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
-    return ix->h_peek + 16 * slot;
+    return w->h_peek + 16 * slot;
 }
 void poke(cudaStream_t st, std::initializer_list<std::pair<uint32_t*, uint32_t>> w) {
     PokeArgs a{};
@@ -319,19 +346,12 @@ void index_to_device(grootgpu_index* ix) {
     ix->d_tables = static_cast<LshTable*>(dt);
     CK(cudaMemcpy(dt, ix->h_tables.data(), ix->h_tables.size() * sizeof(LshTable), cudaMemcpyHostToDevice));
     d.tables = ix->d_tables;
-    CK(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    CK(cudaHostAlloc(reinterpret_cast<void**>(&ix->h_peek), 64 * sizeof(uint32_t), cudaHostAllocMapped));
-    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ix->d_peek), ix->h_peek, 0));
-    CK(cudaStreamCreateWithFlags(&ix->st_side, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&ix->ev_fork, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&ix->ev_join, cudaEventDisableTiming));
+    for (Workspace& w : ix->ws) w.create();
+    ix->len_params.need(60002 * sizeof(LenParam));   // never reallocated: the lanes' kernels read it while prepare_params extends it
     CK(cudaStreamCreateWithFlags(&ix->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ix->st_out, cudaStreamNonBlocking));
     for (auto& e : ix->ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : ix->ev_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    for (auto& e : ix->ev_out) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreate(&ix->ev_t0)); CK(cudaEventCreate(&ix->ev_t1));
-    for (auto& e : ix->ev) CK(cudaEventCreate(&e));
-    for (auto& e : ix->kev) CK(cudaEventCreate(&e));
     if (h.kmer_freq.size() != h.nodes.size()) h.kmer_freq.assign(h.nodes.size(), 0.0);
     if (h.kmer_total.size() != h.n_graphs) h.kmer_total.assign(h.n_graphs, 0);
     if (h.node_marked.size() != h.nodes.size()) h.node_marked.assign(h.nodes.size(), 0);
@@ -408,6 +428,7 @@ LenParam param_for(grootgpu_index* ix, uint32_t q, double t) {
 
 // make sure len_params[len] is on the device for every len in [min_len, max_len] and the tables exist
 void prepare_params(grootgpu_index* ix, uint32_t min_len, uint32_t max_len, double t) {
+    std::lock_guard<std::mutex> lock(ix->params_mu);   // the two lanes of the chunked host path share the tables
     const uint32_t k = ix->h.p.k;
     if (ix->lp_threshold == t && min_len >= ix->lp_min && max_len <= ix->lp_max) return;
     uint32_t lo = std::min(min_len, ix->lp_threshold == t ? ix->lp_min : min_len);
@@ -418,7 +439,7 @@ void prepare_params(grootgpu_index* ix, uint32_t min_len, uint32_t max_len, doub
         ix->h_len_params[len] = lp;
         if (lp.eq_min <= ix->h.p.S && lp.K >= 1) build_tables(ix, lp.K);
     }
-    ix->len_params.need(ix->h_len_params.size() * sizeof(LenParam));
+    if (ix->h_len_params.size() * sizeof(LenParam) > ix->len_params.cap) throw std::length_error("read longer than 60000 bases (documented limit)");
     CK(cudaMemcpy(ix->len_params.p, ix->h_len_params.data(), ix->h_len_params.size() * sizeof(LenParam), cudaMemcpyHostToDevice));
     ix->lp_threshold = t; ix->lp_min = lo; ix->lp_max = hi;
 }
@@ -501,55 +522,57 @@ void push_weights_to_device(grootgpu_index* ix) {
 //   project_begin   per-mapping item counts + their exclusive scan (no host round trip)
 //   project_finish  item total -> host, expand, stable sort by node, one ordered f64 chain per node
 // The caller runs the record emit on the main stream between the two.
-ProjectArgs project_args(grootgpu_index* ix, const uint32_t* d_off, uint32_t n) {
+ProjectArgs project_args(grootgpu_index* ix, Workspace* w, const uint32_t* d_off, uint32_t n) {
     ProjectArgs pa{};
-    pa.off = d_off; pa.hits = ix->hits.as<uint32_t>(); pa.hit_read = ix->hit_read.as<uint32_t>(); pa.pairs = ix->pairs.as<PairOut>();
-    pa.n_segs_ptr = ix->scalars.as<uint32_t>(); pa.n_hits_ptr = ix->hit_off.as<uint32_t>() + n;
-    pa.cn_count = ix->d_cn_count; pa.cn_ratio = ix->d_cn_ratio; pa.item_cnt = ix->item_cnt.as<uint32_t>(); pa.item_off = ix->item_off.as<uint32_t>();
+    pa.off = d_off; pa.hits = w->hits.as<uint32_t>(); pa.hit_read = w->hit_read.as<uint32_t>(); pa.pairs = w->pairs.as<PairOut>();
+    pa.n_segs_ptr = w->scalars.as<uint32_t>(); pa.n_hits_ptr = w->hit_off.as<uint32_t>() + n;
+    pa.cn_count = ix->d_cn_count; pa.cn_ratio = ix->d_cn_ratio; pa.item_cnt = w->item_cnt.as<uint32_t>(); pa.item_off = w->item_off.as<uint32_t>();
     pa.kmer_total = ix->d_kmer_total; pa.k = ix->h.p.k;
     return pa;
 }
 template <class KB, class KE>
-void project_begin(grootgpu_index* ix, const uint32_t* d_off, uint32_t n, uint32_t n_segs, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
+void project_begin(grootgpu_index* ix, Workspace* w, const uint32_t* d_off, uint32_t n, uint32_t n_segs, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
     push_weights_to_device(ix);
-    ix->item_cnt.need(4ull * H); ix->item_off.need(4ull * (H + 1));
-    ProjectArgs pa = project_args(ix, d_off, n);
+    w->item_cnt.need(4ull * H); w->item_off.need(4ull * (H + 1));
+    ProjectArgs pa = project_args(ix, w, d_off, n);
     const int blocks = std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8));
     kbegin(6); project_count_kernel<<<blocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
     size_t tmp = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(H), st);
-    ix->cub_tmp2.need(tmp + 16);
-    cub::DeviceScan::ExclusiveSum(ix->cub_tmp2.p, tmp, pa.item_cnt, ix->item_off.as<uint32_t>(), static_cast<int>(H), st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, pa.item_cnt, w->item_off.as<uint32_t>(), static_cast<int>(H), st);
+    w->cub_tmp2.need(tmp + 16);
+    cub::DeviceScan::ExclusiveSum(w->cub_tmp2.p, tmp, pa.item_cnt, w->item_off.as<uint32_t>(), static_cast<int>(H), st);
 }
 template <class KB, class KE>
-void project_finish(grootgpu_index* ix, const uint32_t* d_off, uint32_t n, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
-    ProjectArgs pa = project_args(ix, d_off, n);
-    const uint32_t* pk = peek(ix, st, {ix->item_off.as<uint32_t>() + (H - 1), ix->item_cnt.as<uint32_t>() + (H - 1)}, 1);
+void project_finish(grootgpu_index* ix, Workspace* w, const uint32_t* d_off, uint32_t n, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
+    ProjectArgs pa = project_args(ix, w, d_off, n);
+    const uint32_t* pk = peek(w, st, {w->item_off.as<uint32_t>() + (H - 1), w->item_cnt.as<uint32_t>() + (H - 1)}, 1);
     const uint64_t n_items = static_cast<uint64_t>(pk[0]) + pk[1];
     if (n_items == 0) return;
     if (n_items >= (1ull << 31)) throw std::length_error("too many weight increments in one batch: use smaller batches");
-    ix->pkeys.need(4 * n_items); ix->pkeys2.need(4 * n_items); ix->pvals.need(8 * n_items); ix->pvals2.need(8 * n_items);
-    pa.keys = ix->pkeys.as<uint32_t>(); pa.vals = ix->pvals.as<double>();
+    w->pkeys.need(4 * n_items); w->pkeys2.need(4 * n_items); w->pvals.need(8 * n_items); w->pvals2.need(8 * n_items);
+    pa.keys = w->pkeys.as<uint32_t>(); pa.vals = w->pvals.as<double>();
     const int eblocks = std::max(1, std::min<int>((H + 255) / 256, sms * 8));
     kbegin(6); project_expand_kernel<<<eblocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
     int end_bit = 1;
     while ((1ull << end_bit) < ix->h.nodes.size()) end_bit++;
     size_t sort_tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, ix->pkeys.as<uint32_t>(), ix->pkeys2.as<uint32_t>(), ix->pvals.as<double>(), ix->pvals2.as<double>(),
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, w->pkeys.as<uint32_t>(), w->pkeys2.as<uint32_t>(), w->pvals.as<double>(), w->pvals2.as<double>(),
                                     static_cast<int>(n_items), 0, end_bit, st);
-    ix->cub_tmp2.need(sort_tmp + 16);
-    cub::DeviceRadixSort::SortPairs(ix->cub_tmp2.p, sort_tmp, ix->pkeys.as<uint32_t>(), ix->pkeys2.as<uint32_t>(), ix->pvals.as<double>(), ix->pvals2.as<double>(),
+    w->cub_tmp2.need(sort_tmp + 16);
+    cub::DeviceRadixSort::SortPairs(w->cub_tmp2.p, sort_tmp, w->pkeys.as<uint32_t>(), w->pkeys2.as<uint32_t>(), w->pvals.as<double>(), w->pvals2.as<double>(),
                                     static_cast<int>(n_items), 0, end_bit, st);
     const uint32_t n32 = static_cast<uint32_t>(n_items);
-    poke(st, {{ix->item_off.as<uint32_t>() + H, n32}});
+    poke(st, {{w->item_off.as<uint32_t>() + H, n32}});
     const uint32_t n_nodes = static_cast<uint32_t>(ix->h.nodes.size());
     const int ablocks = std::max(1, std::min<int>(static_cast<int>((n_nodes + 7) / 8), sms * 8));
-    kbegin(6); project_accumulate_kernel<<<ablocks, 256, 0, st>>>(ix->pkeys2.as<uint32_t>(), ix->pvals2.as<double>(), ix->item_off.as<uint32_t>() + H, n_nodes, ix->d_kmer_freq); launches++; kend();
+    if (w->acc_before) w->acc_before(st);   // the previous chunk's chains (other lane) come first
+    kbegin(6); project_accumulate_kernel<<<ablocks, 256, 0, st>>>(w->pkeys2.as<uint32_t>(), w->pvals2.as<double>(), w->item_off.as<uint32_t>() + H, n_nodes, ix->d_kmer_freq); launches++; kend();
     CK(cudaGetLastError());
+    if (w->acc_after) w->acc_after(st);
 }
 
 // The batch pipeline on the device. d_seq / d_off already resident.
-void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, uint32_t n, uint32_t min_len, uint32_t max_len,
+void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uint32_t* d_off, uint32_t n, uint32_t min_len, uint32_t max_len,
                const grootgpu_align_params* prm, cudaStream_t st, grootgpu_batch_result* out) {
     const bool copy_back = out && !prm->results_on_device;
     const FlatIndex& h = ix->h;
@@ -559,30 +582,30 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
     prepare_params(ix, std::max(min_len, 1u), max_len, prm->containment_threshold);
     const int sms = g_num_sms(ix->device);
     uint32_t launches = 0;
-    ix->kev_n = 0;
-    auto kbegin = [&](int cat) { if (ix->kev_n < 32) { ix->kev_cat[ix->kev_n] = cat; cudaEventRecord(ix->kev[2 * ix->kev_n], st); } };
-    auto kend = [&]() { if (ix->kev_n < 32) { cudaEventRecord(ix->kev[2 * ix->kev_n + 1], st); ix->kev_n++; } };
-    cudaStream_t st2 = ix->st_side;
-    auto kbegin2 = [&](int cat) { if (ix->kev_n < 32) { ix->kev_cat[ix->kev_n] = cat; cudaEventRecord(ix->kev[2 * ix->kev_n], st2); } };
-    auto kend2 = [&]() { if (ix->kev_n < 32) { cudaEventRecord(ix->kev[2 * ix->kev_n + 1], st2); ix->kev_n++; } };
+    w->kev_n = 0;
+    auto kbegin = [&](int cat) { if (w->kev_n < 32) { w->kev_cat[w->kev_n] = cat; cudaEventRecord(w->kev[2 * w->kev_n], st); } };
+    auto kend = [&]() { if (w->kev_n < 32) { cudaEventRecord(w->kev[2 * w->kev_n + 1], st); w->kev_n++; } };
+    cudaStream_t st2 = w->st_side;
+    auto kbegin2 = [&](int cat) { if (w->kev_n < 32) { w->kev_cat[w->kev_n] = cat; cudaEventRecord(w->kev[2 * w->kev_n], st2); } };
+    auto kend2 = [&]() { if (w->kev_n < 32) { cudaEventRecord(w->kev[2 * w->kev_n + 1], st2); w->kev_n++; } };
     const bool project = prm->project_on_device != 0;
     CK(cudaStreamSynchronize(st2));   // idle unless a previous batch failed between fork and join
 
-    ix->n_hits.need(4ull * n); ix->hit_off.need(4ull * (n + 1)); ix->stage.need(4ull * HSTAGE * n);
-    ix->scalars.need(64); ix->tile_counter.need(16); ix->error.need(16);
+    w->n_hits.need(4ull * n); w->hit_off.need(4ull * (n + 1)); w->stage.need(4ull * HSTAGE * n);
+    w->scalars.need(64); w->tile_counter.need(16); w->error.need(16);
     // scalars: [0]=n_segs (u32), counters as u64 at +8: [0]=mapped,[1]=multimapped,[2]=records
-    ix->qcount.need(64);
-    zero_words(st, {{ix->scalars.p, 16}, {ix->tile_counter.p, 4}, {ix->error.p, 4}, {ix->qcount.p, 16}});
-    uint32_t* d_nsegs = ix->scalars.as<uint32_t>();
-    unsigned long long* d_counters = reinterpret_cast<unsigned long long*>(ix->scalars.as<uint8_t>() + 8);
+    w->qcount.need(64);
+    zero_words(st, {{w->scalars.p, 16}, {w->tile_counter.p, 4}, {w->error.p, 4}, {w->qcount.p, 16}});
+    uint32_t* d_nsegs = w->scalars.as<uint32_t>();
+    unsigned long long* d_counters = reinterpret_cast<unsigned long long*>(w->scalars.as<uint8_t>() + 8);
     uint64_t* d_sk = nullptr;
-    if (prm->keep_sketches) { ix->sketches.need(8ull * S * n); d_sk = ix->sketches.as<uint64_t>(); }
+    if (prm->keep_sketches) { w->sketches.need(8ull * S * n); d_sk = w->sketches.as<uint64_t>(); }
 
     // ---- K1+K2: sketch + probe + verify ----
     SeedArgs sa{};
     sa.seq = d_seq; sa.off = d_off; sa.n_reads = n; sa.max_len = max_len; sa.len_params = ix->len_params.as<LenParam>();
-    sa.n_hits = ix->n_hits.as<uint32_t>(); sa.stage = ix->stage.as<uint32_t>(); sa.sketches_out = d_sk;
-    sa.tile_counter = ix->tile_counter.as<uint32_t>(); sa.error = ix->error.as<int>();
+    sa.n_hits = w->n_hits.as<uint32_t>(); sa.stage = w->stage.as<uint32_t>(); sa.sketches_out = d_sk;
+    sa.tile_counter = w->tile_counter.as<uint32_t>(); sa.error = w->error.as<int>();
     uint32_t tile_bytes = ((static_cast<uint32_t>(kTileReads) * max_len + 31u) & ~15u) + 16u;   // per warp, per buffer
     if (tile_bytes > 20 * 1024) tile_bytes = 0;  // very long reads: no staging, threads read global memory
     sa.tile_bytes = tile_bytes;
@@ -591,40 +614,40 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
     if (occ <= 0) throw std::runtime_error(std::string("unsupported sketch size (compiled: ") + kSupportedS + ")");
     const uint32_t n_tiles = (n + kTileReads - 1) / kTileReads;
     int seed_blocks = static_cast<int>(std::min<uint64_t>((n_tiles + kSeedThreads / 32 - 1) / (kSeedThreads / 32), static_cast<uint64_t>(sms) * occ));
-    CK(cudaEventRecord(ix->ev[0], st));
+    CK(cudaEventRecord(w->ev[0], st));
     kbegin(0); seed_dispatch(S, ix->d, sa, k, seed_smem, std::max(seed_blocks, 1), st); launches++; kend();
     CK(cudaGetLastError());
-    CK(cudaEventRecord(ix->ev[1], st));
+    CK(cudaEventRecord(w->ev[1], st));
 
     // ---- exclusive scan of per-read hit counts ----
     size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, ix->n_hits.as<uint32_t>(), ix->hit_off.as<uint32_t>(), static_cast<int>(n), st);
-    ix->cub_tmp.need(tmp_bytes + 16);
-    cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, tmp_bytes, ix->n_hits.as<uint32_t>(), ix->hit_off.as<uint32_t>(), static_cast<int>(n), st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, w->n_hits.as<uint32_t>(), w->hit_off.as<uint32_t>(), static_cast<int>(n), st);
+    w->cub_tmp.need(tmp_bytes + 16);
+    cub::DeviceScan::ExclusiveSum(w->cub_tmp.p, tmp_bytes, w->n_hits.as<uint32_t>(), w->hit_off.as<uint32_t>(), static_cast<int>(n), st);
     uint32_t H = 0;
     {
-        const uint32_t* pk = peek(ix, st, {ix->hit_off.as<uint32_t>() + (n - 1), ix->n_hits.as<uint32_t>() + (n - 1),
-                                           ix->error.as<uint32_t>(), ix->error.as<uint32_t>() + 1});
+        const uint32_t* pk = peek(w, st, {w->hit_off.as<uint32_t>() + (n - 1), w->n_hits.as<uint32_t>() + (n - 1),
+                                           w->error.as<uint32_t>(), w->error.as<uint32_t>() + 1});
         const int err0 = static_cast<int>(pk[2]), err1 = static_cast<int>(pk[3]);
         if (err0 == GROOTGPU_ERR_SHORT_READ) throw std::invalid_argument("read " + std::to_string(err1) + " is shorter than k (the reference panics at boss.go:164-166)");
         if (err0 != 0) throw std::length_error("read " + std::to_string(err1) + " exceeds the declared maximum length");
         H = pk[0] + pk[1];
     }
-    poke(st, {{ix->hit_off.as<uint32_t>() + n, H}});
+    poke(st, {{w->hit_off.as<uint32_t>() + n, H}});
 
     uint32_t n_segs = 0;
     uint64_t R = 0;
     if (H > 0) {
-        ix->hits.need(4ull * H); ix->hit_read.need(4ull * H); ix->seg_flag.need(H); ix->seg_begin.need(4ull * H);
+        w->hits.need(4ull * H); w->hit_read.need(4ull * H); w->seg_flag.need(H); w->seg_begin.need(4ull * H);
         FillArgs fa{};
-        fa.seq = d_seq; fa.off = d_off; fa.n_reads = n; fa.len_params = ix->len_params.as<LenParam>(); fa.n_hits = ix->n_hits.as<uint32_t>();
-        fa.hit_off = ix->hit_off.as<uint32_t>(); fa.stage = ix->stage.as<uint32_t>(); fa.hits = ix->hits.as<uint32_t>();
-        fa.hit_read = ix->hit_read.as<uint32_t>(); fa.seg_flag = ix->seg_flag.as<uint8_t>(); fa.counters = d_counters;
+        fa.seq = d_seq; fa.off = d_off; fa.n_reads = n; fa.len_params = ix->len_params.as<LenParam>(); fa.n_hits = w->n_hits.as<uint32_t>();
+        fa.hit_off = w->hit_off.as<uint32_t>(); fa.stage = w->stage.as<uint32_t>(); fa.hits = w->hits.as<uint32_t>();
+        fa.hit_read = w->hit_read.as<uint32_t>(); fa.seg_flag = w->seg_flag.as<uint8_t>(); fa.counters = d_counters;
         // 2-bit copies of the seeded reads (both orientations) for the packed walk; reads longer than 256 bases go byte-wise
         uint32_t nw32 = 0;   // words of 16 bases per orientation: 8 (<= 128 bases) .. 64 (<= 1024); longer reads go byte-wise
         if (!prm->no_align && max_len <= 1024) { nw32 = 8; while (nw32 * 16u < max_len) nw32 *= 2; }
-        if (nw32) { ix->reads2.need(8ull * nw32 * n + 64); ix->read_ok2.need(n); }
-        fa.reads2 = ix->reads2.as<uint32_t>(); fa.read_ok2 = ix->read_ok2.as<uint8_t>(); fa.nw32 = nw32;
+        if (nw32) { w->reads2.need(8ull * nw32 * n + 64); w->read_ok2.need(n); }
+        fa.reads2 = w->reads2.as<uint32_t>(); fa.read_ok2 = w->read_ok2.as<uint8_t>(); fa.nw32 = nw32;
         int fill_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
         kbegin(1); fill_dispatch(S, ix->d, fa, k, fill_blocks, st); launches += 2;
         if (nw32) { pack_reads_kernel<<<std::max(1, std::min<int>((n + 31) / 32, sms * 8)), 256, 0, st>>>(fa); launches++; }
@@ -633,35 +656,35 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         // ---- (read, graph) segment starts ----
         thrust::counting_iterator<uint32_t> counting(0);
         size_t sel_bytes = 0;
-        cub::DeviceSelect::Flagged(nullptr, sel_bytes, counting, ix->seg_flag.as<uint8_t>(), ix->seg_begin.as<uint32_t>(), d_nsegs, static_cast<int>(H), st);
-        ix->cub_tmp.need(sel_bytes + 16);
-        cub::DeviceSelect::Flagged(ix->cub_tmp.p, sel_bytes, counting, ix->seg_flag.as<uint8_t>(), ix->seg_begin.as<uint32_t>(), d_nsegs, static_cast<int>(H), st);
-        n_segs = peek(ix, st, {d_nsegs})[0];
+        cub::DeviceSelect::Flagged(nullptr, sel_bytes, counting, w->seg_flag.as<uint8_t>(), w->seg_begin.as<uint32_t>(), d_nsegs, static_cast<int>(H), st);
+        w->cub_tmp.need(sel_bytes + 16);
+        cub::DeviceSelect::Flagged(w->cub_tmp.p, sel_bytes, counting, w->seg_flag.as<uint8_t>(), w->seg_begin.as<uint32_t>(), d_nsegs, static_cast<int>(H), st);
+        n_segs = peek(w, st, {d_nsegs})[0];
 
         // ---- K3: align (thread per pair) -> scan -> emit ----
-        ix->pairs.need(sizeof(PairOut) * static_cast<size_t>(n_segs)); ix->seg_nrec.need(4ull * n_segs); ix->seg_locus.need(8ull * n_segs);
-        ix->rec_off.need(4ull * (n_segs + 1)); ix->seg_ntrav.need(4ull * n_segs);
-        ix->seg_mask.need(4ull * kMaskWordsInline * n_segs);
+        w->pairs.need(sizeof(PairOut) * static_cast<size_t>(n_segs)); w->seg_nrec.need(4ull * n_segs); w->seg_locus.need(8ull * n_segs);
+        w->rec_off.need(4ull * (n_segs + 1)); w->seg_ntrav.need(4ull * n_segs);
+        w->seg_mask.need(4ull * kMaskWordsInline * n_segs);
         const int vthreads = 128;
         int verify_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + vthreads - 1) / vthreads, static_cast<uint64_t>(sms) * 8));
         verify_blocks = std::max(verify_blocks, 1);
-        ix->stack_ws.need(static_cast<size_t>(verify_blocks) * vthreads * (max_len + 2) * sizeof(DfsFrame));
-        ix->mask_ws.need(static_cast<size_t>(verify_blocks) * vthreads * (max_len + 2) * kMaskWordsInline * 4);
+        w->stack_ws.need(static_cast<size_t>(verify_blocks) * vthreads * (max_len + 2) * sizeof(DfsFrame));
+        w->mask_ws.need(static_cast<size_t>(verify_blocks) * vthreads * (max_len + 2) * kMaskWordsInline * 4);
         AlignArgs aa{};
-        aa.seq = d_seq; aa.off = d_off; aa.hits = ix->hits.as<uint32_t>(); aa.hit_read = ix->hit_read.as<uint32_t>();
-        aa.seg_begin = ix->seg_begin.as<uint32_t>(); aa.n_segs_ptr = d_nsegs; aa.n_hits_ptr = ix->hit_off.as<uint32_t>() + n;
-        aa.pairs = ix->pairs.as<PairOut>(); aa.seg_nrec = ix->seg_nrec.as<uint32_t>(); aa.seg_locus = ix->seg_locus.as<uint2>();
-        aa.seg_mask = ix->seg_mask.as<uint32_t>(); aa.seg_ntrav = ix->seg_ntrav.as<uint32_t>();
-        aa.stack_ws = ix->stack_ws.as<DfsFrame>(); aa.mask_ws = ix->mask_ws.as<uint32_t>();
-        aa.max_len = max_len; aa.no_align = prm->no_align; aa.error = ix->error.as<int>();
+        aa.seq = d_seq; aa.off = d_off; aa.hits = w->hits.as<uint32_t>(); aa.hit_read = w->hit_read.as<uint32_t>();
+        aa.seg_begin = w->seg_begin.as<uint32_t>(); aa.n_segs_ptr = d_nsegs; aa.n_hits_ptr = w->hit_off.as<uint32_t>() + n;
+        aa.pairs = w->pairs.as<PairOut>(); aa.seg_nrec = w->seg_nrec.as<uint32_t>(); aa.seg_locus = w->seg_locus.as<uint2>();
+        aa.seg_mask = w->seg_mask.as<uint32_t>(); aa.seg_ntrav = w->seg_ntrav.as<uint32_t>();
+        aa.stack_ws = w->stack_ws.as<DfsFrame>(); aa.mask_ws = w->mask_ws.as<uint32_t>();
+        aa.max_len = max_len; aa.no_align = prm->no_align; aa.error = w->error.as<int>();
         aa.counters = d_counters;
-        aa.reads2 = ix->reads2.as<uint32_t>(); aa.read_ok2 = ix->read_ok2.as<uint8_t>(); aa.nw32 = nw32;
+        aa.reads2 = w->reads2.as<uint32_t>(); aa.read_ok2 = w->read_ok2.as<uint8_t>(); aa.nw32 = nw32;
         // screen/walk rounds over a shrinking, compacted queue; the queue counts stay on the device
-        ix->cursor.need(8ull * n_segs); ix->cand.need(8ull * n_segs); ix->queue_a.need(4ull * n_segs); ix->queue_b.need(4ull * n_segs);
-        uint32_t* qc = ix->qcount.as<uint32_t>();
-        CK(cudaEventRecord(ix->ev[2], st));
-        ix->qkey.need(4ull * n_segs); ix->qkey2.need(4ull * n_segs); ix->order.need(4ull * n_segs); ix->slow_q.need(4ull * n_segs);
-        kbegin(2); align_init_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ix->d, aa, ix->cursor.as<PairCursor>(), ix->queue_b.as<uint32_t>(), ix->qkey.as<uint32_t>(), qc); launches++; kend();
+        w->cursor.need(8ull * n_segs); w->cand.need(8ull * n_segs); w->queue_a.need(4ull * n_segs); w->queue_b.need(4ull * n_segs);
+        uint32_t* qc = w->qcount.as<uint32_t>();
+        CK(cudaEventRecord(w->ev[2], st));
+        w->qkey.need(4ull * n_segs); w->qkey2.need(4ull * n_segs); w->order.need(4ull * n_segs); w->slow_q.need(4ull * n_segs);
+        kbegin(2); align_init_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ix->d, aa, w->cursor.as<PairCursor>(), w->queue_b.as<uint32_t>(), w->qkey.as<uint32_t>(), qc); launches++; kend();
         CK(cudaGetLastError());
         {   // pair order by window id: the 32 pairs a warp walks together sit on the same graph region (same nodes, same
             // branch pattern), instead of 32 unrelated walks of very different lengths idling on each other. The order
@@ -669,21 +692,21 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
             int wbits = 1;
             while ((1ull << wbits) < ix->h.wins.size()) wbits++;
             size_t qs = 0;
-            cub::DeviceRadixSort::SortPairs(nullptr, qs, ix->qkey.as<uint32_t>(), ix->qkey2.as<uint32_t>(), ix->queue_b.as<uint32_t>(), ix->order.as<uint32_t>(),
+            cub::DeviceRadixSort::SortPairs(nullptr, qs, w->qkey.as<uint32_t>(), w->qkey2.as<uint32_t>(), w->queue_b.as<uint32_t>(), w->order.as<uint32_t>(),
                                             static_cast<int>(n_segs), 0, wbits, st);
-            ix->cub_tmp.need(qs + 16);
-            cub::DeviceRadixSort::SortPairs(ix->cub_tmp.p, qs, ix->qkey.as<uint32_t>(), ix->qkey2.as<uint32_t>(), ix->queue_b.as<uint32_t>(), ix->order.as<uint32_t>(),
+            w->cub_tmp.need(qs + 16);
+            cub::DeviceRadixSort::SortPairs(w->cub_tmp.p, qs, w->qkey.as<uint32_t>(), w->qkey2.as<uint32_t>(), w->queue_b.as<uint32_t>(), w->order.as<uint32_t>(),
                                             static_cast<int>(n_segs), 0, wbits, st);
         }
         int screen_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8));
         screen_blocks = std::max(screen_blocks, 1);
         const int kRounds = 2;   // later rounds hold a handful of stragglers: align_finish_kernel takes them in one launch
         RoundArgs ra{};
-        ra.a = aa; ra.cursor = ix->cursor.as<PairCursor>(); ra.cand = ix->cand.as<uint2>();
-        ra.slow_queue = ix->slow_q.as<uint32_t>(); ra.n_slow = qc + 3;
+        ra.a = aa; ra.cursor = w->cursor.as<PairCursor>(); ra.cand = w->cand.as<uint2>();
+        ra.slow_queue = w->slow_q.as<uint32_t>(); ra.n_slow = qc + 3;
         for (int round = 0; round < kRounds; round++) {
-            uint32_t* qa = round == 0 ? ix->order.as<uint32_t>() : (round & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
-            uint32_t* qb = (round & 1) ? ix->queue_a.as<uint32_t>() : ix->queue_b.as<uint32_t>();
+            uint32_t* qa = round == 0 ? w->order.as<uint32_t>() : (round & 1) ? w->queue_b.as<uint32_t>() : w->queue_a.as<uint32_t>();
+            uint32_t* qb = (round & 1) ? w->queue_a.as<uint32_t>() : w->queue_b.as<uint32_t>();
             ra.queue = qa; ra.queue_next = qb; ra.n_queue = qc + (round & 1); ra.n_queue_next = qc + ((round + 1) & 1);
             kbegin(2); align_screen_kernel<<<screen_blocks, 256, 0, st>>>(ix->d, ra); launches++; kend();
             kbegin(3); align_walk_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++; kend();
@@ -691,42 +714,42 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
             poke(st, {{qc + (round & 1), 0u}});   // this round's count becomes the next round's "next"
         }
         {
-            uint32_t* qa = (kRounds & 1) ? ix->queue_b.as<uint32_t>() : ix->queue_a.as<uint32_t>();
+            uint32_t* qa = (kRounds & 1) ? w->queue_b.as<uint32_t>() : w->queue_a.as<uint32_t>();
             ra.queue = qa; ra.queue_next = nullptr; ra.n_queue = qc + (kRounds & 1); ra.n_queue_next = nullptr;
             kbegin(4); align_finish_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++; kend();
-            ra.queue = ix->slow_q.as<uint32_t>(); ra.n_queue = qc + 3;        // pairs the packed walk could not take
+            ra.queue = w->slow_q.as<uint32_t>(); ra.n_queue = qc + 3;        // pairs the packed walk could not take
             kbegin(4); align_finish_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ra); launches++; kend();
             CK(cudaGetLastError());
         }
-        CK(cudaEventRecord(ix->ev[3], st));
+        CK(cudaEventRecord(w->ev[3], st));
         // ---- a10: the ordered graph weighting starts on the side stream; it needs the pairs, not their records ----
         if (project) {
-            CK(cudaEventRecord(ix->ev_fork, st));
-            CK(cudaStreamWaitEvent(st2, ix->ev_fork, 0));
-            project_begin(ix, d_off, n, n_segs, H, sms, st2, kbegin2, kend2, launches);
+            CK(cudaEventRecord(w->ev_fork, st));
+            CK(cudaStreamWaitEvent(st2, w->ev_fork, 0));
+            project_begin(ix, w, d_off, n, n_segs, H, sms, st2, kbegin2, kend2, launches);
         }
         // ---- scan record counts, emit ----
         size_t scan2 = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, scan2, ix->seg_nrec.as<uint32_t>(), ix->rec_off.as<uint32_t>(), static_cast<int>(n_segs), st);
-        ix->cub_tmp.need(scan2 + 16);
-        cub::DeviceScan::ExclusiveSum(ix->cub_tmp.p, scan2, ix->seg_nrec.as<uint32_t>(), ix->rec_off.as<uint32_t>(), static_cast<int>(n_segs), st);
+        cub::DeviceScan::ExclusiveSum(nullptr, scan2, w->seg_nrec.as<uint32_t>(), w->rec_off.as<uint32_t>(), static_cast<int>(n_segs), st);
+        w->cub_tmp.need(scan2 + 16);
+        cub::DeviceScan::ExclusiveSum(w->cub_tmp.p, scan2, w->seg_nrec.as<uint32_t>(), w->rec_off.as<uint32_t>(), static_cast<int>(n_segs), st);
         uint32_t lo = 0, lc = 0;
         {
-            const uint32_t* pk = peek(ix, st, {ix->rec_off.as<uint32_t>() + (n_segs - 1), ix->seg_nrec.as<uint32_t>() + (n_segs - 1),
-                                               ix->error.as<uint32_t>(), ix->error.as<uint32_t>() + 1});
+            const uint32_t* pk = peek(w, st, {w->rec_off.as<uint32_t>() + (n_segs - 1), w->seg_nrec.as<uint32_t>() + (n_segs - 1),
+                                               w->error.as<uint32_t>(), w->error.as<uint32_t>() + 1});
             lo = pk[0]; lc = pk[1];
             if (static_cast<int>(pk[2]) == GROOTGPU_ERR_BAD_BASE) throw std::domain_error("read " + std::to_string(static_cast<int>(pk[3])) + " holds a base > 'T' and had to be reverse complemented (the reference panics at seqio.go:122)");
         }
         R = static_cast<uint64_t>(lo) + lc;
-        ix->rec_path.need(4ull * std::max<uint64_t>(R, 1)); ix->rec_pos.need(4ull * std::max<uint64_t>(R, 1));
+        w->rec_path.need(4ull * std::max<uint64_t>(R, 1)); w->rec_pos.need(4ull * std::max<uint64_t>(R, 1));
         EmitArgs ea{};
-        ea.seq = d_seq; ea.off = d_off; ea.n_segs_ptr = d_nsegs; ea.pairs = ix->pairs.as<PairOut>(); ea.rec_off = ix->rec_off.as<uint32_t>();
-        ea.seg_locus = ix->seg_locus.as<uint2>(); ea.seg_mask = ix->seg_mask.as<uint32_t>(); ea.seg_ntrav = ix->seg_ntrav.as<uint32_t>();
-        ea.rec_path = ix->rec_path.as<uint32_t>(); ea.rec_pos = ix->rec_pos.as<int32_t>();
-        ea.stack_ws = ix->stack_ws.as<DfsFrame>(); ea.mask_ws = ix->mask_ws.as<uint32_t>(); ea.max_len = max_len;
-        ea.reads2 = ix->reads2.as<uint32_t>(); ea.read_ok2 = ix->read_ok2.as<uint8_t>(); ea.nw32 = nw32;
-        ea.multi_queue = ix->queue_a.as<uint32_t>(); ea.n_multi = qc + 2;      // the align queues are free by now
-        ea.order = prm->no_align ? nullptr : ix->order.as<uint32_t>();
+        ea.seq = d_seq; ea.off = d_off; ea.n_segs_ptr = d_nsegs; ea.pairs = w->pairs.as<PairOut>(); ea.rec_off = w->rec_off.as<uint32_t>();
+        ea.seg_locus = w->seg_locus.as<uint2>(); ea.seg_mask = w->seg_mask.as<uint32_t>(); ea.seg_ntrav = w->seg_ntrav.as<uint32_t>();
+        ea.rec_path = w->rec_path.as<uint32_t>(); ea.rec_pos = w->rec_pos.as<int32_t>();
+        ea.stack_ws = w->stack_ws.as<DfsFrame>(); ea.mask_ws = w->mask_ws.as<uint32_t>(); ea.max_len = max_len;
+        ea.reads2 = w->reads2.as<uint32_t>(); ea.read_ok2 = w->read_ok2.as<uint8_t>(); ea.nw32 = nw32;
+        ea.multi_queue = w->queue_a.as<uint32_t>(); ea.n_multi = qc + 2;      // the align queues are free by now
+        ea.order = prm->no_align ? nullptr : w->order.as<uint32_t>();
         {
             poke(st, {{qc + 2, 0u}});
             const int emit_blocks = std::max(1, static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8)));
@@ -737,34 +760,34 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         }
         CK(cudaGetLastError());
         if (project) {
-            project_finish(ix, d_off, n, H, sms, st2, kbegin2, kend2, launches);
-            CK(cudaEventRecord(ix->ev_join, st2));
-            CK(cudaStreamWaitEvent(st, ix->ev_join, 0));
+            project_finish(ix, w, d_off, n, H, sms, st2, kbegin2, kend2, launches);
+            CK(cudaEventRecord(w->ev_join, st2));
+            CK(cudaStreamWaitEvent(st, w->ev_join, 0));
         }
     } else {
-        CK(cudaEventRecord(ix->ev[2], st));
-        CK(cudaEventRecord(ix->ev[3], st));
+        CK(cudaEventRecord(w->ev[2], st));
+        CK(cudaEventRecord(w->ev[3], st));
     }
-    CK(cudaEventRecord(ix->ev[4], st));
+    CK(cudaEventRecord(w->ev[4], st));
 
     // ---- results ----
     unsigned long long counters[4] = {0, 0, 0, 0};
     if (copy_back) {
         ix->r_hit_off.need(4ull * (n + 1)); ix->r_hits.need(4ull * std::max<uint32_t>(H, 1)); ix->r_pairs.need(sizeof(PairOut) * std::max<size_t>(n_segs, 1));
         ix->r_rec_path.need(4ull * std::max<uint64_t>(R, 1)); ix->r_rec_pos.need(4ull * std::max<uint64_t>(R, 1));
-        CK(cudaMemcpyAsync(ix->r_hit_off.p, ix->hit_off.p, 4ull * (n + 1), cudaMemcpyDeviceToHost, st));
-        if (H) CK(cudaMemcpyAsync(ix->r_hits.p, ix->hits.p, 4ull * H, cudaMemcpyDeviceToHost, st));
-        if (n_segs) CK(cudaMemcpyAsync(ix->r_pairs.p, ix->pairs.p, sizeof(PairOut) * static_cast<size_t>(n_segs), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ix->r_hit_off.p, w->hit_off.p, 4ull * (n + 1), cudaMemcpyDeviceToHost, st));
+        if (H) CK(cudaMemcpyAsync(ix->r_hits.p, w->hits.p, 4ull * H, cudaMemcpyDeviceToHost, st));
+        if (n_segs) CK(cudaMemcpyAsync(ix->r_pairs.p, w->pairs.p, sizeof(PairOut) * static_cast<size_t>(n_segs), cudaMemcpyDeviceToHost, st));
         if (R) {
-            CK(cudaMemcpyAsync(ix->r_rec_path.p, ix->rec_path.p, 4ull * R, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ix->r_rec_pos.p, ix->rec_pos.p, 4ull * R, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ix->r_rec_path.p, w->rec_path.p, 4ull * R, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ix->r_rec_pos.p, w->rec_pos.p, 4ull * R, cudaMemcpyDeviceToHost, st));
         }
-        if (prm->keep_sketches) { ix->r_sketches.need(8ull * S * n); CK(cudaMemcpyAsync(ix->r_sketches.p, ix->sketches.p, 8ull * S * n, cudaMemcpyDeviceToHost, st)); }
+        if (prm->keep_sketches) { ix->r_sketches.need(8ull * S * n); CK(cudaMemcpyAsync(ix->r_sketches.p, w->sketches.p, 8ull * S * n, cudaMemcpyDeviceToHost, st)); }
     }
-    CK(cudaEventRecord(ix->ev[5], st));
+    CK(cudaEventRecord(w->ev[5], st));
     {
         const uint32_t* c32 = reinterpret_cast<const uint32_t*>(d_counters);
-        const uint32_t* pk = peek(ix, st, {c32, c32 + 1, c32 + 2, c32 + 3, c32 + 4, c32 + 5, c32 + 6, c32 + 7});   // synchronises the stream
+        const uint32_t* pk = peek(w, st, {c32, c32 + 1, c32 + 2, c32 + 3, c32 + 4, c32 + 5, c32 + 6, c32 + 7});   // synchronises the stream
         for (int i = 0; i < 4; i++) counters[i] = static_cast<unsigned long long>(pk[2 * i]) | (static_cast<unsigned long long>(pk[2 * i + 1]) << 32);
     }
     if (out) {
@@ -778,17 +801,17 @@ void run_batch(grootgpu_index* ix, const uint8_t* d_seq, const uint32_t* d_off, 
         }
         out->received = n; out->mapped = counters[0]; out->multimapped = counters[1]; out->alignments = R;
         float seed_ms = 0, align_ms = 0, dev_ms = 0, all_ms = 0;
-        cudaEventElapsedTime(&seed_ms, ix->ev[0], ix->ev[1]);
-        cudaEventElapsedTime(&align_ms, ix->ev[2], ix->ev[3]);
-        cudaEventElapsedTime(&dev_ms, ix->ev[0], ix->ev[4]);
-        cudaEventElapsedTime(&all_ms, ix->ev[0], ix->ev[5]);
+        cudaEventElapsedTime(&seed_ms, w->ev[0], w->ev[1]);
+        cudaEventElapsedTime(&align_ms, w->ev[2], w->ev[3]);
+        cudaEventElapsedTime(&dev_ms, w->ev[0], w->ev[4]);
+        cudaEventElapsedTime(&all_ms, w->ev[0], w->ev[5]);
         out->ms[0] = all_ms; out->ms[1] = seed_ms; out->ms[2] = align_ms; out->ms[3] = dev_ms - seed_ms - align_ms;
         out->kernel_launches = launches;
-        for (int i = 0; i < ix->kev_n; i++) { float ms = 0; cudaEventElapsedTime(&ms, ix->kev[2 * i], ix->kev[2 * i + 1]); out->kernel_ms[ix->kev_cat[i]] += ms; }
+        for (int i = 0; i < w->kev_n; i++) { float ms = 0; cudaEventElapsedTime(&ms, w->kev[2 * i], w->kev[2 * i + 1]); out->kernel_ms[w->kev_cat[i]] += ms; }
         out->slow_path_pairs = counters[3];
-        out->d_hit_off = ix->hit_off.as<uint32_t>(); out->d_hits = ix->hits.as<uint32_t>();
-        out->d_pairs = reinterpret_cast<const grootgpu_pair*>(ix->pairs.p);
-        out->d_rec_path = ix->rec_path.as<uint32_t>(); out->d_rec_pos = ix->rec_pos.as<int32_t>();
+        out->d_hit_off = w->hit_off.as<uint32_t>(); out->d_hits = w->hits.as<uint32_t>();
+        out->d_pairs = reinterpret_cast<const grootgpu_pair*>(w->pairs.p);
+        out->d_rec_path = w->rec_path.as<uint32_t>(); out->d_rec_pos = w->rec_pos.as<int32_t>();
     }
 }
 
@@ -835,125 +858,209 @@ void grow_keep(HBuf& b, size_t need, size_t used, cudaStream_t drain) {
 uint32_t chunk_reads_setting() {   // reads per pipeline chunk; GROOTGPU_CHUNK_READS overrides (tests force many small chunks)
     const char* e = getenv("GROOTGPU_CHUNK_READS");
     const long x = e ? atol(e) : 0;
-    return static_cast<uint32_t>(x > 0 ? x : 2500000l);
+    return static_cast<uint32_t>(x > 0 ? x : 1600000l);
 }
 
-// Host buffers in, host results out, as a 3-stage pipeline over chunks of reads: while chunk i runs on the compute
-// stream, chunk i+1's bases and offsets are copied in (st_in) and chunk i-1's result arrays are copied out (st_out)
-// from the other set of result buffers, straight to their final place in the batch-wide host arrays. The chunks are
-// processed in read order on one stream, so the ordered graph weighting sees the same sequence as a single batch.
+// Host buffers in, host results out, as a pipeline over chunks of reads on TWO LANES (workspaces with their own
+// streams, each driven by its own host thread): chunk c runs on lane c & 1 while
+//   * the bases and offsets of the next chunks are copied in (st_in, up to two chunks ahead),
+//   * the result arrays of finished chunks are copied out (st_out) straight to their final place in the batch-wide
+//     host arrays, after a small kernel has rebased the chunk-local indices,
+//   * the other lane runs the neighbouring chunk: its kernels fill the GPU during this chunk's latency-bound tails
+//     (stragglers of the walk, the ordered f64 chains) and during the host round trips that size its buffers.
+// What stays ordered: chunk c's graph weighting chain runs after chunk c-1's (an event between the lanes' side
+// streams), and the batch-wide offsets of chunk c are fixed once chunk c-1 has published its totals — so every
+// output word and every f64 weight equals the single-batch result.
+struct ChunkShared {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::vector<uint64_t> hit_end, pair_end, rec_end;   // inclusive prefix sums, valid for chunks < published
+    uint32_t published = 0, inputs_issued = 0;
+    uint32_t acc_recorded = 0;   // chunks whose "weighting done" event has been recorded (or skipped), in chunk order
+    bool failed = false;
+    std::exception_ptr error;
+    grootgpu_batch_result total{};
+};
+
 void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* seq_off, uint32_t n, const grootgpu_align_params* prm,
                        grootgpu_batch_result* out) {
-    cudaStream_t st = ix->stream, st_in = ix->st_in, st_out = ix->st_out;
+    cudaStream_t st_in = ix->st_in, st_out = ix->st_out;
     const uint32_t S = ix->h.p.S;
-    // chunk boundaries: ~chunk_reads_setting() reads and always < 4 GiB of bases; the first and the last chunk are a
-    // quarter of that, because the first copy-in and the last copy-out are the two transfers nothing overlaps
+    // chunk boundaries (always < 4 GiB of bases per chunk). The copy-in link is only ~1.25x faster than the kernels,
+    // so the schedule starts with a small chunk (the first copy-in is a transfer nothing overlaps), grows by at most
+    // that factor per chunk up to chunk_reads_setting() — the next chunk's bases then arrive before the current one
+    // is done — and ends with a small chunk again (the last copy-out is the other exposed transfer).
     std::vector<uint32_t> cb{0};
     {
         const uint32_t target = chunk_reads_setting(), edge = std::max(1u, target / 4);
         const uint64_t max_bytes = (1ull << 32) - 4096;
+        uint32_t want = std::max(1u, target / 2);
         while (cb.back() < n) {
             const uint32_t r0 = cb.back(), left = n - r0;
-            uint32_t want = r0 == 0 ? edge : target;
-            if (left > edge && left - edge < want) want = left - edge;   // leave a last chunk of `edge` reads
-            uint32_t r1 = r0 + std::min(left, want);
+            uint32_t take = std::min(want, left);
+            if (left > edge && left - take < edge) take = left - edge;   // leave a last chunk of `edge` reads
+            uint32_t r1 = r0 + std::max(1u, take);
             while (r1 > r0 + 1 && seq_off[r1] - seq_off[r0] >= max_bytes) r1 = r0 + (r1 - r0) / 2;
             if (seq_off[r1] - seq_off[r0] >= max_bytes) throw std::length_error("a read of 4 GiB or more");
             cb.push_back(r1);
+            want = std::min<uint64_t>(target, static_cast<uint64_t>(want) + want / 4 + 1);
         }
     }
     const uint32_t C = static_cast<uint32_t>(cb.size()) - 1;
     struct Drain {   // nothing may still be copying from / into caller or handle memory when we leave, also on errors
         grootgpu_index* ix;
-        ~Drain() { cudaStreamSynchronize(ix->st_in); cudaStreamSynchronize(ix->stream); cudaStreamSynchronize(ix->st_out); }
+        ~Drain() {
+            cudaStreamSynchronize(ix->st_in);
+            for (Workspace& w : ix->ws) { cudaStreamSynchronize(w.stream); cudaStreamSynchronize(w.st_side); }
+            cudaStreamSynchronize(ix->st_out);
+        }
     } drain{ix};
-    auto issue_input = [&](uint32_t c) {
-        const uint32_t r0 = cb[c], nc = cb[c + 1] - r0, b = c & 1;
-        const uint64_t bytes = seq_off[cb[c + 1]] - seq_off[r0];
-        ix->in_seq[b].need(bytes + 64); ix->in_off64[b].need(8ull * (nc + 1)); ix->in_off32[b].need(4ull * (nc + 1));
-        CK(cudaMemcpyAsync(ix->in_seq[b].p, seq + seq_off[r0], bytes, cudaMemcpyHostToDevice, st_in));
-        CK(cudaMemsetAsync(ix->in_seq[b].as<uint8_t>() + bytes, 0, 64, st_in));
-        CK(cudaMemcpyAsync(ix->in_off64[b].p, seq_off + r0, 8ull * (nc + 1), cudaMemcpyHostToDevice, st_in));
-        CK(cudaEventRecord(ix->ev_in[b], st_in));
-    };
-    auto swap_buf = [](DBuf& x, DBuf& y) { std::swap(x.p, y.p); std::swap(x.cap, y.cap); };   // DBuf owns its pointer: swap fields, not objects
-    auto swap_result_sets = [&] {
-        swap_buf(ix->hits, ix->alt_hits); swap_buf(ix->pairs, ix->alt_pairs); swap_buf(ix->rec_path, ix->alt_rec_path);
-        swap_buf(ix->rec_pos, ix->alt_rec_pos); swap_buf(ix->hit_off, ix->alt_hit_off); swap_buf(ix->sketches, ix->alt_sketches);
-    };
-    ix->len_minmax.need(16);
     ix->r_hit_off.need(4ull * (static_cast<size_t>(n) + 1));
     if (prm->keep_sketches) ix->r_sketches.need(8ull * S * n);
+    if (prm->project_on_device) push_weights_to_device(ix);
     grootgpu_align_params cprm = *prm;
     cprm.results_on_device = 1;
-    uint64_t hit_base = 0, pair_base = 0, rec_base = 0;
-    grootgpu_batch_result total{};
+    ChunkShared sh;
+    sh.hit_end.assign(C, 0); sh.pair_end.assign(C, 0); sh.rec_end.assign(C, 0);
     const bool trace = getenv("GROOTGPU_TRACE") != nullptr;   // host-side timeline of the chunk pipeline on stderr
     const auto t_begin = std::chrono::steady_clock::now();
     auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
-    CK(cudaEventRecord(ix->ev_t0, st_in));
-    issue_input(0);
-    for (uint32_t c = 0; c < C; c++) {
-        const uint32_t r0 = cb[c], nc = cb[c + 1] - r0, b = c & 1;
-        const double t_c0 = now_ms();
-        if (c + 1 < C) issue_input(c + 1);      // its buffers were last read by chunk c-1, which has completed (run_batch returns synchronised)
-        CK(cudaStreamWaitEvent(st, ix->ev_in[b], 0));
-        poke(st, {{ix->len_minmax.as<uint32_t>(), 0xffffffffu}, {ix->len_minmax.as<uint32_t>() + 1, 0u}});
-        chunk_offsets_kernel<<<std::max(1u, std::min<uint32_t>((nc + 256) / 256, 1184u)), 256, 0, st>>>(ix->in_off64[b].as<uint64_t>(), nc, ix->in_off32[b].as<uint32_t>(),
-                                                                                                     ix->len_minmax.as<uint32_t>());
-        uint32_t mm[2] = {0, 0};
-        { const uint32_t* pk = peek(ix, st, {ix->len_minmax.as<uint32_t>(), ix->len_minmax.as<uint32_t>() + 1}); mm[0] = pk[0]; mm[1] = pk[1]; }
-        if (mm[0] < ix->h.p.k) throw std::invalid_argument("a read is shorter than k (the reference panics at boss.go:164-166)");
-        swap_result_sets();                      // this chunk writes the set the copy-out of chunk c-2 has released
-        if (c >= 2) CK(cudaStreamWaitEvent(st, ix->ev_out[b], 0));
-        grootgpu_batch_result r{};
-        const double t_c1 = now_ms();
-        run_batch(ix, ix->in_seq[b].as<uint8_t>(), ix->in_off32[b].as<uint32_t>(), nc, mm[0], mm[1], &cprm, st, &r);
-        const double t_c2 = now_ms();
-        if (hit_base + r.n_hits >= (1ull << 32) || rec_base + r.n_records >= (1ull << 32))
-            throw std::length_error("more than 2^32 hits or records in one batch: use smaller batches");
-        const uint32_t n_off = nc + (c + 1 == C ? 1u : 0u);
-        const uint32_t np = static_cast<uint32_t>(r.n_pairs);
-        chunk_rebase_kernel<<<std::max(1u, std::min<uint32_t>((std::max(np, n_off) + 255) / 256, 1184u)), 256, 0, st>>>(
-            ix->pairs.as<PairOut>(), np, ix->hit_off.as<uint32_t>(), n_off, r0, static_cast<uint32_t>(hit_base), static_cast<uint32_t>(rec_base));
-        CK(cudaGetLastError());
-        CK(cudaEventRecord(ix->ev_done[b], st));
-        // copy-out, straight to the final place; the pinned arrays grow by extrapolating this chunk's yield
-        const double scale = 1.15 * static_cast<double>(n) / static_cast<double>(cb[c + 1]);
-        auto want = [&](uint64_t used_after, size_t elem) { return static_cast<size_t>(static_cast<double>(used_after) * scale) * elem + 4096; };
-        if ((hit_base + r.n_hits) * 4 > ix->r_hits.cap) grow_keep(ix->r_hits, want(hit_base + r.n_hits, 4), hit_base * 4, st_out);
-        if ((pair_base + r.n_pairs) * sizeof(PairOut) > ix->r_pairs.cap) grow_keep(ix->r_pairs, want(pair_base + r.n_pairs, sizeof(PairOut)), pair_base * sizeof(PairOut), st_out);
-        if ((rec_base + r.n_records) * 4 > ix->r_rec_path.cap) grow_keep(ix->r_rec_path, want(rec_base + r.n_records, 4), rec_base * 4, st_out);
-        if ((rec_base + r.n_records) * 4 > ix->r_rec_pos.cap) grow_keep(ix->r_rec_pos, want(rec_base + r.n_records, 4), rec_base * 4, st_out);
-        CK(cudaStreamWaitEvent(st_out, ix->ev_done[b], 0));
-        CK(cudaMemcpyAsync(ix->r_hit_off.as<uint32_t>() + r0, ix->hit_off.p, 4ull * n_off, cudaMemcpyDeviceToHost, st_out));
-        if (r.n_hits) CK(cudaMemcpyAsync(ix->r_hits.as<uint32_t>() + hit_base, ix->hits.p, 4ull * r.n_hits, cudaMemcpyDeviceToHost, st_out));
-        if (r.n_pairs) CK(cudaMemcpyAsync(ix->r_pairs.as<PairOut>() + pair_base, ix->pairs.p, sizeof(PairOut) * r.n_pairs, cudaMemcpyDeviceToHost, st_out));
-        if (r.n_records) {
-            CK(cudaMemcpyAsync(ix->r_rec_path.as<uint32_t>() + rec_base, ix->rec_path.p, 4ull * r.n_records, cudaMemcpyDeviceToHost, st_out));
-            CK(cudaMemcpyAsync(ix->r_rec_pos.as<int32_t>() + rec_base, ix->rec_pos.p, 4ull * r.n_records, cudaMemcpyDeviceToHost, st_out));
+    const int device = ix->device;
+
+    // copy-in of chunk c into input buffer c & 3; issued in chunk order, at most two chunks ahead of the chunk that
+    // is starting (buffer c & 3 was last read by chunk c - 4, which completed before chunk c - 2 could start)
+    auto issue_inputs_upto = [&](uint32_t last) {   // sh.mu held
+        for (; sh.inputs_issued <= last && sh.inputs_issued < C; sh.inputs_issued++) {
+            const uint32_t c = sh.inputs_issued, r0 = cb[c], nc = cb[c + 1] - r0, b = c & 3;
+            const uint64_t bytes = seq_off[cb[c + 1]] - seq_off[r0];
+            ix->in_seq[b].need(bytes + 64); ix->in_off64[b].need(8ull * (nc + 1)); ix->in_off32[b].need(4ull * (nc + 1));
+            CK(cudaMemcpyAsync(ix->in_seq[b].p, seq + seq_off[r0], bytes, cudaMemcpyHostToDevice, st_in));
+            CK(cudaMemsetAsync(ix->in_seq[b].as<uint8_t>() + bytes, 0, 64, st_in));
+            CK(cudaMemcpyAsync(ix->in_off64[b].p, seq_off + r0, 8ull * (nc + 1), cudaMemcpyHostToDevice, st_in));
+            CK(cudaEventRecord(ix->ev_in[b], st_in));
         }
-        if (prm->keep_sketches) CK(cudaMemcpyAsync(ix->r_sketches.as<uint64_t>() + static_cast<size_t>(r0) * S, ix->sketches.p, 8ull * S * nc, cudaMemcpyDeviceToHost, st_out));
-        CK(cudaEventRecord(ix->ev_out[b], st_out));
-        if (trace) fprintf(stderr, "[grootgpu] chunk %u: %u reads  start %.2f ms  input ready %.2f  kernels done %.2f (device %.2f ms)  copy-out issued %.2f\n",
-                           c, nc, t_c0, t_c1, t_c2, r.ms[1] + r.ms[2] + r.ms[3], now_ms());
-        hit_base += r.n_hits; pair_base += r.n_pairs; rec_base += r.n_records;
-        total.mapped += r.mapped; total.multimapped += r.multimapped; total.slow_path_pairs += r.slow_path_pairs;
-        total.kernel_launches += r.kernel_launches + 2;
-        for (int i = 1; i < 4; i++) total.ms[i] += r.ms[i];
-        for (int i = 0; i < 8; i++) total.kernel_ms[i] += r.kernel_ms[i];
+    };
+
+    auto lane_main = [&](uint32_t lane) {
+        Workspace* w = &ix->ws[lane];
+        Workspace* other = &ix->ws[lane ^ 1];
+        cudaStream_t st = w->stream;
+        try {
+            pick_device(device);
+            for (uint32_t c = lane; c < C; c += 2) {
+                const uint32_t r0 = cb[c], nc = cb[c + 1] - r0, b = c & 3;
+                const double t_c0 = now_ms();
+                {
+                    std::unique_lock<std::mutex> lk(sh.mu);
+                    if (sh.failed) return;
+                    issue_inputs_upto(c + 2);
+                }
+                CK(cudaStreamWaitEvent(st, ix->ev_in[b], 0));
+                poke(st, {{w->len_minmax.as<uint32_t>(), 0xffffffffu}, {w->len_minmax.as<uint32_t>() + 1, 0u}});
+                chunk_offsets_kernel<<<std::max(1u, std::min<uint32_t>((nc + 256) / 256, 1184u)), 256, 0, st>>>(ix->in_off64[b].as<uint64_t>(), nc, ix->in_off32[b].as<uint32_t>(),
+                                                                                                             w->len_minmax.as<uint32_t>());
+                uint32_t mm[2] = {0, 0};
+                { const uint32_t* pk = peek(w, st, {w->len_minmax.as<uint32_t>(), w->len_minmax.as<uint32_t>() + 1}); mm[0] = pk[0]; mm[1] = pk[1]; }
+                if (mm[0] < ix->h.p.k) throw std::invalid_argument("a read is shorter than k (the reference panics at boss.go:164-166)");
+                w->swap_result_sets();                                   // write the result set the lane's previous chunk is NOT being copied out of
+                CK(cudaStreamWaitEvent(st, w->ev_out[w->rset], 0));      // ... whose own copy-out (two chunks of this lane ago) has completed
+                // chunk c's f64 chains go after chunk c-1's: wait (host) until the other lane has RECORDED its event — a
+                // cudaStreamWaitEvent issued before the record would refer to an older chunk — then wait for it on the stream
+                bool acc_passed = false;
+                if (cprm.project_on_device) {
+                    w->acc_before = [&, c](cudaStream_t s2) {
+                        std::unique_lock<std::mutex> lk(sh.mu);
+                        sh.cv.wait(lk, [&] { return sh.failed || sh.acc_recorded >= c; });
+                        if (sh.failed) throw std::runtime_error("the other lane of the batch failed");
+                        if (c > 0) CK(cudaStreamWaitEvent(s2, other->ev_acc, 0));
+                    };
+                    w->acc_after = [&, c](cudaStream_t s2) {
+                        CK(cudaEventRecord(w->ev_acc, s2));
+                        { std::unique_lock<std::mutex> lk(sh.mu); sh.acc_recorded = c + 1; }
+                        sh.cv.notify_all();
+                        acc_passed = true;
+                    };
+                }
+                grootgpu_batch_result r{};
+                const double t_c1 = now_ms();
+                run_batch(ix, w, ix->in_seq[b].as<uint8_t>(), ix->in_off32[b].as<uint32_t>(), nc, mm[0], mm[1], &cprm, st, &r);
+                const double t_c2 = now_ms();
+                if (cprm.project_on_device && !acc_passed) { w->acc_before(w->st_side); w->acc_after(w->st_side); }   // nothing to weight in this chunk: pass the baton
+                w->acc_before = nullptr; w->acc_after = nullptr;
+                // batch-wide offsets: chunk c-1 has to have published its totals
+                uint64_t hit_base = 0, pair_base = 0, rec_base = 0;
+                {
+                    std::unique_lock<std::mutex> lk(sh.mu);
+                    sh.cv.wait(lk, [&] { return sh.failed || sh.published >= c; });
+                    if (sh.failed) return;
+                    if (c > 0) { hit_base = sh.hit_end[c - 1]; pair_base = sh.pair_end[c - 1]; rec_base = sh.rec_end[c - 1]; }
+                    if (hit_base + r.n_hits >= (1ull << 32) || rec_base + r.n_records >= (1ull << 32))
+                        throw std::length_error("more than 2^32 hits or records in one batch: use smaller batches");
+                    sh.hit_end[c] = hit_base + r.n_hits; sh.pair_end[c] = pair_base + r.n_pairs; sh.rec_end[c] = rec_base + r.n_records;
+                    // the pinned arrays grow by extrapolating the yield so far; copies into them are drained first (grow_keep)
+                    const double scale = 1.15 * static_cast<double>(n) / static_cast<double>(cb[c + 1]);
+                    auto want = [&](uint64_t used_after, size_t elem) { return static_cast<size_t>(static_cast<double>(used_after) * scale) * elem + 4096; };
+                    if (sh.hit_end[c] * 4 > ix->r_hits.cap) grow_keep(ix->r_hits, want(sh.hit_end[c], 4), hit_base * 4, st_out);
+                    if (sh.pair_end[c] * sizeof(PairOut) > ix->r_pairs.cap) grow_keep(ix->r_pairs, want(sh.pair_end[c], sizeof(PairOut)), pair_base * sizeof(PairOut), st_out);
+                    if (sh.rec_end[c] * 4 > ix->r_rec_path.cap) grow_keep(ix->r_rec_path, want(sh.rec_end[c], 4), rec_base * 4, st_out);
+                    if (sh.rec_end[c] * 4 > ix->r_rec_pos.cap) grow_keep(ix->r_rec_pos, want(sh.rec_end[c], 4), rec_base * 4, st_out);
+                    const uint32_t n_off = nc + (c + 1 == C ? 1u : 0u);
+                    const uint32_t np = static_cast<uint32_t>(r.n_pairs);
+                    chunk_rebase_kernel<<<std::max(1u, std::min<uint32_t>((std::max(np, n_off) + 255) / 256, 1184u)), 256, 0, st>>>(
+                        w->pairs.as<PairOut>(), np, w->hit_off.as<uint32_t>(), n_off, r0, static_cast<uint32_t>(hit_base), static_cast<uint32_t>(rec_base));
+                    CK(cudaGetLastError());
+                    CK(cudaEventRecord(w->ev_done, st));
+                    // copy-out, straight to the final place (st_out is shared: enqueue under the lock)
+                    CK(cudaStreamWaitEvent(st_out, w->ev_done, 0));
+                    CK(cudaMemcpyAsync(ix->r_hit_off.as<uint32_t>() + r0, w->hit_off.p, 4ull * n_off, cudaMemcpyDeviceToHost, st_out));
+                    if (r.n_hits) CK(cudaMemcpyAsync(ix->r_hits.as<uint32_t>() + hit_base, w->hits.p, 4ull * r.n_hits, cudaMemcpyDeviceToHost, st_out));
+                    if (r.n_pairs) CK(cudaMemcpyAsync(ix->r_pairs.as<PairOut>() + pair_base, w->pairs.p, sizeof(PairOut) * r.n_pairs, cudaMemcpyDeviceToHost, st_out));
+                    if (r.n_records) {
+                        CK(cudaMemcpyAsync(ix->r_rec_path.as<uint32_t>() + rec_base, w->rec_path.p, 4ull * r.n_records, cudaMemcpyDeviceToHost, st_out));
+                        CK(cudaMemcpyAsync(ix->r_rec_pos.as<int32_t>() + rec_base, w->rec_pos.p, 4ull * r.n_records, cudaMemcpyDeviceToHost, st_out));
+                    }
+                    if (prm->keep_sketches) CK(cudaMemcpyAsync(ix->r_sketches.as<uint64_t>() + static_cast<size_t>(r0) * S, w->sketches.p, 8ull * S * nc, cudaMemcpyDeviceToHost, st_out));
+                    CK(cudaEventRecord(w->ev_out[w->rset], st_out));
+                    sh.total.mapped += r.mapped; sh.total.multimapped += r.multimapped; sh.total.slow_path_pairs += r.slow_path_pairs;
+                    sh.total.kernel_launches += r.kernel_launches + 2;
+                    for (int i = 1; i < 4; i++) sh.total.ms[i] += r.ms[i];
+                    for (int i = 0; i < 8; i++) sh.total.kernel_ms[i] += r.kernel_ms[i];
+                    sh.published = c + 1;
+                    if (trace) fprintf(stderr, "[grootgpu] chunk %u (lane %u): %u reads  start %.2f ms  launched %.2f  kernels done %.2f (device %.2f ms)  copy-out issued %.2f\n",
+                                       c, lane, nc, t_c0, t_c1, t_c2, r.ms[1] + r.ms[2] + r.ms[3], now_ms());
+                }
+                sh.cv.notify_all();
+            }
+        } catch (...) {
+            std::unique_lock<std::mutex> lk(sh.mu);
+            if (!sh.failed) { sh.failed = true; sh.error = std::current_exception(); }
+            lk.unlock();
+            sh.cv.notify_all();
+        }
+    };
+
+    CK(cudaEventRecord(ix->ev_t0, st_in));
+    for (Workspace& w : ix->ws) { w.len_minmax.need(16); w.acc_before = nullptr; w.acc_after = nullptr; }
+    if (C > 1) {
+        std::thread helper(lane_main, 1u);
+        lane_main(0u);
+        helper.join();
+    } else {
+        lane_main(0u);
     }
+    for (Workspace& w : ix->ws) { w.acc_before = nullptr; w.acc_after = nullptr; }
+    if (sh.failed) std::rethrow_exception(sh.error);
     CK(cudaEventRecord(ix->ev_t1, st_out));
     CK(cudaStreamSynchronize(st_out));
     if (trace) fprintf(stderr, "[grootgpu] batch of %u reads in %u chunks done at %.2f ms\n", n, C, now_ms());
     memset(out, 0, sizeof *out);
-    *out = total;
-    out->n_reads = n; out->n_hits = hit_base; out->n_pairs = pair_base; out->n_records = rec_base;
+    *out = sh.total;
+    out->n_reads = n; out->n_hits = sh.hit_end[C - 1]; out->n_pairs = sh.pair_end[C - 1]; out->n_records = sh.rec_end[C - 1];
     out->hit_off = ix->r_hit_off.as<uint32_t>(); out->hits = ix->r_hits.as<uint32_t>();
     out->pairs = reinterpret_cast<const grootgpu_pair*>(ix->r_pairs.p);
     out->rec_path = ix->r_rec_path.as<uint32_t>(); out->rec_pos = ix->r_rec_pos.as<int32_t>();
     out->sketches = prm->keep_sketches ? ix->r_sketches.as<uint64_t>() : nullptr;
-    out->received = n; out->alignments = rec_base;
+    out->received = n; out->alignments = out->n_records;
     cudaEventElapsedTime(&out->ms[0], ix->ev_t0, ix->ev_t1);
 }
 
@@ -1135,7 +1242,7 @@ int grootgpu_align_batch_device(grootgpu_index* idx, const uint8_t* d_seq, const
     if (!idx || !d_seq || !d_seq_off || !params || n_reads == 0 || max_len < min_len) return fail(GROOTGPU_ERR_ARG, "bad argument");
     return guarded([&] {
         pick_device(idx->device);
-        run_batch(idx, d_seq, d_seq_off, n_reads, min_len, max_len, params, stream ? static_cast<cudaStream_t>(stream) : idx->stream, out);
+        run_batch(idx, &idx->ws[0], d_seq, d_seq_off, n_reads, min_len, max_len, params, stream ? static_cast<cudaStream_t>(stream) : idx->ws[0].stream, out);
     });
 }
 
@@ -1148,17 +1255,18 @@ int grootgpu_align_batch(grootgpu_index* idx, const uint8_t* seq, const uint64_t
         // results stay on the device: one shot (the d_* pointers of the result must cover the whole batch)
         const uint64_t total = seq_off[n_reads] - seq_off[0];
         if (total >= (1ull << 32) - 64) throw std::length_error("a batch whose results stay on the device holds at most 4 GiB of bases: split it");
-        cudaStream_t st = idx->stream;
+        Workspace* w = &idx->ws[0];
+        cudaStream_t st = w->stream;
         std::vector<uint32_t> off32(n_reads + 1);
         uint32_t mn = 0xffffffffu, mx = 0;
         for (uint32_t i = 0; i <= n_reads; i++) off32[i] = static_cast<uint32_t>(seq_off[i] - seq_off[0]);
         for (uint32_t i = 0; i < n_reads; i++) { uint32_t l = off32[i + 1] - off32[i]; mn = std::min(mn, l); mx = std::max(mx, l); }
         if (mn < idx->h.p.k) throw std::invalid_argument("a read is shorter than k (the reference panics at boss.go:164-166)");
-        idx->seq.need(total + 64); idx->off.need(4ull * (n_reads + 1));
-        CK(cudaMemcpyAsync(idx->seq.p, seq + seq_off[0], total, cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(idx->seq.as<uint8_t>() + total, 0, 64, st));
-        CK(cudaMemcpyAsync(idx->off.p, off32.data(), 4ull * (n_reads + 1), cudaMemcpyHostToDevice, st));
-        run_batch(idx, idx->seq.as<uint8_t>(), idx->off.as<uint32_t>(), n_reads, mn, mx, params, st, out);
+        w->seq.need(total + 64); w->off.need(4ull * (n_reads + 1));
+        CK(cudaMemcpyAsync(w->seq.p, seq + seq_off[0], total, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(w->seq.as<uint8_t>() + total, 0, 64, st));
+        CK(cudaMemcpyAsync(w->off.p, off32.data(), 4ull * (n_reads + 1), cudaMemcpyHostToDevice, st));
+        run_batch(idx, w, w->seq.as<uint8_t>(), w->off.as<uint32_t>(), n_reads, mn, mx, params, st, out);
     });
 }
 
