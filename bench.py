@@ -214,13 +214,13 @@ def run_ours(args):
             gatherer.submit(gd.result_tensors_from_raw(raw, dev))   # staging copies while the next batch is being mapped
         return raw
 
-    e2e_parts = {"align_batch_ms": 0.0, "device_ms": 0.0}
+    e2e_parts = {"align_batch_ms": 0.0, "copy_in_to_copy_out_ms": 0.0}
 
     def step_e2e():
         t0 = time.perf_counter()
         raw = idx.map_reads_raw(h_seq.data_ptr(), h_off.data_ptr(), n, THRESHOLD, project_on_device=True)
         e2e_parts["align_batch_ms"] += (time.perf_counter() - t0) * 1e3
-        e2e_parts["device_ms"] = e2e_parts.get("device_ms", 0.0) + raw.ms[1] + raw.ms[2] + raw.ms[3]
+        e2e_parts["copy_in_to_copy_out_ms"] += raw.ms[0]   # CUDA events: first copy-in issued -> last copy-out complete
         return raw
 
     # ---- value: inputs resident in HBM ----
@@ -256,7 +256,7 @@ def run_ours(args):
     for _ in range(max(1, args.warmup // 2)):
         raw = step_e2e()
     torch.cuda.synchronize(); barrier()
-    e2e_parts.update(align_batch_ms=0.0, device_ms=0.0)
+    e2e_parts.update(align_batch_ms=0.0, copy_in_to_copy_out_ms=0.0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         raw = step_e2e()
@@ -325,7 +325,8 @@ def run_ours(args):
                        "parallelism": "reads sharded over %d GPU(s), index replicated%s" % (world, ", one NCCL gather of results to rank 0 per step" if world > 1 else ""),
                        "per_read": stats, "index_build_s": t_index},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "includes": "pinned host buffers -> grootgpu_align_batch (H2D, sketch+query+align+ordered graph weighting kernels, D2H of hits/pairs/records)",
+                    "includes": "pinned host buffers -> grootgpu_align_batch (H2D, sketch+query+align+ordered graph weighting kernels, D2H of hits/pairs/records); "
+                                "inside the call the batch is streamed through the device in chunks on two lanes, copies overlapped with kernels",
                     "per_step_ms": e2e_parts},
             "gpu_launches": launches,
             "kernel_ms": fam_avg,
