@@ -198,7 +198,7 @@ struct Workspace {
     uint32_t* h_peek = nullptr;        // mapped pinned words the device writes scalars into (peek()): no copy engine involved
     uint32_t* d_peek = nullptr;
     DBuf seq, off, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
-        rec_path, rec_pos, stack_ws, cub_tmp, cub_tmp2, sketches, tile_counter, error, reads2, read_ok2, qkey, qkey2, order, slow_q, len_minmax,
+        rec_path, rec_pos, stack_ws, cub_tmp, cub_tmp2, sketches, tile_counter, error, reads2, read_ok2, qkey, qkey2, order, slow_q, len_minmax, seed_q,
         item_cnt, item_off, pkeys, pkeys2, pvals, pvals2;
     DBuf alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches;   // the other result set of the chunked host path
     // ordering of the graph weighting across lanes (chunked host path): called around the accumulate of a chunk
@@ -448,8 +448,13 @@ void prepare_params(grootgpu_index* ix, uint32_t min_len, uint32_t max_len, doub
 struct SeedLaunch {
     template <int S>
     static void seed(const DevIndex& d, const SeedArgs& a, uint32_t k, size_t smem, int blocks, cudaStream_t st) {
-        CK(cudaFuncSetAttribute(seed_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        seed_kernel<S, 4><<<blocks, kSeedThreads, smem, st>>>(d, a, make_mult(k));
+        CK(cudaFuncSetAttribute(seed_kernel<S, 4, SEED_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        seed_kernel<S, 4, SEED_FULL><<<blocks, kSeedThreads, smem, st>>>(d, a, make_mult(k));
+    }
+    template <int S>
+    static void seed_queued(const DevIndex& d, const SeedArgs& a, uint32_t k, size_t smem, int blocks, cudaStream_t st) {
+        CK(cudaFuncSetAttribute(seed_kernel<S, 4, SEED_QUEUED>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        seed_kernel<S, 4, SEED_QUEUED><<<blocks, kSeedThreads, smem, st>>>(d, a, make_mult(k));
     }
     template <int S>
     static void fill(const DevIndex& d, const FillArgs& a, uint32_t k, int blocks, cudaStream_t st) {
@@ -459,8 +464,8 @@ struct SeedLaunch {
     template <int S>
     static int seed_occupancy(size_t smem) {
         int nb = 0;
-        cudaFuncSetAttribute(seed_kernel<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_kernel<S, 4>, kSeedThreads, smem);
+        cudaFuncSetAttribute(seed_kernel<S, 4, SEED_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, seed_kernel<S, 4, SEED_FULL>, kSeedThreads, smem);
         return nb;
     }
 };
@@ -471,6 +476,14 @@ struct SeedLaunch {
 bool seed_dispatch(uint32_t S, const DevIndex& d, const SeedArgs& a, uint32_t k, size_t smem, int blocks, cudaStream_t st) {
     switch (S) {
 #define X(s) case s: SeedLaunch::seed<s>(d, a, k, smem, blocks, st); return true;
+        GROOT_S_LIST(X)
+#undef X
+        default: return false;
+    }
+}
+bool seed_queued_dispatch(uint32_t S, const DevIndex& d, const SeedArgs& a, uint32_t k, size_t smem, int blocks, cudaStream_t st) {
+    switch (S) {
+#define X(s) case s: SeedLaunch::seed_queued<s>(d, a, k, smem, blocks, st); return true;
         GROOT_S_LIST(X)
 #undef X
         default: return false;
@@ -614,8 +627,34 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
     if (occ <= 0) throw std::runtime_error(std::string("unsupported sketch size (compiled: ") + kSupportedS + ")");
     const uint32_t n_tiles = (n + kTileReads - 1) / kTileReads;
     int seed_blocks = static_cast<int>(std::min<uint64_t>((n_tiles + kSeedThreads / 32 - 1) / (kSeedThreads / 32), static_cast<uint64_t>(sms) * occ));
+    // two passes when the optimiser probes a single band for every read length of the batch (see SEED_PRESCREEN)
+    bool two_pass = !prm->keep_sketches && getenv("GROOTGPU_SEED_ONEPASS") == nullptr;
+    {
+        std::lock_guard<std::mutex> lock(ix->params_mu);
+        for (uint32_t len = std::max(min_len, k); len <= max_len && two_pass; len++) {
+            const LenParam lp = ix->h_len_params[len];
+            if (lp.eq_min <= S && lp.K != 0 && lp.L != 1) two_pass = false;
+        }
+    }
     CK(cudaEventRecord(w->ev[0], st));
-    kbegin(0); seed_dispatch(S, ix->d, sa, k, seed_smem, std::max(seed_blocks, 1), st); launches++; kend();
+    if (two_pass) {
+        w->seed_q.need(4ull * n);
+        sa.queue = w->seed_q.as<uint32_t>(); sa.n_queue = w->qcount.as<uint32_t>() + 4;
+        int pocc = 0;
+        CK(cudaFuncSetAttribute(seed_kernel<4, 4, SEED_PRESCREEN>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(seed_smem)));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pocc, seed_kernel<4, 4, SEED_PRESCREEN>, kSeedThreads, seed_smem);
+        const int pblocks = static_cast<int>(std::min<uint64_t>((n_tiles + kSeedThreads / 32 - 1) / (kSeedThreads / 32), static_cast<uint64_t>(sms) * std::max(pocc, 1)));
+        kbegin(0); seed_kernel<4, 4, SEED_PRESCREEN><<<std::max(pblocks, 1), kSeedThreads, seed_smem, st>>>(ix->d, sa, make_mult(k)); launches++; kend();
+        CK(cudaGetLastError());
+        SeedArgs sq = sa;
+        sq.tile_counter = w->tile_counter.as<uint32_t>() + 1;
+        const uint32_t qstride = (((max_len + 7u) >> 2) | 1u) * 4u;                 // bytes per read slot: odd number of words
+        sq.tile_bytes = qstride * kTileReads <= 20 * 1024 ? qstride * kTileReads : 0u;   // per warp; very long reads: straight from global
+        const size_t qsmem = sizeof(SeedTabs) + 64 + 2ull * sq.tile_bytes * (kSeedThreads / 32);
+        kbegin(0); seed_queued_dispatch(S, ix->d, sq, k, qsmem, std::max(seed_blocks, 1), st); launches++; kend();
+    } else {
+        kbegin(0); seed_dispatch(S, ix->d, sa, k, seed_smem, std::max(seed_blocks, 1), st); launches++; kend();
+    }
     CK(cudaGetLastError());
     CK(cudaEventRecord(w->ev[1], st));
 

@@ -191,11 +191,11 @@ __device__ __forceinline__ void lsh_probe(const DevIndex& ix, const uint64_t (&s
 // shuffle. (With one thread walking its own bucket, a warp ran the candidate loop with ~2 active lanes: the
 // ~11 candidates of a seeded read — neighbouring windows share their first K minima — against 0 for the
 // other half of the reads; 35 % of the kernel's issue slots, profiles/r01_ncu_summary.md.)
-// stage_tile = stage slots of lane 0's read; returns this lane's hit count. Same hits as lsh_probe, in
+// r = this lane's read (its stage slots are stage[r * HSTAGE ..]); returns this lane's hit count. Same hits as lsh_probe, in
 // the same order (band, then window id ascending).
 template <int S, int MAXK>
 __device__ __forceinline__ uint32_t warp_probe(const DevIndex& ix, const uint64_t (&sk)[S], LenParam lp, bool valid, uint32_t lane,
-                                               uint32_t* __restrict__ stage_tile) {
+                                               uint32_t* __restrict__ stage, uint32_t r) {
     constexpr int NB = S / MAXK;
     constexpr uint32_t FULL = 0xffffffffu;
     const bool probing = valid && lp.eq_min <= S && lp.K != 0;
@@ -247,7 +247,7 @@ __device__ __forceinline__ uint32_t warp_probe(const DevIndex& ix, const uint64_
             const uint32_t o_excl = __shfl_sync(FULL, excl, o), o_incl = __shfl_sync(FULL, incl, o);
             const uint32_t o_start = __shfl_sync(FULL, start, o);
             const uint32_t o_K = __shfl_sync(FULL, static_cast<uint32_t>(lp.K), o), o_eqmin = __shfl_sync(FULL, static_cast<uint32_t>(lp.eq_min), o);
-            const uint32_t o_nh = __shfl_sync(FULL, nh, o);
+            const uint32_t o_nh = __shfl_sync(FULL, nh, o), o_r = __shfl_sync(FULL, r, o);
             uint32_t w = 0;
             const uint64_t* ws = ix.sketches;
             if (live) {
@@ -279,7 +279,7 @@ __device__ __forceinline__ uint32_t warp_probe(const DevIndex& ix, const uint64_
             };
             if (pass) {
                 const uint32_t slot = o_nh + __popc(pass_mask & range_mask(o_excl, o_incl) & lt_mask);
-                if (slot < HSTAGE) stage_tile[o * HSTAGE + slot] = w;
+                if (slot < HSTAGE) stage[static_cast<size_t>(o_r) * HSTAGE + slot] = w;
             }
             if (incl > base && excl < base + 32) nh += __popc(pass_mask & range_mask(excl, incl));
         }
@@ -299,7 +299,17 @@ struct SeedArgs {
     uint32_t* tile_counter;    // zeroed before launch
     int* error;                // [0]=code, [1]=read index
     uint32_t tile_bytes;       // shared-memory bytes per tile buffer (0 => read straight from global)
+    uint32_t* queue;           // SEED_PRESCREEN: reads whose first band found a bucket (out); SEED_QUEUED: the reads to process (in)
+    uint32_t* n_queue;         // device scalar
 };
+
+// seed_kernel modes. SEED_FULL: every read gets its full sketch and probe in one pass. The two-pass form exploits
+// that most reads of a metagenome seed nowhere: SEED_PRESCREEN computes only the first band's MAXK sketch slots (a
+// fifth of the hashing at S = 21), looks the band key up and queues the reads that found a bucket (possible when
+// the optimiser probes a single band, L == 1: the reference default); SEED_QUEUED then runs the full sketch + pooled
+// verification for the queued reads only. Reads that are not queued have no candidates, hence n_hits = 0 — the same
+// result as SEED_FULL.
+enum { SEED_FULL = 0, SEED_PRESCREEN = 1, SEED_QUEUED = 2 };
 
 __device__ __forceinline__ void set_error(int* err, int code, uint32_t read) {
     if (atomicCAS(err, 0, code) == 0) err[1] = static_cast<int>(read);
@@ -332,15 +342,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 // other warps of the block (an earlier block-wide version lost ~30 % of its issue slots at __syncthreads).
 constexpr int kTileReads = 32;
 
-template <int S, int MAXK>
-__global__ void __launch_bounds__(kSeedThreads, GROOT_SEED_MIN_BLOCKS) seed_kernel(DevIndex ix, SeedArgs a, MultTable M) {
+template <int S, int MAXK, int MODE>
+__global__ void __launch_bounds__(kSeedThreads, MODE == SEED_PRESCREEN ? 8 : GROOT_SEED_MIN_BLOCKS) seed_kernel(DevIndex ix, SeedArgs a, MultTable M) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SeedTabs* T = reinterpret_cast<SeedTabs*>(smem_raw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + sizeof(SeedTabs));  // 2 mbarriers per warp
     uint8_t* bufs_all = smem_raw + sizeof(SeedTabs) + 64;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t n_tiles = (a.n_reads + kTileReads - 1) / kTileReads;
-    const bool staged = a.tile_bytes != 0;
+    const uint32_t n_units = MODE == SEED_QUEUED ? *a.n_queue : a.n_reads;   // reads, or queue entries
+    const uint32_t n_tiles = (n_units + kTileReads - 1) / kTileReads;
+    const bool staged = MODE != SEED_QUEUED && a.tile_bytes != 0;       // queued reads are scattered: no tile to bulk-copy
     uint8_t* bufs = bufs_all + static_cast<size_t>(warp) * 2 * a.tile_bytes;
     uint64_t* bar = bars + warp * 2;
 
@@ -374,8 +385,10 @@ __global__ void __launch_bounds__(kSeedThreads, GROOT_SEED_MIN_BLOCKS) seed_kern
     while (tile < n_tiles) {
         const uint32_t tnext = next_tile();
         if (staged && lane == 0 && tnext < n_tiles) issue(tnext, cur ^ 1);  // the other buffer was released by the __syncwarp below
-        const uint32_t r0 = tile * kTileReads, r1 = min(a.n_reads, r0 + kTileReads);
-        const uint32_t r = r0 + lane;
+        const uint32_t r0 = tile * kTileReads, r1 = min(n_units, r0 + kTileReads);
+        uint32_t r = r0 + lane;
+        const bool live = r < n_units;
+        if (MODE == SEED_QUEUED) r = live ? a.queue[r] : 0u;
         bool in_smem = false;
         uint32_t b0 = 0;
         if (staged) {
@@ -389,12 +402,41 @@ __global__ void __launch_bounds__(kSeedThreads, GROOT_SEED_MIN_BLOCKS) seed_kern
         uint64_t sk[S];
         LenParam lp{0, 0, 0xffff};
         bool valid = false;
-        if (r < a.n_reads) {
-            const uint32_t o = a.off[r], len = a.off[r + 1] - o;
+        const uint32_t o = live ? a.off[r] : 0u, len = live ? a.off[r + 1] - o : 0u;
+        const uint8_t* qread = nullptr;
+        if (MODE == SEED_QUEUED && a.tile_bytes != 0) {
+            // queued reads are scattered over the batch: the warp copies its 32 reads into its shared-memory buffer, one
+            // read per step with the lanes striding over aligned 32-bit words, at a word stride that is odd (the per-thread
+            // byte reads of the hash loop then fall into 32 different banks)
+            const uint32_t stride = a.tile_bytes / kTileReads;
+            const uint32_t max_nw = (a.max_len + 6u) >> 2;
+            for (uint32_t wbase = 0; wbase < max_nw; wbase += 32) {
+                const uint32_t wj = wbase + lane;
+#pragma unroll
+                for (uint32_t i0 = 0; i0 < kTileReads; i0 += 8) {   // eight reads' loads in flight before the first store
+                    uint32_t v[8];
+                    bool ok[8];
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; j++) {
+                        const uint32_t oi = __shfl_sync(0xffffffffu, o, i0 + j), li = __shfl_sync(0xffffffffu, len, i0 + j);
+                        const uint32_t nw = (li == 0 || li > a.max_len) ? 0u : ((oi & 3u) + li + 3u) >> 2;
+                        ok[j] = wj < nw;
+                        v[j] = ok[j] ? __ldg(reinterpret_cast<const uint32_t*>(a.seq + (oi & ~3u)) + wj) : 0u;
+                    }
+#pragma unroll
+                    for (uint32_t j = 0; j < 8; j++)
+                        if (ok[j]) reinterpret_cast<uint32_t*>(bufs + (i0 + j) * stride)[wj] = v[j];
+                }
+            }
+            __syncwarp();
+            qread = bufs + lane * stride + (o & 3u);
+        }
+        if (live) {
             if (len < ix.k || len > a.max_len) {
                 set_error(a.error, len < ix.k ? -5 : -7, r);  // GROOTGPU_ERR_SHORT_READ / _CAPACITY
             } else {
-                if (in_smem) khf_sketch<S>(bufs + static_cast<size_t>(cur) * a.tile_bytes + (o - b0), len, ix.k, *T, M, sk);   // LDS path
+                if (qread) khf_sketch<S>(qread, len, ix.k, *T, M, sk);                                                              // LDS path, queued reads
+                else if (in_smem) khf_sketch<S>(bufs + static_cast<size_t>(cur) * a.tile_bytes + (o - b0), len, ix.k, *T, M, sk);   // LDS path
                 else khf_sketch<S>(a.seq + o, len, ix.k, *T, M, sk);                                                          // LDG path
                 lp = a.len_params[len];
                 valid = true;
@@ -405,9 +447,35 @@ __global__ void __launch_bounds__(kSeedThreads, GROOT_SEED_MIN_BLOCKS) seed_kern
             }
         }
         __syncwarp();
-        // ---- probe + containment check: the warp's 32 reads pool their candidates (warp_probe) ----
-        const uint32_t nh = warp_probe<S, MAXK>(ix, sk, lp, valid, lane, a.stage + static_cast<size_t>(r0) * HSTAGE);
-        if (r < a.n_reads) a.n_hits[r] = nh;
+        if (MODE == SEED_PRESCREEN) {
+            // ---- first band only: does the key have a bucket? (S == MAXK slots were hashed) ----
+            bool found = false;
+            if (valid && lp.eq_min <= ix.S && lp.K != 0 && lp.K <= S) {
+                uint32_t key[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int j = 0; j < MAXK && j < S; j++) key[j] = j < lp.K ? static_cast<uint32_t>(sk[j]) : 0u;
+                const LshTable tab = ix.tables[(lp.K - 1) * ix.n_bands];
+                uint32_t h = band_key_hash(key) & tab.mask;
+                while (true) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(tab.slots + h);
+                    const uint4 kq = __ldg(sp), rest = __ldg(sp + 1);
+                    if (rest.y == 0) break;  // empty
+                    if (kq.x == key[0] && kq.y == key[1] && kq.z == key[2] && kq.w == key[3]) { found = true; break; }
+                    h = (h + 1) & tab.mask;
+                }
+            }
+            __syncwarp();
+            const uint32_t ball = __ballot_sync(0xffffffffu, found);
+            uint32_t base = 0;
+            if (lane == 0 && ball) base = atomicAdd(a.n_queue, static_cast<uint32_t>(__popc(ball)));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (found) a.queue[base + __popc(ball & ((1u << lane) - 1u))] = r;
+            if (live) a.n_hits[r] = 0;
+        } else {
+            // ---- probe + containment check: the warp's 32 reads pool their candidates (warp_probe) ----
+            const uint32_t nh = warp_probe<S, MAXK>(ix, sk, lp, valid, lane, a.stage, r);
+            if (live) a.n_hits[r] = nh;
+        }
         __syncwarp();  // every lane is done with buffer `cur`
         cur ^= 1;
         tile = tnext;
