@@ -263,6 +263,55 @@ def test_align_edge_cases(argannot):
         assert_same_result(gr, orr)
 
 
+def test_align_walk_variants(argannot, db_dirs, root):
+    """The three walks must agree with the oracle: the packed 2-bit walk (reads of upper-case ACGT), the byte-wise walk
+    (a read holding an 'N' near its end still seeds at t = 0.9 and is aligned through the slow queue, forward and
+    reverse) and the packed walk at the wider read copies (250 bp reads against -w 250: 16 words per orientation)."""
+    g, o = argannot
+    seqs = synth.db_sequences(db_dirs["arg-annot.90"])
+    rng = np.random.default_rng(5)
+    reads = []
+    for i in range(600):
+        s = seqs[int(rng.integers(len(seqs)))]
+        if len(s) < 120:
+            continue
+        a = int(rng.integers(0, len(s) - 100))
+        r = bytearray(bytes(s[a:a + 100]))
+        if i % 2:
+            r = bytearray(revcomp(bytes(r)))
+        if i % 3 == 0:
+            r[int(rng.choice([0, 1, 98, 99]))] = ord("N")
+        reads.append(bytes(r))
+    blob, off = pack_reads(reads)
+    for t in (0.9, 0.99):
+        g.reset_weights(); o.reset_weights()
+        gr = g.map_reads(blob, off, t, project=True)
+        orr = o.map_reads(blob, off, t, threads=8)
+        assert_same_result(gr, orr)
+        assert np.array_equal(g.weights()[0], o.weights()[0])
+    assert orr.counts["mapped"] > 100
+    msa = [os.path.join(root, "data", "graph", "test-genes.msa")]
+    g2 = api.Index.build(msa_files=msa, k=31, S=21, w=250)
+    o2 = po.Index(msa_files=msa, k=31, S=21, w=250)
+    assert g2.dump_hash() == o2.dump_hash()
+    import re
+    txt = open(msa[0]).read()
+    genes = [re.sub(r"[^ACGTacgt]", "", "".join(b.split("\n")[1:])).upper().encode() for b in txt.split(">")[1:]]
+    genes = [x for x in genes if len(x) >= 300]
+    reads = []
+    for i in range(400):
+        s = genes[int(rng.integers(len(genes)))]
+        a = int(rng.integers(0, len(s) - 250))
+        r = s[a:a + 250]
+        reads.append(revcomp(r) if i % 2 else r)
+    blob, off = pack_reads(reads)
+    gr = g2.map_reads(blob, off, 0.99, project=True)
+    orr = o2.map_reads(blob, off, 0.99, threads=8)
+    assert orr.counts["mapped"] > 100
+    assert_same_result(gr, orr)
+    assert np.array_equal(g2.weights()[0], o2.weights()[0])
+
+
 def test_align_lowercase_read_needing_revcomp_is_an_error(argannot, db_dirs):
     """seqio.go:17-23,122: complementBases is indexed by the base; a byte > 'T' panics. Lower-case reads hash
     like upper-case ones (nthash seed table), so a lower-case copy of a reverse-strand read seeds, fails the
