@@ -24,7 +24,7 @@ struct Args {
         return def;
     }
 };
-const char* kBoolFlags[] = {"--fasta", "--noAlign", "--profiling", nullptr};
+const char* kBoolFlags[] = {"--fasta", "--noAlign", "--profiling", "--lowCov", nullptr};
 Args parse(int argc, char** argv, int from) {
     Args a;
     for (int i = from; i < argc; i++) {
@@ -85,6 +85,7 @@ static int run_align(const Args& a) {
     info.GraphDir = a.get("-g", "--graphDir", "./groot-graphs");
     info.Device = atoi(a.get("--device", "", "0").c_str());
     info.BatchReads = static_cast<uint32_t>(atoi(a.get("--batchReads", "", "1048576").c_str()));
+    info.BamLevel = atoi(a.get("--bamLevel", "", "-1").c_str());   // no counterpart: deflate level of the BAM (default = zlib's, as biogo's writer)
     std::vector<std::string> fastq = split_commas(a.get("-f", "--fastq", ""));
     const double t0 = now_s();
     grootgpu_index* idx = nullptr;
@@ -122,13 +123,32 @@ static int run_align(const Args& a) {
     return 0;
 }
 
+// cmd/report.go:35-129: --bamFile (STDIN when absent), -c/--covCutoff 0.97, --lowCov (overrides -c)
+static int run_report(const Args& a) {
+    const std::string bamFile = a.get("--bamFile", "", "");
+    double cutoff = atof(a.get("-c", "--covCutoff", "0.97").c_str());
+    const bool lowCov = a.has("--lowCov");
+    if (!bamFile.empty()) {
+        struct stat sb;
+        if (stat(bamFile.c_str(), &sb) != 0) fatal("BAM file does not exist: " + bamFile);
+        if (bamFile.size() < 4 || bamFile.substr(bamFile.size() - 4) != ".bam") fatal("the BAM file does not have a `.bam` extension: " + bamFile);
+    }
+    if (cutoff > 1.0) fatal("supplied coverage cutoff exceeds 1.0 (100%): " + std::to_string(cutoff));
+    if (lowCov) cutoff = 0.97;
+    try {
+        for (const ReportLine& l : RunReport(bamFile, cutoff, lowCov)) printf("%s\t%zu\t%d\t%s\n", l.arg.c_str(), l.count, l.length, l.cigar.c_str());
+    } catch (std::exception& e) { fatal(e.what()); }
+    return 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 2) { fprintf(stderr, "usage: groot-b200 {index,align,version} [flags]\n"); return 1; }
+    if (argc < 2) { fprintf(stderr, "usage: groot-b200 {index,align,report,version} [flags]\n"); return 1; }
     std::string cmd = argv[1];
     Args a = parse(argc, argv, 2);
     if (cmd == "version") { printf("%s\n", grootgpu_version()); return 0; }
     if (cmd == "index") return run_index(a);
     if (cmd == "align") return run_align(a);
+    if (cmd == "report") return run_report(a);
     fprintf(stderr, "unknown command \"%s\" for \"groot-b200\"\n", cmd.c_str());
     return 1;
 }

@@ -8,6 +8,7 @@
 #include <ctime>
 #include <memory>
 #include <stdexcept>
+#include <thread>
 
 namespace groot_host {
 
@@ -107,7 +108,7 @@ int reg2bin(int64_t beg, int64_t end) {  // SAM spec 5.3
 const size_t kBgzfBlock = 0xff00;
 }  // namespace
 
-BamWriter::BamWriter(FILE* out, const std::string& text, const std::vector<std::pair<std::string, int32_t>>& refs) : out_(out) {
+BamWriter::BamWriter(FILE* out, const std::string& text, const std::vector<std::pair<std::string, int32_t>>& refs, int level) : out_(out), level_(level) {
     buf_.insert(buf_.end(), {'B', 'A', 'M', 1});
     put32(buf_, static_cast<uint32_t>(text.size()));
     buf_.insert(buf_.end(), text.begin(), text.end());
@@ -121,57 +122,79 @@ BamWriter::BamWriter(FILE* out, const std::string& text, const std::vector<std::
 }
 BamWriter::~BamWriter() { if (!closed_) close(); }
 
+void BamWriter::compress_blocks(const uint8_t* data, size_t n, int level, std::vector<uint8_t>& out) {
+    std::vector<uint8_t> comp(compressBound(kBgzfBlock) + 64);
+    for (size_t at = 0; at < n; at += kBgzfBlock) {
+        const size_t m = std::min(n - at, kBgzfBlock);
+        z_stream zs{};
+        if (deflateInit2(&zs, level < 0 ? Z_DEFAULT_COMPRESSION : level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("deflateInit2 failed");
+        zs.next_in = const_cast<Bytef*>(data + at); zs.avail_in = static_cast<uInt>(m);
+        zs.next_out = comp.data(); zs.avail_out = static_cast<uInt>(comp.size());
+        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); throw std::runtime_error("deflate failed"); }
+        const size_t clen = zs.total_out;
+        deflateEnd(&zs);
+        uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
+        const uint16_t bsize = static_cast<uint16_t>(clen + 25);
+        hdr[16] = static_cast<uint8_t>(bsize); hdr[17] = static_cast<uint8_t>(bsize >> 8);
+        out.insert(out.end(), hdr, hdr + 18);
+        out.insert(out.end(), comp.data(), comp.data() + clen);
+        const uint32_t crc = static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), data + at, static_cast<uInt>(m)));
+        for (int i = 0; i < 4; i++) out.push_back(static_cast<uint8_t>(crc >> (8 * i)));
+        for (int i = 0; i < 4; i++) out.push_back(static_cast<uint8_t>(static_cast<uint32_t>(m) >> (8 * i)));
+    }
+}
+
 void BamWriter::flush_block() {
-    size_t n = std::min(buf_.size(), kBgzfBlock);
-    std::vector<uint8_t> comp(compressBound(n) + 64);
-    z_stream zs{};
-    if (deflateInit2(&zs, Z_DEFAULT_COMPRESSION, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("deflateInit2 failed");
-    zs.next_in = buf_.data(); zs.avail_in = static_cast<uInt>(n);
-    zs.next_out = comp.data(); zs.avail_out = static_cast<uInt>(comp.size());
-    if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); throw std::runtime_error("deflate failed"); }
-    size_t clen = zs.total_out;
-    deflateEnd(&zs);
-    uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
-    uint16_t bsize = static_cast<uint16_t>(clen + 25);
-    hdr[16] = static_cast<uint8_t>(bsize); hdr[17] = static_cast<uint8_t>(bsize >> 8);
-    fwrite(hdr, 1, 18, out_);
-    fwrite(comp.data(), 1, clen, out_);
-    uint32_t crc = static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), buf_.data(), static_cast<uInt>(n)));
-    uint8_t tail[8];
-    for (int i = 0; i < 4; i++) { tail[i] = static_cast<uint8_t>(crc >> (8 * i)); tail[4 + i] = static_cast<uint8_t>(static_cast<uint32_t>(n) >> (8 * i)); }
-    fwrite(tail, 1, 8, out_);
+    const size_t n = std::min(buf_.size(), kBgzfBlock);
+    std::vector<uint8_t> blk;
+    compress_blocks(buf_.data(), n, level_, blk);
+    fwrite(blk.data(), 1, blk.size(), out_);
     buf_.erase(buf_.begin(), buf_.begin() + n);
+}
+
+void BamWriter::append_blocks(const std::vector<uint8_t>& bgzf) {
+    while (!buf_.empty()) flush_block();
+    fwrite(bgzf.data(), 1, bgzf.size(), out_);
+}
+
+void BamWriter::format_record(std::vector<uint8_t>& buf, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
+                              uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual) {
+    static const struct Nt16 {
+        uint8_t t[256];
+        Nt16() {
+            static const char* codes = "=ACMGRSVTWYHKDBN";
+            memset(t, 15, sizeof t);
+            for (int i = 0; i < 16; i++) { t[static_cast<uint8_t>(codes[i])] = static_cast<uint8_t>(i); t[static_cast<uint8_t>(codes[i] | 0x20)] = static_cast<uint8_t>(i); }
+        }
+    } nt16;
+    const uint32_t n_cigar = 1 + (clip_start ? 1 : 0) + (clip_end ? 1 : 0);
+    const uint32_t block = 32 + name_len + 1 + 4 * n_cigar + (match_len + 1) / 2 + match_len;
+    put32(buf, block);
+    put32(buf, static_cast<uint32_t>(ref_id));
+    put32(buf, static_cast<uint32_t>(pos));
+    buf.push_back(static_cast<uint8_t>(name_len + 1));
+    buf.push_back(30);                                               // MapQ (alignment.go:143)
+    put16(buf, static_cast<uint16_t>(reg2bin(pos, pos + std::max<int64_t>(1, match_len))));
+    put16(buf, static_cast<uint16_t>(n_cigar));
+    put16(buf, flag);
+    put32(buf, match_len);
+    put32(buf, 0xffffffffu);                                         // MateRef nil
+    put32(buf, 0xffffffffu);                                         // no mate position
+    put32(buf, 0);                                                   // TempLen
+    buf.insert(buf.end(), name, name + name_len); buf.push_back(0);
+    if (clip_start) put32(buf, (clip_start << 4) | 5);               // H (alignment.go:132-134)
+    put32(buf, (match_len << 4) | 0);                                // M (alignment.go:135)
+    if (clip_end) put32(buf, (clip_end << 4) | 5);                   // H (alignment.go:136-138)
+    for (uint32_t i = 0; i < match_len; i += 2) {
+        const uint8_t hi = nt16.t[seq[i]], lo = i + 1 < match_len ? nt16.t[seq[i + 1]] : 0;
+        buf.push_back(static_cast<uint8_t>((hi << 4) | lo));
+    }
+    buf.insert(buf.end(), qual, qual + match_len);                  // raw ASCII, not de-offset (alignment.go:121)
 }
 
 void BamWriter::write(const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag, uint32_t clip_start, uint32_t match_len,
                       uint32_t clip_end, const uint8_t* seq, const uint8_t* qual) {
-    static const char* codes = "=ACMGRSVTWYHKDBN";
-    uint8_t nt16[256];
-    memset(nt16, 15, sizeof nt16);
-    for (int i = 0; i < 16; i++) { nt16[static_cast<uint8_t>(codes[i])] = static_cast<uint8_t>(i); nt16[static_cast<uint8_t>(codes[i] | 0x20)] = static_cast<uint8_t>(i); }
-    const uint32_t n_cigar = 1 + (clip_start ? 1 : 0) + (clip_end ? 1 : 0);
-    const uint32_t block = 32 + name_len + 1 + 4 * n_cigar + (match_len + 1) / 2 + match_len;
-    put32(buf_, block);
-    put32(buf_, static_cast<uint32_t>(ref_id));
-    put32(buf_, static_cast<uint32_t>(pos));
-    buf_.push_back(static_cast<uint8_t>(name_len + 1));
-    buf_.push_back(30);                                               // MapQ (alignment.go:143)
-    put16(buf_, static_cast<uint16_t>(reg2bin(pos, pos + std::max<int64_t>(1, match_len))));
-    put16(buf_, static_cast<uint16_t>(n_cigar));
-    put16(buf_, flag);
-    put32(buf_, match_len);
-    put32(buf_, 0xffffffffu);                                         // MateRef nil
-    put32(buf_, 0xffffffffu);                                         // no mate position
-    put32(buf_, 0);                                                   // TempLen
-    buf_.insert(buf_.end(), name, name + name_len); buf_.push_back(0);
-    if (clip_start) put32(buf_, (clip_start << 4) | 5);               // H (alignment.go:132-134)
-    put32(buf_, (match_len << 4) | 0);                                // M (alignment.go:135)
-    if (clip_end) put32(buf_, (clip_end << 4) | 5);                   // H (alignment.go:136-138)
-    for (uint32_t i = 0; i < match_len; i += 2) {
-        uint8_t hi = nt16[seq[i]], lo = i + 1 < match_len ? nt16[seq[i + 1]] : 0;
-        buf_.push_back(static_cast<uint8_t>((hi << 4) | lo));
-    }
-    buf_.insert(buf_.end(), qual, qual + match_len);                  // raw ASCII, not de-offset (alignment.go:121)
+    format_record(buf_, name, name_len, ref_id, pos, flag, clip_start, match_len, clip_end, seq, qual);
     while (buf_.size() >= kBgzfBlock) flush_block();
 }
 
@@ -214,14 +237,13 @@ int ReadMapper::Run(FastqStream& reads) {
         char dt[64]; time_t now = time(nullptr); strftime(dt, sizeof dt, "%Y-%m-%dT%H:%M:%S%z", localtime(&now));
         text += "@RG\tID:readsID\tDT:" + std::string(dt) + "\tPG:groot align\tPI:1000\tPL:illumina\tSM:sampleID\n";
         text += "@PG\tID:1\tPN:groot\tCL:groot align\tVN:" + info_->Version + "\n";
-        bam.reset(new BamWriter(fh, text, refs));
+        bam.reset(new BamWriter(fh, text, refs, info_->BamLevel));
     }
     grootgpu_align_params prm{};
     prm.containment_threshold = info_->ContainmentThreshold;
     prm.no_align = info_->Sketch.NoExactAlign ? 1 : 0;
     prm.project_on_device = 1;   // graphminion.go:67 IncrementSubPath: ordered f64 weighting on the GPU, bit-identical to the host replay
     ReadBatch b;
-    std::vector<uint8_t> rc_seq, rc_qual;
     uint8_t ctab[256];                     // complementBases (seqio.go:17-23): everything else maps to 0
     memset(ctab, 0, sizeof ctab);
     ctab['A'] = 'T'; ctab['T'] = 'A'; ctab['C'] = 'G'; ctab['G'] = 'C'; ctab['N'] = 'N';
@@ -232,32 +254,70 @@ int ReadMapper::Run(FastqStream& reads) {
         read_stats_[0] += res.received; read_stats_[1] += res.mapped; read_stats_[2] += res.multimapped;
         alignment_count_ += res.alignments;
         if (!bam) continue;
-        for (uint64_t i = 0; i < res.n_pairs; i++) {
-            const grootgpu_pair& p = res.pairs[i];
-            if (p.rec_count == 0) continue;
-            const uint64_t so = b.seq_off[p.read], sl = b.seq_off[p.read + 1] - so;
-            const uint64_t qo = b.qual_off[p.read], ql = b.qual_off[p.read + 1] - qo;
-            const uint8_t* seq = b.seq.data() + so;
-            const uint8_t* qual = b.qual.data() + qo;
-            if (ql < sl) {   // FASTA mode / truncated qualities: the reference panics in RevComplement or when slicing Qual (seqio.go:125-127, alignment.go:121)
-                err_ = "read without a full quality string reached the BAM writer (the reference panics here)";
-                return GROOTGPU_ERR_FORMAT;
+        // Records of the batch, in pair order == (read, graph) order. NumProc workers each format and deflate a
+        // contiguous slice of the pairs (slices of roughly equal record count) into ready-made BGZF blocks; the slices
+        // are appended in order. One worker reproduces the serial writer byte for byte up to block boundaries.
+        const unsigned workers = static_cast<unsigned>(std::max(1, info_->NumProc));
+        std::vector<uint64_t> cut(workers + 1, res.n_pairs);
+        cut[0] = 0;
+        {
+            uint64_t i = 0;
+            for (unsigned t = 1; t < workers; t++) {
+                const uint64_t want = res.n_records * t / workers;
+                while (i < res.n_pairs && res.pairs[i].rec_begin < want) i++;
+                cut[t] = i;
             }
-            if (p.reverse) {                                           // read.RevComplement() (seqio.go:120-133)
-                rc_seq.resize(sl); rc_qual.resize(sl);
-                for (uint64_t k = 0; k < sl; k++) { rc_seq[k] = ctab[seq[sl - 1 - k]]; rc_qual[k] = qual[sl - 1 - k]; }
-                seq = rc_seq.data(); qual = rc_qual.data();
-            }
-            const uint32_t match = static_cast<uint32_t>(sl) - p.clip_start - p.clip_end;     // alignment.go:117
-            const uint64_t io = b.id_off[p.read], il = b.id_off[p.read + 1] - io;
-            for (uint32_t j = 0; j < p.rec_count; j++) {
-                uint16_t flag = 0;
-                if (p.rec_count > 1 && j != 0) flag |= 0x100;          // sam.Secondary (alignment.go:147-149)
-                if (p.reverse) flag |= 0x10;                           // sam.Reverse (alignment.go:150-152)
-                bam->write(b.id.data() + io + 1, static_cast<uint32_t>(il ? il - 1 : 0),                  // Name = ID[1:] (alignment.go:119)
-                           static_cast<int32_t>(graph_ref_base[p.graph] + res.rec_path[p.rec_begin + j]), res.rec_pos[p.rec_begin + j], flag,
-                           p.clip_start, match, p.clip_end, seq, qual);  // Seq/Qual = read[0:seqLength] (alignment.go:120-121)
-            }
+        }
+        std::vector<std::vector<uint8_t>> outs(workers);
+        std::vector<std::string> errs(workers);
+        auto work = [&](unsigned t) {
+            std::vector<uint8_t> raw, rc_seq, rc_qual;
+            std::vector<uint8_t>& out = outs[t];
+            try {
+                for (uint64_t i = cut[t]; i < cut[t + 1]; i++) {
+                    const grootgpu_pair& p = res.pairs[i];
+                    if (p.rec_count == 0) continue;
+                    const uint64_t so = b.seq_off[p.read], sl = b.seq_off[p.read + 1] - so;
+                    const uint64_t qo = b.qual_off[p.read], ql = b.qual_off[p.read + 1] - qo;
+                    const uint8_t* seq = b.seq.data() + so;
+                    const uint8_t* qual = b.qual.data() + qo;
+                    if (ql < sl) {   // FASTA mode / truncated qualities: the reference panics in RevComplement or when slicing Qual (seqio.go:125-127, alignment.go:121)
+                        errs[t] = "read without a full quality string reached the BAM writer (the reference panics here)";
+                        return;
+                    }
+                    if (p.reverse) {                                           // read.RevComplement() (seqio.go:120-133)
+                        rc_seq.resize(sl); rc_qual.resize(sl);
+                        for (uint64_t k = 0; k < sl; k++) { rc_seq[k] = ctab[seq[sl - 1 - k]]; rc_qual[k] = qual[sl - 1 - k]; }
+                        seq = rc_seq.data(); qual = rc_qual.data();
+                    }
+                    const uint32_t match = static_cast<uint32_t>(sl) - p.clip_start - p.clip_end;     // alignment.go:117
+                    const uint64_t io = b.id_off[p.read], il = b.id_off[p.read + 1] - io;
+                    for (uint32_t j = 0; j < p.rec_count; j++) {
+                        uint16_t flag = 0;
+                        if (p.rec_count > 1 && j != 0) flag |= 0x100;          // sam.Secondary (alignment.go:147-149)
+                        if (p.reverse) flag |= 0x10;                           // sam.Reverse (alignment.go:150-152)
+                        BamWriter::format_record(raw, b.id.data() + io + 1, static_cast<uint32_t>(il ? il - 1 : 0),          // Name = ID[1:] (alignment.go:119)
+                                                 static_cast<int32_t>(graph_ref_base[p.graph] + res.rec_path[p.rec_begin + j]), res.rec_pos[p.rec_begin + j], flag,
+                                                 p.clip_start, match, p.clip_end, seq, qual);  // Seq/Qual = read[0:seqLength] (alignment.go:120-121)
+                    }
+                    if (raw.size() >= (1u << 20)) {                            // deflate whole blocks, keep the remainder
+                        const size_t whole = raw.size() / kBgzfBlock * kBgzfBlock;
+                        BamWriter::compress_blocks(raw.data(), whole, info_->BamLevel, out);
+                        raw.erase(raw.begin(), raw.begin() + whole);
+                    }
+                }
+                BamWriter::compress_blocks(raw.data(), raw.size(), info_->BamLevel, out);
+            } catch (std::exception& e) { errs[t] = e.what(); }
+        };
+        {
+            std::vector<std::thread> th;
+            for (unsigned t = 1; t < workers; t++) th.emplace_back(work, t);
+            work(0);
+            for (auto& x : th) x.join();
+        }
+        for (unsigned t = 0; t < workers; t++) {
+            if (!errs[t].empty()) { err_ = errs[t]; return GROOTGPU_ERR_FORMAT; }
+            bam->append_blocks(outs[t]);
         }
     }
     if (reads.rawCount() == 0) { err_ = "no fastq reads received"; return GROOTGPU_ERR_EMPTY; }   // sketch.go:275-277
@@ -286,6 +346,104 @@ int GraphPruner::Run() {
         }
     }
     return 0;
+}
+
+// ---- groot report (src/reporting/reporting.go) ---------------------------------------------------------------------
+// reporting.go:178-213, kept statement for statement (including what it does with the last element)
+std::string cigarClean(const std::vector<char>& str, bool* internal_d) {
+    int counter = 1;
+    char preVal = str.empty() ? 'M' : str[0];
+    std::string cigar;
+    int nD = 0, nM = 0;
+    auto bump = [&](char v) { if (v == 'D') nD++; else nM++; };
+    for (size_t i = 0; i < str.size(); i++) {
+        const char val = str[i];
+        if (i == 0) continue;
+        if (i == str.size() - 1) {
+            if (val == preVal) { counter++; cigar += std::to_string(counter) + val; bump(val); }
+            else { cigar += std::to_string(counter) + preVal + "1" + val; bump(val); }
+            break;
+        }
+        if (val == preVal) counter++;
+        else { bump(preVal); cigar += std::to_string(counter) + preVal; preVal = val; counter = 1; }
+    }
+    *internal_d = !(((nD + nM) <= 2) || (nD == 2 && nM == 1));
+    return cigar;
+}
+
+std::vector<ReportLine> RunReport(const std::string& input_file, double coverage_cutoff, bool low_cov) {
+    gzFile gz = input_file.empty() ? gzdopen(0, "rb") : gzopen(input_file.c_str(), "rb");   // BGZF == concatenated gzip members
+    if (!gz) throw std::runtime_error("could not open BAM file " + input_file);
+    gzbuffer(gz, 1 << 20);
+    auto need = [&](void* dst, size_t n) {
+        size_t got = 0;
+        while (got < n) {
+            const int r = gzread(gz, static_cast<char*>(dst) + got, static_cast<unsigned>(std::min<size_t>(n - got, 1u << 30)));
+            if (r <= 0) return got;
+            got += static_cast<size_t>(r);
+        }
+        return got;
+    };
+    auto fail = [&](const char* m) { gzclose(gz); throw std::runtime_error(std::string("could not read BAM file: ") + m); };
+    char magic[4];
+    if (need(magic, 4) != 4 || memcmp(magic, "BAM\1", 4) != 0) fail("bad magic");
+    int32_t l_text = 0, n_ref = 0;
+    if (need(&l_text, 4) != 4 || l_text < 0) fail("truncated header");
+    std::string text(static_cast<size_t>(l_text), 0);
+    if (need(&text[0], text.size()) != text.size() || need(&n_ref, 4) != 4 || n_ref < 0) fail("truncated header");
+    std::vector<std::pair<std::string, int32_t>> refs(static_cast<size_t>(n_ref));
+    for (auto& r : refs) {
+        int32_t l_name = 0;
+        if (need(&l_name, 4) != 4 || l_name < 1) fail("truncated reference list");
+        r.first.assign(static_cast<size_t>(l_name), 0);
+        if (need(&r.first[0], r.first.size()) != r.first.size() || need(&r.second, 4) != 4) fail("truncated reference list");
+        r.first.pop_back();
+    }
+    // records: (start, reference length of the alignment) per reference; Flags == 4 (unaligned) are skipped (reporting.go:79-83)
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> recs(refs.size());
+    std::vector<uint8_t> rec;
+    while (true) {
+        int32_t block = 0;
+        const size_t g = need(&block, 4);
+        if (g == 0) break;
+        if (g != 4 || block < 32) fail("truncated record");
+        rec.resize(static_cast<size_t>(block));
+        if (need(rec.data(), rec.size()) != rec.size()) fail("truncated record");
+        int32_t ref_id, pos; uint16_t n_cig, flag; uint8_t l_name;
+        memcpy(&ref_id, &rec[0], 4); memcpy(&pos, &rec[4], 4); l_name = rec[8]; memcpy(&n_cig, &rec[12], 2); memcpy(&flag, &rec[14], 2);
+        if (flag == 4) continue;
+        if (ref_id < 0 || static_cast<size_t>(ref_id) >= refs.size() || 32u + l_name + 4u * n_cig > rec.size()) fail("bad record");
+        int32_t len = 0;                                       // sam.Record.Len(): reference bases consumed (M, D, N, =, X)
+        for (uint16_t c = 0; c < n_cig; c++) {
+            uint32_t op; memcpy(&op, &rec[32 + l_name + 4 * c], 4);
+            const uint32_t t = op & 15u;
+            if (t == 0 || t == 2 || t == 3 || t == 7 || t == 8) len += static_cast<int32_t>(op >> 4);
+        }
+        recs[static_cast<size_t>(ref_id)].push_back({pos, len});
+    }
+    gzclose(gz);
+    std::vector<ReportLine> out;
+    for (size_t r = 0; r < refs.size(); r++) {
+        if (recs[r].empty() || refs[r].second <= 0) continue;
+        std::vector<int> pileup(static_cast<size_t>(refs[r].second), 0);
+        for (auto& pr : recs[r]) {
+            int start = pr.first, end = pr.first + pr.second;                 // inclusive end, as the reference iterates (reporting.go:108-121)
+            if (end > static_cast<int>(pileup.size()) - 1) end = static_cast<int>(pileup.size()) - 1;
+            for (int i = std::max(start, 0); i <= end; i++) pileup[static_cast<size_t>(i)]++;
+        }
+        size_t covered = 0;
+        for (int v : pileup) covered += v != 0;
+        if (static_cast<double>(covered) / static_cast<double>(pileup.size()) < coverage_cutoff) continue;
+        std::vector<char> cig(pileup.size());
+        for (size_t i = 0; i < pileup.size(); i++) cig[i] = pileup[i] == 0 ? 'D' : 'M';
+        bool internal_d = false;
+        std::string clean = cigarClean(cig, &internal_d);
+        if (internal_d && low_cov) continue;
+        std::string name = refs[r].first;
+        if (!name.empty() && name[0] == '*') name.erase(0, 1);                // cluster representative marker (reporting.go:130-133)
+        out.push_back({name, recs[r].size(), refs[r].second, clean});
+    }
+    return out;
 }
 
 }  // namespace groot_host

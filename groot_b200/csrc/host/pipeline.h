@@ -36,6 +36,7 @@ struct Info {
     std::string GraphDir = "./groot-graphs";  // -g
     uint32_t BatchReads = 1u << 20;           // reads per device batch (no counterpart: the reference streams single reads)
     int Device = 0;
+    int BamLevel = -1;                        // deflate level of the BGZF blocks (-1 = zlib default, like bam.NewWriter; 0..9)
 };
 
 // seqio.FASTQread for a whole batch (src/seqio/seqio.go:26-37), struct-of-arrays
@@ -68,19 +69,29 @@ class FastqStream {
     uint64_t raw_count_ = 0, length_total_ = 0;
 };
 
-// Minimal BAM writer (what the reference gets from biogo/hts: bam.NewWriter + Write + Close, boss.go:45-105,225-241)
+// Minimal BAM writer (what the reference gets from biogo/hts: bam.NewWriter + Write + Close, boss.go:45-105,225-241).
+// Records can be written one by one (write) or formatted and compressed elsewhere — by NumProc worker threads, each
+// on its own slice of a batch — and appended as ready-made BGZF blocks (append_blocks): a BAM stream is a
+// concatenation of independently deflated blocks, and a record may straddle two of them.
 class BamWriter {
   public:
-    BamWriter(FILE* out, const std::string& sam_header_text, const std::vector<std::pair<std::string, int32_t>>& refs);
+    BamWriter(FILE* out, const std::string& sam_header_text, const std::vector<std::pair<std::string, int32_t>>& refs, int level = -1);
     ~BamWriter();
     // one sam.Record as AlignRead builds it (src/graph/alignment.go:114-156)
     void write(const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag, uint32_t clip_start, uint32_t match_len,
                uint32_t clip_end, const uint8_t* seq, const uint8_t* qual);
+    void append_blocks(const std::vector<uint8_t>& bgzf);   // flushes what write() buffered, then appends the blocks as they are
     void close();  // flushes and appends the BGZF EOF block
+    // the same record, appended to a caller-owned buffer of uncompressed BAM bytes
+    static void format_record(std::vector<uint8_t>& buf, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
+                              uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual);
+    // deflates data[0, n) into BGZF blocks of at most 0xff00 input bytes, appended to out
+    static void compress_blocks(const uint8_t* data, size_t n, int level, std::vector<uint8_t>& out);
   private:
     void flush_block();
     FILE* out_;
     std::vector<uint8_t> buf_;
+    int level_;
     bool closed_ = false;
 };
 
@@ -101,6 +112,15 @@ class ReadMapper {
     uint64_t alignment_count_ = 0;
     std::string err_;
 };
+
+// `groot report` (cmd/report.go:104-129 -> reporting.BAMreader.Run, src/reporting/reporting.go:33-173): BAM from a file
+// or STDIN -> per-reference pileup -> references whose breadth of coverage reaches the cutoff, one line each:
+// gene \t read count \t gene length \t coverage cigar (cigarClean, reporting.go:178-213). The reference prints in Go
+// map order; here the lines come in @SQ order.
+struct ReportLine { std::string arg; size_t count; int32_t length; std::string cigar; };
+// input_file == "" reads STDIN. Throws std::runtime_error on a malformed BAM.
+std::vector<ReportLine> RunReport(const std::string& input_file, double coverage_cutoff, bool low_cov);
+std::string cigarClean(const std::vector<char>& str, bool* internal_d);
 
 class GraphPruner {
   public:

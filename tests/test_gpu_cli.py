@@ -49,6 +49,11 @@ def test_cli_oxa_cluster_bam_and_gfa(root, tmp_path):
     total_kmers = int(o.weights()[1].sum())
     gfa = open(tmp_path / "graphs" / "groot-graph-0.gfa").read()
     assert gfa == o.gfa_text(0, total_kmers)
+    # -p 5: five workers format and deflate slices of every batch; the decoded stream is the serial writer's, record for record
+    _run("align", "-i", str(tmp_path / "idx"), "-f", fq, "-t", "0.99", "-c", "10", "-g", str(tmp_path / "graphs5"),
+         "--bamOut", str(tmp_path / "out5.bam"), "--batchReads", "700", "-p", "5", "--bamLevel", "1")
+    text5, refs5, recs5 = read_bam(str(tmp_path / "out5.bam"))
+    assert refs5 == refs and recs5 == recs
 
 
 def test_cli_travis_blaB7(db_dirs, root, tmp_path):
@@ -62,6 +67,13 @@ def test_cli_travis_blaB7(db_dirs, root, tmp_path):
     ref_len = dict(refs)
     rep = report([(r["ref"], r["pos"], int(r["cigar"].rstrip("MH").split("H")[-1])) for r in recs if r["flag"] != 4], ref_len, 0.97)
     assert list(rep) == ["argannot~~~(Bla)B-7~~~AF189304:1-747"]
+    # the same through the driver's own report command, fed from STDIN like `groot align | groot report` (run_travis_tests.sh:43-56)
+    with open(tmp_path / "groot.bam", "rb") as f:
+        r = subprocess.run([CLI, "report", "-c", "0.97"], stdin=f, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()
+    lines = [l.split("\t") for l in r.stdout.decode().splitlines()]
+    assert [l[0] for l in lines] == ["argannot~~~(Bla)B-7~~~AF189304:1-747"] and int(lines[0][2]) == 747
+    assert int(lines[0][1]) == rep["argannot~~~(Bla)B-7~~~AF189304:1-747"][0]
 
 
 def test_cli_errors(tmp_path, root):

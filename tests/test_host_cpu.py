@@ -81,3 +81,76 @@ def test_synth_reads_deterministic_and_composed(db_dirs):
     assert set(np.unique(b1)) <= set(b"ACGTN")
     res = po.Index(msa_dir=db_dirs["arg-annot.90"]).map_reads(b1[:100 * 1000], o1[:1001], 0.99, threads=4)
     assert 0.4 < res.counts["mapped"] / 1000 < 0.6         # ~50 % exact substrings seed, the rest never does
+
+
+def _cigar_clean_py(s):
+    """src/reporting/reporting.go:178-213, statement for statement."""
+    counter, pre, cigar, dm = 1, s[0], "", {"D": 0, "M": 0}
+    for i, v in enumerate(s):
+        if i == 0:
+            continue
+        if i == len(s) - 1:
+            if v == pre:
+                counter += 1
+                cigar += "%d%s" % (counter, v)
+            else:
+                cigar += "%d%s1%s" % (counter, pre, v)
+            dm[v] += 1
+            break
+        if v == pre:
+            counter += 1
+        else:
+            dm[pre] += 1
+            cigar += "%d%s" % (counter, pre)
+            pre, counter = v, 1
+    return cigar, not ((dm["D"] + dm["M"]) <= 2 or (dm["D"] == 2 and dm["M"] == 1))
+
+
+def _bam_bytes(refs, recs):
+    """Uncompressed BAM of records (ref_id, pos, flag, cigar ops [(len, op)]) with empty names / sequences."""
+    import struct
+    out = b"BAM\x01" + struct.pack("<i", 0) + struct.pack("<i", len(refs))
+    for name, ln in refs:
+        out += struct.pack("<i", len(name) + 1) + name.encode() + b"\0" + struct.pack("<i", ln)
+    for ref_id, pos, flag, cig in recs:
+        body = struct.pack("<iiBBHHHiiii", ref_id, pos, 2, 30, 0, len(cig), flag, 0, -1, -1, 0) + b"r\0"
+        body += b"".join(struct.pack("<I", (n << 4) | op) for n, op in cig)
+        out += struct.pack("<i", len(body)) + body
+    return out
+
+
+def test_cli_report_matches_reference_logic(root, tmp_path):
+    """`groot-b200 report` (host only, no device): pileup with the reference's inclusive end, coverage cutoff, asterisk
+    stripping, Flags == 4 skipped, cigarClean incl. its last-element quirk, --lowCov dropping internal gaps
+    (src/reporting/reporting.go:33-213, cmd/report.go:104-129)."""
+    import gzip
+    import subprocess
+    cli = os.path.join(root, "groot_b200", "groot-b200")
+    refs = [("*geneA", 300), ("geneB", 200), ("geneC", 150), ("geneD", 100)]
+    recs = [(0, p, 0, [(100, 0)]) for p in (0, 90, 180, 199)]                       # geneA fully covered
+    recs += [(1, 0, 16, [(1, 5), (99, 0)]), (1, 120, 256, [(79, 0), (1, 5)])]      # geneB: internal gap, hard clips do not count
+    recs += [(2, 10, 0, [(100, 0)])]                                               # geneC: 5' and 3' uncovered
+    recs += [(3, 0, 4, [(100, 0)])]                                                # geneD: unaligned flag only
+    raw = _bam_bytes(refs, recs)
+    open(tmp_path / "x.bam", "wb").write(gzip.compress(raw[:200]) + gzip.compress(raw[200:]))    # two gzip members, like BGZF blocks
+    def run(*extra):
+        r = subprocess.run([cli, "report", "--bamFile", str(tmp_path / "x.bam")] + list(extra), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr.decode()
+        return [l.split("\t") for l in r.stdout.decode().splitlines()]
+    def expect(name, n, positions):
+        cov = ["D"] * n
+        for pos, ln in positions:
+            for i in range(pos, min(pos + ln, n - 1) + 1):
+                cov[i] = "M"
+        return cov
+    a = expect("geneA", 300, [(0, 100), (90, 100), (180, 100), (199, 100)])
+    b = expect("geneB", 200, [(0, 99), (120, 79)])
+    c = expect("geneC", 150, [(10, 100)])
+    assert a.count("M") == 300
+    got = run("-c", "0.5")
+    assert got == [["geneA", "4", "300", _cigar_clean_py(a)[0]], ["geneB", "2", "200", _cigar_clean_py(b)[0]], ["geneC", "1", "150", _cigar_clean_py(c)[0]]]
+    assert run() == [["geneA", "4", "300", _cigar_clean_py(a)[0]]]                  # default cutoff 0.97
+    assert _cigar_clean_py(b)[1] and not _cigar_clean_py(c)[1]
+    assert run("-c", "0.5", "--lowCov") == [["geneA", "4", "300", _cigar_clean_py(a)[0]]]   # --lowCov forces 0.97 (cmd/report.go:118-122)
+    r = subprocess.run([cli, "report", "--bamFile", str(tmp_path / "x.txt")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0
