@@ -7,6 +7,8 @@
 #include <cstring>
 #include <ctime>
 #include <memory>
+#include <mutex>
+#include <condition_variable>
 #include <stdexcept>
 #include <thread>
 
@@ -37,57 +39,87 @@ bool FastqStream::open_next() {
     }
     if (!gz_) throw std::runtime_error("cannot open input");
     gzbuffer(static_cast<gzFile>(gz_), 1 << 20);
+    pos_ = end_ = 0; eof_ = false;
     return true;
 }
 
-// bufio.Scanner with ScanLines: strips the trailing "\n" and an optional "\r"
-bool FastqStream::getline(std::string& line) {
-    line.clear();
+// more bytes of the current file behind the unconsumed tail; false when the file has no more
+bool FastqStream::refill() {
+    if (eof_) return false;
+    if (buf_.size() < (8u << 20)) buf_.resize(8u << 20);
+    if (pos_ > 0) { memmove(buf_.data(), buf_.data() + pos_, end_ - pos_); end_ -= pos_; pos_ = 0; }
+    if (end_ == buf_.size()) buf_.resize(buf_.size() * 2);           // one line longer than the buffer
+    const int got = gzread(static_cast<gzFile>(gz_), buf_.data() + end_, static_cast<unsigned>(std::min<size_t>(buf_.size() - end_, 1u << 30)));
+    if (got < 0) throw std::runtime_error("error reading input file");
+    if (got == 0) { eof_ = true; return false; }
+    end_ += static_cast<size_t>(got);
+    return true;
+}
+
+// bufio.Scanner with ScanLines: strips the trailing "\n" and an optional "\r"; the last line of a file needs no newline;
+// every file is scanned on its own (sketch.go:55-75)
+bool FastqStream::getline(const char*& line, size_t& len) {
     while (true) {
         if (!gz_ && !open_next()) return false;
-        char buf[1 << 16];
-        bool got = false;
-        while (gzgets(static_cast<gzFile>(gz_), buf, sizeof buf)) {
-            got = true;
-            size_t n = strlen(buf);
-            line.append(buf, n);
-            if (n && buf[n - 1] == '\n') { line.pop_back(); if (!line.empty() && line.back() == '\r') line.pop_back(); return true; }
+        while (true) {
+            const char* nl = pos_ < end_ ? static_cast<const char*>(memchr(buf_.data() + pos_, '\n', end_ - pos_)) : nullptr;
+            if (nl) {
+                line = buf_.data() + pos_; len = static_cast<size_t>(nl - line);
+                pos_ += len + 1;
+                if (len && line[len - 1] == '\r') len--;
+                return true;
+            }
+            if (!refill()) break;
         }
-        if (got) return true;                                   // last line of a file without a trailing newline
-        gzclose(static_cast<gzFile>(gz_)); gz_ = nullptr;       // end of this file: the next one is scanned on its own (sketch.go:55-75)
+        if (pos_ < end_) {                                          // unterminated last line
+            line = buf_.data() + pos_; len = end_ - pos_;
+            pos_ = end_;
+            if (len && line[len - 1] == '\r') len--;
+            return true;
+        }
+        gzclose(static_cast<gzFile>(gz_)); gz_ = nullptr;           // end of this file
     }
 }
 
 // ---- FastqHandler (sketch.go:175-238) + FastqChecker (sketch.go:259-282) ---------------------------------------
 bool FastqStream::next(ReadBatch& b, uint32_t max_reads) {
     b.clear();
-    std::string l1, l2, l3, l4;
-    auto push = [&](const std::string& id, const std::string& seq, const std::string& qual) {
-        b.id.insert(b.id.end(), id.begin(), id.end()); b.id_off.push_back(b.id.size());
-        b.seq.insert(b.seq.end(), seq.begin(), seq.end()); b.seq_off.push_back(b.seq.size());
-        b.qual.insert(b.qual.end(), qual.begin(), qual.end()); b.qual_off.push_back(b.qual.size());
-        raw_count_++; length_total_ += seq.size();
+    auto push = [&](const char* id, size_t id_n, const char* seq, size_t seq_n, const char* qual, size_t qual_n) {
+        b.id.insert(b.id.end(), id, id + id_n); b.id_off.push_back(b.id.size());
+        b.seq.insert(b.seq.end(), seq, seq + seq_n); b.seq_off.push_back(b.seq.size());
+        b.qual.insert(b.qual.end(), qual, qual + qual_n); b.qual_off.push_back(b.qual.size());
+        raw_count_++; length_total_ += seq_n;
     };
+    const char* p; size_t n;
     if (fasta_) {
         // '>' starts an entry, sequence lines are concatenated, an empty line ends the input (sketch.go:179-212)
-        std::string line;
+        auto flush = [&] { pending_header_[0] = '@'; push(pending_header_.data(), pending_header_.size(), fasta_seq_.data(), fasta_seq_.size(), "", 0); };
         while (b.size() < max_reads) {
-            if (!getline(line) || line.empty()) {
-                if (!pending_header_.empty()) { pending_header_[0] = '@'; push(pending_header_, l2, ""); pending_header_.clear(); }
+            if (!getline(p, n) || n == 0) {
+                if (!pending_header_.empty()) { flush(); pending_header_.clear(); }
                 break;
             }
-            if (line[0] == '>') {
-                if (!pending_header_.empty()) { pending_header_[0] = '@'; push(pending_header_, l2, ""); }
-                pending_header_ = line; l2.clear();
-            } else l2 += line;
+            if (p[0] == '>') {
+                if (!pending_header_.empty()) flush();
+                pending_header_.assign(p, n); fasta_seq_.clear();
+            } else fasta_seq_.append(p, n);
         }
         return b.size() > 0;
     }
+    // a record's four lines are copied into the batch as they are found (a view does not survive the next getline)
     while (b.size() < max_reads) {
-        if (!getline(l1) || !getline(l2) || !getline(l3) || !getline(l4)) break;   // an incomplete trailing record is dropped (sketch.go:216-236)
-        if (l1.empty() || l1[0] != '@')   // seqio.NewFASTQread (seqio.go:178-180) -> log.Fatal
-            throw std::runtime_error("read ID in fastq file does not begin with @: " + l1);
-        push(l1, l2, l4);
+        if (!getline(p, n)) break;
+        if (n == 0 || p[0] != '@')   // seqio.NewFASTQread (seqio.go:178-180) -> log.Fatal
+            throw std::runtime_error("read ID in fastq file does not begin with @: " + std::string(p, n));
+        const size_t id0 = b.id.size(), seq0 = b.seq.size(), qual0 = b.qual.size();
+        b.id.insert(b.id.end(), p, p + n);
+        bool ok = getline(p, n);
+        if (ok) { b.seq.insert(b.seq.end(), p, p + n); ok = getline(p, n); }          // line 3 ('+') is dropped
+        if (ok) ok = getline(p, n);
+        if (!ok) { b.id.resize(id0); b.seq.resize(seq0); b.qual.resize(qual0); break; }   // an incomplete trailing record is dropped (sketch.go:216-236)
+        b.qual.insert(b.qual.end(), p, p + n);
+        b.id_off.push_back(b.id.size()); b.seq_off.push_back(b.seq.size()); b.qual_off.push_back(b.qual.size());
+        raw_count_++; length_total_ += b.seq.size() - seq0;
     }
     return b.size() > 0;
 }
@@ -243,11 +275,49 @@ int ReadMapper::Run(FastqStream& reads) {
     prm.containment_threshold = info_->ContainmentThreshold;
     prm.no_align = info_->Sketch.NoExactAlign ? 1 : 0;
     prm.project_on_device = 1;   // graphminion.go:67 IncrementSubPath: ordered f64 weighting on the GPU, bit-identical to the host replay
-    ReadBatch b;
     uint8_t ctab[256];                     // complementBases (seqio.go:17-23): everything else maps to 0
     memset(ctab, 0, sizeof ctab);
     ctab['A'] = 'T'; ctab['T'] = 'A'; ctab['C'] = 'G'; ctab['G'] = 'C'; ctab['N'] = 'N';
-    while (reads.next(b, info_->BatchReads)) {
+    // DataStreamer/FastqHandler run ahead on their own thread, as the reference's stages do (pipeline.go:36-45): the
+    // next batch is parsed while this one is on the GPU and in the BAM workers. Two batch buffers, handed back and forth.
+    struct BatchFeed {
+        FastqStream& reads; uint32_t batch_reads;
+        ReadBatch slot[2];
+        int state[2] = {0, 0};             // 0 = free, 1 = filled, 2 = end of input
+        bool stop = false;
+        std::exception_ptr error;
+        std::mutex mu; std::condition_variable cv;
+        std::thread th;
+        BatchFeed(FastqStream& r, uint32_t n) : reads(r), batch_reads(n) {
+            th = std::thread([this] {
+                try {
+                    for (int i = 0;; i ^= 1) {
+                        { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || state[i] == 0; }); if (stop) return; }
+                        const bool ok = reads.next(slot[i], batch_reads);
+                        { std::lock_guard<std::mutex> lk(mu); state[i] = ok ? 1 : 2; }
+                        cv.notify_all();
+                        if (!ok) return;
+                    }
+                } catch (...) {
+                    { std::lock_guard<std::mutex> lk(mu); error = std::current_exception(); state[0] = state[1] = 2; }
+                    cv.notify_all();
+                }
+            });
+        }
+        ReadBatch* take(int i) {           // nullptr at the end of the input; rethrows the reader's error
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return state[i] != 0; });
+            if (error) std::rethrow_exception(error);
+            return state[i] == 1 ? &slot[i] : nullptr;
+        }
+        void release(int i) { { std::lock_guard<std::mutex> lk(mu); state[i] = 0; } cv.notify_all(); }
+        ~BatchFeed() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); }
+    } feed(reads, info_->BatchReads);
+    for (int slot_i = 0;; slot_i ^= 1) {
+        ReadBatch* bp = feed.take(slot_i);
+        if (!bp) break;
+        struct Release { BatchFeed& f; int i; ~Release() { f.release(i); } } release_slot{feed, slot_i};
+        ReadBatch& b = *bp;
         grootgpu_batch_result res;
         rc = grootgpu_align_batch(index_, b.seq.data(), b.seq_off.data(), b.size(), &prm, &res);
         if (rc) { err_ = grootgpu_last_error(); return rc; }

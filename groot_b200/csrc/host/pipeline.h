@@ -58,14 +58,18 @@ class FastqStream {
     uint64_t lengthTotal() const { return length_total_; }
 
   private:
-    bool getline(std::string& line);
+    bool getline(const char*& line, size_t& len);   // view into the block buffer, valid until the next call
     bool open_next();
+    bool refill();
     std::vector<std::string> files_;
     size_t file_i_ = 0;
     void* gz_ = nullptr;  // gzFile: zlib reads plain files transparently
     bool fasta_;
     bool use_stdin_ = false, stdin_done_ = false;
-    std::string pending_header_;
+    std::string pending_header_, fasta_seq_;
+    std::vector<char> buf_;        // block buffer: lines are found with memchr and copied once, into the batch
+    size_t pos_ = 0, end_ = 0;
+    bool eof_ = true;              // of the current file
     uint64_t raw_count_ = 0, length_total_ = 0;
 };
 

@@ -154,3 +154,36 @@ def test_cli_report_matches_reference_logic(root, tmp_path):
     assert run("-c", "0.5", "--lowCov") == [["geneA", "4", "300", _cigar_clean_py(a)[0]]]   # --lowCov forces 0.97 (cmd/report.go:118-122)
     r = subprocess.run([cli, "report", "--bamFile", str(tmp_path / "x.txt")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode != 0
+
+
+def test_fastq_stream_edge_cases(root, tmp_path):
+    """The host driver's reader (block buffer + memchr) keeps the reference's line semantics (src/pipeline/sketch.go:41-77,
+    175-238): CRLF, a last line without newline, an incomplete trailing record dropped, every file scanned on its own,
+    gzip by content, FASTA mode ('>' entries, an empty line ends the input), '@' check -> fatal, batches of any size."""
+    import gzip
+    import subprocess
+    exe = str(tmp_path / "fastq_dump")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cpp", "fastq_dump.cpp"),
+                           os.path.join(root, "groot_b200", "csrc", "host", "pipeline.cpp"), "-L" + os.path.join(root, "groot_b200"), "-lgrootgpu", "-lz",
+                           "-pthread", "-Wl,-rpath," + os.path.join(root, "groot_b200")])
+    def run(*args):
+        r = subprocess.run([exe] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        return r.returncode, r.stdout.decode().splitlines(), r.stderr.decode()
+    a = tmp_path / "a.fq"; a.write_bytes(b"@r1 x y\nACGT\n+\nIIII\n@r2\r\nAC\r\n+r2\r\nI#\r\n@r3\nGG\n+\n!!")           # no newline at the end
+    b = tmp_path / "b.fq.gz"; b.write_bytes(gzip.compress(b"@r4\nTTTT\n+\nJJJJ\n@r5\nAAAA\n+\n"))                      # r5 lacks its quality line
+    rc, out, _ = run(a, b)
+    assert rc == 0 and out == ["@r1 x y\tACGT\tIIII", "@r2\tAC\tI#", "@r3\tGG\t!!", "@r4\tTTTT\tJJJJ", "#4 12"]
+    assert run("--batch", "1", a, b)[1] == out and run("--batch", "1000", a, b)[1] == out
+    big = tmp_path / "big.fq"                                                                                           # lines across buffer refills
+    long_seq = "ACGT" * 3_000_000
+    big.write_text("@L\n%s\n+\n%s\n@S\nA\n+\nI\n" % (long_seq, "I" * len(long_seq)))
+    rc, out, _ = run(big)
+    assert rc == 0 and out[-1] == "#2 %d" % (len(long_seq) + 1) and out[1] == "@S\tA\tI" and len(out[0]) == 4 + 2 * len(long_seq)
+    bad = tmp_path / "bad.fq"; bad.write_bytes(b"@ok\nA\n+\nI\nnot a header\nA\n+\nI\n")
+    rc, _, err = run(bad)
+    assert rc == 2 and "does not begin with @" in err
+    fa = tmp_path / "x.fa"; fa.write_bytes(b">s1 d\nACGT\nAC\n>s2\nGG\n\n>never\nTT\n")
+    rc, out, _ = run("--fasta", fa)
+    assert rc == 0 and out == ["@s1 d\tACGTAC\t", "@s2\tGG\t", "#2 8"]
+    rc, _, err = run(tmp_path / "missing.fq")
+    assert rc == 2 and "no such file" in err
