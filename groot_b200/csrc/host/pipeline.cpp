@@ -94,9 +94,10 @@ bool FastqStream::next(ReadBatch& b, uint32_t max_reads) {
     if (fasta_) {
         // '>' starts an entry, sequence lines are concatenated, an empty line ends the input (sketch.go:179-212)
         auto flush = [&] { pending_header_[0] = '@'; push(pending_header_.data(), pending_header_.size(), fasta_seq_.data(), fasta_seq_.size(), "", 0); };
-        while (b.size() < max_reads) {
-            if (!getline(p, n) || n == 0) {
+        while (b.size() < max_reads && !fasta_done_) {
+            if (!getline(p, n) || n == 0) {                       // an empty line ends the input for good (sketch.go:180-182)
                 if (!pending_header_.empty()) { flush(); pending_header_.clear(); }
+                fasta_done_ = true;
                 break;
             }
             if (p[0] == '>') {

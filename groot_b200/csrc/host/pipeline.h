@@ -70,6 +70,7 @@ class FastqStream {
     std::vector<char> buf_;        // block buffer: lines are found with memchr and copied once, into the batch
     size_t pos_ = 0, end_ = 0;
     bool eof_ = true;              // of the current file
+    bool fasta_done_ = false;
     uint64_t raw_count_ = 0, length_total_ = 0;
 };
 
