@@ -39,7 +39,7 @@ for extra in (["--noAlign"], ["-p", "1", "--bamLevel", "1"], ["-p", "16", "--bam
     out = os.path.join(tmp, "out.bam")
     t0 = time.time()
     with open(out, "wb") as f:
-        r = subprocess.run([CLI, "align", "-i", os.path.join(tmp, "idx"), "-f", fq, "-g", os.path.join(tmp, "graphs"), "--batchReads", "2000000"] + extra,
+        r = subprocess.run([CLI, "align", "-i", os.path.join(tmp, "idx"), "-f", fq, "-g", os.path.join(tmp, "graphs")] + extra,
                            stdout=f, stderr=subprocess.PIPE)
     dt = time.time() - t0
     assert r.returncode == 0, r.stderr.decode()
