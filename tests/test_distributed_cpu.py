@@ -55,6 +55,15 @@ def _worker(rank, world, port, tmp):
         local = _oracle_result_arrays(idx, blob, off)
         tens = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.uint8).reshape(-1).copy()) for k, v in local.items()}
         gathered = gd.gather_results(tens, dst=0)
+        # the bench's OverlappedGather must hand rank 0 the same bytes (on CPU / gloo it degrades to the blocking gather;
+        # its stream-ordered NCCL form runs in bench.py --gpus N on the GPU box)
+        og = gd.OverlappedGather(torch.device("cpu"), dst=0)
+        og.submit(tens)
+        again = og.flush()
+        if rank == 0:
+            assert all(torch.equal(again[r][k], gathered[r][k]) for r in range(world) for k in gd.RESULT_KEYS)
+        else:
+            assert again is None
         if rank == 0:
             from groot_b200.api import PAIR_DTYPE
             dt = {"hit_off": np.uint32, "hits": np.uint32, "pairs": PAIR_DTYPE, "rec_path": np.uint32, "rec_pos": np.int32}
