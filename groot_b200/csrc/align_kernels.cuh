@@ -181,6 +181,7 @@ struct AlignArgs {
     unsigned long long* counters;  // [3] += pairs that needed the sequential continuation (diagnostic)
     const uint32_t* reads2;        // 2-bit copies of the seeded reads, both orientations (seed_kernels.cuh, pack_reads_kernel)
     const uint8_t* read_ok2;       // [n_reads] 1 when reads2 holds the read
+    const uint4* read_oh;          // [n_reads] one-hot 8-base prefixes of the read / its reverse complement (pack_reads_kernel)
     uint32_t nw32;                 // words per orientation; 0 = no packed copies
 };
 
@@ -464,9 +465,8 @@ __device__ __forceinline__ void warp_read_prefix(const AlignArgs& a, uint32_t r,
                                                  uint32_t (&oh)[2]) {
     constexpr uint32_t m2 = (1u << (2 * kPrefixBases)) - 1u, m1 = (1u << kPrefixBases) - 1u;
     if (a.nw32 && a.read_ok2[r]) {
-        const uint32_t* rd2 = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32 + (rc ? a.nw32 : 0u);
-        const uint32_t base0 = rc ? a.nw32 * 16u - len : 0u;
-        oh[0] = read_onehot(extract16(rd2, base0) & m2, 0u); oh[1] = read_onehot(extract16(rd2, base0 + 1) & m2, 0u);   // prefix_pass never looks past the read's end
+        const uint4 q = __ldg(a.read_oh + r);
+        oh[0] = rc ? q.z : q.x; oh[1] = rc ? q.w : q.y;
         return;
     }
     uint32_t code = 4;
@@ -557,9 +557,8 @@ __global__ void __launch_bounds__(256) align_screen_kernel(DevIndex ix, RoundArg
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t q = gwarp; q < n_queue; q += total_warps) {
         const uint32_t s = ra.queue[q];
-        const uint32_t hb = a.seg_begin[s];
-        const uint32_t he = (s + 1 < n_segs) ? a.seg_begin[s + 1] : n_hits;
-        const uint32_t r = a.hit_read[hb];
+        const PairOut pp = a.pairs[s];                                 // one sector: read, hit range (filled by align_init_kernel)
+        const uint32_t hb = pp.hit_begin, he = hb + pp.hit_count, r = pp.read;
         const uint32_t o = a.off[r], len = a.off[r + 1] - o;
         const uint8_t* rp = a.seq + o;
         const PairCursor cur = ra.cursor[s];
@@ -671,9 +670,8 @@ __global__ void __launch_bounds__(128, 5) align_finish_kernel(DevIndex ix, Round
     uint32_t* mask_ws = a.mask_ws + static_cast<size_t>(gthread) * depth_cap * kMaskWordsInline;
     for (uint32_t q = gwarp; q < n_queue; q += total_warps) {
         const uint32_t s = ra.queue[q];
-        const uint32_t hb = a.seg_begin[s];
-        const uint32_t he = (s + 1 < n_segs) ? a.seg_begin[s + 1] : n_hits;
-        const uint32_t r = a.hit_read[hb];
+        const PairOut pp = a.pairs[s];                                 // one sector: read, hit range (filled by align_init_kernel)
+        const uint32_t hb = pp.hit_begin, he = hb + pp.hit_count, r = pp.read;
         const uint32_t o = a.off[r], len = a.off[r + 1] - o;
         const uint8_t* rp = a.seq + o;
         const PairCursor cur = ra.cursor[s];

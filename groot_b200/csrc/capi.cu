@@ -198,7 +198,7 @@ struct Workspace {
     uint32_t* h_peek = nullptr;        // mapped pinned words the device writes scalars into (peek()): no copy engine involved
     uint32_t* d_peek = nullptr;
     DBuf seq, off, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
-        rec_path, rec_pos, stack_ws, cub_tmp, cub_tmp2, sketches, tile_counter, error, reads2, read_ok2, qkey, qkey2, order, slow_q, len_minmax, seed_q,
+        rec_path, rec_pos, stack_ws, cub_tmp, cub_tmp2, sketches, tile_counter, error, reads2, read_ok2, read_oh, qkey, qkey2, order, slow_q, len_minmax, seed_q,
         item_cnt, item_off, pkeys, pkeys2, pvals, pvals2;
     DBuf alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches;   // the other result set of the chunked host path
     // ordering of the graph weighting across lanes (chunked host path): called around the accumulate of a chunk
@@ -685,8 +685,8 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         // 2-bit copies of the seeded reads (both orientations) for the packed walk; reads longer than 256 bases go byte-wise
         uint32_t nw32 = 0;   // words of 16 bases per orientation: 8 (<= 128 bases) .. 64 (<= 1024); longer reads go byte-wise
         if (!prm->no_align && max_len <= 1024) { nw32 = 8; while (nw32 * 16u < max_len) nw32 *= 2; }
-        if (nw32) { w->reads2.need(8ull * nw32 * n + 64); w->read_ok2.need(n); }
-        fa.reads2 = w->reads2.as<uint32_t>(); fa.read_ok2 = w->read_ok2.as<uint8_t>(); fa.nw32 = nw32;
+        if (nw32) { w->reads2.need(8ull * nw32 * n + 64); w->read_ok2.need(n); w->read_oh.need(16ull * n); }
+        fa.reads2 = w->reads2.as<uint32_t>(); fa.read_ok2 = w->read_ok2.as<uint8_t>(); fa.read_oh = w->read_oh.as<uint4>(); fa.nw32 = nw32;
         int fill_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
         kbegin(1); fill_dispatch(S, ix->d, fa, k, fill_blocks, st); launches += 2;
         if (nw32) { pack_reads_kernel<<<std::max(1, std::min<int>((n + 31) / 32, sms * 8)), 256, 0, st>>>(fa); launches++; }
@@ -717,7 +717,7 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         aa.stack_ws = w->stack_ws.as<DfsFrame>(); aa.mask_ws = w->mask_ws.as<uint32_t>();
         aa.max_len = max_len; aa.no_align = prm->no_align; aa.error = w->error.as<int>();
         aa.counters = d_counters;
-        aa.reads2 = w->reads2.as<uint32_t>(); aa.read_ok2 = w->read_ok2.as<uint8_t>(); aa.nw32 = nw32;
+        aa.reads2 = w->reads2.as<uint32_t>(); aa.read_ok2 = w->read_ok2.as<uint8_t>(); aa.read_oh = w->read_oh.as<uint4>(); aa.nw32 = nw32;
         // screen/walk rounds over a shrinking, compacted queue; the queue counts stay on the device
         w->cursor.need(8ull * n_segs); w->cand.need(8ull * n_segs); w->queue_a.need(4ull * n_segs); w->queue_b.need(4ull * n_segs);
         uint32_t* qc = w->qcount.as<uint32_t>();

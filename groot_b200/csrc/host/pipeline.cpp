@@ -110,14 +110,14 @@ bool FastqStream::next(ReadBatch& b, uint32_t max_reads) {
     // a record's four lines are copied into the batch as they are found (a view does not survive the next getline)
     while (b.size() < max_reads) {
         if (!getline(p, n)) break;
-        if (n == 0 || p[0] != '@')   // seqio.NewFASTQread (seqio.go:178-180) -> log.Fatal
-            throw std::runtime_error("read ID in fastq file does not begin with @: " + std::string(p, n));
         const size_t id0 = b.id.size(), seq0 = b.seq.size(), qual0 = b.qual.size();
         b.id.insert(b.id.end(), p, p + n);
         bool ok = getline(p, n);
         if (ok) { b.seq.insert(b.seq.end(), p, p + n); ok = getline(p, n); }          // line 3 ('+') is dropped
         if (ok) ok = getline(p, n);
         if (!ok) { b.id.resize(id0); b.seq.resize(seq0); b.qual.resize(qual0); break; }   // an incomplete trailing record is dropped (sketch.go:216-236)
+        if (b.id.size() == id0 || b.id[id0] != '@')   // only a complete record reaches seqio.NewFASTQread (seqio.go:178-180) -> log.Fatal
+            throw std::runtime_error("read ID in fastq file does not begin with @: " + std::string(b.id.begin() + id0, b.id.end()));
         b.qual.insert(b.qual.end(), p, p + n);
         b.id_off.push_back(b.id.size()); b.seq_off.push_back(b.seq.size()); b.qual_off.push_back(b.qual.size());
         raw_count_++; length_total_ += b.seq.size() - seq0;

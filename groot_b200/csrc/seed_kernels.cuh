@@ -518,6 +518,7 @@ struct FillArgs {
     unsigned long long* counters;  // [0]=mapped reads, [1]=multimapped reads
     uint32_t* reads2;              // [n * 2 * nw32 + 1] packed copies of the seeded reads (pack_reads_kernel), or nullptr
     uint8_t* read_ok2;             // [n] 1 when reads2 holds the read
+    uint4* read_oh;                // [n] one-hot prefixes for the screen: x/y = bases [0,8) / [1,9) of the read, z/w = of its reverse complement
     uint32_t nw32;                 // words per orientation (16 bases each); 0 = packing off
 };
 
@@ -579,7 +580,29 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(FillArgs a) {
             }
         }
         const uint32_t bad = __ballot_sync(0xffffffffu, live && !ok);
-        if (live && gl == 0) a.read_ok2[r] = (bad & gmask) ? 0 : 1;
+        __syncwarp();                                                   // the group's stores are visible to its reads below
+        // what align_screen compares against the allele sets (prefix_pass): the first 9 bases of the read and of its
+        // reverse complement one-hot, 4 bits per base (bit pack_base2(b)); lane i of the group converts base i (lane 0
+        // also base 8) from the packed words just written, an OR over the group assembles them. Only meaningful for
+        // reads of upper-case ACGT (read_ok2): the others build theirs byte-wise in the screen.
+        uint64_t f = 0, c = 0;
+        if (live && !(bad & gmask)) {
+            const uint32_t len = a.off[r + 1] - a.off[r];
+            const uint32_t* out = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32;
+            const uint32_t pad = a.nw32 * 16u - len, wi = pad >> 4;
+            const uint32_t f2 = out[0];
+            const uint64_t c2 = (static_cast<uint64_t>(wi + 1 < a.nw32 ? out[a.nw32 + wi + 1] : 0u) << 32 | out[a.nw32 + wi]) >> ((pad & 15u) * 2u);
+            for (uint32_t i = gl; i < 9 && i < len; i += 8) {
+                f |= static_cast<uint64_t>(1u << ((f2 >> (2 * i)) & 3u)) << (4 * i);
+                c |= static_cast<uint64_t>(1u << (static_cast<uint32_t>(c2 >> (2 * i)) & 3u)) << (4 * i);
+            }
+        }
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) { f |= __shfl_xor_sync(0xffffffffu, f, d); c |= __shfl_xor_sync(0xffffffffu, c, d); }
+        if (live && gl == 0) {
+            a.read_ok2[r] = (bad & gmask) ? 0 : 1;
+            a.read_oh[r] = make_uint4(static_cast<uint32_t>(f), static_cast<uint32_t>(f >> 4), static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 4));
+        }
     }
 }
 

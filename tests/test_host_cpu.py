@@ -171,9 +171,11 @@ def test_fastq_stream_edge_cases(root, tmp_path):
         return r.returncode, r.stdout.decode().splitlines(), r.stderr.decode()
     a = tmp_path / "a.fq"; a.write_bytes(b"@r1 x y\nACGT\n+\nIIII\n@r2\r\nAC\r\n+r2\r\nI#\r\n@r3\nGG\n+\n!!")           # no newline at the end
     b = tmp_path / "b.fq.gz"; b.write_bytes(gzip.compress(b"@r4\nTTTT\n+\nJJJJ\n@r5\nAAAA\n+\n"))                      # r5 lacks its quality line
+    c = tmp_path / "c.fq"; c.write_bytes(b"@r6\nT\n+\nJ\n\n")                                                          # a trailing blank line never completes a record
     rc, out, _ = run(a, b)
     assert rc == 0 and out == ["@r1 x y\tACGT\tIIII", "@r2\tAC\tI#", "@r3\tGG\t!!", "@r4\tTTTT\tJJJJ", "#4 12"]
     assert run("--batch", "1", a, b)[1] == out and run("--batch", "1000", a, b)[1] == out
+    assert run(c) == (0, ["@r6\tT\tJ", "#1 1"], "")
     big = tmp_path / "big.fq"                                                                                           # lines across buffer refills
     long_seq = "ACGT" * 3_000_000
     big.write_text("@L\n%s\n+\n%s\n@S\nA\n+\nI\n" % (long_seq, "I" * len(long_seq)))
