@@ -39,6 +39,7 @@
 namespace groot {
 
 constexpr int kMaskWordsInline = 8; // path bitsets of up to 256 paths travel from verify to emit without a second DFS
+constexpr int kTravWords = 24;       // words of seg_mask per pair: the path bitsets of the pair's first traversals (24 / mw of them)
 constexpr uint32_t kTravRewalk = 0x80000000u;  // seg_ntrav flag: the traversals' bitsets did not fit seg_mask, the emit walks again
 
 struct DfsFrame {
@@ -171,7 +172,7 @@ struct AlignArgs {
     PairOut* pairs;                // [n_segs]
     uint32_t* seg_nrec;            // [n_segs]
     uint2* seg_locus;              // [n_segs] (node, offset) of the successful start
-    uint32_t* seg_mask;            // [n_segs * kMaskWordsInline] path bitset when exactly one traversal carried ids
+    uint32_t* seg_mask;            // [n_segs * kTravWords] path bitsets of the pair's first traversals, mw words each
     uint32_t* seg_ntrav;           // [n_segs]
     DfsFrame* stack_ws;            // [threads * (max_len + 2)]
     uint32_t* mask_ws;             // [threads * (max_len + 2) * kMaskWordsInline]
@@ -354,9 +355,9 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
                             }
                         }
                     } else {
-                        // the path bitsets of the first traversals are kept (as many as fit the pair's kMaskWordsInline
+                        // the path bitsets of the first traversals are kept (as many as fit the pair's kTravWords
                         // words): the emit kernel expands them without walking again
-                        const bool keep = (ntrav + 1) * mw <= static_cast<uint32_t>(kMaskWordsInline);
+                        const bool keep = (ntrav + 1) * mw <= static_cast<uint32_t>(kTravWords);
                         uint32_t c = 0;
 #pragma unroll
                         for (int wi = 0; wi < kMaskWordsInline; wi++)
@@ -600,8 +601,8 @@ __device__ __forceinline__ int walk_try(const DevIndex& ix, const AlignArgs& a, 
         const uint32_t* rd2 = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32 + (strand ? a.nw32 : 0u);
         const uint32_t base0 = (strand ? a.nw32 * 16u - len : 0u) + (stage == 3 ? 1u : 0u);
         dfs_packed<false>(ix, node, off0, rd2, base0, rlen, mw, ix.graph_has_n[wr.graph] != 0, stack, mask_ws, depth_cap, &res,
-                          a.seg_mask + static_cast<size_t>(s) * kMaskWordsInline);
-        inline_masks = res.ntrav * mw <= static_cast<uint32_t>(kMaskWordsInline);
+                          a.seg_mask + static_cast<size_t>(s) * kTravWords);
+        inline_masks = res.ntrav * mw <= static_cast<uint32_t>(kTravWords);
     } else if (PACKED_ONLY) {
         return -1;
     } else {
@@ -610,7 +611,7 @@ __device__ __forceinline__ int walk_try(const DevIndex& ix, const AlignArgs& a, 
             dfs_masked(ix, node, off0, rd, rlen, mw, stack, mask_ws, depth_cap, &res);
             if (res.ntrav == 1) {
                 inline_masks = true;
-                for (uint32_t wi = 0; wi < mw; wi++) a.seg_mask[static_cast<size_t>(s) * kMaskWordsInline + wi] = res.mask[wi];
+                for (uint32_t wi = 0; wi < mw; wi++) a.seg_mask[static_cast<size_t>(s) * kTravWords + wi] = res.mask[wi];
             }
         } else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
     }
@@ -722,7 +723,7 @@ struct EmitArgs {
 };
 
 // ONE WARP PER PAIR: write the pair's records at the scanned offset. The walk kept the path bitset of every traversal
-// that fits the pair's kMaskWordsInline words (8 traversals in a graph of <= 32 paths, 1 in a graph of 129..256):
+// that fits the pair's kTravWords words (24 traversals in a graph of <= 32 paths, 4 in a graph of 161..192, 3 in one of 225..256):
 // each is expanded with the lanes striding over the start node's path list (path ids ascending == record order).
 // Pairs with more traversals than that (kTravRewalk) are left to align_emit_multi_kernel.
 __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a) {
@@ -743,7 +744,7 @@ __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a
             const NodeRec n0 = ix.nodes[loc.x];
             uint32_t written = 0;
             for (uint32_t t = 0; t < ntrav; t++) {                     // traversals in DFS order, path ids ascending inside one
-                const uint32_t* mk = a.seg_mask + static_cast<size_t>(s) * kMaskWordsInline + t * mw;
+                const uint32_t* mk = a.seg_mask + static_cast<size_t>(s) * kTravWords + t * mw;
                 for (uint32_t j0 = 0; j0 < n0.path_cnt; j0 += 32) {
                     const uint32_t j = j0 + lane;
                     uint32_t pid = 0; bool on = false;

@@ -682,6 +682,7 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         fa.seq = d_seq; fa.off = d_off; fa.n_reads = n; fa.len_params = ix->len_params.as<LenParam>(); fa.n_hits = w->n_hits.as<uint32_t>();
         fa.hit_off = w->hit_off.as<uint32_t>(); fa.stage = w->stage.as<uint32_t>(); fa.hits = w->hits.as<uint32_t>();
         fa.hit_read = w->hit_read.as<uint32_t>(); fa.seg_flag = w->seg_flag.as<uint8_t>(); fa.counters = d_counters;
+        fa.n_overflow = w->qcount.as<uint32_t>() + 5;   // zeroed with the other scalars at the start of the batch
         // 2-bit copies of the seeded reads (both orientations) for the packed walk; reads longer than 256 bases go byte-wise
         uint32_t nw32 = 0;   // words of 16 bases per orientation: 8 (<= 128 bases) .. 64 (<= 1024); longer reads go byte-wise
         if (!prm->no_align && max_len <= 1024) { nw32 = 8; while (nw32 * 16u < max_len) nw32 *= 2; }
@@ -703,7 +704,7 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         // ---- K3: align (thread per pair) -> scan -> emit ----
         w->pairs.need(sizeof(PairOut) * static_cast<size_t>(n_segs)); w->seg_nrec.need(4ull * n_segs); w->seg_locus.need(8ull * n_segs);
         w->rec_off.need(4ull * (n_segs + 1)); w->seg_ntrav.need(4ull * n_segs);
-        w->seg_mask.need(4ull * kMaskWordsInline * n_segs);
+        w->seg_mask.need(4ull * kTravWords * n_segs);
         const int vthreads = 128;
         int verify_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + vthreads - 1) / vthreads, static_cast<uint64_t>(sms) * 8));
         verify_blocks = std::max(verify_blocks, 1);

@@ -516,6 +516,7 @@ struct FillArgs {
     uint32_t* hit_read;
     uint8_t* seg_flag;
     unsigned long long* counters;  // [0]=mapped reads, [1]=multimapped reads
+    uint32_t* n_overflow;          // device scalar: reads with more than HSTAGE hits, counted by the lean kernel, read by the refill kernel
     uint32_t* reads2;              // [n * 2 * nw32 + 1] packed copies of the seeded reads (pack_reads_kernel), or nullptr
     uint8_t* read_ok2;             // [n] 1 when reads2 holds the read
     uint4* read_oh;                // [n] one-hot prefixes for the screen: x/y = bases [0,8) / [1,9) of the read, z/w = of its reverse complement
@@ -612,10 +613,14 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(FillArgs a) {
 template <int S, int MAXK, bool REFILL>
 __global__ void __launch_bounds__(kSeedThreads) fill_kernel(DevIndex ix, FillArgs a, MultTable M) {
     __shared__ SeedTabs T;
-    if (REFILL) { build_seed_tabs(&T, ix.k); __syncthreads(); }
-    unsigned mapped = 0, multi = 0;
+    if (REFILL) {
+        if (*a.n_overflow == 0) return;                 // the usual case: nothing to redo, the whole grid leaves at once
+        build_seed_tabs(&T, ix.k); __syncthreads();
+    }
+    unsigned mapped = 0, multi = 0, overflow = 0;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
         const uint32_t nh = a.n_hits[r];
+        if (!REFILL && nh > HSTAGE) overflow++;
         if (nh == 0 || (nh > HSTAGE) != REFILL) continue;
         const uint32_t base = a.hit_off[r];
         if (!REFILL) {
@@ -646,6 +651,8 @@ __global__ void __launch_bounds__(kSeedThreads) fill_kernel(DevIndex ix, FillArg
     }
     mapped = __reduce_add_sync(0xffffffffu, mapped);
     multi = __reduce_add_sync(0xffffffffu, multi);
+    overflow = __reduce_add_sync(0xffffffffu, overflow);
+    if ((threadIdx.x & 31) == 0 && overflow) atomicAdd(a.n_overflow, overflow);
     if ((threadIdx.x & 31) == 0) {
         if (mapped) atomicAdd(&a.counters[0], static_cast<unsigned long long>(mapped));
         if (multi) atomicAdd(&a.counters[1], static_cast<unsigned long long>(multi));
