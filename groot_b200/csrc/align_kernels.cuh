@@ -722,20 +722,22 @@ struct EmitArgs {
     uint32_t* n_multi;         // device scalar, zeroed before align_emit_kernel
 };
 
-// ONE WARP PER PAIR: write the pair's records at the scanned offset. The walk kept the path bitset of every traversal
+// A GROUP OF 8 LANES PER PAIR (four pairs per warp: the kernel is bound by the chain of dependent loads per pair — order,
+// pair, locus, start node, path list — so more pairs in flight per warp is what speeds it up): write the pair's
+// records at the scanned offset. The walk kept the path bitset of every traversal
 // that fits the pair's kTravWords words (24 traversals in a graph of <= 32 paths, 4 in a graph of 161..192, 3 in one of 225..256):
 // each is expanded with the lanes striding over the start node's path list (path ids ascending == record order).
 // Pairs with more traversals than that (kTravRewalk) are left to align_emit_multi_kernel.
 __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a) {
     const uint32_t n_segs = *a.n_segs_ptr;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t gwarp = gthread >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t q = gwarp; q < n_segs; q += total_warps) {
-        const uint32_t s = a.order ? a.order[q] : q;   // window order: neighbouring warps expand the same start nodes (L1 hits)
+    const uint32_t lane = threadIdx.x & 31, gl = lane & 7u, gshift = lane & 24u;
+    const uint32_t gmask = 0xffu << gshift;                         // the group's lanes: every vote below is among them only
+    const uint32_t group = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, total_groups = (gridDim.x * blockDim.x) >> 3;
+    for (uint32_t q = group; q < n_segs; q += total_groups) {
+        const uint32_t s = a.order ? a.order[q] : q;   // window order: neighbouring groups expand the same start nodes (L1 hits)
         const PairOut p = a.pairs[s];
         const uint32_t rb = a.rec_off[s];
-        if (lane == 0) a.pairs[s].rec_begin = rb;
+        if (gl == 0) a.pairs[s].rec_begin = rb;
         if (p.rec_count == 0) continue;
         const uint32_t ntrav = a.seg_ntrav[s];
         if (!(ntrav & kTravRewalk)) {
@@ -745,13 +747,13 @@ __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a
             uint32_t written = 0;
             for (uint32_t t = 0; t < ntrav; t++) {                     // traversals in DFS order, path ids ascending inside one
                 const uint32_t* mk = a.seg_mask + static_cast<size_t>(s) * kTravWords + t * mw;
-                for (uint32_t j0 = 0; j0 < n0.path_cnt; j0 += 32) {
-                    const uint32_t j = j0 + lane;
+                for (uint32_t j0 = 0; j0 < n0.path_cnt; j0 += 8) {
+                    const uint32_t j = j0 + gl;
                     uint32_t pid = 0; bool on = false;
                     if (j < n0.path_cnt) { pid = ix.node_path_id[n0.path_off + j]; on = (mk[pid >> 5] >> (pid & 31)) & 1u; }
-                    const uint32_t ball = __ballot_sync(0xffffffffu, on);
+                    const uint32_t ball = (__ballot_sync(gmask, on) >> gshift) & 0xffu;
                     if (on) {
-                        const uint32_t slot = rb + written + __popc(ball & ((1u << lane) - 1u));
+                        const uint32_t slot = rb + written + __popc(ball & ((1u << gl) - 1u));
                         a.rec_path[slot] = pid;
                         a.rec_pos[slot] = ix.node_path_pos[n0.path_off + j] + static_cast<int32_t>(loc.y);   // alignment.go:296
                     }

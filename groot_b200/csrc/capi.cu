@@ -792,7 +792,7 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         ea.order = prm->no_align ? nullptr : w->order.as<uint32_t>();
         {
             poke(st, {{qc + 2, 0u}});
-            const int emit_blocks = std::max(1, static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 7) / 8, static_cast<uint64_t>(sms) * 8)));
+            const int emit_blocks = std::max(1, static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 31) / 32, static_cast<uint64_t>(sms) * 8)));   // 32 groups of 8 lanes per block
             kbegin(5); align_emit_kernel<<<emit_blocks, 256, 0, st>>>(ix->d, ea); launches++; kend();
             kbegin(5); align_emit_classify_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ea); launches++; kend();
             // thread stacks: stack_ws / mask_ws hold verify_blocks * vthreads of them
