@@ -49,12 +49,16 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe). nvidia-smi takes
+    up to a second to start, so it is launched before the warm-up; every line is stamped on arrival and only the
+    samples that fall inside the timed region are used (if the region was too short to catch one, the samples taken
+    under the warm-up load are reported instead, and the line says so)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.gpu, self.proc, self.lines = gpu_index, None, []
+        self.t_begin = self.t_end = None
 
     def start(self):
         try:
@@ -67,30 +71,47 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx = float(f[2])
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+        def stats(lines):
+            sm, mx, reasons = [], None, set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx = float(f[2])
+                except ValueError:
+                    continue
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, reasons
+        inside = [x for x in self.lines if self.t_begin is not None and self.t_begin <= x[0] <= (self.t_end or time.time()) + 0.03]
+        sm, mx, reasons = stats(inside)
+        out = {"window": "timed region"}
+        if not sm:
+            sm, mx, reasons = stats(self.lines)
+            out = {"window": "warm-up + timed region (the timed region was shorter than one sampling interval)"}
+        out.update({"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)})
+        return out
 
 
 def prepare_db():
@@ -224,18 +245,19 @@ def run_ours(args):
         return raw
 
     # ---- value: inputs resident in HBM ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         raw = step_device()
     if gatherer is not None:
         gatherer.flush()
     torch.cuda.synchronize(); barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     fam_ms = {k: [] for k in api.KERNEL_FAMILIES}
     launches = 0
     torch.cuda.synchronize(); barrier()
+    sampler.mark_begin()
     e0.record()
     for _ in range(args.steps):
         raw = step_device()
@@ -246,6 +268,7 @@ def run_ours(args):
         gatherer.flush()            # every gather of the K steps completes inside the timed region
     e1.record()
     torch.cuda.synchronize(); barrier()
+    sampler.mark_end()
     dev_ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
     total_reads = sum_over_ranks(float(n))

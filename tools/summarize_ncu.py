@@ -12,7 +12,7 @@ n_reads = int(sys.argv[4]) if len(sys.argv) > 4 else 2_000_000
 out_dir = os.path.join(ROOT, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
-FAMILY = [("seed_kernel", "seed"), ("fill_kernel", "fill"), ("align_init", "align_screen"), ("align_screen", "align_screen"),
+FAMILY = [("seed_kernel", "seed"), ("fill_kernel", "fill"), ("pack_reads", "fill"), ("align_init", "align_screen"), ("align_screen", "align_screen"),
           ("align_walk", "align_walk"), ("align_finish", "align_finish"), ("align_emit", "align_emit"), ("project_", "project"), ("peek_kernel", "scalars"), ("poke_kernel", "scalars"), ("zero_kernel", "scalars"),
           ("chunk_", "chunk glue"),
           ("sketch_kernel", "sketch(index)")]
@@ -60,9 +60,9 @@ seen, md, traffic = set(), [], {}
 for r in rd[2:]:
     name = r[ix["Kernel Name"]]
     fam = family(name)
-    if fam in seen:
+    if name in seen:                 # first launch of every distinct kernel (template instances count separately)
         continue
-    seen.add(fam)
+    seen.add(name)
     md.append("### %s  (`%s`)" % (fam, name[:90]))
     md.append("| metric | value |")
     md.append("|---|---|")
@@ -82,9 +82,10 @@ for r in rd[2:]:
     def num(key):
         v, u = float(r[ix[key]].replace(",", "")), units[ix[key]]
         return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(u, 1)
-    try:
-        traffic[fam] = {"dram_bytes_per_read": (num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) / n_reads,
-                        "reads_in_profiled_launch": n_reads, "source": os.path.basename(rep)}
+    try:   # a family's traffic = the sum over its distinct kernels of one batch (e.g. seed = prescreen + queued pass)
+        t = traffic.setdefault(fam, {"dram_bytes_per_read": 0.0, "reads_in_profiled_launch": n_reads, "source": os.path.basename(rep), "kernels": []})
+        t["dram_bytes_per_read"] += (num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) / n_reads
+        t["kernels"].append(name[:60])
     except Exception:
         pass
 
