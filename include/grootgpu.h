@@ -168,7 +168,12 @@ typedef struct {
  * mappings, AlignRead forward then reverse complement, stop at the first mapping that aligns).
  * seq = concatenated read bases (raw FASTQ line 2 bytes), seq_off[n_reads+1] = byte offsets.
  * Host buffers in, host results out (H2D / D2H inside); pinned buffers from grootgpu_host_alloc make
- * the copies asynchronous. Does NOT touch graph weights: call grootgpu_project_batch for that. */
+ * the copies asynchronous. Any batch size: the batch is streamed through the device in chunks on two
+ * lanes (copy-in, kernels and copy-out of neighbouring chunks overlap; one helper thread is started and
+ * joined inside the call), and the result arrays are batch-wide, exactly as if the batch had run in one
+ * piece. Graph weights: untouched unless params->project_on_device is set (then the ordered f64 weighting
+ * runs on the device, chained across chunks); otherwise call grootgpu_project_batch for the batch.
+ * With params->results_on_device the batch runs in one piece (at most 4 GiB of bases). */
 int grootgpu_align_batch(grootgpu_index* idx, const uint8_t* seq, const uint64_t* seq_off, uint32_t n_reads,
                          const grootgpu_align_params* params, grootgpu_batch_result* out);
 
