@@ -12,23 +12,27 @@
 // 1-base start clip and a 1-base end clip; forward strand first, then the reverse complement; mappings in
 // (Node, OffSet) order. It stops at the first try whose DFS yields at least one path id.
 //
-//   align_init_kernel    one thread per pair: default (unaligned) result, cursor at the first try, pair queued.
-//   align_screen_kernel  ONE WARP PER QUEUED PAIR. From the pair's cursor, the 32 lanes test 32 consecutive tries at
-//                        once against the prefix table (host/prefix_table.cpp: the read's first 8 bases must equal
-//                        one of the 8-base traversal prefixes of the start position — a necessary condition for
-//                        dfsRecursive to succeed there, two loads and a masked XOR per try, no DFS); a ballot picks
-//                        the lowest-numbered survivor == the next try the sequential loop could stop at.
-//   align_walk_kernel    ONE THREAD PER QUEUED PAIR, 32 independent walks per warp in a FLAT loop (<= 8 bases of
-//                        the current node per iteration, node changes as per-lane events) with the path bitset
-//                        carried as a running AND. A pair whose walk yields no path id is re-queued with its cursor
-//                        just past that try. The host runs a fixed number of screen/walk rounds over the shrinking,
-//                        compacted queue (no host sync: counts live on the device), then
-//   align_finish_kernel  one thread per leftover pair continues the reference's sequential enumeration to the end.
+//   align_init_kernel    one thread per pair: default (unaligned) result, cursor at the first try; the host radix-sorts
+//                        the pair queue by window id, so that the pairs a warp handles sit on the same graph region.
+//   align_screen_kernel  ONE WARP PER QUEUED PAIR. From the pair's cursor the lanes test the tries that can exist at
+//                        all (offsets beyond a node are never enumerated; the offsets of up to 32 contained nodes are
+//                        pooled) against the allele sets of host/prefix_table.cpp: each of the read's first 8 bases
+//                        must lie in the set of its step — a necessary condition for dfsRecursive to succeed there,
+//                        one load and an AND per try, no DFS; a ballot picks the lowest-numbered survivor == the next
+//                        try the sequential loop could stop at.
+//   align_walk_kernel    ONE THREAD PER QUEUED PAIR: the DFS on 2-bit data (dfs_packed: 16 bases per XOR, path bitset
+//                        as a running AND, a stack of branch nodes only, the bitsets of the traversals kept for the
+//                        emit). A pair whose walk yields no path id is re-queued with its cursor just past that try;
+//                        a pair that cannot take the packed walk goes to the slow queue. The host runs two screen/walk
+//                        rounds over the shrinking queue (no host sync: counts live on the device), then
+//   align_finish_kernel  one warp per leftover / slow pair alternates screen steps and walks (byte-wise walk
+//                        available: dfs_masked, dfs_align) to the end of the reference's sequential enumeration.
 //                        (Earlier layouts — a warp per pair doing everything, one thread per pair doing everything,
-//                        in-kernel warp-synchronous rounds — lost 5-10x to lanes idling on each other; see
-//                        profiles/r01_notes.md.)
-//   align_emit_kernel    ONE THREAD PER PAIR, after an exclusive scan of the record counts: expands the
-//                        traversal's path bitset into (path, pos) records at the pair's exact offset.
+//                        in-kernel warp-synchronous rounds, byte-wise walks with a frame per node — lost 5-10x to
+//                        lanes idling on each other; see profiles/r01_notes.md.)
+//   align_emit_kernel    8 lanes per pair, after an exclusive scan of the record counts: expands the kept traversal
+//                        bitsets into (path, pos) records at the pair's exact offset; align_emit_classify_kernel +
+//                        align_emit_multi_kernel walk the few pairs again whose traversals did not fit.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -57,10 +61,6 @@ __device__ __forceinline__ uint8_t complement_base(uint8_t b) {  // src/seqio/se
     switch (b) { case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; case 'N': return 'N'; default: return 0; }
 }
 // read views
-struct SmemRead {
-    const uint8_t* p;
-    __device__ __forceinline__ uint8_t operator()(uint32_t i) const { return p[i]; }
-};
 struct GlobalRead {  // forward or reverse-complement view of a read in global memory, optional 1-base start clip
     const uint8_t* p;
     uint32_t len;    // full read length
@@ -554,7 +554,7 @@ __device__ __forceinline__ void check_revcomp_bytes(const AlignArgs& a, uint32_t
 __global__ void __launch_bounds__(256) align_screen_kernel(DevIndex ix, RoundArgs ra) {
     const AlignArgs& a = ra.a;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t n_queue = *ra.n_queue, n_segs = *a.n_segs_ptr, n_hits = *a.n_hits_ptr;
+    const uint32_t n_queue = *ra.n_queue;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t q = gwarp; q < n_queue; q += total_warps) {
         const uint32_t s = ra.queue[q];
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(128, 5) align_finish_kernel(DevIndex ix, Round
     __syncthreads();
     const AlignArgs& a = ra.a;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t n_queue = *ra.n_queue, n_segs = *a.n_segs_ptr, n_hits = *a.n_hits_ptr;
+    const uint32_t n_queue = *ra.n_queue;
     const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t gwarp = gthread >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t depth_cap = a.max_len + 2;

@@ -6,13 +6,15 @@
 //   ContainmentIndex.Query -> lshensemble Query + Containment > t      (src/lshe/lshe.go:153-175)
 //   the sketch worker loop of theBoss.mapReads                         (src/pipeline/boss.go:145-201)
 //
-// Mapping: ONE THREAD PER READ. The S running minima (2*S registers), the two rolling hashes and the
-// probe all stay in that thread's registers: no shuffles, no idle lanes (a warp-per-read layout would
-// waste 26 of 96 lane-slots on 70 k-mers), and the rolling hash stays a 1-step roll. Read bytes come
-// in through a TMA bulk copy (cp.async.bulk, global -> shared, mbarrier completion) of each warp's
-// 32-read tile, double buffered; the 100-byte read stride is co-prime with the 32 banks so the
-// per-thread byte reads are conflict free. The kernel is INT-ALU bound (~18k integer ops per 100 bp read versus
-// ~320 algorithmic bytes), see DESIGN.md "Rooflines".
+// Mapping: ONE THREAD PER READ for the hashing. The S running minima (2*S registers) and the two rolling hashes stay
+// in that thread's registers: no shuffles, no idle lanes (a warp-per-read layout would waste 26 of 96 lane-slots on
+// 70 k-mers), and the rolling hash stays a 1-step roll. Read bytes come in through a TMA bulk copy (cp.async.bulk,
+// global -> shared, mbarrier completion) of each warp's 32-read tile, double buffered; the 100-byte read stride is
+// co-prime with the 32 banks so the per-thread byte reads are conflict free. The probe is warp-cooperative: the
+// candidate buckets of the warp's 32 reads are pooled and verified 32 at a time (warp_probe). With a single band
+// probed (the default) the kernel runs in two passes — a first-band prescreen over all reads, the full sketch only
+// for the reads that found a bucket (SEED_PRESCREEN / SEED_QUEUED). Integer-issue bound (~18k integer ops per
+// 100 bp read versus ~320 algorithmic bytes), see DESIGN.md §4.
 #pragma once
 #include <cuda_runtime.h>
 
