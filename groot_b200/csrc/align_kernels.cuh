@@ -161,6 +161,7 @@ __device__ uint32_t dfs_align(const DevIndex& ix, uint32_t node0, uint32_t off0,
     return nrec;
 }
 
+struct ScreenDesc;
 struct AlignArgs {
     const uint8_t* seq;
     const uint32_t* off;
@@ -183,6 +184,7 @@ struct AlignArgs {
     const uint32_t* reads2;        // 2-bit copies of the seeded reads, both orientations (seed_kernels.cuh, pack_reads_kernel)
     const uint8_t* read_ok2;       // [n_reads] 1 when reads2 holds the read
     const uint4* read_oh;          // [n_reads] one-hot 8-base prefixes of the read / its reverse complement (pack_reads_kernel)
+    ScreenDesc* sdesc;             // [n_segs]
     uint32_t nw32;                 // words per orientation; 0 = no packed copies
 };
 
@@ -429,6 +431,20 @@ __device__ __forceinline__ void decode_try(const DevIndex& ix, const WinRec& wr,
 struct PairCursor { uint32_t m_strand; uint32_t t; };   // m_strand = (mapping index inside the pair) << 1 | strand
 constexpr uint32_t kNoCand = 0xffffffffu;
 
+// What the screen needs to start on a pair, gathered once by align_init_kernel (one thread per pair, latency hidden by
+// sheer parallelism) into 80 contiguous bytes: the screen is one warp per pair, and more than half of its time went
+// into a chain of six dependent, mostly DRAM-missing loads (queue -> pair -> read offsets / hits -> window -> seed
+// node -> read prefix) before the first try was tested (profiles/r01_notes.md).
+struct ScreenDesc {
+    uint32_t read, len, hit_begin, hit_count;
+    uint4 oh;                    // read_oh[read] when packed != 0
+    WinRec w0;                   // the first mapping's window
+    uint32_t sn_seq_off, sn_seq_len;   // its seed node
+    uint32_t packed;             // the read has a packed copy (upper-case ACGT, fits)
+    uint32_t pad;
+};
+static_assert(sizeof(ScreenDesc) == 80, "ScreenDesc is five 16-byte words");
+
 struct RoundArgs {
     AlignArgs a;
     PairCursor* cursor;        // [n_segs] next try to examine
@@ -455,6 +471,17 @@ __global__ void __launch_bounds__(256) align_init_kernel(DevIndex ix, AlignArgs 
         cursor[s] = PairCursor{0u, 0u};
         queue[s] = s;
         qkey[s] = a.hits[hb];                       // first mapping's window: the queue is sorted by it (pairs of one warp walk the same graph region)
+        if (!a.no_align) {
+            ScreenDesc d;
+            d.read = p.read; d.len = a.off[p.read + 1] - a.off[p.read]; d.hit_begin = hb; d.hit_count = he - hb;
+            d.w0 = ix.wins[a.hits[hb]];
+            const NodeRec sn = ix.nodes[d.w0.node];
+            d.sn_seq_off = sn.seq_off; d.sn_seq_len = sn.seq_len;
+            d.packed = a.nw32 && a.read_ok2[p.read] ? 1u : 0u;
+            d.oh = d.packed ? a.read_oh[p.read] : make_uint4(0, 0, 0, 0);
+            d.pad = 0;
+            a.sdesc[s] = d;
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *n_queue = a.no_align ? 0u : n_segs;   // graphminion.go:70-72 (--noAlign)
 }
@@ -489,16 +516,16 @@ __device__ __forceinline__ void warp_read_prefix(const AlignArgs& a, uint32_t r,
 // are never enumerated: stage 1 covers only the offsets that exist on the seed node, stage 2 pools the existing
 // offsets 0..10 of up to 32 contained nodes at a time (inclusive scan + owner search, as in warp_probe); the try
 // NUMBERING stays the reference's (decode_try), so cursors and results are unchanged. wr, sn, t0, len are uniform.
-__device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinRec& wr, const NodeRec& sn, uint32_t t0, const uint32_t (&oh)[2],
-                                                  uint32_t len, uint32_t lane) {
+__device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinRec& wr, uint32_t sn_seq_off, uint32_t sn_seq_len, uint32_t t0,
+                                                  const uint32_t (&oh)[2], uint32_t len, uint32_t lane) {
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t T1 = wr.merge_span + wr.win_size + 1u;
     // stage 1: offsets OffSet + t on the seed node
-    const uint32_t room = sn.seq_len > wr.offset ? sn.seq_len - wr.offset : 0u;
+    const uint32_t room = sn_seq_len > wr.offset ? sn_seq_len - wr.offset : 0u;
     const uint32_t n1 = T1 < room ? T1 : room;
     for (uint32_t base = t0 & ~31u; base < n1; base += 32) {
         const uint32_t t = base + lane;
-        const bool ok = t >= t0 && t < n1 && prefix_pass(ix, sn.seq_off + wr.offset + t, oh[0], len);
+        const bool ok = t >= t0 && t < n1 && prefix_pass(ix, sn_seq_off + wr.offset + t, oh[0], len);
         const uint32_t ball = __ballot_sync(FULL, ok);
         if (ball) return base + (__ffs(ball) - 1);
     }
@@ -536,7 +563,7 @@ __device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinR
     const uint32_t tA = T1 + 11u * wr.cn_cnt;
     {
         const uint32_t t = tA + lane;
-        const bool ok = lane < 2 && t >= t0 && room > 0 && prefix_pass(ix, sn.seq_off + wr.offset, lane == 0 ? oh[1] : oh[0], len - 1);
+        const bool ok = lane < 2 && t >= t0 && room > 0 && prefix_pass(ix, sn_seq_off + wr.offset, lane == 0 ? oh[1] : oh[0], len - 1);
         const uint32_t ball = __ballot_sync(FULL, ok);
         if (ball) return tA + (__ffs(ball) - 1);
     }
@@ -551,29 +578,34 @@ __device__ __forceinline__ void check_revcomp_bytes(const AlignArgs& a, uint32_t
     if (__any_sync(0xffffffffu, badb) && lane == 0) { if (atomicCAS(a.error, 0, -6) == 0) a.error[1] = static_cast<int>(r); }
 }
 
-__global__ void __launch_bounds__(256) align_screen_kernel(DevIndex ix, RoundArgs ra) {
+__global__ void __launch_bounds__(256, 4) align_screen_kernel(DevIndex ix, RoundArgs ra) {
     const AlignArgs& a = ra.a;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_queue = *ra.n_queue;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t q = gwarp; q < n_queue; q += total_warps) {
         const uint32_t s = ra.queue[q];
-        const PairOut pp = a.pairs[s];                                 // one sector: read, hit range (filled by align_init_kernel)
-        const uint32_t hb = pp.hit_begin, he = hb + pp.hit_count, r = pp.read;
-        const uint32_t o = a.off[r], len = a.off[r + 1] - o;
-        const uint8_t* rp = a.seq + o;
+        const ScreenDesc d = a.sdesc[s];                               // everything the first mapping needs, five 16-byte loads
         const PairCursor cur = ra.cursor[s];
+        const uint32_t hb = d.hit_begin, he = hb + d.hit_count, r = d.read, len = d.len;
+        const uint8_t* rp = d.packed ? a.seq : a.seq + a.off[r];       // read bytes: only reads without a packed copy look at them
         uint32_t m = hb + (cur.m_strand >> 1), strand = cur.m_strand & 1u, t0 = cur.t;
         uint2 cand = make_uint2(kNoCand, 0u);
         while (m < he) {
-            const WinRec wr = ix.wins[a.hits[m]];
-            const NodeRec sn = ix.nodes[wr.node];
+            WinRec wr = d.w0;
+            uint32_t sn_off = d.sn_seq_off, sn_len = d.sn_seq_len;
+            if (m != hb) {                                             // further mappings of the pair (rare): fetched on demand
+                wr = ix.wins[a.hits[m]];
+                const NodeRec sn = ix.nodes[wr.node];
+                sn_off = sn.seq_off; sn_len = sn.seq_len;
+            }
             uint32_t oh[2];
-            warp_read_prefix(a, r, rp, len, strand != 0, lane, oh);
-            const uint32_t t = screen_strand(ix, wr, sn, t0, oh, len, lane);
+            if (d.packed) { oh[0] = strand ? d.oh.z : d.oh.x; oh[1] = strand ? d.oh.w : d.oh.y; }
+            else warp_read_prefix(a, r, rp, len, strand != 0, lane, oh);
+            const uint32_t t = screen_strand(ix, wr, sn_off, sn_len, t0, oh, len, lane);
             if (t != kNoCand) { cand = make_uint2(((m - hb) << 1) | strand, t); break; }
             t0 = 0;
-            if (strand == 0) { strand = 1; check_revcomp_bytes(a, r, rp, len, lane); }
+            if (strand == 0) { strand = 1; if (!d.packed) check_revcomp_bytes(a, r, rp, len, lane); }
             else { strand = 0; m++; }
         }
         if (lane == 0) ra.cand[s] = cand;
@@ -684,7 +716,7 @@ __global__ void __launch_bounds__(128, 5) align_finish_kernel(DevIndex ix, Round
             uint32_t oh[2];
             warp_read_prefix(a, r, rp, len, strand != 0, lane, oh);
             while (!done) {
-                const uint32_t t = screen_strand(ix, wr, sn, t0, oh, len, lane);
+                const uint32_t t = screen_strand(ix, wr, sn.seq_off, sn.seq_len, t0, oh, len, lane);
                 if (t == kNoCand) break;
                 uint32_t okw = 0;
                 if (lane == 0) okw = walk_try<false>(ix, a, lut, s, hb, m, strand, t, stack, mask_ws, depth_cap) > 0 ? 1u : 0u;

@@ -198,7 +198,7 @@ struct Workspace {
     uint32_t* h_peek = nullptr;        // mapped pinned words the device writes scalars into (peek()): no copy engine involved
     uint32_t* d_peek = nullptr;
     DBuf seq, off, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
-        rec_path, rec_pos, stack_ws, cub_tmp, cub_tmp2, sketches, tile_counter, error, reads2, read_ok2, read_oh, qkey, qkey2, order, slow_q, len_minmax, seed_q,
+        rec_path, rec_pos, stack_ws, cub_tmp, cub_tmp2, sketches, tile_counter, error, reads2, read_ok2, read_oh, sdesc, qkey, qkey2, order, slow_q, len_minmax, seed_q,
         item_cnt, item_off, pkeys, pkeys2, pvals, pvals2;
     DBuf alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches;   // the other result set of the chunked host path
     // ordering of the graph weighting across lanes (chunked host path): called around the accumulate of a chunk
@@ -719,6 +719,8 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         aa.max_len = max_len; aa.no_align = prm->no_align; aa.error = w->error.as<int>();
         aa.counters = d_counters;
         aa.reads2 = w->reads2.as<uint32_t>(); aa.read_ok2 = w->read_ok2.as<uint8_t>(); aa.read_oh = w->read_oh.as<uint4>(); aa.nw32 = nw32;
+        if (!prm->no_align) w->sdesc.need(sizeof(ScreenDesc) * static_cast<size_t>(n_segs));
+        aa.sdesc = w->sdesc.as<ScreenDesc>();
         // screen/walk rounds over a shrinking, compacted queue; the queue counts stay on the device
         w->cursor.need(8ull * n_segs); w->cand.need(8ull * n_segs); w->queue_a.need(4ull * n_segs); w->queue_b.need(4ull * n_segs);
         uint32_t* qc = w->qcount.as<uint32_t>();
