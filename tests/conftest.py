@@ -13,6 +13,18 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(scope="session", autouse=True)
+def _native_build():
+    """libgrootgpu.so, the groot-b200 driver and the oracle are built in-tree by __graft_entry__.build(); the tests make
+    sure they exist and are not older than their sources (a no-op when they are current; nvcc cross-compiles without a GPU)."""
+    from groot_b200 import build as gb
+    gb.build()
+    if not os.path.exists(gb.CLI):
+        gb.build_cli()
+    from oracle import pyoracle
+    pyoracle.build()
+
+
 @pytest.fixture(scope="session")
 def root():
     return ROOT
