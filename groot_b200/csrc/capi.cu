@@ -1213,7 +1213,7 @@ int grootgpu_index_load(const char* path, int device, grootgpu_index** out) {
     if (!path || !out) return fail(GROOTGPU_ERR_ARG, "bad argument");
     *out = nullptr;
     grootgpu_index* ix = new grootgpu_index();
-    int rc = guarded([&] { pick_device(device); ix->device = device; load_index(ix->h, path); index_to_device(ix); });
+    int rc = guarded([&] { load_index(ix->h, path); pick_device(device); ix->device = device; index_to_device(ix); });   // the file is parsed and validated before a device is needed
     if (rc != GROOTGPU_OK) { delete ix; return rc; }
     *out = ix;
     return GROOTGPU_OK;

@@ -6,6 +6,7 @@
 // dump_index writes the text form that tests compare against the oracle's dump of the same database.
 #include <cstdio>
 #include <cstring>
+#include <ios>
 #include <stdexcept>
 
 #include "../flat_index.h"
@@ -50,9 +51,48 @@ void save_index(const FlatIndex& idx, const std::string& path) {
     if (fclose(f) != 0) throw std::runtime_error("cannot write " + path);
 }
 
+// Every CSR offset / count and every node, path or window index of a loaded file is range-checked against the array it
+// points into, and the parameters against each other: a truncated, corrupt or version-skewed file must fail here
+// (GROOTGPU_ERR_FORMAT) instead of reading out of bounds on the host (index_to_device, build_prefix_sets) or in the kernels.
+static void validate_index(const FlatIndex& idx) {
+    auto bad = [](const char* what) { throw std::runtime_error(std::string("inconsistent index file: ") + what); };
+    const IndexParams& p = idx.p;
+    if (p.k < 1 || p.w < p.k || p.max_k < 1 || p.S < p.max_k) bad("parameters (need 1 <= k <= w, 1 <= maxK <= sketch size)");
+    const size_t G = idx.n_graphs, N = idx.nodes.size(), P = idx.path_name.size(), W = idx.wins.size();
+    if (idx.graph_node_base.size() != G + 1 || idx.graph_path_base.size() != G + 1 || idx.graph_mask_words.size() != G ||
+        idx.graph_masked.size() != G || idx.graph_raw_windows.size() != G) bad("per-graph array sizes");
+    if (idx.path_len.size() != P || idx.kmer_freq.size() != N || idx.kmer_total.size() != G) bad("per-path / per-node array sizes");
+    if (idx.node_path_pos.size() != idx.node_path_id.size() || idx.cn_count.size() != idx.cn_node.size()) bad("paired array sizes");
+    if (idx.sketches.size() != W * static_cast<size_t>(p.S)) bad("sketch array size");
+    if (G == 0 || idx.graph_node_base[0] != 0 || idx.graph_path_base[0] != 0 || idx.graph_node_base[G] != N || idx.graph_path_base[G] != P) bad("graph bases");
+    for (size_t g = 0; g < G; g++) {
+        if (idx.graph_node_base[g] > idx.graph_node_base[g + 1] || idx.graph_path_base[g] > idx.graph_path_base[g + 1]) bad("graph bases not ascending");
+        const uint32_t np = idx.graph_path_base[g + 1] - idx.graph_path_base[g];
+        if (idx.graph_mask_words[g] != (np + 31) / 32) bad("path bitset width");
+        const uint32_t nb = idx.graph_node_base[g], ne = idx.graph_node_base[g + 1], mw = idx.graph_mask_words[g];
+        for (uint32_t n = nb; n < ne; n++) {
+            const NodeRec& nr = idx.nodes[n];
+            if (static_cast<uint64_t>(nr.seq_off) + nr.seq_len > idx.node_seq.size()) bad("node sequence range");
+            if (static_cast<uint64_t>(nr.edge_off) + nr.edge_cnt > idx.edges.size()) bad("node edge range");
+            if (static_cast<uint64_t>(nr.path_off) + nr.path_cnt > idx.node_path_id.size()) bad("node path range");
+            if (static_cast<uint64_t>(nr.mask_off) + mw > idx.node_mask.size()) bad("node bitset range");
+            for (uint32_t e = 0; e < nr.edge_cnt; e++) { const uint32_t t = idx.edges[nr.edge_off + e]; if (t < nb || t >= ne) bad("edge target outside its graph"); }
+            for (uint32_t j = 0; j < nr.path_cnt; j++) if (idx.node_path_id[nr.path_off + j] >= np) bad("path id outside its graph");
+        }
+    }
+    for (const WinRec& w : idx.wins) {
+        if (w.graph >= G) bad("window graph id");
+        const uint32_t nb = idx.graph_node_base[w.graph], ne = idx.graph_node_base[w.graph + 1];
+        if (w.node < nb || w.node >= ne) bad("window seed node outside its graph");
+        if (w.cn_cnt == 0 || static_cast<uint64_t>(w.cn_off) + w.cn_cnt > idx.cn_node.size()) bad("window contained-node range");
+        for (uint32_t j = 0; j < w.cn_cnt; j++) { const uint32_t c = idx.cn_node[w.cn_off + j]; if (c < nb || c >= ne) bad("contained node outside its graph"); }
+    }
+    if (W == 0) throw std::runtime_error("loaded an empty index file");  // lshe.go:103-105
+}
+
 void load_index(FlatIndex& idx, const std::string& path) {
     FILE* f = fopen(path.c_str(), "rb");
-    if (!f) throw std::runtime_error("cannot open " + path);
+    if (!f) throw std::ios_base::failure("cannot open " + path);
     try {
         Reader r{f};
         char magic[8]; r.raw(magic, 8);
@@ -68,10 +108,7 @@ void load_index(FlatIndex& idx, const std::string& path) {
         r.vec(idx.wins); r.vec(idx.cn_node); r.vec(idx.cn_count); r.vec(idx.sketches);
         r.vec(idx.kmer_freq); r.vec(idx.kmer_total);
         idx.node_marked.assign(idx.nodes.size(), 0);
-        if (idx.graph_node_base.size() != idx.n_graphs + 1 || idx.sketches.size() != idx.wins.size() * static_cast<size_t>(idx.p.S) ||
-            idx.kmer_freq.size() != idx.nodes.size())
-            throw std::runtime_error("inconsistent index file");
-        if (idx.wins.empty()) throw std::runtime_error("loaded an empty index file");  // lshe.go:103-105
+        validate_index(idx);
     } catch (...) { fclose(f); throw; }
     fclose(f);
 }

@@ -107,11 +107,15 @@ static int run_align(const Args& a) {
         if (pruner.Run()) fatal(grootgpu_last_error());
         size_t kept = 0;
         for (uint8_t k : pruner.kept()) kept += k;
-        fprintf(stderr, "\ttotal number of graphs remaining: %zu\n\ttotal number of possible haplotypes found: %zu\n", kept, pruner.CollectOutput().size());
-        if (kept) {                                                    // cmd/align.go:153-161
+        if (kept == 0) fprintf(stderr, "\tno graphs remaining after pruning\n");          // sketch.go:421-424
+        else fprintf(stderr, "\ttotal number of graphs remaining: %zu\n\ttotal number of possible haplotypes found: %zu\n", kept, pruner.CollectOutput().size());
+        {   // cmd/align.go:153-161 saves every graph of info.Store. GraphPruner replaces the store by the kept graphs only
+            // when at least one survives (sketch.go:421-428): with none kept the ORIGINAL store is still in place, and
+            // since Prune returns false before touching a graph (graph.go:476-478) every graph that received reads is
+            // written unpruned (SaveGraphAsGFA itself skips the unused ones, graphio.go:67-69).
             mkdir(info.GraphDir.c_str(), 0777);
             for (uint32_t g = 0; g < pruner.kept().size(); g++) {
-                if (!pruner.kept()[g]) continue;
+                if (kept && !pruner.kept()[g]) continue;
                 int written = 0;
                 if (grootgpu_graph_save_gfa(idx, g, (info.GraphDir + "/groot-graph-" + std::to_string(g) + ".gfa").c_str(), static_cast<int64_t>(st[3]), &written))
                     fatal(grootgpu_last_error());

@@ -107,14 +107,18 @@ bool FastqStream::next(ReadBatch& b, uint32_t max_reads) {
         }
         return b.size() > 0;
     }
-    // a record's four lines are copied into the batch as they are found (a view does not survive the next getline)
+    // a record's four lines are copied into the batch as they are found (a view does not survive the next getline).
+    // An EMPTY line never fills a slot: the DataStreamer forwards it as a nil slice (append([]byte(nil), ...) of nothing,
+    // sketch.go:49,70) and the handler's `l1 == nil / l2 == nil / ...` tests take the next line for the same slot
+    // (sketch.go:216-236), so blank lines anywhere in a FASTQ stream are skipped.
+    auto next_line = [&](const char*& q, size_t& m) { while (getline(q, m)) if (m != 0) return true; return false; };
     while (b.size() < max_reads) {
-        if (!getline(p, n)) break;
+        if (!next_line(p, n)) break;
         const size_t id0 = b.id.size(), seq0 = b.seq.size(), qual0 = b.qual.size();
         b.id.insert(b.id.end(), p, p + n);
-        bool ok = getline(p, n);
-        if (ok) { b.seq.insert(b.seq.end(), p, p + n); ok = getline(p, n); }          // line 3 ('+') is dropped
-        if (ok) ok = getline(p, n);
+        bool ok = next_line(p, n);
+        if (ok) { b.seq.insert(b.seq.end(), p, p + n); ok = next_line(p, n); }        // line 3 ('+') is dropped
+        if (ok) ok = next_line(p, n);
         if (!ok) { b.id.resize(id0); b.seq.resize(seq0); b.qual.resize(qual0); break; }   // an incomplete trailing record is dropped (sketch.go:216-236)
         if (b.id.size() == id0 || b.id[id0] != '@')   // only a complete record reaches seqio.NewFASTQread (seqio.go:178-180) -> log.Fatal
             throw std::runtime_error("read ID in fastq file does not begin with @: " + std::string(b.id.begin() + id0, b.id.end()));

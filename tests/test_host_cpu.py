@@ -34,6 +34,24 @@ def test_no_cpu_fallback_without_device(root):
     assert e.value.code == -2
 
 
+def test_index_file_is_validated_before_a_device_is_needed(tmp_path):
+    """grootgpu_index_load parses and range-checks the file on the host first: a missing file is an I/O error, a file
+    that is not an index (or is cut short) a format error — on a box without a GPU too."""
+    with pytest.raises(api.GrootGpuError) as e:
+        api.Index.load(str(tmp_path / "missing.grootb200"))
+    assert e.value.code == -3
+    junk = tmp_path / "junk.grootb200"
+    junk.write_bytes(b"not an index at all" * 10)
+    with pytest.raises(api.GrootGpuError) as e:
+        api.Index.load(str(junk))
+    assert e.value.code == -4
+    cut = tmp_path / "cut.grootb200"
+    cut.write_bytes(b"GRTB200\x01" + b"\x1f\0\0\0" * 5 + b"\x01\0\0\0" + b"\xff" * 8)      # magic, params, one graph, absurd array length
+    with pytest.raises(api.GrootGpuError) as e:
+        api.Index.load(str(cut))
+    assert e.value.code == -4
+
+
 def test_graph_builder_matches_oracle(db_dirs, root, tmp_path):
     """Product MSA->graph builder (groot_b200/csrc/host/graph_build.cpp) vs the oracle's restatement of
     gfa.MSA2GFA + graph.CreateGrootGraph on every cluster of arg-annot.90 and on the OXA test cluster."""
@@ -176,6 +194,11 @@ def test_fastq_stream_edge_cases(root, tmp_path):
     assert rc == 0 and out == ["@r1 x y\tACGT\tIIII", "@r2\tAC\tI#", "@r3\tGG\t!!", "@r4\tTTTT\tJJJJ", "#4 12"]
     assert run("--batch", "1", a, b)[1] == out and run("--batch", "1000", a, b)[1] == out
     assert run(c) == (0, ["@r6\tT\tJ", "#1 1"], "")
+    # blank lines never fill a record slot in the reference (an empty scanner line is a nil slice, sketch.go:49,70,216-236):
+    # between records, inside a record, many at the end — every read still comes through
+    d = tmp_path / "d.fq"; d.write_bytes(b"\n@r7\nACGT\n+\nIIII\n\n\n@r8\n\nGGCC\n+\n\nJJJJ\n\n\n\n\n\n")
+    assert run(d) == (0, ["@r7\tACGT\tIIII", "@r8\tGGCC\tJJJJ", "#2 8"], "")
+    assert run("--batch", "1", d)[1] == ["@r7\tACGT\tIIII", "@r8\tGGCC\tJJJJ", "#2 8"]
     big = tmp_path / "big.fq"                                                                                           # lines across buffer refills
     long_seq = "ACGT" * 3_000_000
     big.write_text("@L\n%s\n+\n%s\n@S\nA\n+\nI\n" % (long_seq, "I" * len(long_seq)))
