@@ -26,9 +26,21 @@ sys.path.insert(0, ROOT)
 
 METRIC = "groot_align_reads_per_sec_100bp_argannot90"
 UNIT = "reads/s"
-DB_TAR = os.path.join(ROOT, "data", "db", "arg-annot.90.tar")
-INDEX_PARAMS = dict(k=31, S=21, w=100, num_part=8, max_k=4)
 THRESHOLD = 0.99
+
+# BASELINE.json configs[1..3] (C2, C3, C4). `workload` is the string both arms print.
+CONFIGS = {
+    "C2": dict(db="arg-annot.90", read_len=100, no_align=True, index=dict(k=31, S=21, w=100, num_part=8, max_k=4),
+               workload="10M x 100bp synthetic reads vs arg-annot.90 (-w 100 -k 31 -s 21 -x 8 -y 4, t=0.99), seeding only "
+                        "(sketch + LSH Ensemble query, every mapping weighted: --noAlign) [BASELINE.json configs[1]]"),
+    "C3": dict(db="arg-annot.90", read_len=100, no_align=False, index=dict(k=31, S=21, w=100, num_part=8, max_k=4),
+               workload="10M x 100bp synthetic reads vs arg-annot.90 (-w 100 -k 31 -s 21 -x 8 -y 4, t=0.99), full align path "
+                        "(sketch + LSH Ensemble query + exact graph alignment) [BASELINE.json configs[2]]"),
+    "C4": dict(db="card.90", read_len=150, no_align=False, index=dict(k=31, S=21, w=150, num_part=8, max_k=4),
+               workload="10M x 150bp synthetic reads vs card.90 (-w 150 -k 31 -s 21 -x 8 -y 4, t=0.99), full align path "
+                        "(sketch + LSH Ensemble query + exact graph alignment) [BASELINE.json configs[3]]"),
+}
+INDEX_PARAMS = CONFIGS["C3"]["index"]
 
 
 def env_int(name, default):
@@ -114,10 +126,10 @@ class ClockSampler:
         return out
 
 
-def prepare_db():
+def prepare_db(db="arg-annot.90"):
     from groot_b200 import synth
     cache = os.path.join(tempfile.gettempdir(), "groot_b200_db_%d" % os.getuid())
-    return synth.unpack_db(DB_TAR, cache)
+    return synth.unpack_db(os.path.join(ROOT, "data", "db", db + ".tar"), cache)
 
 
 def algorithmic_bytes_per_read(L, S, hits_per_read, pairs_per_read, recs_per_read):

@@ -99,6 +99,7 @@ def lib():
         L.grootgpu_weights.argtypes = [vp, vp, vp]
         L.grootgpu_reset_weights.argtypes = [vp]
         L.grootgpu_sketch_batch.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
+        L.grootgpu_int_issue_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.grootgpu_prune.argtypes = [vp, C.c_double, vp]
         L.grootgpu_graph_save_gfa.argtypes = [vp, C.c_uint32, C.c_char_p, C.c_int64, C.POINTER(C.c_int)]
         _lib = L
@@ -111,6 +112,7 @@ EXPORTED_SYMBOLS = [
     "grootgpu_index_query_params", "grootgpu_query_params_host", "grootgpu_align_batch", "grootgpu_align_batch_device", "grootgpu_project_batch",
     "grootgpu_weights", "grootgpu_reset_weights", "grootgpu_sketch_batch", "grootgpu_prune", "grootgpu_graph_save_gfa",
     "grootgpu_host_alloc", "grootgpu_host_free", "grootgpu_device_count", "grootgpu_last_error", "grootgpu_version",
+    "grootgpu_int_issue_peak",
 ]
 
 
@@ -123,6 +125,13 @@ def device_count():
     n = C.c_int()
     rc = lib().grootgpu_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+def int_issue_peak(device=0):
+    """Measured integer issue rate (warp instructions / s) for IMAD only, shift/xor only, and their 1:1 mix."""
+    out = (C.c_double * 3)()
+    _check(lib().grootgpu_int_issue_peak(device, out))
+    return dict(imad=out[0], alu=out[1], mixed=out[2])
 
 
 def _np(ptr, n, dtype):

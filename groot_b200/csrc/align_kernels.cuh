@@ -57,6 +57,10 @@ struct PairOut {  // == grootgpu_pair (include/grootgpu.h); kept in sync by a st
     uint8_t reverse, clip_start, clip_end, stage;
 };
 
+// == grootgpu_cpair (include/grootgpu.h): the compact, BAM-oriented form of a pair; kept in sync by a static_assert in capi.cu
+struct CPairOut { uint32_t read, node, offset_flags, rec_count; };
+constexpr uint32_t kCPairReverse = 1u << 28, kCPairClipStart = 1u << 29, kCPairClipEnd = 1u << 30, kCPairOffsetMask = (1u << 28) - 1u;
+
 __device__ __forceinline__ uint8_t complement_base(uint8_t b) {  // src/seqio/seqio.go:17-23
     switch (b) { case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; case 'N': return 'N'; default: return 0; }
 }
@@ -85,9 +89,11 @@ struct DfsResult {
 //   DFS_EXISTS: true as soon as any traversal completes (no path bookkeeping) — used by the bounded screen
 //   DFS_COUNT : counts records / traversals and keeps the path bitset
 //   DFS_EMIT  : additionally writes (path, pos) records
-template <int MODE, class RD>
+// PT = element type of out_path (uint32_t, or uint8_t / uint16_t for the compact output, which carries no positions:
+// out_pos == nullptr).
+template <int MODE, class RD, class PT = uint32_t>
 __device__ uint32_t dfs_align(const DevIndex& ix, uint32_t node0, uint32_t off0, RD rd, uint32_t rlen, uint32_t mw,
-                              DfsFrame* __restrict__ stack, uint32_t max_depth, DfsResult* res, uint32_t* out_path, int32_t* out_pos) {
+                              DfsFrame* __restrict__ stack, uint32_t max_depth, DfsResult* res, PT* out_path, int32_t* out_pos) {
     uint32_t nrec = 0, depth = 0;
     uint32_t cur = node0, off = off0, dist = 0;
     while (true) {
@@ -120,10 +126,12 @@ __device__ uint32_t dfs_align(const DevIndex& ix, uint32_t node0, uint32_t off0,
                         while (m) {
                             const uint32_t pid = wi * 32 + (__ffs(m) - 1);
                             m &= m - 1;
-                            while (j < n0.path_cnt && ix.node_path_id[n0.path_off + j] < pid) j++;   // both ascending
-                            const int32_t pos = (j < n0.path_cnt && ix.node_path_id[n0.path_off + j] == pid) ? ix.node_path_pos[n0.path_off + j] : 0;
-                            out_path[nrec] = pid;
-                            out_pos[nrec] = pos + static_cast<int32_t>(off0);  // alignment.go:296
+                            out_path[nrec] = static_cast<PT>(pid);
+                            if (out_pos) {
+                                while (j < n0.path_cnt && ix.node_path_id[n0.path_off + j] < pid) j++;   // both ascending
+                                const int32_t pos = (j < n0.path_cnt && ix.node_path_id[n0.path_off + j] == pid) ? ix.node_path_pos[n0.path_off + j] : 0;
+                                out_pos[nrec] = pos + static_cast<int32_t>(off0);  // alignment.go:296
+                            }
                             nrec++;
                         }
                         return 0u;
@@ -307,11 +315,11 @@ __device__ __forceinline__ uint32_t extract16(const uint32_t* __restrict__ w, ui
 
 // EMIT: additionally writes the (path, pos) records of every successful traversal, traversals in DFS order, path ids
 // ascending inside one (processTraversal, alignment.go:263-317).
-template <bool EMIT>
+template <bool EMIT, class PT = uint32_t>
 __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, uint32_t off0, const uint32_t* __restrict__ rd2, uint32_t base0,
                                            uint32_t rlen, uint32_t mw, bool has_n, DfsFrame* __restrict__ stack, uint32_t* __restrict__ mask_ws,
                                            uint32_t max_depth, DfsResult* res, uint32_t* __restrict__ trav_masks,
-                                           uint32_t* __restrict__ out_path = nullptr, int32_t* __restrict__ out_pos = nullptr) {
+                                           PT* __restrict__ out_path = nullptr, int32_t* __restrict__ out_pos = nullptr) {
     uint32_t nrec = 0, ntrav = 0, depth = 0;
     const uint32_t p0_off = ix.nodes[node0].path_off, p0_cnt = ix.nodes[node0].path_cnt;
     uint32_t cur = node0, off = off0, dist = 0;
@@ -349,10 +357,12 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
                             while (m) {
                                 const uint32_t pid = wi * 32 + (__ffs(m) - 1);
                                 m &= m - 1;
-                                while (j < p0_cnt && ix.node_path_id[p0_off + j] < pid) j++;
-                                const int32_t pos = (j < p0_cnt && ix.node_path_id[p0_off + j] == pid) ? ix.node_path_pos[p0_off + j] : 0;
-                                out_path[nrec] = pid;
-                                out_pos[nrec] = pos + static_cast<int32_t>(off0);   // alignment.go:296
+                                out_path[nrec] = static_cast<PT>(pid);
+                                if (out_pos) {
+                                    while (j < p0_cnt && ix.node_path_id[p0_off + j] < pid) j++;
+                                    const int32_t pos = (j < p0_cnt && ix.node_path_id[p0_off + j] == pid) ? ix.node_path_pos[p0_off + j] : 0;
+                                    out_pos[nrec] = pos + static_cast<int32_t>(off0);   // alignment.go:296
+                                }
                                 nrec++;
                             }
                         }
@@ -743,6 +753,8 @@ struct EmitArgs {
     const uint32_t* seg_ntrav;
     uint32_t* rec_path;
     int32_t* rec_pos;
+    void* rec_c;               // compact output: path ids only, 1 or 2 bytes each (RECW); rec_path / rec_pos unused then
+    CPairOut* cpairs;          // compact output: [n_segs]
     DfsFrame* stack_ws;
     uint32_t* mask_ws;
     uint32_t max_len;
@@ -760,6 +772,11 @@ struct EmitArgs {
 // that fits the pair's kTravWords words (24 traversals in a graph of <= 32 paths, 4 in a graph of 161..192, 3 in one of 225..256):
 // each is expanded with the lanes striding over the start node's path list (path ids ascending == record order).
 // Pairs with more traversals than that (kTravRewalk) are left to align_emit_multi_kernel.
+// RECW selects the record format: 0 = (u32 path id, i32 position) pairs; 1 / 2 = the compact output — the path id alone
+// in 1 or 2 bytes plus one CPairOut per pair carrying the start locus, from which the host derives every position as
+// Position[path] of the start node + offset (alignment.go:296): an eighth of the record bytes written here and moved to
+// the host.
+template <int RECW>
 __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a) {
     const uint32_t n_segs = *a.n_segs_ptr;
     const uint32_t lane = threadIdx.x & 31, gl = lane & 7u, gshift = lane & 24u;
@@ -770,6 +787,11 @@ __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a
         const PairOut p = a.pairs[s];
         const uint32_t rb = a.rec_off[s];
         if (gl == 0) a.pairs[s].rec_begin = rb;
+        if (RECW != 0 && gl == 0) {
+            const uint2 l = p.rec_count ? a.seg_locus[s] : make_uint2(0xffffffffu, 0u);
+            a.cpairs[s] = CPairOut{p.read, l.x, (l.y & kCPairOffsetMask) | (p.reverse ? kCPairReverse : 0u) | (p.clip_start ? kCPairClipStart : 0u) | (p.clip_end ? kCPairClipEnd : 0u),
+                                   p.rec_count};
+        }
         if (p.rec_count == 0) continue;
         const uint32_t ntrav = a.seg_ntrav[s];
         if (!(ntrav & kTravRewalk)) {
@@ -786,8 +808,11 @@ __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a
                     const uint32_t ball = (__ballot_sync(gmask, on) >> gshift) & 0xffu;
                     if (on) {
                         const uint32_t slot = rb + written + __popc(ball & ((1u << gl) - 1u));
-                        a.rec_path[slot] = pid;
-                        a.rec_pos[slot] = ix.node_path_pos[n0.path_off + j] + static_cast<int32_t>(loc.y);   // alignment.go:296
+                        if (RECW == 0) {
+                            a.rec_path[slot] = pid;
+                            a.rec_pos[slot] = ix.node_path_pos[n0.path_off + j] + static_cast<int32_t>(loc.y);   // alignment.go:296
+                        } else if (RECW == 1) static_cast<uint8_t*>(a.rec_c)[slot] = static_cast<uint8_t>(pid);
+                        else static_cast<uint16_t*>(a.rec_c)[slot] = static_cast<uint16_t>(pid);
                     }
                     written += __popc(ball);
                 }
@@ -818,6 +843,27 @@ __global__ void __launch_bounds__(256) align_emit_classify_kernel(EmitArgs a) {
 
 // ONE THREAD PER QUEUED PAIR: re-runs the DFS from the pair's successful start in emit mode — several traversals
 // spell the read (typically through an 'N' node next to the read's own allele), each contributes its own records.
+template <class PT>
+__device__ __forceinline__ void emit_rewalk(const DevIndex& ix, const EmitArgs& a, uint32_t s, DfsFrame* stack, uint32_t* mask_ws, uint32_t depth_cap,
+                                            PT* out_path, int32_t* out_pos) {
+    const PairOut p = a.pairs[s];
+    const uint2 loc = a.seg_locus[s];
+    const uint32_t mw = ix.graph_mask_words[p.graph];
+    const uint32_t o = a.off[p.read], len = a.off[p.read + 1] - o;
+    const uint32_t rlen = len - p.clip_start - p.clip_end;
+    DfsResult res;
+    res.nrec = 0; res.ntrav = 0;
+    if (a.nw32 && mw <= kMaskWordsInline && a.read_ok2[p.read]) {
+        const uint32_t* rd2 = a.reads2 + static_cast<size_t>(p.read) * 2u * a.nw32 + (p.reverse ? a.nw32 : 0u);
+        const uint32_t base0 = (p.reverse ? a.nw32 * 16u - len : 0u) + (p.clip_start ? 1u : 0u);
+        dfs_packed<true, PT>(ix, loc.x, loc.y, rd2, base0, rlen, mw, ix.graph_has_n[p.graph] != 0, stack, mask_ws, depth_cap, &res, nullptr, out_path, out_pos);
+    } else {
+        GlobalRead rd{a.seq + o, len, p.clip_start ? 1u : 0u, p.reverse != 0};
+        dfs_align<DFS_EMIT, GlobalRead, PT>(ix, loc.x, loc.y, rd, rlen, mw, stack, depth_cap, &res, out_path, out_pos);
+    }
+}
+
+template <int RECW>
 __global__ void __launch_bounds__(128) align_emit_multi_kernel(DevIndex ix, EmitArgs a) {
     const uint32_t n = *a.n_multi;
     const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
@@ -826,23 +872,10 @@ __global__ void __launch_bounds__(128) align_emit_multi_kernel(DevIndex ix, Emit
     uint32_t* mask_ws = a.mask_ws + static_cast<size_t>(gthread) * depth_cap * kMaskWordsInline;
     for (uint32_t q = gthread; q < n; q += total) {
         const uint32_t s = a.multi_queue[q];
-        const PairOut p = a.pairs[s];
         const uint32_t rb = a.rec_off[s];
-        const uint2 loc = a.seg_locus[s];
-        const uint32_t mw = ix.graph_mask_words[p.graph];
-        const uint32_t o = a.off[p.read], len = a.off[p.read + 1] - o;
-        const uint32_t rlen = len - p.clip_start - p.clip_end;
-        DfsResult res;
-        res.nrec = 0; res.ntrav = 0;
-        if (a.nw32 && mw <= kMaskWordsInline && a.read_ok2[p.read]) {
-            const uint32_t* rd2 = a.reads2 + static_cast<size_t>(p.read) * 2u * a.nw32 + (p.reverse ? a.nw32 : 0u);
-            const uint32_t base0 = (p.reverse ? a.nw32 * 16u - len : 0u) + (p.clip_start ? 1u : 0u);
-            dfs_packed<true>(ix, loc.x, loc.y, rd2, base0, rlen, mw, ix.graph_has_n[p.graph] != 0, stack, mask_ws, depth_cap, &res, nullptr,
-                             a.rec_path + rb, a.rec_pos + rb);
-        } else {
-            GlobalRead rd{a.seq + o, len, p.clip_start ? 1u : 0u, p.reverse != 0};
-            dfs_align<DFS_EMIT>(ix, loc.x, loc.y, rd, rlen, mw, stack, depth_cap, &res, a.rec_path + rb, a.rec_pos + rb);
-        }
+        if (RECW == 0) emit_rewalk<uint32_t>(ix, a, s, stack, mask_ws, depth_cap, a.rec_path + rb, a.rec_pos + rb);
+        else if (RECW == 1) emit_rewalk<uint8_t>(ix, a, s, stack, mask_ws, depth_cap, static_cast<uint8_t*>(a.rec_c) + rb, nullptr);
+        else emit_rewalk<uint16_t>(ix, a, s, stack, mask_ws, depth_cap, static_cast<uint16_t*>(a.rec_c) + rb, nullptr);
     }
 }
 

@@ -123,6 +123,34 @@ __global__ void zero_kernel(ZeroArgs a) {
         for (uint32_t i = threadIdx.x; i < a.words[b]; i += blockDim.x) a.p[b][i] = 0u;
 }
 
+// ---- measured integer-issue peak ("measure the INT peak with a micro-benchmark rather than assuming lane count") ----
+// 16 independent chains per thread of the instruction classes seed_kernel's hash loop is made of: MODE 0 multiply-adds
+// only (IMAD: FMA pipe), MODE 1 shift + xor only (SHF / LOP3: ALU pipe), MODE 2 both in the 1:1 pipe mix that lets a
+// scheduler issue every cycle. Full occupancy, no memory traffic in the loop; the result is warp instructions per second.
+template <int MODE>
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t* __restrict__ out, uint32_t iters, uint32_t a, uint32_t b, uint32_t sh) {
+    uint32_t x[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) x[i] = threadIdx.x * 16u + i + blockIdx.x;
+#pragma unroll 1
+    for (uint32_t it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 4; rep++) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                if (MODE == 0) { x[i] = x[i] * a + b; x[i] = x[i] * b + a; }
+                else if (MODE == 1) { x[i] ^= x[i] >> sh; x[i] ^= x[i] << sh; }
+                else { x[i] = x[i] * a + b; x[i] ^= x[i] >> sh; x[i] = x[i] * b + a; }
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc ^= x[i];
+    if (acc == 0x12345678u) out[0] = acc;   // keeps the chains alive, practically never taken
+}
+constexpr uint32_t kIntPeakInstPerIter[3] = {4 * 16 * 2, 4 * 16 * 4, 4 * 16 * 4};   // body instructions per thread and iteration: IMAD+IMAD / SHF+LOP3+SHF+LOP3 / IMAD+SHF+LOP3+IMAD
+
 int pick_device(int device) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw CudaError("no CUDA device available (libgrootgpu has no CPU fallback)");
@@ -1362,6 +1390,34 @@ int grootgpu_reset_weights(grootgpu_index* idx) {
     std::fill(idx->h.kmer_freq.begin(), idx->h.kmer_freq.end(), 0.0);
     std::fill(idx->h.kmer_total.begin(), idx->h.kmer_total.end(), 0);
     return GROOTGPU_OK;
+}
+
+int grootgpu_int_issue_peak(int device, double* warp_inst_per_s) {
+    if (!warp_inst_per_s) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    return guarded([&] {
+        pick_device(device);
+        DBuf out; out.need(64);
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+        const int blocks = g_num_sms(device) * 8;
+        const uint32_t iters = 2048;
+        for (int mode = 0; mode < 3; mode++) {
+            float best = 1e30f;
+            for (int rep = 0; rep < 4; rep++) {      // first repetition warms up; best of the rest
+                CK(cudaEventRecord(e0, 0));
+                if (mode == 0) int_peak_kernel<0><<<blocks, 256>>>(out.as<uint32_t>(), iters, 0x9E3779B1u, 0x85EBCA77u, 7u);
+                else if (mode == 1) int_peak_kernel<1><<<blocks, 256>>>(out.as<uint32_t>(), iters, 0x9E3779B1u, 0x85EBCA77u, 7u);
+                else int_peak_kernel<2><<<blocks, 256>>>(out.as<uint32_t>(), iters, 0x9E3779B1u, 0x85EBCA77u, 7u);
+                CK(cudaEventRecord(e1, 0));
+                CK(cudaEventSynchronize(e1));
+                float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+                if (rep > 0) best = std::min(best, ms);
+            }
+            const double warps = static_cast<double>(blocks) * 256.0 / 32.0;
+            warp_inst_per_s[mode] = warps * iters * kIntPeakInstPerIter[mode] / (best * 1e-3);
+        }
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    });
 }
 
 int grootgpu_sketch_batch(int device, const uint8_t* seq, const uint64_t* seq_off, uint32_t n, uint32_t k, uint32_t S, uint64_t* out) {

@@ -214,6 +214,10 @@ int grootgpu_graph_save_gfa(const grootgpu_index* idx, uint32_t graph_id, const 
 int grootgpu_host_alloc(void** ptr, size_t bytes); /* pinned host memory */
 int grootgpu_host_free(void* ptr);
 int grootgpu_device_count(int* n);
+/* Measurement aid (no reference counterpart): the integer-instruction issue rate the device sustains, in warp
+ * instructions per second, for [0] multiply-adds only (FMA pipe), [1] shift/xor only (ALU pipe), [2] the 1:1 mix of the
+ * two that the KHF hash loop (src/minhash/khf.go:44-53) compiles to — the roofline that bounds the sketch kernel. */
+int grootgpu_int_issue_peak(int device, double* warp_inst_per_s);
 const char* grootgpu_last_error(void);
 const char* grootgpu_version(void);
 

@@ -13,7 +13,7 @@ import pytest
 
 from groot_b200 import api, synth
 from oracle import pyoracle as po
-from tests.util import load_fastq, pack_reads, revcomp
+from tests.util import assert_same_result_fast, load_fastq, pack_reads, revcomp
 
 pytestmark = pytest.mark.gpu
 
@@ -128,6 +128,18 @@ def test_index_save_load_roundtrip(oxa, tmp_path):
     assert g2.dump_hash() == g.dump_hash()
     with pytest.raises(api.GrootGpuError):
         api.Index.load(str(tmp_path / "missing.grootb200"))
+    # a cut or patched file must be rejected by the loader's range checks, not crash a kernel later
+    raw = open(p, "rb").read()
+    open(tmp_path / "cut.grootb200", "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(api.GrootGpuError) as e:
+        api.Index.load(str(tmp_path / "cut.grootb200"))
+    assert e.value.code == -4
+    patched = bytearray(raw)
+    patched[8 + 4:8 + 8] = (0).to_bytes(4, "little")          # sketch size 0
+    open(tmp_path / "s0.grootb200", "wb").write(bytes(patched))
+    with pytest.raises(api.GrootGpuError) as e:
+        api.Index.load(str(tmp_path / "s0.grootb200"))
+    assert e.value.code == -4
 
 
 # ------------------------------------------------------------------------------------------------- align
@@ -380,3 +392,118 @@ def test_full_size_properties(argannot, db_dirs):
     sub = g.map_reads(blob[s0 * L:s1 * L], off[s0:s1 + 1] - off[s0], 0.99)
     orr = o.map_reads(blob[s0 * L:s1 * L], off[s0:s1 + 1] - off[s0], 0.99, threads=8)
     assert_same_result(sub, orr)
+
+
+def _stage_forcing_reads(seqs, n, L=100, seed=9):
+    """Reads that cannot be placed by the first stage of AlignRead (alignment.go:35-103): first / last base substituted
+    (1-base start / end clip: stages 3 and 4), reads from the tail of a sequence (the never-emitted final window group of
+    a path, graph.go:285-338: they seed through merged neighbours or not at all), reads overhanging a sequence end by one
+    base on either side, reads from the head of a sequence; every second group reverse-complemented."""
+    rng = np.random.default_rng(seed)
+    seqs = [bytes(s) for s in seqs if len(s) >= 2 * L]
+
+    def mut(b):
+        return b"ACGT"[(b"ACGT".index(bytes([b])) + int(rng.integers(1, 4))) % 4] if bytes([b]) in b"ACGT" else ord("A")
+    reads = []
+    for i in range(n):
+        s = seqs[int(rng.integers(len(seqs)))]
+        kind = i % 6
+        if kind == 0:
+            a = int(rng.integers(0, len(s) - L)); r = bytearray(s[a:a + L]); r[0] = mut(r[0])
+        elif kind == 1:
+            a = int(rng.integers(0, len(s) - L)); r = bytearray(s[a:a + L]); r[L - 1] = mut(r[L - 1])
+        elif kind == 2:
+            a = len(s) - L - int(rng.integers(0, 25)); r = bytearray(s[a:a + L])
+        elif kind == 3:
+            r = bytearray(s[len(s) - (L - 1):] + b"ACGT"[int(rng.integers(4)):][:1])
+        elif kind == 4:
+            r = bytearray(b"ACGT"[int(rng.integers(4)):][:1] + s[:L - 1])
+        else:
+            a = int(rng.integers(0, 12)); r = bytearray(s[a:a + L])
+        r = bytes(r)
+        reads.append(revcomp(r) if (i // 6) % 2 else r)
+    return pack_reads(reads)
+
+
+def test_align_stages_2_3_4_at_scale(argannot, db_dirs):
+    """240 k reads built so that the hierarchy has to go past stage 1: every stage must occur, with both clips, on both
+    strands, and every hit / pair / record / f64 weight must equal the oracle's."""
+    g, o = argannot
+    blob, off = _stage_forcing_reads(synth.db_sequences(db_dirs["arg-annot.90"]), 240_000)
+    g.reset_weights(); o.reset_weights()
+    gr = g.map_reads(blob, off, 0.99, project_on_device=True)
+    orr = o.map_reads(blob, off, 0.99, threads=os.cpu_count() or 8)
+    assert_same_result_fast(gr, orr)
+    assert np.array_equal(g.weights()[0], o.weights()[0]) and np.array_equal(g.weights()[1], o.weights()[1])
+    aligned = gr.pairs[gr.pairs["rec_count"] > 0]
+    stages = np.bincount(aligned["stage"], minlength=5)
+    assert stages[1] > 10_000 and stages[3] > 1_000 and stages[4] > 1_000, stages
+    assert stages[2] > 0, stages
+    assert (aligned["clip_start"] == (aligned["stage"] == 3)).all() and (aligned["clip_end"] == (aligned["stage"] == 4)).all()
+    for st in (3, 4):
+        assert set(np.unique(aligned["reverse"][aligned["stage"] == st])) == {0, 1}
+
+
+def test_c3_full_size_vs_oracle(argannot, db_dirs):
+    """BASELINE config C3 at full size (10 M x 100 bp, seed 42, the bench workload): the batch runs (a) in ONE piece with
+    the reads resident in HBM — grootgpu_align_batch_device, the call bench.py's `value` times — and (b) through the
+    chunked two-lane host path — grootgpu_align_batch, the call `e2e` times. Both must give the same arrays, and those
+    must equal the oracle's: hits, pairs and every record of a 1 M-read subsample, hits / pairs /
+    counters on all 10 M, and the order-dependent f64 graph weights after all 10 M."""
+    import torch
+    g, o = argannot
+    n, L = 10_000_000, 100
+    blob, off = synth.synth_reads(n, L, synth.db_sequences(db_dirs["arg-annot.90"]), seed=42)
+    dev = torch.device("cuda", 0)
+    d_seq = torch.zeros(n * L + 64, dtype=torch.uint8, device=dev)
+    d_seq[: n * L].copy_(torch.from_numpy(blob))
+    d_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).to(dev)
+    torch.cuda.synchronize()
+    g.reset_weights()
+    one = g.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, 0.99, copy_back=True, project_on_device=True)
+    w_one = g.weights()
+    del d_seq, d_off
+    g.reset_weights()
+    chunked = g.map_reads(blob, off, 0.99, project_on_device=True)
+    w_chunked = g.weights()
+    assert one.counts == chunked.counts and one.counts["received"] == n
+    for k in ("hit_off", "hits", "pairs", "rec_path", "rec_pos"):
+        assert np.array_equal(getattr(one, k), getattr(chunked, k)), k
+    assert np.array_equal(w_one[0], w_chunked[0]) and np.array_equal(w_one[1], w_chunked[1])
+    # the oracle, 1 M reads at a time (reads are independent; the weights carry over from slice to slice)
+    o.reset_weights()
+    step = 1_000_000
+    tot = dict(received=0, mapped=0, multimapped=0, alignments=0)
+    threads = os.cpu_count() or 8
+    for s0 in range(0, n, step):
+        s1 = s0 + step
+        orr = o.map_reads(blob[s0 * L:s1 * L], off[s0:s1 + 1] - off[s0], 0.99, threads=threads)
+        for k in tot:
+            tot[k] += orr.counts[k]
+        h0, h1 = int(one.hit_off[s0]), int(one.hit_off[s1])
+        assert np.array_equal(one.hit_off[s0:s1 + 1].astype(np.uint64) - np.uint64(h0), orr.hit_off)
+        assert np.array_equal(one.hits[h0:h1], orr.hits)
+        p0, p1 = np.searchsorted(one.pairs["read"], [s0, s1])
+        pr = one.pairs[p0:p1]
+        assert len(pr) == len(orr.pairs)
+        assert np.array_equal(pr["read"] - np.uint32(s0), orr.pairs[:, 0]) and np.array_equal(pr["graph"], orr.pairs[:, 1])
+        assert np.array_equal(pr["n_incremented"], orr.pairs[:, 2]) and np.array_equal(pr["rec_count"], orr.pairs[:, 3])
+        if s0 == 3 * step:                              # the 1 M-read subsample: every record
+            class _Slice:
+                pass
+            sl = _Slice()
+            sl.counts = orr.counts
+            sl.hit_off = one.hit_off[s0:s1 + 1] - np.uint32(h0)
+            sl.hits = one.hits[h0:h1]
+            sl.n_pairs = len(pr)
+            sl.pairs = pr.copy()
+            r0 = int(pr["rec_begin"][0]) if len(pr) else 0
+            sl.pairs["read"] -= np.uint32(s0)
+            sl.pairs["rec_begin"] -= np.uint32(r0)
+            sl.n_records = int(pr["rec_count"].sum())
+            sl.rec_path = one.rec_path[r0:r0 + sl.n_records]
+            sl.rec_pos = one.rec_pos[r0:r0 + sl.n_records]
+            assert_same_result_fast(sl, orr)
+    assert tot == one.counts
+    ow = o.weights()
+    assert np.array_equal(w_one[0], ow[0]) and np.array_equal(w_one[1], ow[1])

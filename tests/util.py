@@ -114,3 +114,30 @@ def canonical_records_from_oracle(idx, res, names, seqs, quals):
         cigar = ("%dH" % sclip if sclip else "") + "%dM" % mlen + ("%dH" % eclip if eclip else "")
         out.append((names[ri][1:].decode(), idx.ref_name(g, path)[0], pos, cigar, flag, s[:mlen].decode(), bytes(q[:mlen])))
     return sorted(out)
+
+
+def assert_same_result_fast(g, o, check_records=True):
+    """Vectorised form of the bit-exact comparison for large batches. g: groot_b200.api.BatchResult (or any object with
+    the same arrays), o: oracle.pyoracle.MapResult. Hits, pairs, every record (path, pos, flags, clips) and the counters."""
+    assert g.counts == o.counts, (g.counts, o.counts)
+    assert np.array_equal(g.hit_off.astype(np.uint64), o.hit_off)
+    assert np.array_equal(g.hits, o.hits)
+    assert g.n_pairs == len(o.pairs)
+    for col, name in enumerate(("read", "graph", "n_incremented", "rec_count")):
+        assert np.array_equal(g.pairs[name], o.pairs[:, col]), name
+    if not check_records:
+        return
+    rc = g.pairs["rec_count"].astype(np.int64)
+    assert int(rc.sum()) == g.n_records == len(o.records)
+    assert np.array_equal(g.pairs["rec_begin"][rc > 0], (np.cumsum(rc) - rc)[rc > 0].astype(np.uint32))
+    rec = o.records
+    assert np.array_equal(np.repeat(g.pairs["read"], rc), rec[:, 0].astype(np.uint32))
+    assert np.array_equal(np.repeat(g.pairs["graph"], rc), rec[:, 1].astype(np.uint32))
+    assert np.array_equal(g.rec_path, rec[:, 2].astype(np.uint32))
+    assert np.array_equal(g.rec_pos, rec[:, 3])
+    first = np.zeros(len(rec), dtype=bool)
+    first[(np.cumsum(rc) - rc)[rc > 0]] = True
+    flags = np.where(first, 0, 0x100) | np.repeat(np.where(g.pairs["reverse"] != 0, 0x10, 0), rc)
+    assert np.array_equal(flags, rec[:, 4])
+    assert np.array_equal(np.repeat(g.pairs["clip_start"], rc), rec[:, 5])
+    assert np.array_equal(np.repeat(g.pairs["clip_end"], rc), rec[:, 6])
