@@ -273,7 +273,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         raw = step_device()
-        for k, v in zip(api.KERNEL_FAMILIES, list(raw.kernel_ms)[:7]):
+        for k, v in zip(api.KERNEL_FAMILIES, list(raw.kernel_ms)[:8]):
             fam_ms[k].append(v)
         launches += raw.kernel_launches
     if gatherer is not None:

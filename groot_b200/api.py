@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("GROOTGPU_LIB") or os.path.join(_HERE, "libgrootgpu.so")   # GROOTGPU_LIB: tuning variants only
 
 ERR_NAMES = {0: "OK", -1: "ERR_ARG", -2: "ERR_CUDA", -3: "ERR_IO", -4: "ERR_FORMAT", -5: "ERR_SHORT_READ",
-             -6: "ERR_BAD_BASE", -7: "ERR_CAPACITY", -8: "ERR_EMPTY"}
+             -6: "ERR_BAD_BASE", -7: "ERR_CAPACITY", -8: "ERR_EMPTY", -9: "ERR_COMM"}
 
 
 class GrootGpuError(RuntimeError):
@@ -37,7 +37,7 @@ class IndexInfo(C.Structure):
 
 class AlignParams(C.Structure):
     _fields_ = [("containment_threshold", C.c_double), ("no_align", C.c_int32), ("keep_sketches", C.c_int32),
-                ("project_on_device", C.c_int32), ("results_on_device", C.c_int32)]
+                ("project_on_device", C.c_int32), ("results_on_device", C.c_int32), ("compact_records", C.c_int32)]
 
 
 class Pair(C.Structure):
@@ -52,6 +52,15 @@ PAIR_DTYPE = np.dtype([("read", "<u4"), ("graph", "<u4"), ("hit_begin", "<u4"), 
 assert PAIR_DTYPE.itemsize == C.sizeof(Pair) == 32
 
 
+class CPair(C.Structure):
+    _fields_ = [("read", C.c_uint32), ("node", C.c_uint32), ("offset_flags", C.c_uint32), ("rec_count", C.c_uint32)]
+
+
+CPAIR_DTYPE = np.dtype([("read", "<u4"), ("node", "<u4"), ("offset_flags", "<u4"), ("rec_count", "<u4")])
+CPAIR_OFFSET_MASK, CPAIR_REVERSE, CPAIR_CLIP_START, CPAIR_CLIP_END = 0x0fffffff, 0x10000000, 0x20000000, 0x40000000
+COMM_ID_BYTES = 256
+
+
 class BatchResultC(C.Structure):
     _fields_ = [("n_reads", C.c_uint32), ("n_hits", C.c_uint64), ("n_pairs", C.c_uint64), ("n_records", C.c_uint64),
                 ("hit_off", C.POINTER(C.c_uint32)), ("hits", C.POINTER(C.c_uint32)), ("pairs", C.POINTER(Pair)),
@@ -59,10 +68,12 @@ class BatchResultC(C.Structure):
                 ("received", C.c_uint64), ("mapped", C.c_uint64), ("multimapped", C.c_uint64), ("alignments", C.c_uint64),
                 ("ms", C.c_float * 4), ("kernel_ms", C.c_float * 8), ("kernel_launches", C.c_uint32), ("slow_path_pairs", C.c_uint64),
                 ("d_hit_off", C.c_void_p), ("d_hits", C.c_void_p), ("d_pairs", C.c_void_p), ("d_rec_path", C.c_void_p),
-                ("d_rec_pos", C.c_void_p)]
+                ("d_rec_pos", C.c_void_p),
+                ("cpairs", C.POINTER(CPair)), ("rec_path_c", C.c_void_p), ("rec_path_bytes", C.c_uint32),
+                ("d_cpairs", C.c_void_p), ("d_rec_path_c", C.c_void_p)]
 
 
-KERNEL_FAMILIES = ("seed", "fill", "align_screen", "align_walk", "align_finish", "align_emit", "project")
+KERNEL_FAMILIES = ("seed", "fill", "align_screen", "align_walk", "align_finish", "align_emit", "project", "project_accumulate")
 
 _lib = None
 
@@ -96,6 +107,14 @@ def lib():
         L.grootgpu_align_batch.argtypes = [vp, vp, vp, C.c_uint32, C.POINTER(AlignParams), C.POINTER(BatchResultC)]
         L.grootgpu_align_batch_device.argtypes = [vp, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(AlignParams), vp, C.POINTER(BatchResultC)]
         L.grootgpu_project_batch.argtypes = [vp, C.POINTER(BatchResultC), vp]
+        L.grootgpu_index_node_paths.argtypes = [vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.POINTER(C.c_int32)),
+                                                C.POINTER(C.c_uint32)]
+        L.grootgpu_comm_id.argtypes = [C.c_char_p]
+        L.grootgpu_comm_create.argtypes = [vp, C.c_char_p, C.c_int, C.c_int, C.POINTER(vp)]
+        L.grootgpu_comm_destroy.argtypes = [vp]
+        L.grootgpu_comm_destroy.restype = None
+        L.grootgpu_comm_sync.argtypes = [vp]
+        L.grootgpu_gather.argtypes = [vp, C.POINTER(BatchResultC), C.c_int, C.POINTER(BatchResultC)]
         L.grootgpu_weights.argtypes = [vp, vp, vp]
         L.grootgpu_reset_weights.argtypes = [vp]
         L.grootgpu_sketch_batch.argtypes = [C.c_int, vp, vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]
@@ -112,7 +131,8 @@ EXPORTED_SYMBOLS = [
     "grootgpu_index_query_params", "grootgpu_query_params_host", "grootgpu_align_batch", "grootgpu_align_batch_device", "grootgpu_project_batch",
     "grootgpu_weights", "grootgpu_reset_weights", "grootgpu_sketch_batch", "grootgpu_prune", "grootgpu_graph_save_gfa",
     "grootgpu_host_alloc", "grootgpu_host_free", "grootgpu_device_count", "grootgpu_last_error", "grootgpu_version",
-    "grootgpu_int_issue_peak",
+    "grootgpu_int_issue_peak", "grootgpu_index_node_paths", "grootgpu_comm_id", "grootgpu_comm_create", "grootgpu_comm_destroy", "grootgpu_comm_sync",
+    "grootgpu_gather",
 ]
 
 
@@ -152,9 +172,17 @@ class BatchResult:
                            alignments=int(raw.alignments))
         self.ms = dict(total=raw.ms[0], seed=raw.ms[1], align=raw.ms[2], other=raw.ms[3])
         self.kernel_launches = raw.kernel_launches
-        self.kernel_ms = dict(zip(KERNEL_FAMILIES, list(raw.kernel_ms)[:7]))
+        self.kernel_ms = dict(zip(KERNEL_FAMILIES, list(raw.kernel_ms)[:8]))
         self.slow_path_pairs = int(raw.slow_path_pairs)
-        if copied:
+        self.compact = raw.rec_path_bytes != 0
+        if copied and self.compact:
+            self.cpairs = (np.ctypeslib.as_array(C.cast(raw.cpairs, C.POINTER(C.c_uint8)), shape=(self.n_pairs * 16,)).view(CPAIR_DTYPE).copy()
+                           if self.n_pairs else np.zeros(0, dtype=CPAIR_DTYPE))
+            dt = np.uint8 if raw.rec_path_bytes == 1 else np.uint16
+            self.rec_path_c = (np.ctypeslib.as_array(C.cast(raw.rec_path_c, C.POINTER(C.c_uint8)), shape=(self.n_records * raw.rec_path_bytes,)).view(dt).copy()
+                               if self.n_records else np.zeros(0, dtype=dt))
+            self.sketches = (_np(raw.sketches, raw.n_reads * S, np.uint64).reshape(raw.n_reads, S) if raw.sketches else None)
+        elif copied:
             self.hit_off = _np(raw.hit_off, raw.n_reads + 1, np.uint32)
             self.hits = _np(raw.hits, raw.n_hits, np.uint32)
             self.pairs = (np.ctypeslib.as_array(C.cast(raw.pairs, C.POINTER(C.c_uint8)), shape=(self.n_pairs * 32,)).view(PAIR_DTYPE).copy()
@@ -162,6 +190,35 @@ class BatchResult:
             self.rec_path = _np(raw.rec_path, raw.n_records, np.uint32)
             self.rec_pos = _np(raw.rec_pos, raw.n_records, np.int32)
             self.sketches = (_np(raw.sketches, raw.n_reads * S, np.uint64).reshape(raw.n_reads, S) if raw.sketches else None)
+
+    def decode_compact(self, index):
+        """Compact output -> the (read, graph, path, pos, flags, startClip, endClip) rows records_table() gives for the full
+        output: what a BAM writer does with cpairs / rec_path_c and the nodes' path tables (grootgpu_index_node_paths)."""
+        cp = self.cpairs
+        rc = cp["rec_count"].astype(np.int64)
+        al = cp[rc > 0]
+        nodes, inv = np.unique(al["node"], return_inverse=True)
+        width = 256 if self.rec_path_c.dtype == np.uint8 else 65536
+        table = np.zeros((len(nodes), width), dtype=np.int64)
+        graph_of = np.zeros(len(nodes), dtype=np.int64)
+        for i, nd in enumerate(nodes):
+            g, ids, pos = index.node_paths(int(nd))
+            graph_of[i] = g
+            table[i, ids] = pos
+        rca = rc[rc > 0]
+        row = np.repeat(inv, rca)
+        out = np.zeros((self.n_records, 7), dtype=np.int64)
+        path = self.rec_path_c.astype(np.int64)
+        out[:, 0] = np.repeat(al["read"], rca)
+        out[:, 1] = graph_of[row]
+        out[:, 2] = path
+        out[:, 3] = table[row, path] + np.repeat((al["offset_flags"] & CPAIR_OFFSET_MASK).astype(np.int64), rca)
+        first = np.zeros(self.n_records, dtype=bool)
+        first[(np.cumsum(rca) - rca)] = True
+        out[:, 4] = np.where(first, 0, 0x100) | np.repeat(np.where(al["offset_flags"] & CPAIR_REVERSE, 0x10, 0), rca)
+        out[:, 5] = np.repeat((al["offset_flags"] & CPAIR_CLIP_START) != 0, rca)
+        out[:, 6] = np.repeat((al["offset_flags"] & CPAIR_CLIP_END) != 0, rca)
+        return out
 
     def records_table(self):
         """(read, graph, path, pos, flags, startClip, endClip, seqLength-less) rows in (read, graph, emission) order,
@@ -257,11 +314,11 @@ class Index:
         return K.value, L.value, e.value
 
     # -- the hot path -----------------------------------------------------------------------------
-    def map_reads(self, seqs, off, threshold=0.99, no_align=False, keep_sketches=False, project=False, project_on_device=False):
+    def map_reads(self, seqs, off, threshold=0.99, no_align=False, keep_sketches=False, project=False, project_on_device=False, compact=False):
         """theBoss.mapReads for one batch (src/pipeline/boss.go:108-242): host buffers in, host result out."""
         seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint64)
-        prm = AlignParams(threshold, int(no_align), int(keep_sketches), int(project_on_device), 0)
+        prm = AlignParams(threshold, int(no_align), int(keep_sketches), int(project_on_device), 0, int(compact))
         raw = BatchResultC()
         _check(lib().grootgpu_align_batch(self.h, seqs.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(prm), C.byref(raw)))
         res = BatchResult(raw, self.info()["S"], True)
@@ -269,21 +326,28 @@ class Index:
             self.project(res, off)
         return res
 
-    def map_reads_raw(self, seq_ptr, off_ptr, n_reads, threshold=0.99, no_align=False, project_on_device=False):
+    def map_reads_raw(self, seq_ptr, off_ptr, n_reads, threshold=0.99, no_align=False, project_on_device=False, compact=False, results_on_device=False):
         """Same call on raw host pointers (pinned buffers), returning only the C struct: what bench.py times."""
-        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), 0)
+        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), int(results_on_device), int(compact))
         raw = BatchResultC()
         _check(lib().grootgpu_align_batch(self.h, seq_ptr, off_ptr, n_reads, C.byref(prm), C.byref(raw)))
         return raw
 
     def map_reads_device(self, d_seq_ptr, d_off_ptr, n_reads, min_len, max_len, threshold=0.99, no_align=False, stream=None, copy_back=False,
-                         project_on_device=False):
+                         project_on_device=False, compact=False):
         """Reads already resident in HBM (device pointers as ints)."""
-        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), 0 if copy_back else 1)
+        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), 0 if copy_back else 1, int(compact))
         raw = BatchResultC()
         _check(lib().grootgpu_align_batch_device(self.h, d_seq_ptr, d_off_ptr, n_reads, min_len, max_len, C.byref(prm), stream,
                                                  C.byref(raw)))
         return BatchResult(raw, self.info()["S"], True) if copy_back else raw
+
+    def node_paths(self, node):
+        """(GraphID, PathIDs, Position[pathID]) of a node (src/graph/node.go:13-22): turns a compact record into (Ref, Pos)."""
+        g, n = C.c_uint32(), C.c_uint32()
+        ids, pos = C.POINTER(C.c_uint32)(), C.POINTER(C.c_int32)()
+        _check(lib().grootgpu_index_node_paths(self.h, node, C.byref(g), C.byref(ids), C.byref(pos), C.byref(n)))
+        return g.value, np.ctypeslib.as_array(ids, shape=(n.value,)).copy(), np.ctypeslib.as_array(pos, shape=(n.value,)).copy()
 
     def project(self, res, off):
         """Ordered replay of GrootGraph.IncrementSubPath (src/graph/graph.go:401-451)."""
@@ -310,6 +374,39 @@ class Index:
         w = C.c_int()
         _check(lib().grootgpu_graph_save_gfa(self.h, graph, path.encode(), total_kmers, C.byref(w)))
         return bool(w.value)
+
+
+class Comm:
+    """One rank of a multi-GPU run (grootgpu_comm): the weight ring and the gather of results to rank 0."""
+
+    def __init__(self, index, comm_id, rank, world_size):
+        self.index, self.rank, self.world = index, rank, world_size
+        h = C.c_void_p()
+        _check(lib().grootgpu_comm_create(index.h, bytes(comm_id), rank, world_size, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def new_id():
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        _check(lib().grootgpu_comm_id(buf))
+        return buf.raw
+
+    def gather(self, raw, to_host=False):
+        """raw: BatchResultC of this rank's last align call (results_on_device). Rank 0 gets the merged batch: a
+        BatchResult with host arrays when to_host, else the raw C struct (device pointers)."""
+        merged = BatchResultC()
+        _check(lib().grootgpu_gather(self.h, C.byref(raw), int(to_host), C.byref(merged)))
+        if self.rank != 0:
+            return None
+        return BatchResult(merged, self.index.info()["S"], True) if to_host else merged
+
+    def sync(self):
+        _check(lib().grootgpu_comm_sync(self.h))
+
+    def close(self):
+        if self.h:
+            lib().grootgpu_comm_destroy(self.h)
+            self.h = None
 
 
 def graphs_dump(msa_files, dump_path=None, k=31, S=21, w=100, num_part=8, max_k=4):

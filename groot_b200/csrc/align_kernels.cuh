@@ -655,7 +655,7 @@ __device__ __forceinline__ int walk_try(const DevIndex& ix, const AlignArgs& a, 
                 inline_masks = true;
                 for (uint32_t wi = 0; wi < mw; wi++) a.seg_mask[static_cast<size_t>(s) * kTravWords + wi] = res.mask[wi];
             }
-        } else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, nullptr, nullptr);
+        } else dfs_align<DFS_COUNT>(ix, node, off0, rd, rlen, mw, stack, depth_cap, &res, static_cast<uint32_t*>(nullptr), nullptr);
     }
     if (res.nrec == 0) return 0;
     PairOut p = a.pairs[s];

@@ -31,6 +31,7 @@
 #include "align_kernels.cuh"
 #include "device_types.cuh"
 #include "flat_index.h"
+#include "nccl_dyn.h"
 #include "project_kernels.cuh"
 #include "seed_kernels.cuh"
 
@@ -39,6 +40,9 @@ using namespace groot;
 static_assert(sizeof(PairOut) == sizeof(grootgpu_pair), "PairOut and grootgpu_pair must match");
 static_assert(offsetof(PairOut, rec_count) == offsetof(grootgpu_pair, rec_count), "PairOut layout");
 static_assert(offsetof(PairOut, stage) == offsetof(grootgpu_pair, stage), "PairOut layout");
+static_assert(sizeof(CPairOut) == sizeof(grootgpu_cpair) && sizeof(CPairOut) == 16, "CPairOut and grootgpu_cpair must match");
+static_assert(kCPairReverse == GROOTGPU_CPAIR_REVERSE && kCPairClipStart == GROOTGPU_CPAIR_CLIP_START && kCPairClipEnd == GROOTGPU_CPAIR_CLIP_END &&
+              kCPairOffsetMask == GROOTGPU_CPAIR_OFFSET_MASK, "compact pair flags");
 
 namespace {
 
@@ -46,6 +50,12 @@ thread_local std::string g_err;
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct CommError : std::runtime_error { using std::runtime_error::runtime_error; };
+#define NK(call)                                                                                         \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess) throw CommError(std::string(#call) + ": " + nccl().GetErrorString(r_));   \
+    } while (0)
 #define CK(call)                                                                                         \
     do {                                                                                                 \
         cudaError_t e_ = (call);                                                                         \
@@ -213,28 +223,40 @@ std::string slurp(const std::string& path) {
 // =================================================================================================
 // Everything one batch in flight needs besides the (read-only) index: device scratch, result arrays, streams, events.
 // The handle owns two of them ("lanes").
+// The sorted (node, increment) items of one batch / chunk, waiting for their turn on the accumulate stream.
+struct AccSlot {
+    DBuf keys, vals;
+    cudaEvent_t ev_sorted = nullptr, ev_done = nullptr;   // items complete (side stream) / the accumulate that read them has finished
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;         // around the accumulate kernel (read back by a later batch)
+    bool timed = false;
+};
+
 struct Workspace {
     cudaStream_t stream = nullptr;     // the lane's compute stream
-    cudaStream_t st_side = nullptr;    // the ordered graph weighting runs here, next to the record emit on the compute stream
+    cudaStream_t st_side = nullptr;    // the graph weighting's count / expand / sort run here, next to the record emit on the compute stream
     cudaEvent_t ev[6] = {};
     cudaEvent_t kev[64] = {};          // per-launch timing: pairs (begin, end) tagged with a category
     int kev_cat[32] = {};
     int kev_n = 0;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr, ev_acc = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_done = nullptr;
     cudaEvent_t ev_out[2] = {};        // copy-out of the chunk that last used result set 0 / 1 has completed
     int rset = 0;                      // result set in use: the lane alternates so that a chunk never waits for the previous copy-out
     uint32_t* h_peek = nullptr;        // mapped pinned words the device writes scalars into (peek()): no copy engine involved
     uint32_t* d_peek = nullptr;
     DBuf seq, off, n_hits, hit_off, stage, hits, hit_read, seg_flag, seg_begin, scalars, pairs, seg_nrec, seg_locus, rec_off, seg_mask, seg_ntrav, mask_ws, cursor, cand, queue_a, queue_b, qcount,
         rec_path, rec_pos, stack_ws, cub_tmp, cub_tmp2, sketches, tile_counter, error, reads2, read_ok2, read_oh, sdesc, qkey, qkey2, order, slow_q, len_minmax, seed_q,
-        item_cnt, item_off, pkeys, pkeys2, pvals, pvals2;
-    DBuf alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches;   // the other result set of the chunked host path
-    // ordering of the graph weighting across lanes (chunked host path): called around the accumulate of a chunk
-    std::function<void(cudaStream_t)> acc_before, acc_after;
+        item_cnt, item_off, pkeys, pvals, cpairs, rec_c;
+    DBuf alt_hits, alt_pairs, alt_rec_path, alt_rec_pos, alt_hit_off, alt_sketches, alt_cpairs, alt_rec_c;   // the other result set
+    AccSlot acc[2];                    // the accumulate runs behind the batch (st_acc): two sets of sorted items per lane
+    int acc_i = 0;
+    bool ring_first = true, ring_last = true;   // this batch / chunk opens / closes the call's turn in the multi-GPU weight ring
+    // ordering of the accumulates across lanes (chunked host path): called on the host around the enqueue on st_acc
+    std::function<void()> acc_before, acc_after;
 
     void swap_result_sets() {          // DBuf owns its pointer: swap fields, not objects
         auto sw = [](DBuf& x, DBuf& y) { std::swap(x.p, y.p); std::swap(x.cap, y.cap); };
         sw(hits, alt_hits); sw(pairs, alt_pairs); sw(rec_path, alt_rec_path); sw(rec_pos, alt_rec_pos); sw(hit_off, alt_hit_off); sw(sketches, alt_sketches);
+        sw(cpairs, alt_cpairs); sw(rec_c, alt_rec_c);
         rset ^= 1;
     }
     void create() {
@@ -242,14 +264,17 @@ struct Workspace {
         CK(cudaStreamCreateWithFlags(&st_side, cudaStreamNonBlocking));
         for (auto& e : ev) CK(cudaEventCreate(&e));
         for (auto& e : kev) CK(cudaEventCreate(&e));
-        for (cudaEvent_t* e : {&ev_fork, &ev_join, &ev_done, &ev_acc, &ev_out[0], &ev_out[1]}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t* e : {&ev_fork, &ev_join, &ev_done, &ev_out[0], &ev_out[1], &acc[0].ev_sorted, &acc[0].ev_done, &acc[1].ev_sorted, &acc[1].ev_done})
+            CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (AccSlot& a : acc) { CK(cudaEventCreate(&a.ev_t0)); CK(cudaEventCreate(&a.ev_t1)); }
         CK(cudaHostAlloc(reinterpret_cast<void**>(&h_peek), 64 * sizeof(uint32_t), cudaHostAllocMapped));
         CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&d_peek), h_peek, 0));
     }
     ~Workspace() {
         for (auto& e : ev) if (e) cudaEventDestroy(e);
         for (auto& e : kev) if (e) cudaEventDestroy(e);
-        for (cudaEvent_t e : {ev_fork, ev_join, ev_done, ev_acc, ev_out[0], ev_out[1]}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {ev_fork, ev_join, ev_done, ev_out[0], ev_out[1]}) if (e) cudaEventDestroy(e);
+        for (AccSlot& a : acc) for (cudaEvent_t e : {a.ev_sorted, a.ev_done, a.ev_t0, a.ev_t1}) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
         if (st_side) cudaStreamDestroy(st_side);
         if (h_peek) cudaFreeHost(h_peek);
@@ -269,9 +294,17 @@ struct grootgpu_index {
     std::map<std::pair<uint32_t, double>, LenParam> param_cache;
     DBuf len_params;                   // per read length: (K, L, eq_min), shared by the lanes (prepare_params, under params_mu)
     std::mutex params_mu;
-    HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches;   // batch-wide host result arrays
+    HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_cpairs, r_rec_c;   // batch-wide host result arrays
     Workspace ws[2];                   // two lanes: the chunked host path runs consecutive chunks on alternating lanes
     cudaStream_t st_in = nullptr, st_out = nullptr;   // copy-in / copy-out of the chunked host path
+    cudaStream_t st_acc = nullptr;     // the ordered f64 chains of the graph weighting (and the multi-GPU weight ring): runs behind the batches
+    std::mutex acc_mu;                 // enqueues on st_acc come from both lanes' host threads
+    float acc_ms_pending = 0.f;        // accumulate kernel time of earlier batches, not yet reported
+    grootgpu_comm* comm = nullptr;     // attached by grootgpu_comm_create
+    uint32_t rec_width = 1;            // bytes per path id of the compact output
+    // batch-wide result arrays on the DEVICE (chunked host path with results_on_device): two sets, alternating per call
+    struct DevResult { DBuf hit_off, hits, pairs, rec_path, rec_pos, cpairs, rec_c; } bres[2];
+    int call_parity = 0;               // flips with every align call: which result set (workspace or bres) the call writes
     DBuf in_seq[4], in_off64[4], in_off32[4];
     cudaEvent_t ev_in[4] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     // graph weights live on the device once a batch was projected there; the host copy is refreshed lazily
@@ -287,9 +320,34 @@ struct grootgpu_index {
         for (void* p : owned) cudaFree(p);
         if (st_in) cudaStreamDestroy(st_in);
         if (st_out) cudaStreamDestroy(st_out);
+        if (st_acc) cudaStreamDestroy(st_acc);
         for (auto& e : ev_in) if (e) cudaEventDestroy(e);
         if (ev_t0) cudaEventDestroy(ev_t0);
         if (ev_t1) cudaEventDestroy(ev_t1);
+    }
+};
+
+// One rank of a multi-GPU run (include/grootgpu.h "multi-GPU"). Two NCCL communicators, so that the weight ring (stream
+// st_acc of the index) and the result gather (st_gather) never serialise behind each other.
+struct grootgpu_comm {
+    grootgpu_index* ix = nullptr;
+    int rank = 0, world = 1;
+    ncclComm_t ring = nullptr, gath = nullptr;
+    cudaStream_t st_gather = nullptr;
+    cudaEvent_t ev_sent[2] = {};           // the gather that read result set 0 / 1 of the index has finished with it
+    cudaEvent_t ev_local = nullptr;
+    bool ring_pending = false;             // rank 0: the last rank has sent (or will send) a weight vector that was not received yet
+    DBuf d_counts;                         // [world * 4] u64: n_reads, n_hits, n_pairs, n_records of every rank
+    uint64_t* h_counts = nullptr;          // pinned, [4 + world * 4]
+    DBuf m_hit_off, m_hits, m_pairs, m_rec_path, m_rec_pos, m_cpairs, m_rec_c;   // rank 0: the merged batch
+    HBuf h_hit_off, h_hits, h_pairs, h_rec_path, h_rec_pos, h_cpairs, h_rec_c;
+    DBuf d_total_tmp;
+    ~grootgpu_comm() {
+        if (ring) nccl().CommDestroy(ring);
+        if (gath) nccl().CommDestroy(gath);
+        if (st_gather) cudaStreamDestroy(st_gather);
+        for (cudaEvent_t e : {ev_sent[0], ev_sent[1], ev_local}) if (e) cudaEventDestroy(e);
+        if (h_counts) cudaFreeHost(h_counts);
     }
 };
 
@@ -378,6 +436,13 @@ void index_to_device(grootgpu_index* ix) {
     ix->len_params.need(60002 * sizeof(LenParam));   // never reallocated: the lanes' kernels read it while prepare_params extends it
     CK(cudaStreamCreateWithFlags(&ix->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ix->st_out, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&ix->st_acc, cudaStreamNonBlocking));
+    {
+        uint32_t max_paths = 0;
+        for (uint32_t g = 0; g < h.n_graphs; g++) max_paths = std::max(max_paths, h.n_paths_of(g));
+        if (max_paths > 65536) throw std::length_error("a graph of more than 65536 paths (documented limit)");
+        ix->rec_width = max_paths <= 256 ? 1u : 2u;
+    }
     for (auto& e : ix->ev_in) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaEventCreate(&ix->ev_t0)); CK(cudaEventCreate(&ix->ev_t1));
     if (h.kmer_freq.size() != h.nodes.size()) h.kmer_freq.assign(h.nodes.size(), 0.0);
@@ -540,9 +605,11 @@ int g_num_sms(int device) {
     return n;
 }
 
-// keep the host copy of the weights authoritative before anything on the host touches them
+// keep the host copy of the weights authoritative before anything on the host touches them (the chains of earlier
+// batches may still be running on st_acc)
 void sync_weights_to_host(grootgpu_index* ix) {
     if (!ix->weights_on_device) return;
+    CK(cudaStreamSynchronize(ix->st_acc));
     FlatIndex& h = ix->h;
     CK(cudaMemcpy(h.kmer_freq.data(), ix->d_kmer_freq, h.kmer_freq.size() * sizeof(double), cudaMemcpyDeviceToHost));
     std::vector<unsigned long long> kt(h.kmer_total.size());
@@ -552,6 +619,7 @@ void sync_weights_to_host(grootgpu_index* ix) {
 }
 void push_weights_to_device(grootgpu_index* ix) {
     if (ix->weights_on_device) return;
+    CK(cudaStreamSynchronize(ix->st_acc));
     FlatIndex& h = ix->h;
     CK(cudaMemcpy(ix->d_kmer_freq, h.kmer_freq.data(), h.kmer_freq.size() * sizeof(double), cudaMemcpyHostToDevice));
     std::vector<unsigned long long> kt(h.kmer_total.begin(), h.kmer_total.end());
@@ -559,10 +627,14 @@ void push_weights_to_device(grootgpu_index* ix) {
     ix->weights_on_device = true;
 }
 
-// a10 on the device in two phases, both on the side stream `st` (slot 1 of the peek buffer, its own CUB scratch):
+// a10 on the device (project_kernels.cuh). Per batch / chunk, on the lane's side stream `st`:
 //   project_begin   per-mapping item counts + their exclusive scan (no host round trip)
-//   project_finish  item total -> host, expand, stable sort by node, one ordered f64 chain per node
-// The caller runs the record emit on the main stream between the two.
+//   project_finish  item total -> host, expand, stable sort by node into one of the lane's two AccSlots
+// (the caller runs the record emit on the main stream between the two), and then, on the index-wide stream st_acc,
+//   acc_enqueue     one ordered f64 chain per node over the slot's items.
+// The chains are the only part that is serial across batches (and, multi-GPU, across ranks: the weight vector arrives
+// from the previous rank before the call's first chain and leaves for the next rank after its last), so they run BEHIND
+// the pipeline: nothing on the lanes waits for them except the reuse of a slot two batches later.
 ProjectArgs project_args(grootgpu_index* ix, Workspace* w, const uint32_t* d_off, uint32_t n) {
     ProjectArgs pa{};
     pa.off = d_off; pa.hits = w->hits.as<uint32_t>(); pa.hit_read = w->hit_read.as<uint32_t>(); pa.pairs = w->pairs.as<PairOut>();
@@ -573,7 +645,6 @@ ProjectArgs project_args(grootgpu_index* ix, Workspace* w, const uint32_t* d_off
 }
 template <class KB, class KE>
 void project_begin(grootgpu_index* ix, Workspace* w, const uint32_t* d_off, uint32_t n, uint32_t n_segs, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
-    push_weights_to_device(ix);
     w->item_cnt.need(4ull * H); w->item_off.need(4ull * (H + 1));
     ProjectArgs pa = project_args(ix, w, d_off, n);
     const int blocks = std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8));
@@ -583,33 +654,76 @@ void project_begin(grootgpu_index* ix, Workspace* w, const uint32_t* d_off, uint
     w->cub_tmp2.need(tmp + 16);
     cub::DeviceScan::ExclusiveSum(w->cub_tmp2.p, tmp, pa.item_cnt, w->item_off.as<uint32_t>(), static_cast<int>(H), st);
 }
+
+// the multi-GPU weight ring, on st_acc: the vector of n_nodes doubles travels rank 0 -> 1 -> ... -> last -> 0
+void ring_recv(grootgpu_index* ix) {
+    grootgpu_comm* c = ix->comm;
+    if (!c || c->world < 2) return;
+    if (c->rank == 0 && !c->ring_pending) return;                 // nothing has been round yet
+    NK(nccl().Recv(ix->d_kmer_freq, ix->h.nodes.size(), ncclDouble, (c->rank + c->world - 1) % c->world, c->ring, ix->st_acc));
+    if (c->rank == 0) c->ring_pending = false;
+}
+void ring_send(grootgpu_index* ix) {
+    grootgpu_comm* c = ix->comm;
+    if (!c || c->world < 2) return;
+    NK(nccl().Send(ix->d_kmer_freq, ix->h.nodes.size(), ncclDouble, (c->rank + 1) % c->world, c->ring, ix->st_acc));
+    if (c->rank == 0) c->ring_pending = true;                     // it comes back from the last rank
+}
+
+// slot == nullptr: the batch / chunk has nothing to add, but still takes its turn (ordering hooks, ring)
+void acc_enqueue(grootgpu_index* ix, Workspace* w, AccSlot* slot, uint32_t n_items, int sms, uint32_t& launches) {
+    if (w->acc_before) w->acc_before();                            // chunk order across the two lanes (host side)
+    {
+        std::lock_guard<std::mutex> lock(ix->acc_mu);
+        cudaStream_t sa = ix->st_acc;
+        if (slot) CK(cudaStreamWaitEvent(sa, slot->ev_sorted, 0));
+        if (w->ring_first) ring_recv(ix);
+        if (slot) {
+            const uint32_t n_nodes = static_cast<uint32_t>(ix->h.nodes.size());
+            const int ablocks = std::max(1, std::min<int>(static_cast<int>((n_nodes + 7) / 8), sms * 8));
+            CK(cudaEventRecord(slot->ev_t0, sa));
+            project_accumulate_kernel<<<ablocks, 256, 0, sa>>>(slot->keys.as<uint32_t>(), slot->vals.as<double>(), n_items, n_nodes, ix->d_kmer_freq); launches++;
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(slot->ev_t1, sa));
+            slot->timed = true;
+        }
+        if (w->ring_last) ring_send(ix);
+        if (slot) CK(cudaEventRecord(slot->ev_done, sa));
+    }
+    if (w->acc_after) w->acc_after();
+}
+
 template <class KB, class KE>
 void project_finish(grootgpu_index* ix, Workspace* w, const uint32_t* d_off, uint32_t n, uint32_t H, int sms, cudaStream_t st, KB kbegin, KE kend, uint32_t& launches) {
     ProjectArgs pa = project_args(ix, w, d_off, n);
     const uint32_t* pk = peek(w, st, {w->item_off.as<uint32_t>() + (H - 1), w->item_cnt.as<uint32_t>() + (H - 1)}, 1);
     const uint64_t n_items = static_cast<uint64_t>(pk[0]) + pk[1];
-    if (n_items == 0) return;
+    if (n_items == 0) { acc_enqueue(ix, w, nullptr, 0, sms, launches); return; }
     if (n_items >= (1ull << 31)) throw std::length_error("too many weight increments in one batch: use smaller batches");
-    w->pkeys.need(4 * n_items); w->pkeys2.need(4 * n_items); w->pvals.need(8 * n_items); w->pvals2.need(8 * n_items);
+    AccSlot* slot = &w->acc[w->acc_i ^= 1];
+    if (slot->timed && cudaEventQuery(slot->ev_t1) == cudaSuccess) {   // the accumulate that used this slot two batches ago: report its time now
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, slot->ev_t0, slot->ev_t1) == cudaSuccess) { std::lock_guard<std::mutex> lock(ix->acc_mu); ix->acc_ms_pending += ms; }
+        slot->timed = false;
+    }
+    w->pkeys.need(4 * n_items); w->pvals.need(8 * n_items);
+    CK(cudaStreamWaitEvent(st, slot->ev_done, 0));                     // ... and it has to be done with the slot before the slot is rewritten
+    if (4 * n_items > slot->keys.cap || 8 * n_items > slot->vals.cap) CK(cudaEventSynchronize(slot->ev_done));   // growing frees the old arrays
+    slot->keys.need(4 * n_items); slot->vals.need(8 * n_items);
     pa.keys = w->pkeys.as<uint32_t>(); pa.vals = w->pvals.as<double>();
     const int eblocks = std::max(1, std::min<int>((H + 255) / 256, sms * 8));
     kbegin(6); project_expand_kernel<<<eblocks, 256, 0, st>>>(ix->d, pa); launches++; kend();
     int end_bit = 1;
     while ((1ull << end_bit) < ix->h.nodes.size()) end_bit++;
     size_t sort_tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, w->pkeys.as<uint32_t>(), w->pkeys2.as<uint32_t>(), w->pvals.as<double>(), w->pvals2.as<double>(),
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, w->pkeys.as<uint32_t>(), slot->keys.as<uint32_t>(), w->pvals.as<double>(), slot->vals.as<double>(),
                                     static_cast<int>(n_items), 0, end_bit, st);
     w->cub_tmp2.need(sort_tmp + 16);
-    cub::DeviceRadixSort::SortPairs(w->cub_tmp2.p, sort_tmp, w->pkeys.as<uint32_t>(), w->pkeys2.as<uint32_t>(), w->pvals.as<double>(), w->pvals2.as<double>(),
+    cub::DeviceRadixSort::SortPairs(w->cub_tmp2.p, sort_tmp, w->pkeys.as<uint32_t>(), slot->keys.as<uint32_t>(), w->pvals.as<double>(), slot->vals.as<double>(),
                                     static_cast<int>(n_items), 0, end_bit, st);
-    const uint32_t n32 = static_cast<uint32_t>(n_items);
-    poke(st, {{w->item_off.as<uint32_t>() + H, n32}});
-    const uint32_t n_nodes = static_cast<uint32_t>(ix->h.nodes.size());
-    const int ablocks = std::max(1, std::min<int>(static_cast<int>((n_nodes + 7) / 8), sms * 8));
-    if (w->acc_before) w->acc_before(st);   // the previous chunk's chains (other lane) come first
-    kbegin(6); project_accumulate_kernel<<<ablocks, 256, 0, st>>>(w->pkeys2.as<uint32_t>(), w->pvals2.as<double>(), w->item_off.as<uint32_t>() + H, n_nodes, ix->d_kmer_freq); launches++; kend();
     CK(cudaGetLastError());
-    if (w->acc_after) w->acc_after(st);
+    CK(cudaEventRecord(slot->ev_sorted, st));
+    acc_enqueue(ix, w, slot, static_cast<uint32_t>(n_items), sms, launches);
 }
 
 // The batch pipeline on the device. d_seq / d_off already resident.
@@ -630,7 +744,10 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
     auto kbegin2 = [&](int cat) { if (w->kev_n < 32) { w->kev_cat[w->kev_n] = cat; cudaEventRecord(w->kev[2 * w->kev_n], st2); } };
     auto kend2 = [&]() { if (w->kev_n < 32) { cudaEventRecord(w->kev[2 * w->kev_n + 1], st2); w->kev_n++; } };
     const bool project = prm->project_on_device != 0;
+    const bool compact = prm->compact_records != 0;
+    const uint32_t recw = ix->rec_width;
     CK(cudaStreamSynchronize(st2));   // idle unless a previous batch failed between fork and join
+    if (project) push_weights_to_device(ix);   // no-op once the weights live on the device
 
     w->n_hits.need(4ull * n); w->hit_off.need(4ull * (n + 1)); w->stage.need(4ull * HSTAGE * n);
     w->scalars.need(64); w->tile_counter.need(16); w->error.need(16);
@@ -811,11 +928,13 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
             if (static_cast<int>(pk[2]) == GROOTGPU_ERR_BAD_BASE) throw std::domain_error("read " + std::to_string(static_cast<int>(pk[3])) + " holds a base > 'T' and had to be reverse complemented (the reference panics at seqio.go:122)");
         }
         R = static_cast<uint64_t>(lo) + lc;
-        w->rec_path.need(4ull * std::max<uint64_t>(R, 1)); w->rec_pos.need(4ull * std::max<uint64_t>(R, 1));
+        if (compact) { w->rec_c.need(static_cast<size_t>(recw) * std::max<uint64_t>(R, 1)); w->cpairs.need(sizeof(CPairOut) * static_cast<size_t>(n_segs)); }
+        else { w->rec_path.need(4ull * std::max<uint64_t>(R, 1)); w->rec_pos.need(4ull * std::max<uint64_t>(R, 1)); }
         EmitArgs ea{};
         ea.seq = d_seq; ea.off = d_off; ea.n_segs_ptr = d_nsegs; ea.pairs = w->pairs.as<PairOut>(); ea.rec_off = w->rec_off.as<uint32_t>();
         ea.seg_locus = w->seg_locus.as<uint2>(); ea.seg_mask = w->seg_mask.as<uint32_t>(); ea.seg_ntrav = w->seg_ntrav.as<uint32_t>();
         ea.rec_path = w->rec_path.as<uint32_t>(); ea.rec_pos = w->rec_pos.as<int32_t>();
+        ea.rec_c = w->rec_c.p; ea.cpairs = w->cpairs.as<CPairOut>();
         ea.stack_ws = w->stack_ws.as<DfsFrame>(); ea.mask_ws = w->mask_ws.as<uint32_t>(); ea.max_len = max_len;
         ea.reads2 = w->reads2.as<uint32_t>(); ea.read_ok2 = w->read_ok2.as<uint8_t>(); ea.nw32 = nw32;
         ea.multi_queue = w->queue_a.as<uint32_t>(); ea.n_multi = qc + 2;      // the align queues are free by now
@@ -823,10 +942,19 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         {
             poke(st, {{qc + 2, 0u}});
             const int emit_blocks = std::max(1, static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n_segs) + 31) / 32, static_cast<uint64_t>(sms) * 8)));   // 32 groups of 8 lanes per block
-            kbegin(5); align_emit_kernel<<<emit_blocks, 256, 0, st>>>(ix->d, ea); launches++; kend();
+            const int recfmt = compact ? static_cast<int>(recw) : 0;   // record format of the emit kernels (align_kernels.cuh, RECW)
+            kbegin(5);
+            if (recfmt == 0) align_emit_kernel<0><<<emit_blocks, 256, 0, st>>>(ix->d, ea);
+            else if (recfmt == 1) align_emit_kernel<1><<<emit_blocks, 256, 0, st>>>(ix->d, ea);
+            else align_emit_kernel<2><<<emit_blocks, 256, 0, st>>>(ix->d, ea);
+            launches++; kend();
             kbegin(5); align_emit_classify_kernel<<<std::max(1, std::min<int>((n_segs + 255) / 256, sms * 8)), 256, 0, st>>>(ea); launches++; kend();
             // thread stacks: stack_ws / mask_ws hold verify_blocks * vthreads of them
-            kbegin(5); align_emit_multi_kernel<<<verify_blocks, vthreads, 0, st>>>(ix->d, ea); launches++; kend();
+            kbegin(5);
+            if (recfmt == 0) align_emit_multi_kernel<0><<<verify_blocks, vthreads, 0, st>>>(ix->d, ea);
+            else if (recfmt == 1) align_emit_multi_kernel<1><<<verify_blocks, vthreads, 0, st>>>(ix->d, ea);
+            else align_emit_multi_kernel<2><<<verify_blocks, vthreads, 0, st>>>(ix->d, ea);
+            launches++; kend();
         }
         CK(cudaGetLastError());
         if (project) {
@@ -837,12 +965,17 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
     } else {
         CK(cudaEventRecord(w->ev[2], st));
         CK(cudaEventRecord(w->ev[3], st));
+        if (project) acc_enqueue(ix, w, nullptr, 0, sms, launches);   // nothing to weight, but the batch still takes its turn
     }
     CK(cudaEventRecord(w->ev[4], st));
 
     // ---- results ----
     unsigned long long counters[4] = {0, 0, 0, 0};
-    if (copy_back) {
+    if (copy_back && compact) {
+        ix->r_cpairs.need(sizeof(CPairOut) * std::max<size_t>(n_segs, 1)); ix->r_rec_c.need(static_cast<size_t>(recw) * std::max<uint64_t>(R, 1));
+        if (n_segs) CK(cudaMemcpyAsync(ix->r_cpairs.p, w->cpairs.p, sizeof(CPairOut) * static_cast<size_t>(n_segs), cudaMemcpyDeviceToHost, st));
+        if (R) CK(cudaMemcpyAsync(ix->r_rec_c.p, w->rec_c.p, static_cast<size_t>(recw) * R, cudaMemcpyDeviceToHost, st));
+    } else if (copy_back) {
         ix->r_hit_off.need(4ull * (n + 1)); ix->r_hits.need(4ull * std::max<uint32_t>(H, 1)); ix->r_pairs.need(sizeof(PairOut) * std::max<size_t>(n_segs, 1));
         ix->r_rec_path.need(4ull * std::max<uint64_t>(R, 1)); ix->r_rec_pos.need(4ull * std::max<uint64_t>(R, 1));
         CK(cudaMemcpyAsync(ix->r_hit_off.p, w->hit_off.p, 4ull * (n + 1), cudaMemcpyDeviceToHost, st));
@@ -863,12 +996,15 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
     if (out) {
         memset(out, 0, sizeof *out);
         out->n_reads = n; out->n_hits = H; out->n_pairs = n_segs; out->n_records = R;
-        if (copy_back) {
+        if (copy_back && compact) {
+            out->cpairs = reinterpret_cast<const grootgpu_cpair*>(ix->r_cpairs.p); out->rec_path_c = ix->r_rec_c.p;
+        } else if (copy_back) {
             out->hit_off = ix->r_hit_off.as<uint32_t>(); out->hits = ix->r_hits.as<uint32_t>();
             out->pairs = reinterpret_cast<const grootgpu_pair*>(ix->r_pairs.p);
             out->rec_path = ix->r_rec_path.as<uint32_t>(); out->rec_pos = ix->r_rec_pos.as<int32_t>();
-            out->sketches = prm->keep_sketches ? ix->r_sketches.as<uint64_t>() : nullptr;
         }
+        if (copy_back) out->sketches = prm->keep_sketches ? ix->r_sketches.as<uint64_t>() : nullptr;
+        out->rec_path_bytes = compact ? recw : 0u;
         out->received = n; out->mapped = counters[0]; out->multimapped = counters[1]; out->alignments = R;
         float seed_ms = 0, align_ms = 0, dev_ms = 0, all_ms = 0;
         cudaEventElapsedTime(&seed_ms, w->ev[0], w->ev[1]);
@@ -881,7 +1017,9 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         out->slow_path_pairs = counters[3];
         out->d_hit_off = w->hit_off.as<uint32_t>(); out->d_hits = w->hits.as<uint32_t>();
         out->d_pairs = reinterpret_cast<const grootgpu_pair*>(w->pairs.p);
-        out->d_rec_path = w->rec_path.as<uint32_t>(); out->d_rec_pos = w->rec_pos.as<int32_t>();
+        if (compact) { out->d_cpairs = reinterpret_cast<const grootgpu_cpair*>(w->cpairs.p); out->d_rec_path_c = w->rec_c.p; }
+        else { out->d_rec_path = w->rec_path.as<uint32_t>(); out->d_rec_pos = w->rec_pos.as<int32_t>(); }
+        { std::lock_guard<std::mutex> lock(ix->acc_mu); out->kernel_ms[7] = ix->acc_ms_pending; ix->acc_ms_pending = 0.f; }
     }
 }
 
@@ -923,6 +1061,19 @@ void grow_keep(HBuf& b, size_t need, size_t used, cudaStream_t drain) {
     nb.need(need);
     if (used) memcpy(nb.p, b.p, used);
     std::swap(b.p, nb.p); std::swap(b.cap, nb.cap);
+}
+
+void grow_keep(DBuf& b, size_t need, size_t used, cudaStream_t drain) {   // the same for a batch-wide array in device memory
+    if (need <= b.cap) return;
+    CK(cudaStreamSynchronize(drain));
+    DBuf nb;
+    nb.need(need);
+    if (used) CK(cudaMemcpy(nb.p, b.p, used, cudaMemcpyDeviceToDevice));
+    std::swap(b.p, nb.p); std::swap(b.cap, nb.cap);
+}
+
+__global__ void __launch_bounds__(256) chunk_rebase_compact_kernel(CPairOut* __restrict__ cpairs, uint32_t n_pairs, uint32_t read_base) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pairs; i += gridDim.x * blockDim.x) cpairs[i].read += read_base;
 }
 
 uint32_t chunk_reads_setting() {   // reads per pipeline chunk; GROOTGPU_CHUNK_READS overrides (tests force many small chunks)
@@ -985,9 +1136,14 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
             cudaStreamSynchronize(ix->st_out);
         }
     } drain{ix};
-    ix->r_hit_off.need(4ull * (static_cast<size_t>(n) + 1));
+    const bool on_device = prm->results_on_device != 0, compact = prm->compact_records != 0;
+    grootgpu_index::DevResult& dres = ix->bres[ix->call_parity];
+    if (on_device) { if (!compact) dres.hit_off.need(4ull * (static_cast<size_t>(n) + 1)); }
+    else if (!compact) ix->r_hit_off.need(4ull * (static_cast<size_t>(n) + 1));
+    if (on_device && prm->keep_sketches) throw std::runtime_error("keep_sketches needs host results");
     if (prm->keep_sketches) ix->r_sketches.need(8ull * S * n);
     if (prm->project_on_device) push_weights_to_device(ix);
+    if (on_device && ix->comm) CK(cudaStreamWaitEvent(st_out, ix->comm->ev_sent[ix->call_parity], 0));   // the gather of two calls ago has read this result set
     grootgpu_align_params cprm = *prm;
     cprm.results_on_device = 1;
     ChunkShared sh;
@@ -1013,7 +1169,6 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
 
     auto lane_main = [&](uint32_t lane) {
         Workspace* w = &ix->ws[lane];
-        Workspace* other = &ix->ws[lane ^ 1];
         cudaStream_t st = w->stream;
         try {
             pick_device(device);
@@ -1034,18 +1189,17 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
                 if (mm[0] < ix->h.p.k) throw std::invalid_argument("a read is shorter than k (the reference panics at boss.go:164-166)");
                 w->swap_result_sets();                                   // write the result set the lane's previous chunk is NOT being copied out of
                 CK(cudaStreamWaitEvent(st, w->ev_out[w->rset], 0));      // ... whose own copy-out (two chunks of this lane ago) has completed
-                // chunk c's f64 chains go after chunk c-1's: wait (host) until the other lane has RECORDED its event — a
-                // cudaStreamWaitEvent issued before the record would refer to an older chunk — then wait for it on the stream
+                // chunk c's f64 chains go after chunk c-1's: both lanes enqueue them on the one accumulate stream, in chunk
+                // order — the host thread of chunk c waits until chunk c-1's have been enqueued (or skipped)
                 bool acc_passed = false;
+                w->ring_first = c == 0; w->ring_last = c + 1 == C;
                 if (cprm.project_on_device) {
-                    w->acc_before = [&, c](cudaStream_t s2) {
+                    w->acc_before = [&, c]() {
                         std::unique_lock<std::mutex> lk(sh.mu);
                         sh.cv.wait(lk, [&] { return sh.failed || sh.acc_recorded >= c; });
                         if (sh.failed) throw std::runtime_error("the other lane of the batch failed");
-                        if (c > 0) CK(cudaStreamWaitEvent(s2, other->ev_acc, 0));
                     };
-                    w->acc_after = [&, c](cudaStream_t s2) {
-                        CK(cudaEventRecord(w->ev_acc, s2));
+                    w->acc_after = [&, c]() {
                         { std::unique_lock<std::mutex> lk(sh.mu); sh.acc_recorded = c + 1; }
                         sh.cv.notify_all();
                         acc_passed = true;
@@ -1055,7 +1209,7 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
                 const double t_c1 = now_ms();
                 run_batch(ix, w, ix->in_seq[b].as<uint8_t>(), ix->in_off32[b].as<uint32_t>(), nc, mm[0], mm[1], &cprm, st, &r);
                 const double t_c2 = now_ms();
-                if (cprm.project_on_device && !acc_passed) { w->acc_before(w->st_side); w->acc_after(w->st_side); }   // nothing to weight in this chunk: pass the baton
+                if (cprm.project_on_device && !acc_passed) { uint32_t l = 0; acc_enqueue(ix, w, nullptr, 0, 148, l); }   // defensive: run_batch always takes the chunk's turn
                 w->acc_before = nullptr; w->acc_after = nullptr;
                 // batch-wide offsets: chunk c-1 has to have published its totals
                 uint64_t hit_base = 0, pair_base = 0, rec_base = 0;
@@ -1067,27 +1221,36 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
                     if (hit_base + r.n_hits >= (1ull << 32) || rec_base + r.n_records >= (1ull << 32))
                         throw std::length_error("more than 2^32 hits or records in one batch: use smaller batches");
                     sh.hit_end[c] = hit_base + r.n_hits; sh.pair_end[c] = pair_base + r.n_pairs; sh.rec_end[c] = rec_base + r.n_records;
-                    // the pinned arrays grow by extrapolating the yield so far; copies into them are drained first (grow_keep)
+                    // the batch-wide arrays (pinned host memory, or device memory when the results stay there) grow by
+                    // extrapolating the yield so far; copies into them are drained first (grow_keep)
                     const double scale = 1.15 * static_cast<double>(n) / static_cast<double>(cb[c + 1]);
                     auto want = [&](uint64_t used_after, size_t elem) { return static_cast<size_t>(static_cast<double>(used_after) * scale) * elem + 4096; };
-                    if (sh.hit_end[c] * 4 > ix->r_hits.cap) grow_keep(ix->r_hits, want(sh.hit_end[c], 4), hit_base * 4, st_out);
-                    if (sh.pair_end[c] * sizeof(PairOut) > ix->r_pairs.cap) grow_keep(ix->r_pairs, want(sh.pair_end[c], sizeof(PairOut)), pair_base * sizeof(PairOut), st_out);
-                    if (sh.rec_end[c] * 4 > ix->r_rec_path.cap) grow_keep(ix->r_rec_path, want(sh.rec_end[c], 4), rec_base * 4, st_out);
-                    if (sh.rec_end[c] * 4 > ix->r_rec_pos.cap) grow_keep(ix->r_rec_pos, want(sh.rec_end[c], 4), rec_base * 4, st_out);
+                    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+                    auto place = [&](auto& host_buf, auto& dev_buf, uint64_t base, uint64_t count, size_t elem, const void* src) {   // chunk array -> its place in the batch-wide array
+                        const uint64_t end_elems = base + count;
+                        if (on_device) { if (end_elems * elem > dev_buf.cap) grow_keep(dev_buf, want(end_elems, elem), base * elem, st_out); }
+                        else if (end_elems * elem > host_buf.cap) grow_keep(host_buf, want(end_elems, elem), base * elem, st_out);
+                        uint8_t* dst = (on_device ? static_cast<uint8_t*>(dev_buf.p) : static_cast<uint8_t*>(host_buf.p)) + base * elem;
+                        if (count) CK(cudaMemcpyAsync(dst, src, count * elem, kind, st_out));
+                    };
                     const uint32_t n_off = nc + (c + 1 == C ? 1u : 0u);
                     const uint32_t np = static_cast<uint32_t>(r.n_pairs);
-                    chunk_rebase_kernel<<<std::max(1u, std::min<uint32_t>((std::max(np, n_off) + 255) / 256, 1184u)), 256, 0, st>>>(
+                    if (compact) chunk_rebase_compact_kernel<<<std::max(1u, std::min<uint32_t>((np + 255) / 256, 1184u)), 256, 0, st>>>(w->cpairs.as<CPairOut>(), np, r0);
+                    else chunk_rebase_kernel<<<std::max(1u, std::min<uint32_t>((std::max(np, n_off) + 255) / 256, 1184u)), 256, 0, st>>>(
                         w->pairs.as<PairOut>(), np, w->hit_off.as<uint32_t>(), n_off, r0, static_cast<uint32_t>(hit_base), static_cast<uint32_t>(rec_base));
                     CK(cudaGetLastError());
                     CK(cudaEventRecord(w->ev_done, st));
                     // copy-out, straight to the final place (st_out is shared: enqueue under the lock)
                     CK(cudaStreamWaitEvent(st_out, w->ev_done, 0));
-                    CK(cudaMemcpyAsync(ix->r_hit_off.as<uint32_t>() + r0, w->hit_off.p, 4ull * n_off, cudaMemcpyDeviceToHost, st_out));
-                    if (r.n_hits) CK(cudaMemcpyAsync(ix->r_hits.as<uint32_t>() + hit_base, w->hits.p, 4ull * r.n_hits, cudaMemcpyDeviceToHost, st_out));
-                    if (r.n_pairs) CK(cudaMemcpyAsync(ix->r_pairs.as<PairOut>() + pair_base, w->pairs.p, sizeof(PairOut) * r.n_pairs, cudaMemcpyDeviceToHost, st_out));
-                    if (r.n_records) {
-                        CK(cudaMemcpyAsync(ix->r_rec_path.as<uint32_t>() + rec_base, w->rec_path.p, 4ull * r.n_records, cudaMemcpyDeviceToHost, st_out));
-                        CK(cudaMemcpyAsync(ix->r_rec_pos.as<int32_t>() + rec_base, w->rec_pos.p, 4ull * r.n_records, cudaMemcpyDeviceToHost, st_out));
+                    if (compact) {
+                        place(ix->r_cpairs, dres.cpairs, pair_base, r.n_pairs, sizeof(CPairOut), w->cpairs.p);
+                        place(ix->r_rec_c, dres.rec_c, rec_base, r.n_records, ix->rec_width, w->rec_c.p);
+                    } else {
+                        place(ix->r_hit_off, dres.hit_off, r0, n_off, 4, w->hit_off.p);
+                        place(ix->r_hits, dres.hits, hit_base, r.n_hits, 4, w->hits.p);
+                        place(ix->r_pairs, dres.pairs, pair_base, r.n_pairs, sizeof(PairOut), w->pairs.p);
+                        place(ix->r_rec_path, dres.rec_path, rec_base, r.n_records, 4, w->rec_path.p);
+                        place(ix->r_rec_pos, dres.rec_pos, rec_base, r.n_records, 4, w->rec_pos.p);
                     }
                     if (prm->keep_sketches) CK(cudaMemcpyAsync(ix->r_sketches.as<uint64_t>() + static_cast<size_t>(r0) * S, w->sketches.p, 8ull * S * nc, cudaMemcpyDeviceToHost, st_out));
                     CK(cudaEventRecord(w->ev_out[w->rset], st_out));
@@ -1126,12 +1289,138 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
     memset(out, 0, sizeof *out);
     *out = sh.total;
     out->n_reads = n; out->n_hits = sh.hit_end[C - 1]; out->n_pairs = sh.pair_end[C - 1]; out->n_records = sh.rec_end[C - 1];
-    out->hit_off = ix->r_hit_off.as<uint32_t>(); out->hits = ix->r_hits.as<uint32_t>();
-    out->pairs = reinterpret_cast<const grootgpu_pair*>(ix->r_pairs.p);
-    out->rec_path = ix->r_rec_path.as<uint32_t>(); out->rec_pos = ix->r_rec_pos.as<int32_t>();
+    out->rec_path_bytes = compact ? ix->rec_width : 0u;
+    if (on_device) {
+        if (compact) { out->d_cpairs = reinterpret_cast<const grootgpu_cpair*>(dres.cpairs.p); out->d_rec_path_c = dres.rec_c.p; }
+        else {
+            out->d_hit_off = dres.hit_off.as<uint32_t>(); out->d_hits = dres.hits.as<uint32_t>(); out->d_pairs = reinterpret_cast<const grootgpu_pair*>(dres.pairs.p);
+            out->d_rec_path = dres.rec_path.as<uint32_t>(); out->d_rec_pos = dres.rec_pos.as<int32_t>();
+        }
+    } else if (compact) {
+        out->cpairs = reinterpret_cast<const grootgpu_cpair*>(ix->r_cpairs.p); out->rec_path_c = ix->r_rec_c.p;
+    } else {
+        out->hit_off = ix->r_hit_off.as<uint32_t>(); out->hits = ix->r_hits.as<uint32_t>();
+        out->pairs = reinterpret_cast<const grootgpu_pair*>(ix->r_pairs.p);
+        out->rec_path = ix->r_rec_path.as<uint32_t>(); out->rec_pos = ix->r_rec_pos.as<int32_t>();
+    }
     out->sketches = prm->keep_sketches ? ix->r_sketches.as<uint64_t>() : nullptr;
     out->received = n; out->alignments = out->n_records;
     cudaEventElapsedTime(&out->ms[0], ix->ev_t0, ix->ev_t1);
+}
+
+// ---- multi-GPU gather ------------------------------------------------------------------------------------------
+// One exchange per batch: the per-rank result arrays travel to rank 0 over NVLink (grouped ncclSend / ncclRecv straight
+// into their place in the merged arrays — contiguous shards in rank order, so merging is concatenation), a small kernel
+// per rank turns shard-local indices into batch-wide ones. Everything runs on the communicator's own stream: the
+// transfer of batch b overlaps the mapping of batch b + 1, whose result arrays are the other set.
+constexpr int kCountWords = 8;   // per rank: n_reads, n_hits, n_pairs, n_records, mapped, multimapped, slow_path_pairs, format
+void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, bool to_host, grootgpu_batch_result* merged) {
+    grootgpu_index* ix = c->ix;
+    const NcclApi& N = nccl();
+    cudaStream_t sg = c->st_gather;
+    const bool compact = loc->rec_path_bytes != 0;
+    const int W = c->world, parity = ix->call_parity;
+    const uint32_t recw = ix->rec_width;
+    if (loc->n_pairs && !(compact ? static_cast<const void*>(loc->d_cpairs) : static_cast<const void*>(loc->d_pairs)))
+        throw std::runtime_error("grootgpu_gather needs a result with device pointers (results_on_device = 1)");
+    // 1. everybody's sizes (one small all-gather; the host needs them to lay the merged arrays out)
+    uint64_t* hc = c->h_counts;
+    hc[0] = loc->n_reads; hc[1] = loc->n_hits; hc[2] = loc->n_pairs; hc[3] = loc->n_records;
+    hc[4] = loc->mapped; hc[5] = loc->multimapped; hc[6] = loc->slow_path_pairs; hc[7] = compact ? recw : 0u;
+    uint64_t* dc = c->d_counts.as<uint64_t>();
+    CK(cudaMemcpyAsync(dc, hc, 8ull * kCountWords, cudaMemcpyHostToDevice, sg));
+    NK(N.AllGather(dc, dc + kCountWords, kCountWords, ncclUint64, c->gath, sg));
+    CK(cudaMemcpyAsync(hc + kCountWords, dc + kCountWords, 8ull * kCountWords * W, cudaMemcpyDeviceToHost, sg));
+    CK(cudaStreamSynchronize(sg));   // also: the previous gather (it had the whole mapping of this batch to finish) is done
+    const uint64_t* all = hc + kCountWords;
+    std::vector<uint64_t> rb(W + 1, 0), hb(W + 1, 0), pb(W + 1, 0), cb(W + 1, 0);
+    uint64_t mapped = 0, multi = 0, slow = 0;
+    for (int r = 0; r < W; r++) {
+        const uint64_t* a = all + static_cast<size_t>(r) * kCountWords;
+        if (a[7] != hc[7]) throw std::runtime_error("grootgpu_gather: the ranks use different output formats");
+        rb[r + 1] = rb[r] + a[0]; hb[r + 1] = hb[r] + a[1]; pb[r + 1] = pb[r] + a[2]; cb[r + 1] = cb[r] + a[3];
+        mapped += a[4]; multi += a[5]; slow += a[6];
+    }
+    if (rb[W] >= (1ull << 32) || hb[W] >= (1ull << 32) || cb[W] >= (1ull << 32) || pb[W] >= (1ull << 32))
+        throw std::length_error("more than 2^32 reads, hits or records in one merged batch: use smaller batches");
+    auto bytes_of = [&](int sec, int r) -> size_t {   // sections: full = hit_off, hits, pairs, rec_path, rec_pos; compact = cpairs, rec_c
+        const uint64_t* a = all + static_cast<size_t>(r) * kCountWords;
+        if (compact) return sec == 0 ? a[2] * sizeof(CPairOut) : a[3] * recw;
+        switch (sec) { case 0: return a[0] * 4; case 1: return a[1] * 4; case 2: return a[2] * sizeof(PairOut); default: return a[3] * 4; }
+    };
+    const int n_sec = compact ? 2 : 5;
+    const void* src[5];
+    if (compact) { src[0] = loc->d_cpairs; src[1] = loc->d_rec_path_c; }
+    else { src[0] = loc->d_hit_off; src[1] = loc->d_hits; src[2] = loc->d_pairs; src[3] = loc->d_rec_path; src[4] = loc->d_rec_pos; }
+    if (c->rank != 0) {
+        NK(N.GroupStart());
+        for (int sec = 0; sec < n_sec; sec++) { const size_t b = bytes_of(sec, c->rank); if (b) NK(N.Send(src[sec], b, ncclUint8, 0, c->gath, sg)); }
+        NK(N.GroupEnd());
+        CK(cudaEventRecord(c->ev_sent[parity], sg));
+        if (merged) memset(merged, 0, sizeof *merged);
+        return;
+    }
+    // 2. rank 0: receive every shard at its place
+    DBuf* mb[5];
+    HBuf* hbuf[5];
+    size_t elem[5], base_of[5][2];   // element size; per section: which prefix array gives the base
+    (void)base_of;
+    if (compact) {
+        mb[0] = &c->m_cpairs; mb[1] = &c->m_rec_c; hbuf[0] = &c->h_cpairs; hbuf[1] = &c->h_rec_c; elem[0] = sizeof(CPairOut); elem[1] = recw;
+        c->m_cpairs.need(std::max<size_t>(16, pb[W] * sizeof(CPairOut))); c->m_rec_c.need(std::max<size_t>(16, cb[W] * recw));
+    } else {
+        mb[0] = &c->m_hit_off; mb[1] = &c->m_hits; mb[2] = &c->m_pairs; mb[3] = &c->m_rec_path; mb[4] = &c->m_rec_pos;
+        hbuf[0] = &c->h_hit_off; hbuf[1] = &c->h_hits; hbuf[2] = &c->h_pairs; hbuf[3] = &c->h_rec_path; hbuf[4] = &c->h_rec_pos;
+        elem[0] = 4; elem[1] = 4; elem[2] = sizeof(PairOut); elem[3] = 4; elem[4] = 4;
+        c->m_hit_off.need(4 * (rb[W] + 1)); c->m_hits.need(std::max<size_t>(16, 4 * hb[W])); c->m_pairs.need(std::max<size_t>(32, pb[W] * sizeof(PairOut)));
+        c->m_rec_path.need(std::max<size_t>(16, 4 * cb[W])); c->m_rec_pos.need(std::max<size_t>(16, 4 * cb[W]));
+    }
+    auto sec_base = [&](int sec, int r) -> uint64_t {   // element offset of rank r's shard inside merged section `sec`
+        if (compact) return sec == 0 ? pb[r] : cb[r];
+        switch (sec) { case 0: return rb[r]; case 1: return hb[r]; case 2: return pb[r]; default: return cb[r]; }
+    };
+    NK(N.GroupStart());
+    for (int r = 1; r < W; r++)
+        for (int sec = 0; sec < n_sec; sec++) {
+            const size_t b = bytes_of(sec, r);
+            if (b) NK(N.Recv(mb[sec]->as<uint8_t>() + sec_base(sec, r) * elem[sec], b, ncclUint8, r, c->gath, sg));
+        }
+    NK(N.GroupEnd());
+    for (int sec = 0; sec < n_sec; sec++) { const size_t b = bytes_of(sec, 0); if (b) CK(cudaMemcpyAsync(mb[sec]->p, src[sec], b, cudaMemcpyDeviceToDevice, sg)); }
+    CK(cudaEventRecord(c->ev_sent[parity], sg));
+    // 3. shard-local indices -> batch-wide ones (rank 0's own shard starts at 0 everywhere)
+    for (int r = 1; r < W; r++) {
+        const uint64_t* a = all + static_cast<size_t>(r) * kCountWords;
+        const uint32_t np = static_cast<uint32_t>(a[2]), nr = static_cast<uint32_t>(a[0]);
+        if (compact) { if (np) chunk_rebase_compact_kernel<<<std::max(1u, std::min<uint32_t>((np + 255) / 256, 1184u)), 256, 0, sg>>>(c->m_cpairs.as<CPairOut>() + pb[r], np, static_cast<uint32_t>(rb[r])); }
+        else if (np || nr)
+            chunk_rebase_kernel<<<std::max(1u, std::min<uint32_t>((std::max(np, nr) + 255) / 256, 1184u)), 256, 0, sg>>>(
+                c->m_pairs.as<PairOut>() + pb[r], np, c->m_hit_off.as<uint32_t>() + rb[r], nr, static_cast<uint32_t>(rb[r]), static_cast<uint32_t>(hb[r]), static_cast<uint32_t>(cb[r]));
+    }
+    if (!compact) poke(sg, {{c->m_hit_off.as<uint32_t>() + rb[W], static_cast<uint32_t>(hb[W])}});
+    CK(cudaGetLastError());
+    memset(merged, 0, sizeof *merged);
+    merged->n_reads = static_cast<uint32_t>(rb[W]); merged->n_hits = hb[W]; merged->n_pairs = pb[W]; merged->n_records = cb[W];
+    merged->received = rb[W]; merged->mapped = mapped; merged->multimapped = multi; merged->alignments = cb[W]; merged->slow_path_pairs = slow;
+    merged->rec_path_bytes = compact ? recw : 0u;
+    if (compact) { merged->d_cpairs = reinterpret_cast<const grootgpu_cpair*>(c->m_cpairs.p); merged->d_rec_path_c = c->m_rec_c.p; }
+    else {
+        merged->d_hit_off = c->m_hit_off.as<uint32_t>(); merged->d_hits = c->m_hits.as<uint32_t>(); merged->d_pairs = reinterpret_cast<const grootgpu_pair*>(c->m_pairs.p);
+        merged->d_rec_path = c->m_rec_path.as<uint32_t>(); merged->d_rec_pos = c->m_rec_pos.as<int32_t>();
+    }
+    if (to_host) {
+        for (int sec = 0; sec < n_sec; sec++) {
+            const uint64_t total_elems = compact ? (sec == 0 ? pb[W] : cb[W]) : (sec == 0 ? rb[W] + 1 : sec == 1 ? hb[W] : sec == 2 ? pb[W] : cb[W]);
+            hbuf[sec]->need(std::max<size_t>(16, total_elems * elem[sec]));
+            if (total_elems) CK(cudaMemcpyAsync(hbuf[sec]->p, mb[sec]->p, total_elems * elem[sec], cudaMemcpyDeviceToHost, sg));
+        }
+        CK(cudaStreamSynchronize(sg));
+        if (compact) { merged->cpairs = reinterpret_cast<const grootgpu_cpair*>(c->h_cpairs.p); merged->rec_path_c = c->h_rec_c.p; }
+        else {
+            merged->hit_off = c->h_hit_off.as<uint32_t>(); merged->hits = c->h_hits.as<uint32_t>(); merged->pairs = reinterpret_cast<const grootgpu_pair*>(c->h_pairs.p);
+            merged->rec_path = c->h_rec_path.as<uint32_t>(); merged->rec_pos = c->h_rec_pos.as<int32_t>();
+        }
+    }
 }
 
 void fnv_sink(void* ctx, const char* d, size_t n) { uint64_t& hsh = *static_cast<uint64_t*>(ctx); for (size_t i = 0; i < n; i++) { hsh ^= static_cast<uint8_t>(d[i]); hsh *= 1099511628211ULL; } }
@@ -1141,6 +1430,7 @@ template <class F>
 int guarded(F f) {
     try { f(); return GROOTGPU_OK; }
     catch (CudaError& e) { return fail(GROOTGPU_ERR_CUDA, e.what()); }
+    catch (CommError& e) { return fail(GROOTGPU_ERR_COMM, e.what()); }
     catch (std::invalid_argument& e) { return fail(GROOTGPU_ERR_SHORT_READ, e.what()); }
     catch (std::domain_error& e) { return fail(GROOTGPU_ERR_BAD_BASE, e.what()); }
     catch (std::length_error& e) { return fail(GROOTGPU_ERR_CAPACITY, e.what()); }
@@ -1312,7 +1602,15 @@ int grootgpu_align_batch_device(grootgpu_index* idx, const uint8_t* d_seq, const
     if (!idx || !d_seq || !d_seq_off || !params || n_reads == 0 || max_len < min_len) return fail(GROOTGPU_ERR_ARG, "bad argument");
     return guarded([&] {
         pick_device(idx->device);
-        run_batch(idx, &idx->ws[0], d_seq, d_seq_off, n_reads, min_len, max_len, params, stream ? static_cast<cudaStream_t>(stream) : idx->ws[0].stream, out);
+        Workspace* w = &idx->ws[0];
+        cudaStream_t st = stream ? static_cast<cudaStream_t>(stream) : w->stream;
+        // consecutive calls write alternating result sets: the arrays of a call stay valid during the next one (a
+        // gather of batch b overlaps the mapping of batch b + 1) and are reused by the call after that
+        idx->call_parity ^= 1;
+        if (w->rset != idx->call_parity) w->swap_result_sets();
+        if (idx->comm) CK(cudaStreamWaitEvent(st, idx->comm->ev_sent[idx->call_parity], 0));
+        w->ring_first = w->ring_last = true; w->acc_before = nullptr; w->acc_after = nullptr;
+        run_batch(idx, w, d_seq, d_seq_off, n_reads, min_len, max_len, params, st, out);
     });
 }
 
@@ -1321,22 +1619,93 @@ int grootgpu_align_batch(grootgpu_index* idx, const uint8_t* seq, const uint64_t
     if (!idx || !seq || !seq_off || !params || !out || n_reads == 0) return fail(GROOTGPU_ERR_ARG, "bad argument");
     return guarded([&] {
         pick_device(idx->device);
-        if (!params->results_on_device) { run_batch_chunked(idx, seq, seq_off, n_reads, params, out); return; }
-        // results stay on the device: one shot (the d_* pointers of the result must cover the whole batch)
-        const uint64_t total = seq_off[n_reads] - seq_off[0];
-        if (total >= (1ull << 32) - 64) throw std::length_error("a batch whose results stay on the device holds at most 4 GiB of bases: split it");
-        Workspace* w = &idx->ws[0];
-        cudaStream_t st = w->stream;
-        std::vector<uint32_t> off32(n_reads + 1);
-        uint32_t mn = 0xffffffffu, mx = 0;
-        for (uint32_t i = 0; i <= n_reads; i++) off32[i] = static_cast<uint32_t>(seq_off[i] - seq_off[0]);
-        for (uint32_t i = 0; i < n_reads; i++) { uint32_t l = off32[i + 1] - off32[i]; mn = std::min(mn, l); mx = std::max(mx, l); }
-        if (mn < idx->h.p.k) throw std::invalid_argument("a read is shorter than k (the reference panics at boss.go:164-166)");
-        w->seq.need(total + 64); w->off.need(4ull * (n_reads + 1));
-        CK(cudaMemcpyAsync(w->seq.p, seq + seq_off[0], total, cudaMemcpyHostToDevice, st));
-        CK(cudaMemsetAsync(w->seq.as<uint8_t>() + total, 0, 64, st));
-        CK(cudaMemcpyAsync(w->off.p, off32.data(), 4ull * (n_reads + 1), cudaMemcpyHostToDevice, st));
-        run_batch(idx, w, w->seq.as<uint8_t>(), w->off.as<uint32_t>(), n_reads, mn, mx, params, st, out);
+        idx->call_parity ^= 1;
+        run_batch_chunked(idx, seq, seq_off, n_reads, params, out);
+    });
+}
+
+int grootgpu_index_node_paths(const grootgpu_index* idx, uint32_t node, uint32_t* graph, const uint32_t** path_ids, const int32_t** positions, uint32_t* n_paths) {
+    if (!idx || node >= idx->h.nodes.size()) return fail(GROOTGPU_ERR_ARG, "node index out of range");
+    const NodeRec& nr = idx->h.nodes[node];
+    if (graph) *graph = idx->h.graph_of_node(node);
+    if (path_ids) *path_ids = idx->h.node_path_id.data() + nr.path_off;
+    if (positions) *positions = idx->h.node_path_pos.data() + nr.path_off;
+    if (n_paths) *n_paths = nr.path_cnt;
+    return GROOTGPU_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------------------------------
+int grootgpu_comm_id(uint8_t id[GROOTGPU_COMM_ID_BYTES]) {
+    if (!id) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    static_assert(GROOTGPU_COMM_ID_BYTES == 2 * NCCL_UNIQUE_ID_BYTES, "one id per communicator");
+    return guarded([&] {
+        ncclUniqueId a, b;
+        NK(nccl().GetUniqueId(&a)); NK(nccl().GetUniqueId(&b));
+        memcpy(id, &a, NCCL_UNIQUE_ID_BYTES); memcpy(id + NCCL_UNIQUE_ID_BYTES, &b, NCCL_UNIQUE_ID_BYTES);
+    });
+}
+
+int grootgpu_comm_create(grootgpu_index* idx, const uint8_t id[GROOTGPU_COMM_ID_BYTES], int rank, int world_size, grootgpu_comm** out) {
+    if (!idx || !id || !out || world_size < 1 || rank < 0 || rank >= world_size) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    if (idx->comm) return fail(GROOTGPU_ERR_ARG, "the index already has a communicator");
+    *out = nullptr;
+    grootgpu_comm* c = new grootgpu_comm();
+    int rc = guarded([&] {
+        pick_device(idx->device);
+        c->ix = idx; c->rank = rank; c->world = world_size;
+        ncclUniqueId a, b;
+        memcpy(&a, id, NCCL_UNIQUE_ID_BYTES); memcpy(&b, id + NCCL_UNIQUE_ID_BYTES, NCCL_UNIQUE_ID_BYTES);
+        NK(nccl().CommInitRank(&c->ring, world_size, a, rank));
+        NK(nccl().CommInitRank(&c->gath, world_size, b, rank));
+        CK(cudaStreamCreateWithFlags(&c->st_gather, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&c->ev_sent[0], &c->ev_sent[1], &c->ev_local}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        c->d_counts.need(8ull * 4 * (world_size + 1));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 8ull * 4 * (world_size + 1), cudaHostAllocDefault));
+        // every rank starts from its own weights; only rank 0's enter the ring (the others' are replaced by what arrives)
+        if (rank != 0) { sync_weights_to_host(idx); idx->weights_on_device = false; std::fill(idx->h.kmer_freq.begin(), idx->h.kmer_freq.end(), 0.0); std::fill(idx->h.kmer_total.begin(), idx->h.kmer_total.end(), 0); }
+    });
+    if (rc != GROOTGPU_OK) { delete c; return rc; }
+    idx->comm = c;
+    *out = c;
+    return GROOTGPU_OK;
+}
+
+void grootgpu_comm_destroy(grootgpu_comm* c) {
+    if (!c) return;
+    if (c->ix) { cudaSetDevice(c->ix->device); cudaStreamSynchronize(c->ix->st_acc); if (c->st_gather) cudaStreamSynchronize(c->st_gather); c->ix->comm = nullptr; }
+    delete c;
+}
+
+int grootgpu_gather(grootgpu_comm* c, const grootgpu_batch_result* local, int to_host, grootgpu_batch_result* merged) {
+    if (!c || !local) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    if (c->rank == 0 && !merged) return fail(GROOTGPU_ERR_ARG, "rank 0 needs a place for the merged result");
+    return guarded([&] {
+        grootgpu_index* ix = c->ix;
+        pick_device(ix->device);
+        gather_results(c, local, to_host != 0, merged);
+    });
+}
+
+int grootgpu_comm_sync(grootgpu_comm* c) {
+    if (!c) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    return guarded([&] {
+        grootgpu_index* ix = c->ix;
+        pick_device(ix->device);
+        CK(cudaStreamSynchronize(c->st_gather));
+        if (c->world > 1) {
+            push_weights_to_device(ix);
+            cudaStream_t sa = ix->st_acc;
+            std::lock_guard<std::mutex> lock(ix->acc_mu);
+            // the weight vector: whatever the last rank sent after the last batch is rank 0's result
+            if (c->rank == 0 && c->ring_pending) { NK(nccl().Recv(ix->d_kmer_freq, ix->h.nodes.size(), ncclDouble, c->world - 1, c->ring, sa)); c->ring_pending = false; }
+            // KmerTotal is an integer sum (graph.go:449): every rank counted its own reads
+            NK(nccl().Reduce(ix->d_kmer_total, ix->d_kmer_total, ix->h.n_graphs, ncclUint64, ncclSum, 0, c->ring, sa));
+            if (c->rank != 0) {
+                CK(cudaMemsetAsync(ix->d_kmer_freq, 0, ix->h.nodes.size() * sizeof(double), sa));
+                CK(cudaMemsetAsync(ix->d_kmer_total, 0, ix->h.n_graphs * sizeof(unsigned long long), sa));
+            }
+        }
+        CK(cudaStreamSynchronize(ix->st_acc));
     });
 }
 

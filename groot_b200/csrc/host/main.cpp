@@ -84,21 +84,29 @@ static int run_align(const Args& a) {
     info.Sketch.BAMout = a.get("--bamOut", "", "");
     info.GraphDir = a.get("-g", "--graphDir", "./groot-graphs");
     info.Device = atoi(a.get("--device", "", "0").c_str());
+    for (const std::string& d : split_commas(a.get("--devices", "", ""))) info.Devices.push_back(atoi(d.c_str()));   // no counterpart: GPUs to shard the reads over
+    if (info.Devices.empty()) info.Devices.push_back(info.Device);
     info.BatchReads = static_cast<uint32_t>(atoi(a.get("--batchReads", "", "1048576").c_str()));
     info.BamLevel = atoi(a.get("--bamLevel", "", "-1").c_str());   // no counterpart: deflate level of the BAM (default = zlib's, as biogo's writer)
     std::vector<std::string> fastq = split_commas(a.get("-f", "--fastq", ""));
     const double t0 = now_s();
-    grootgpu_index* idx = nullptr;
-    if (grootgpu_index_load((info.IndexDir + "/groot.grootb200").c_str(), info.Device, &idx)) fatal(grootgpu_last_error());
+    std::vector<grootgpu_index*> replicas;       // the index is replicated on every GPU of the run; replicas[0] ends up with the results
+    for (int dev : info.Devices) {
+        grootgpu_index* r = nullptr;
+        if (grootgpu_index_load((info.IndexDir + "/groot.grootb200").c_str(), dev, &r)) fatal(grootgpu_last_error());
+        replicas.push_back(r);
+    }
+    grootgpu_index* idx = replicas[0];
+    auto destroy_all = [&] { for (grootgpu_index* r : replicas) grootgpu_index_destroy(r); };
     try {
         FastqStream stream(fastq, info.Sketch.Fasta);
-        ReadMapper mapper(&info, idx);
+        ReadMapper mapper(&info, replicas);
         int rc = mapper.Run(stream);
         if (rc) fatal(mapper.error());
         const uint64_t* st = mapper.CollectReadStats();
         fprintf(stderr, "\tnumber of reads received from input: %llu\n\tmean read length: %.0f\n", static_cast<unsigned long long>(stream.rawCount()),
                 stream.rawCount() ? static_cast<double>(stream.lengthTotal()) / stream.rawCount() : 0.0);
-        if (st[1] == 0) { fprintf(stderr, "no reads could be mapped to the reference graphs\n"); grootgpu_index_destroy(idx); return 0; }   // sketch.go:328-334
+        if (st[1] == 0) { fprintf(stderr, "no reads could be mapped to the reference graphs\n"); destroy_all(); return 0; }   // sketch.go:328-334
         fprintf(stderr, "\ttotal number of unmapped reads: %llu\n\ttotal number of mapped reads: %llu\n\t\tmapped to one graph: %llu\n\t\tmapped to multiple graphs: %llu\n"
                         "\ttotal number of exact alignments: %llu\n\ttotal number of k-mers projected onto graphs: %llu\n",
                 (unsigned long long)(st[0] - st[1]), (unsigned long long)st[1], (unsigned long long)(st[1] - st[2]), (unsigned long long)st[2],
@@ -123,7 +131,7 @@ static int run_align(const Args& a) {
         }
     } catch (std::exception& e) { fatal(e.what()); }
     fprintf(stderr, "finished in %.3fs\n", now_s() - t0);
-    grootgpu_index_destroy(idx);
+    destroy_all();
     return 0;
 }
 

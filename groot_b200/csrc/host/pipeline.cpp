@@ -244,7 +244,93 @@ void BamWriter::close() {
 }
 
 // ---- ReadMapper (sketch.go:308-351 -> boss.go:45-242, graphminion.go:40-103) ------------------------------------
-ReadMapper::ReadMapper(Info* info, grootgpu_index* index) : info_(info), index_(index) {}
+ReadMapper::ReadMapper(Info* info, const std::vector<grootgpu_index*>& indexes) : info_(info), indexes_(indexes), index_(indexes.at(0)) {}
+
+namespace {
+// The ranks of a multi-GPU run inside one process: rank 0 is the caller's thread, ranks 1.. are helper threads that live
+// for the whole stream. Per batch every rank maps its contiguous shard (grootgpu_align_batch, results kept on the
+// device) and takes part in ONE gather to rank 0 (grootgpu_gather, NCCL over NVLink); the graph weights travel round
+// the ranks inside the library. A failure on any rank is agreed on at a barrier BEFORE the collective, so nobody hangs.
+struct RankTeam {
+    std::vector<grootgpu_index*> idx;
+    std::vector<grootgpu_comm*> comm;
+    std::vector<std::thread> th;
+    std::mutex mu; std::condition_variable cv;
+    uint64_t gen = 0;                       // batch generation handed to the helpers
+    int arrived = 0; uint64_t bar_gen = 0;  // barrier
+    bool stop = false;
+    const uint8_t* seq = nullptr; const uint64_t* seq_off = nullptr; uint32_t n = 0;
+    grootgpu_align_params prm{};
+    uint32_t rec_path_bytes = 1;
+    std::vector<int> rc; std::vector<std::string> err;
+    int world() const { return static_cast<int>(idx.size()); }
+
+    void barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        const uint64_t g = bar_gen;
+        if (++arrived == world()) { arrived = 0; bar_gen++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return bar_gen != g; });
+    }
+    static void shard(uint32_t n, int world, int r, uint32_t* lo, uint32_t* hi) {
+        const uint32_t base = n / world, rem = n % world;
+        *lo = r * base + std::min<uint32_t>(r, rem); *hi = *lo + base + (static_cast<uint32_t>(r) < rem ? 1u : 0u);
+    }
+    // one batch on rank r; merged is filled on rank 0
+    void rank_batch(int r, grootgpu_batch_result* merged) {
+        uint32_t lo, hi; shard(n, world(), r, &lo, &hi);
+        grootgpu_batch_result res{};
+        rc[r] = 0;
+        if (hi > lo) {
+            rc[r] = grootgpu_align_batch(idx[r], seq, seq_off + lo, hi - lo, &prm, &res);
+            if (rc[r]) err[r] = grootgpu_last_error();
+        } else res.rec_path_bytes = rec_path_bytes;   // an empty shard still takes part in the gather (same format, no arrays)
+        barrier();
+        bool any = false;
+        for (int x : rc) any = any || x != 0;
+        if (any) return;
+        rc[r] = grootgpu_gather(comm[r], &res, r == 0 ? 1 : 0, merged);
+        if (rc[r]) err[r] = grootgpu_last_error();
+    }
+    int start(std::string* e) {
+        const int W = world();
+        comm.assign(W, nullptr); rc.assign(W, 0); err.assign(W, "");
+        { grootgpu_index_info ii; grootgpu_index_get_info(idx[0], &ii); rec_path_bytes = ii.max_paths_per_graph <= 256 ? 1u : 2u; }
+        uint8_t id[GROOTGPU_COMM_ID_BYTES];
+        if (int x = grootgpu_comm_id(id)) { *e = grootgpu_last_error(); return x; }
+        std::vector<std::thread> init;
+        for (int r = 0; r < W; r++) init.emplace_back([&, r] { rc[r] = grootgpu_comm_create(idx[r], id, r, W, &comm[r]); if (rc[r]) err[r] = grootgpu_last_error(); });
+        for (auto& t : init) t.join();
+        for (int r = 0; r < W; r++) if (rc[r]) { *e = err[r]; return rc[r]; }
+        for (int r = 1; r < W; r++)
+            th.emplace_back([this, r] {
+                uint64_t seen = 0;
+                while (true) {
+                    { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || gen != seen; }); if (stop && gen == seen) break; seen = gen; }
+                    if (seq) rank_batch(r, nullptr);
+                    else { rc[r] = grootgpu_comm_sync(comm[r]); if (rc[r]) err[r] = grootgpu_last_error(); }   // end of stream: the collective sync
+                    barrier();
+                }
+            });
+        return 0;
+    }
+    // rank 0's side of one batch (seq != nullptr) or of the final sync (seq == nullptr)
+    int run(const uint8_t* s, const uint64_t* so, uint32_t nn, grootgpu_batch_result* merged, std::string* e) {
+        { std::lock_guard<std::mutex> lk(mu); seq = s; seq_off = so; n = nn; gen++; }
+        cv.notify_all();
+        if (s) rank_batch(0, merged);
+        else { rc[0] = grootgpu_comm_sync(comm[0]); if (rc[0]) err[0] = grootgpu_last_error(); }
+        barrier();
+        for (int r = 0; r < world(); r++) if (rc[r]) { *e = err[r]; return rc[r]; }
+        return 0;
+    }
+    ~RankTeam() {
+        { std::lock_guard<std::mutex> lk(mu); stop = true; }
+        cv.notify_all();
+        for (auto& t : th) if (t.joinable()) t.join();
+        for (grootgpu_comm* c : comm) if (c) grootgpu_comm_destroy(c);
+    }
+};
+}  // namespace
 
 int ReadMapper::Run(FastqStream& reads) {
     grootgpu_index_info ii;
@@ -280,6 +366,13 @@ int ReadMapper::Run(FastqStream& reads) {
     prm.containment_threshold = info_->ContainmentThreshold;
     prm.no_align = info_->Sketch.NoExactAlign ? 1 : 0;
     prm.project_on_device = 1;   // graphminion.go:67 IncrementSubPath: ordered f64 weighting on the GPU, bit-identical to the host replay
+    prm.compact_records = 1;     // the BAM writer needs (read, start locus, strand, clips, path ids): a fifth of the full output's bytes
+    RankTeam team;
+    if (indexes_.size() > 1) {
+        team.idx = indexes_;
+        team.prm = prm; team.prm.results_on_device = 1;
+        if ((rc = team.start(&err_))) return rc;
+    }
     uint8_t ctab[256];                     // complementBases (seqio.go:17-23): everything else maps to 0
     memset(ctab, 0, sizeof ctab);
     ctab['A'] = 'T'; ctab['T'] = 'A'; ctab['C'] = 'G'; ctab['G'] = 'C'; ctab['N'] = 'N';
@@ -324,11 +417,20 @@ int ReadMapper::Run(FastqStream& reads) {
         struct Release { BatchFeed& f; int i; ~Release() { f.release(i); } } release_slot{feed, slot_i};
         ReadBatch& b = *bp;
         grootgpu_batch_result res;
-        rc = grootgpu_align_batch(index_, b.seq.data(), b.seq_off.data(), b.size(), &prm, &res);
-        if (rc) { err_ = grootgpu_last_error(); return rc; }
+        if (indexes_.size() > 1) {
+            if ((rc = team.run(b.seq.data(), b.seq_off.data(), b.size(), &res, &err_))) return rc;
+        } else {
+            rc = grootgpu_align_batch(index_, b.seq.data(), b.seq_off.data(), b.size(), &prm, &res);
+            if (rc) { err_ = grootgpu_last_error(); return rc; }
+        }
         read_stats_[0] += res.received; read_stats_[1] += res.mapped; read_stats_[2] += res.multimapped;
         alignment_count_ += res.alignments;
         if (!bam) continue;
+        // first record of every pair (the compact output carries counts only)
+        std::vector<uint64_t> rec_begin(res.n_pairs + 1, 0);
+        for (uint64_t i = 0; i < res.n_pairs; i++) rec_begin[i + 1] = rec_begin[i] + res.cpairs[i].rec_count;
+        const uint8_t* path8 = res.rec_path_bytes == 1 ? static_cast<const uint8_t*>(res.rec_path_c) : nullptr;
+        const uint16_t* path16 = res.rec_path_bytes == 2 ? static_cast<const uint16_t*>(res.rec_path_c) : nullptr;
         // Records of the batch, in pair order == (read, graph) order. NumProc workers each format and deflate a
         // contiguous slice of the pairs (slices of roughly equal record count) into ready-made BGZF blocks; the slices
         // are appended in order. One worker reproduces the serial writer byte for byte up to block boundaries.
@@ -339,7 +441,7 @@ int ReadMapper::Run(FastqStream& reads) {
             uint64_t i = 0;
             for (unsigned t = 1; t < workers; t++) {
                 const uint64_t want = res.n_records * t / workers;
-                while (i < res.n_pairs && res.pairs[i].rec_begin < want) i++;
+                while (i < res.n_pairs && rec_begin[i] < want) i++;
                 cut[t] = i;
             }
         }
@@ -350,8 +452,14 @@ int ReadMapper::Run(FastqStream& reads) {
             std::vector<uint8_t>& out = outs[t];
             try {
                 for (uint64_t i = cut[t]; i < cut[t + 1]; i++) {
-                    const grootgpu_pair& p = res.pairs[i];
+                    const grootgpu_cpair& p = res.cpairs[i];
                     if (p.rec_count == 0) continue;
+                    const bool reverse = (p.offset_flags & GROOTGPU_CPAIR_REVERSE) != 0;
+                    const uint32_t clip_start = (p.offset_flags & GROOTGPU_CPAIR_CLIP_START) ? 1u : 0u, clip_end = (p.offset_flags & GROOTGPU_CPAIR_CLIP_END) ? 1u : 0u;
+                    const int32_t offset = static_cast<int32_t>(p.offset_flags & GROOTGPU_CPAIR_OFFSET_MASK);
+                    uint32_t graph = 0, n_node_paths = 0;
+                    const uint32_t* node_ids = nullptr; const int32_t* node_pos = nullptr;
+                    if (grootgpu_index_node_paths(index_, p.node, &graph, &node_ids, &node_pos, &n_node_paths)) { errs[t] = grootgpu_last_error(); return; }
                     const uint64_t so = b.seq_off[p.read], sl = b.seq_off[p.read + 1] - so;
                     const uint64_t qo = b.qual_off[p.read], ql = b.qual_off[p.read + 1] - qo;
                     const uint8_t* seq = b.seq.data() + so;
@@ -360,20 +468,23 @@ int ReadMapper::Run(FastqStream& reads) {
                         errs[t] = "read without a full quality string reached the BAM writer (the reference panics here)";
                         return;
                     }
-                    if (p.reverse) {                                           // read.RevComplement() (seqio.go:120-133)
+                    if (reverse) {                                             // read.RevComplement() (seqio.go:120-133)
                         rc_seq.resize(sl); rc_qual.resize(sl);
                         for (uint64_t k = 0; k < sl; k++) { rc_seq[k] = ctab[seq[sl - 1 - k]]; rc_qual[k] = qual[sl - 1 - k]; }
                         seq = rc_seq.data(); qual = rc_qual.data();
                     }
-                    const uint32_t match = static_cast<uint32_t>(sl) - p.clip_start - p.clip_end;     // alignment.go:117
+                    const uint32_t match = static_cast<uint32_t>(sl) - clip_start - clip_end;         // alignment.go:117
                     const uint64_t io = b.id_off[p.read], il = b.id_off[p.read + 1] - io;
                     for (uint32_t j = 0; j < p.rec_count; j++) {
                         uint16_t flag = 0;
                         if (p.rec_count > 1 && j != 0) flag |= 0x100;          // sam.Secondary (alignment.go:147-149)
-                        if (p.reverse) flag |= 0x10;                           // sam.Reverse (alignment.go:150-152)
+                        if (reverse) flag |= 0x10;                             // sam.Reverse (alignment.go:150-152)
+                        const uint32_t path = path8 ? path8[rec_begin[i] + j] : path16[rec_begin[i] + j];
+                        const uint32_t* it = std::lower_bound(node_ids, node_ids + n_node_paths, path);   // Position[pathID] of the start node (alignment.go:296)
+                        const int32_t pos = (it != node_ids + n_node_paths && *it == path ? node_pos[it - node_ids] : 0) + offset;
                         BamWriter::format_record(raw, b.id.data() + io + 1, static_cast<uint32_t>(il ? il - 1 : 0),          // Name = ID[1:] (alignment.go:119)
-                                                 static_cast<int32_t>(graph_ref_base[p.graph] + res.rec_path[p.rec_begin + j]), res.rec_pos[p.rec_begin + j], flag,
-                                                 p.clip_start, match, p.clip_end, seq, qual);  // Seq/Qual = read[0:seqLength] (alignment.go:120-121)
+                                                 static_cast<int32_t>(graph_ref_base[graph] + path), pos, flag,
+                                                 clip_start, match, clip_end, seq, qual);    // Seq/Qual = read[0:seqLength] (alignment.go:120-121)
                     }
                     if (raw.size() >= (1u << 20)) {                            // deflate whole blocks, keep the remainder
                         const size_t whole = raw.size() / kBgzfBlock * kBgzfBlock;
@@ -397,6 +508,7 @@ int ReadMapper::Run(FastqStream& reads) {
     }
     if (reads.rawCount() == 0) { err_ = "no fastq reads received"; return GROOTGPU_ERR_EMPTY; }   // sketch.go:275-277
     if (bam) { bam->close(); if (fh != stdout) fclose(fh); }
+    if (indexes_.size() > 1 && (rc = team.run(nullptr, nullptr, 0, nullptr, &err_))) return rc;   // collect the graph weights on the first GPU
     std::vector<double> kf(ii.n_nodes);
     std::vector<uint64_t> kt(ii.n_graphs);
     grootgpu_weights(index_, kf.data(), kt.data());

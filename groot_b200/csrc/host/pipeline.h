@@ -36,6 +36,7 @@ struct Info {
     std::string GraphDir = "./groot-graphs";  // -g
     uint32_t BatchReads = 1u << 20;           // reads per device batch (no counterpart: the reference streams single reads)
     int Device = 0;
+    std::vector<int> Devices;                 // --devices 0,1,...: one index replica per GPU, reads sharded, results gathered to the first (empty = {Device})
     int BamLevel = -1;                        // deflate level of the BGZF blocks (-1 = zlib default, like bam.NewWriter; 0..9)
 };
 
@@ -102,7 +103,8 @@ class BamWriter {
 
 class ReadMapper {
   public:
-    ReadMapper(Info* info, grootgpu_index* index);
+    // indexes[r] = the replica on GPU r of the run (indexes[0] receives the merged results and the graph weights)
+    ReadMapper(Info* info, const std::vector<grootgpu_index*>& indexes);
     // theBoss.mapReads: drains the stream; BAM to info->Sketch.BAMout or STDOUT; returns 0 or a GROOTGPU_ERR_* code
     int Run(FastqStream& reads);
     // corresponds to num. reads, total num. mapped, num. multimapped, total k-mers (sketch.go:289,302-305)
@@ -112,7 +114,8 @@ class ReadMapper {
 
   private:
     Info* info_;
-    grootgpu_index* index_;
+    std::vector<grootgpu_index*> indexes_;
+    grootgpu_index* index_;                   // == indexes_[0]
     uint64_t read_stats_[4] = {0, 0, 0, 0};
     uint64_t alignment_count_ = 0;
     std::string err_;

@@ -107,9 +107,8 @@ __global__ void __launch_bounds__(256) project_expand_kernel(DevIndex ix, Projec
 // they pipeline under the DADD latency). One thread per segment with loads ahead of use took ~90 cycles per addend
 // (profiles/r01_ncu_summary.md); this form is bounded by the DADD latency alone.
 __global__ void __launch_bounds__(256) project_accumulate_kernel(const uint32_t* __restrict__ keys, const double* __restrict__ vals,
-                                                                 const uint32_t* __restrict__ n_items_ptr, uint32_t n_nodes,
+                                                                 uint32_t n, uint32_t n_nodes,
                                                                  double* __restrict__ kmer_freq) {
-    const uint32_t n = *n_items_ptr;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t node = gwarp; node < n_nodes; node += total_warps) {

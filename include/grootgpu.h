@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GROOTGPU_VERSION "0.1.0"
+#define GROOTGPU_VERSION "0.2.0"
 #define GROOTGPU_REFERENCE_VERSION "1.1.2" /* src/version/version.go:6-12; enforced at cmd/align.go:96-98 */
 
 enum {
@@ -37,7 +37,8 @@ enum {
     GROOTGPU_ERR_SHORT_READ = -5,  /* a read is shorter than k: the reference panics (boss.go:164-166) */
     GROOTGPU_ERR_BAD_BASE = -6,    /* RevComplement hit a byte > 'T': the reference panics (seqio.go:17-23,122) */
     GROOTGPU_ERR_CAPACITY = -7,    /* a documented limit was exceeded (see DESIGN.md "Limits") */
-    GROOTGPU_ERR_EMPTY = -8        /* nothing to index / empty index (lshe.go:103-105) */
+    GROOTGPU_ERR_EMPTY = -8,       /* nothing to index / empty index (lshe.go:103-105) */
+    GROOTGPU_ERR_COMM = -9         /* NCCL failure / NCCL library not found (multi-GPU entry points only) */
 };
 
 typedef struct grootgpu_index grootgpu_index; /* graph store + containment index + device copies + workspaces */
@@ -113,6 +114,9 @@ typedef struct {
                                      bit-identical to grootgpu_project_batch; do NOT call grootgpu_project_batch for that batch */
     int32_t results_on_device;    /* 1: skip the device->host copy of the result arrays; the d_* pointers of the
                                      result are set instead (multi-GPU gather, kernel-side timing) */
+    int32_t compact_records;      /* 1: BAM-oriented compact output — cpairs[] + rec_path_c[] instead of hit_off / hits / pairs /
+                                     rec_path / rec_pos (about a fifth of the bytes: what crosses PCIe and NVLink). Needs
+                                     project_on_device or no weighting: grootgpu_project_batch wants the full arrays */
 } grootgpu_align_params;
 
 /* One (read, graph) unit == one graphMinionPair (src/pipeline/graphminion.go:14-17). */
@@ -129,6 +133,21 @@ typedef struct {
     uint8_t clip_end;        /* 1H at the end   (alignment.go:88-103,136-138) */
     uint8_t stage;           /* 1..4: hierarchy stage that produced the alignment; 0 = none */
 } grootgpu_pair;
+
+/* Compact form of a pair (params->compact_records): everything the BAM writer needs (boss.go:225-242, alignment.go:114-156).
+ * Record j of the pair has path id rec_path_c[first + j] (first = sum of rec_count of the pairs before it) and position
+ * Position[path] of node `node` + offset (alignment.go:296: grootgpu_index_node_paths gives the node's path table);
+ * the graph is the node's. Unaligned pairs are kept (rec_count == 0, node == 0xffffffff). */
+typedef struct {
+    uint32_t read;           /* read index inside the batch */
+    uint32_t node;           /* global node index of the start node (graphs ascending, SortedNodes order) */
+    uint32_t offset_flags;   /* bits 0..27 offset on that node | GROOTGPU_CPAIR_REVERSE / _CLIP_START / _CLIP_END */
+    uint32_t rec_count;
+} grootgpu_cpair;
+#define GROOTGPU_CPAIR_OFFSET_MASK 0x0fffffffu
+#define GROOTGPU_CPAIR_REVERSE     0x10000000u   /* sam.Reverse (alignment.go:150-152) */
+#define GROOTGPU_CPAIR_CLIP_START  0x20000000u   /* 1H at the start (alignment.go:73-85,132-134) */
+#define GROOTGPU_CPAIR_CLIP_END    0x40000000u   /* 1H at the end (alignment.go:88-103,136-138) */
 
 /* Result of one batch. All pointers are HOST memory owned by the index handle, valid until the next
  * align call on that handle (or its destruction). Record j of a pair is (rec_path[j], rec_pos[j]):
@@ -161,6 +180,13 @@ typedef struct {
     const grootgpu_pair* d_pairs;
     const uint32_t* d_rec_path;
     const int32_t* d_rec_pos;
+    /* compact output (params->compact_records): host arrays (NULL with results_on_device) and their device copies; the
+     * full-format host arrays above are NULL then, and so are d_rec_path / d_rec_pos */
+    const grootgpu_cpair* cpairs;      /* [n_pairs] ordered by (read, graph) */
+    const void* rec_path_c;            /* [n_records] path ids, rec_path_bytes each (1 when no graph has more than 256 paths, else 2) */
+    uint32_t rec_path_bytes;
+    const grootgpu_cpair* d_cpairs;
+    const void* d_rec_path_c;
 } grootgpu_batch_result;
 
 /* Replaces the per-read loop of theBoss.mapReads (src/pipeline/boss.go:134-203: RunMinHash ->
@@ -185,6 +211,11 @@ int grootgpu_align_batch_device(grootgpu_index* idx, const uint8_t* d_seq, const
                                 uint32_t min_len, uint32_t max_len, const grootgpu_align_params* params,
                                 void* stream, grootgpu_batch_result* out);
 
+/* Path table of a node: PathIDs ascending and Position[pathID] (src/graph/node.go:13-22), and the node's GraphID — what
+ * turns a compact record (node, offset, path id) into sam.Record{Ref, Pos}. Pointers stay valid until the index is destroyed. */
+int grootgpu_index_node_paths(const grootgpu_index* idx, uint32_t node, uint32_t* graph, const uint32_t** path_ids,
+                              const int32_t** positions, uint32_t* n_paths);
+
 /* Replaces GrootGraph.IncrementSubPath as driven by the minion loop (src/graph/graph.go:401-451,
  * graphminion.go:60,67): replays, in read order, the weight increments of the first n_incremented
  * mappings of every pair in f64 on the host copy of the graphs (order-dependent float accumulation,
@@ -200,6 +231,35 @@ int grootgpu_reset_weights(grootgpu_index* idx);
  * src/minhash/khf.go:35-56): out[i*sketch_size + j]. Fails with GROOTGPU_ERR_SHORT_READ if any is < k. */
 int grootgpu_sketch_batch(int device, const uint8_t* seq, const uint64_t* seq_off, uint32_t n_seqs,
                           uint32_t kmer_size, uint32_t sketch_size, uint64_t* out);
+
+/* ---- multi-GPU ------------------------------------------------------------------------------ */
+/* Reads are independent units (the reference already fans them over NumProc workers, boss.go:134-203): every rank
+ * (one index handle per GPU, index replicated) maps a contiguous shard of the batch — rank 0 the first reads, rank 1 the
+ * next, ... — with grootgpu_align_batch[_device](results_on_device = 1); no collective on the data path. What crosses
+ * NVLink (NCCL, loaded at run time):
+ *   - ONE gather of the per-rank result arrays to rank 0 per batch (grootgpu_gather), merged there in global read order
+ *     — the single ordered BAM writer of boss.go:225-234;
+ *   - the graph weights: IncrementSubPath is an order-dependent f64 accumulation (graph.go:401-451), so with
+ *     project_on_device every rank expands and sorts its own increments and the per-node chains run rank after rank on
+ *     ONE weight vector that travels round the ranks (send/recv of n_nodes doubles per batch) — bit-identical to one GPU
+ *     mapping the whole batch. The chains run on their own stream, behind the mapping of the following batches. */
+typedef struct grootgpu_comm grootgpu_comm;
+#define GROOTGPU_COMM_ID_BYTES 256
+/* rank 0 creates the id; the host hands it to the other ranks (MPI, torch.distributed, a file, another thread) */
+int grootgpu_comm_id(uint8_t id[GROOTGPU_COMM_ID_BYTES]);
+/* Collective over all ranks (blocks until every rank has called it). The communicator is attached to idx: from now on
+ * the device-side graph weighting of that index takes part in the ring. One rank per index handle per process thread. */
+int grootgpu_comm_create(grootgpu_index* idx, const uint8_t id[GROOTGPU_COMM_ID_BYTES], int rank, int world_size, grootgpu_comm** out);
+/* Collective: `local` is the result of this rank's last align call (results_on_device = 1; either output format, the same
+ * on all ranks). On rank 0 `merged` receives the batch-wide result: read indices global (rank 0's reads first), hit /
+ * record offsets rebased, counters summed; d_* pointers always, host arrays too when to_host != 0 (the call then returns
+ * after the copy; otherwise it only enqueues, and the arrays are complete after grootgpu_comm_sync). Valid until the next
+ * grootgpu_gather on the communicator. Other ranks may pass merged = NULL. The transfer overlaps the next align call. */
+int grootgpu_gather(grootgpu_comm* comm, const grootgpu_batch_result* local, int to_host, grootgpu_batch_result* merged);
+/* Collective: waits for the gathers and the weight ring; afterwards rank 0's index holds the graph weights of everything
+ * mapped so far on all ranks (grootgpu_weights / _prune / _graph_save_gfa on rank 0), the other ranks' weights are zero. */
+int grootgpu_comm_sync(grootgpu_comm* comm);
+void grootgpu_comm_destroy(grootgpu_comm* comm);
 
 /* ---- after the stream ends ------------------------------------------------------------------- */
 

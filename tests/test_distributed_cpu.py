@@ -1,7 +1,8 @@
-"""world_size-2 gloo test of the multi-GPU host logic (groot_b200/distributed.py): reads are sharded into contiguous
-slices, every rank maps its slice independently (here: with the CPU oracle standing in for the per-rank GPU
-result), ONE gather moves the per-rank result arrays to rank 0, and the merge must reproduce what a single rank
-computes on the whole read set."""
+"""world_size-2 gloo test of the multi-GPU host logic (groot_b200/distributed.py): the communicator id reaches every
+rank, reads are sharded into contiguous slices, every rank maps its slice independently (here: with the CPU oracle
+standing in for the per-rank GPU result), the per-rank result arrays are brought to rank 0, and the merge — the host
+restatement of what grootgpu_gather does on the device — must reproduce what a single rank computes on the whole
+read set. (The NCCL path itself runs on the GPU box: tests/test_gpu_multi.py, bench.py --gpus N.)"""
 import os
 import sys
 
@@ -53,17 +54,26 @@ def _worker(rank, world, port, tmp):
         lo, hi = gd.shard_bounds(len(seqs), world, rank)
         blob, off = pack_reads(seqs[lo:hi])
         local = _oracle_result_arrays(idx, blob, off)
+        # the 256-byte communicator id travels from rank 0 to everybody
+        cid = gd.broadcast_comm_id(lambda: bytes(range(256)))
+        assert cid == bytes(range(256))
         tens = {k: torch.from_numpy(np.ascontiguousarray(v).view(np.uint8).reshape(-1).copy()) for k, v in local.items()}
-        gathered = gd.gather_results(tens, dst=0)
-        # the bench's OverlappedGather must hand rank 0 the same bytes (on CPU / gloo it degrades to the blocking gather;
-        # its stream-ordered NCCL form runs in bench.py --gpus N on the GPU box)
-        og = gd.OverlappedGather(torch.device("cpu"), dst=0)
-        og.submit(tens)
-        again = og.flush()
+        sizes = torch.tensor([tens[k].numel() for k in gd.RESULT_KEYS], dtype=torch.int64)
+        all_sizes = [torch.zeros_like(sizes) for _ in range(world)]
+        dist.all_gather(all_sizes, sizes)
+        gathered = None
         if rank == 0:
-            assert all(torch.equal(again[r][k], gathered[r][k]) for r in range(world) for k in gd.RESULT_KEYS)
+            gathered = [tens]
+            for r in range(1, world):
+                bufs = {k: torch.empty(int(all_sizes[r][i]), dtype=torch.uint8) for i, k in enumerate(gd.RESULT_KEYS)}
+                for k in gd.RESULT_KEYS:
+                    if bufs[k].numel():
+                        dist.recv(bufs[k], src=r)
+                gathered.append(bufs)
         else:
-            assert again is None
+            for k in gd.RESULT_KEYS:
+                if tens[k].numel():
+                    dist.send(tens[k], dst=0)
         if rank == 0:
             from groot_b200.api import PAIR_DTYPE
             dt = {"hit_off": np.uint32, "hits": np.uint32, "pairs": PAIR_DTYPE, "rec_path": np.uint32, "rec_pos": np.int32}

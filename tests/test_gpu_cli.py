@@ -81,3 +81,25 @@ def test_cli_errors(tmp_path, root):
     assert r.returncode != 0                                           # misc.ErrorCheck -> log.Fatal
     r = subprocess.run([CLI, "align", "-f", "x.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 1 and b"--indexDir" in r.stdout            # cmd/align.go:57-60
+
+
+def test_cli_two_devices_equal_one(db_dirs, root, tmp_path):
+    """`groot-b200 align --devices 0,1`: one index replica per GPU, every batch sharded over them, ONE NCCL gather of the
+    compact records to the first GPU, the graph weights chained rank after rank. BAM records and weighted GFAs must be
+    those of the one-GPU run (needs 2 GPUs: gpurun --gpus 2)."""
+    import glob
+    if api.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    fq = os.path.join(root, "data", "reads", "full-argannot-perfect-reads-small.fq.gz")
+    _run("index", "-m", db_dirs["arg-annot.90"], "-i", str(tmp_path / "idx"))
+    _run("align", "-i", str(tmp_path / "idx"), "-f", fq, "-g", str(tmp_path / "g1"), "--bamOut", str(tmp_path / "one.bam"), "--batchReads", "301")
+    log = _run("align", "-i", str(tmp_path / "idx"), "-f", fq, "-g", str(tmp_path / "g2"), "--bamOut", str(tmp_path / "two.bam"), "--batchReads", "301",
+               "--devices", "0,1", "-p", "3")
+    t1, refs1, recs1 = read_bam(str(tmp_path / "one.bam"))
+    t2, refs2, recs2 = read_bam(str(tmp_path / "two.bam"))
+    assert refs1 == refs2 and len(recs1) > 1000 and recs1 == recs2
+    g1 = sorted(os.path.basename(f) for f in glob.glob(str(tmp_path / "g1" / "*.gfa")))
+    g2 = sorted(os.path.basename(f) for f in glob.glob(str(tmp_path / "g2" / "*.gfa")))
+    assert g1 == g2 and len(g1) > 0
+    for f in g1:
+        assert open(tmp_path / "g1" / f).read() == open(tmp_path / "g2" / f).read(), f

@@ -507,3 +507,41 @@ def test_c3_full_size_vs_oracle(argannot, db_dirs):
     assert tot == one.counts
     ow = o.weights()
     assert np.array_equal(w_one[0], ow[0]) and np.array_equal(w_one[1], ow[1])
+
+
+def test_compact_output_decodes_to_the_full_records(argannot, db_dirs, monkeypatch):
+    """params->compact_records: cpairs + 1-byte path ids instead of hit_off / hits / pairs / rec_path / rec_pos. Decoded
+    with the nodes' path tables (what a BAM writer does) it must give exactly the records of the full output and of the
+    oracle — single shot on the device, chunked through the host path (ragged chunks), stage 2/3/4 reads included."""
+    import torch
+    g, o = argannot
+    seqs = synth.db_sequences(db_dirs["arg-annot.90"])
+    b1, o1 = _c1_reads(db_dirs["arg-annot.90"], 30_011, 100, seed=5)
+    b2, o2 = _stage_forcing_reads(seqs, 24_000, seed=3)
+    for blob, off in ((b1, o1), (b2, o2)):
+        full = g.map_reads(blob, off, 0.99)
+        orr = o.map_reads(blob, off, 0.99, threads=8)
+        assert np.array_equal(full.records_table(), oracle_records_table(orr))
+        for chunk in (None, "997"):
+            if chunk:
+                monkeypatch.setenv("GROOTGPU_CHUNK_READS", chunk)
+            c = g.map_reads(blob, off, 0.99, compact=True, project_on_device=True)
+            if chunk:
+                monkeypatch.delenv("GROOTGPU_CHUNK_READS")
+            assert c.compact and c.rec_path_c.dtype == np.uint8 and c.counts == full.counts
+            assert c.n_pairs == full.n_pairs and c.n_records == full.n_records
+            assert np.array_equal(c.cpairs["read"], full.pairs["read"]) and np.array_equal(c.cpairs["rec_count"], full.pairs["rec_count"])
+            assert np.array_equal(c.decode_compact(g), full.records_table())
+        n = len(off) - 1
+        dev = torch.device("cuda", 0)
+        d_seq = torch.zeros(len(blob) + 64, dtype=torch.uint8, device=dev)
+        d_seq[: len(blob)].copy_(torch.from_numpy(blob))
+        d_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).to(dev)
+        torch.cuda.synchronize()
+        c = g.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, 100, 100, 0.99, copy_back=True, compact=True)
+        assert np.array_equal(c.decode_compact(g), full.records_table())
+    # the weights are the same whichever output format the batches used
+    g.reset_weights(); o.reset_weights()
+    g.map_reads(b1, o1, 0.99, compact=True, project_on_device=True)
+    o.map_reads(b1, o1, 0.99, threads=8)
+    assert np.array_equal(g.weights()[0], o.weights()[0]) and np.array_equal(g.weights()[1], o.weights()[1])
