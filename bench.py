@@ -2,14 +2,20 @@
 """bench.py — `groot align` hot path on B200: reads/s for 100 bp synthetic reads vs arg-annot.90.
 
 A "step" is one pass of the hot path (KHF sketch -> LSH Ensemble containment query -> hierarchical exact graph
-alignment) over one batch of synthetic reads (BASELINE.json configs[2]: 10 M x 100 bp, arg-annot.90 -w 100,
-full align path). `value` is measured with the batch already resident in HBM; `e2e` goes through the
-reference-facing C-ABI call with pinned HOST buffers (H2D of reads, D2H of hits/pairs/records inside the timed
-region, plus the ordered host replay of the graph weighting). `--impl reference` times the CPU restatement of
-the reference (oracle/, all host threads) on a bounded sample of the same workload — the reference itself is
-Go and cannot be built in this image (DESIGN.md "Oracle").
+alignment -> ordered graph weighting) over one batch of synthetic reads per GPU. The headline workload is
+BASELINE.json configs[2] (C3: 10 M x 100 bp, arg-annot.90 -w 100, full align path); at N = 1 the line also carries
+C2 (seeding only, --noAlign) and C4 (10 M x 150 bp vs card.90 -w 150) under "other_configs".
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--reads R] [--read-len L]
+  value   the batch already resident in HBM, full result arrays left on the device, CUDA events on the launching
+          stream. N > 1: every rank maps its own shard, the result arrays are gathered to rank 0 over NCCL / NVLink
+          (grootgpu_gather) and merged there, the order-dependent f64 graph weights are chained rank after rank
+          (weight ring) — all of it, and the final drain, inside the timed region.
+  e2e     the call a user makes: pinned HOST buffers -> grootgpu_align_batch (H2D, kernels, compact BAM-oriented result)
+          -> host. N > 1: + gather to rank 0 and rank 0's device->host copy of the merged batch.
+  --impl reference   the CPU restatement of the reference (oracle/, all host threads) on a bounded sample of the
+          same workload — the reference itself is Go and cannot be built in this image (DESIGN.md "Oracle").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config C2|C3|C4] [--extra C2,C4|none] [--reads R]
 """
 import argparse
 import json
@@ -40,7 +46,6 @@ CONFIGS = {
                workload="10M x 150bp synthetic reads vs card.90 (-w 150 -k 31 -s 21 -x 8 -y 4, t=0.99), full align path "
                         "(sketch + LSH Ensemble query + exact graph alignment) [BASELINE.json configs[3]]"),
 }
-INDEX_PARAMS = CONFIGS["C3"]["index"]
 
 
 def env_int(name, default):
@@ -147,38 +152,37 @@ def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    import numpy as np
     from groot_b200 import synth
     from oracle import pyoracle as po
-    msa_dir = prepare_db()
+    cfg = CONFIGS[args.config]
+    msa_dir = prepare_db(cfg["db"])
     cores = os.cpu_count() or 1
     t0 = time.time()
-    idx = po.Index(msa_dir=msa_dir, k=INDEX_PARAMS["k"], S=INDEX_PARAMS["S"], w=INDEX_PARAMS["w"])
+    idx = po.Index(msa_dir=msa_dir, **cfg["index"])
     t_index = time.time() - t0
     seqs = synth.db_sequences(msa_dir)
-    L = args.read_len
+    L = cfg["read_len"]
     probe_n = 20000
     blob, off = synth.synth_reads(probe_n, L, seqs, seed=42)
-    t0 = time.time(); idx.map_reads(blob, off, THRESHOLD, threads=cores); probe = probe_n / (time.time() - t0)
+    t0 = time.time(); idx.map_reads(blob, off, THRESHOLD, no_align=cfg["no_align"], threads=cores); probe = probe_n / (time.time() - t0)
     total_budget = 120.0   # seconds for all steps
     per_step = max(20000, min(2_000_000, int(probe * total_budget / max(1, args.steps + args.warmup))))
     blob, off = synth.synth_reads(per_step, L, seqs, seed=42)
     for _ in range(args.warmup):
-        idx.map_reads(blob, off, THRESHOLD, threads=cores)
+        idx.map_reads(blob, off, THRESHOLD, no_align=cfg["no_align"], threads=cores)
     t0 = time.time()
     for _ in range(args.steps):
         idx.reset_weights()
-        res = idx.map_reads(blob, off, THRESHOLD, threads=cores)
+        res = idx.map_reads(blob, off, THRESHOLD, no_align=cfg["no_align"], threads=cores)
     dt = time.time() - t0
     value = per_step * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": "10M x 100bp synthetic reads vs arg-annot.90 (-w 100 -k 31 -s 21), full align path; bounded sample per step",
-                   "reads_per_step": per_step, "read_len": L, "threshold": THRESHOLD},
+        "config": {"workload": cfg["workload"], "config_id": args.config, "read_len": L, "threshold": THRESHOLD},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d reads/step x %d steps of the same synthetic mix (seed 42); oracle index build %.1fs not counted" % (per_step, args.steps, t_index)},
+                         "sample": "%d reads/step x %d steps of the workload's synthetic mix (seed 42); oracle index build %.1fs not counted" % (per_step, args.steps, t_index)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "mapped_fraction": res.counts["mapped"] / res.counts["received"],
@@ -187,51 +191,58 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
-def run_ours(args):
+class Ctx:
+    """Rank plumbing: torch.distributed is used for barriers / reductions of the timing and to carry the communicator id;
+    the data path (gather, weight ring) is libgrootgpu's own NCCL code."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world, self.local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU baseline")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def reduce(self, x, op):
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return float(t.item())
+
+
+def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
+    """Times one BASELINE config on this rank's GPU; returns the result dict (meaningful on rank 0)."""
     import numpy as np
-    import torch
-    import torch.distributed as dist
     from groot_b200 import api, synth
     from groot_b200 import distributed as gd
+    torch = ctx.torch
+    cfg = CONFIGS[name]
+    rank, world, dev = ctx.rank, ctx.world, ctx.dev
+    L, no_align = cfg["read_len"], cfg["no_align"]
 
-    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU baseline")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
-    msa_dir = prepare_db() if rank == 0 else None
-    barrier()
+    msa_dir = prepare_db(cfg["db"]) if rank == 0 else None
+    ctx.barrier()
     if msa_dir is None:
-        msa_dir = prepare_db()
+        msa_dir = prepare_db(cfg["db"])
     t0 = time.time()
-    idx = api.Index.build(msa_dir=msa_dir, device=local, **INDEX_PARAMS)
+    idx = api.Index.build(msa_dir=msa_dir, device=ctx.local, **cfg["index"])
     t_index = time.time() - t0
     info = idx.info()
+    comm = None
+    if world > 1:   # the data-path communicator lives in the library; torch only carries its id
+        comm = api.Comm(idx, gd.broadcast_comm_id(api.Comm.new_id, device=dev), rank, world)
 
-    n, L = args.reads, args.read_len
     seqs = synth.db_sequences(msa_dir)
-    blob, off = synth.synth_reads(n, L, seqs, seed=42 + rank)      # weak scaling: every rank maps its own n reads
+    blob, off = synth.synth_reads(n, L, seqs, seed=42 + rank)      # weak scaling: rank r maps reads [r*n, (r+1)*n) of the global batch
     h_seq = torch.from_numpy(blob).pin_memory()
     h_off = torch.from_numpy(off.view(np.int64)).pin_memory()
     d_seq = torch.zeros(n * L + 64, dtype=torch.uint8, device=dev)
@@ -239,137 +250,188 @@ def run_ours(args):
     d_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).to(dev)
     stream = torch.cuda.current_stream().cuda_stream
 
-    gatherer = gd.OverlappedGather(dev, dst=0) if world > 1 else None
-
     def step_device():
-        raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, THRESHOLD, stream=stream, project_on_device=True)
-        if world > 1:   # the one collective of the path: every rank's result arrays go to rank 0 over NVLink, sent from
-            gatherer.submit(gd.result_tensors_from_raw(raw, dev))   # staging copies while the next batch is being mapped
-        return raw
+        raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, THRESHOLD, no_align=no_align, stream=stream, project_on_device=True)
+        merged = comm.gather(raw, to_host=0) if comm else None     # the one collective of the path: result arrays to rank 0 over NVLink, merged there
+        return raw, merged
 
-    e2e_parts = {"align_batch_ms": 0.0, "copy_in_to_copy_out_ms": 0.0}
+    def drain():
+        if comm:
+            comm.sync()            # gathers done, the weight vector has been round every rank, rank 0 holds the weights
+        else:
+            idx.weights()          # the f64 chains run behind the batches: wait for the last ones
+        torch.cuda.synchronize()
+
+    e2e_parts = {"align_batch_ms": 0.0, "gather_ms": 0.0}
 
     def step_e2e():
         t0 = time.perf_counter()
-        raw = idx.map_reads_raw(h_seq.data_ptr(), h_off.data_ptr(), n, THRESHOLD, project_on_device=True)
-        e2e_parts["align_batch_ms"] += (time.perf_counter() - t0) * 1e3
-        e2e_parts["copy_in_to_copy_out_ms"] += raw.ms[0]   # CUDA events: first copy-in issued -> last copy-out complete
-        return raw
+        raw = idx.map_reads_raw(h_seq.data_ptr(), h_off.data_ptr(), n, THRESHOLD, no_align=no_align, project_on_device=True, compact=True,
+                                results_on_device=comm is not None)
+        t1 = time.perf_counter()
+        merged = comm.gather(raw, to_host=2) if comm else None     # rank 0: merged compact batch -> host, asynchronously (complete at the next gather / sync)
+        e2e_parts["align_batch_ms"] += (t1 - t0) * 1e3
+        e2e_parts["gather_ms"] += (time.perf_counter() - t1) * 1e3
+        return raw, merged
 
     # ---- value: inputs resident in HBM ----
-    sampler = ClockSampler(local)
-    if rank == 0:
+    sampler = ClockSampler(ctx.local) if sample_clocks else None
+    if sampler and rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        raw = step_device()
-    if gatherer is not None:
-        gatherer.flush()
-    torch.cuda.synchronize(); barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(warmup):
+        raw, merged = step_device()
+    drain(); ctx.barrier()
+    e0, e_map, e1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     fam_ms = {k: [] for k in api.KERNEL_FAMILIES}
     launches = 0
-    torch.cuda.synchronize(); barrier()
-    sampler.mark_begin()
+    torch.cuda.synchronize(); ctx.barrier()
+    if sampler:
+        sampler.mark_begin()
     e0.record()
-    for _ in range(args.steps):
-        raw = step_device()
+    for _ in range(steps):
+        raw, merged = step_device()
         for k, v in zip(api.KERNEL_FAMILIES, list(raw.kernel_ms)[:8]):
             fam_ms[k].append(v)
         launches += raw.kernel_launches
-    if gatherer is not None:
-        gatherer.flush()            # every gather of the K steps completes inside the timed region
-    e1.record()
-    torch.cuda.synchronize(); barrier()
-    sampler.mark_end()
-    dev_ms = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop() if rank == 0 else None
-    total_reads = sum_over_ranks(float(n))
-    value = total_reads * args.steps / (dev_ms / 1000.0)
+    e_map.record()         # this rank's mapping stream is done ...
+    drain()                # ... and so is everything behind it on the library's own streams: last gather, last chains of the weight ring
+    e1.record()            # recorded after the drain returned: the event pair spans all of it
+    torch.cuda.synchronize(); ctx.barrier()
+    if sampler:
+        sampler.mark_end()
+    dev_ms = ctx.reduce(e0.elapsed_time(e1), "MAX")
+    map_ms = ctx.reduce(e0.elapsed_time(e_map), "MAX")
+    clocks = sampler.stop() if (sampler and rank == 0) else None
+    total_reads = ctx.reduce(float(n), "SUM")
+    value = total_reads * steps / (dev_ms / 1000.0)
     stats = dict(hits=raw.n_hits / n, pairs=raw.n_pairs / n, records=raw.n_records / n, mapped=raw.mapped / n)
+    merged_check = None
+    if comm and rank == 0:
+        merged_check = dict(reads=int(merged.n_reads), pairs=int(merged.n_pairs), records=int(merged.n_records), mapped=int(merged.mapped))
 
-    # ---- e2e: pinned host buffers through the C ABI + host replay of the graph weighting ----
-    for _ in range(max(1, args.warmup // 2)):
-        raw = step_e2e()
-    torch.cuda.synchronize(); barrier()
-    e2e_parts.update(align_batch_ms=0.0, copy_in_to_copy_out_ms=0.0)
+    # ---- e2e: pinned host buffers through the C ABI, compact result to the host ----
+    for _ in range(max(1, warmup // 2)):
+        raw_e, merged_e = step_e2e()
+    drain(); ctx.barrier()
+    e2e_parts.update(align_batch_ms=0.0, gather_ms=0.0)
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        raw = step_e2e()
-    torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_parts = {k: v / args.steps for k, v in e2e_parts.items()}
-    barrier()
-    e2e_value = total_reads * args.steps / e2e_s
-    h2d = n * L + 4 * (n + 1)
-    d2h = 4 * (n + 1) + 4 * raw.n_hits + 32 * raw.n_pairs + 8 * raw.n_records
+    for _ in range(steps):
+        raw_e, merged_e = step_e2e()
+    drain()
+    e2e_s = ctx.reduce(time.perf_counter() - t0, "MAX")
+    e2e_parts = {k: v / steps for k, v in e2e_parts.items()}
+    ctx.barrier()
+    e2e_value = total_reads * steps / e2e_s
+    recw = raw_e.rec_path_bytes
+    h2d = n * L + 8 * (n + 1)                                         # per rank: bases + u64 offsets
+    d2h_one = 16 * raw_e.n_pairs + recw * raw_e.n_records             # compact: 16-byte pairs + path ids
+    d2h = ctx.reduce(float(d2h_one), "SUM")                           # N > 1: all of it leaves through rank 0 after the gather
 
-    # ---- roofline of the dominant kernel (largest share of the step), algorithmic bytes per DESIGN.md "Rooflines" ----
+    # ---- roofline of the dominant kernel (largest share of the step), algorithmic bytes per DESIGN.md "Kernels" ----
     peak, peak_src = measured_peaks()
     S = info["S"]
     fam_avg = {k: sum(v) / len(v) for k, v in fam_ms.items()}
     fam_bytes = {   # per launch family, for n reads
         "seed": n * (L + 8 + 32 + 4) + raw.n_hits * (8 * S + 8),                # L + 8 + 32 + 8*S*c + 4 + 8*h with c := h
-        "fill": 4 * n + raw.n_hits * 13,                                         # hit counts in, hits + owner + segment flag out
+        "fill": 4 * n + raw.n_hits * 13 + raw.mapped * (L + L // 2),            # hit counts in, hits + owner + segment flag out; seeded reads in, their 2-bit copies (both strands) out
         "align_screen": raw.n_pairs * (L + 16 + 8) + raw.n_hits * 32,            # read + pair bookkeeping + window records
         "align_walk": raw.n_pairs * (L + 16 + 32 + 8 + 32),                      # re-read read + window meta + pair out + locus + path bitset
         "align_finish": 0,
         "align_emit": raw.n_pairs * (32 + 8 + 32) + raw.n_records * 8,           # pair + locus + bitset in, 8-byte records out
         "project": raw.n_pairs * 40,                                             # pair in; the (node, f64) items are internal traffic
+        "project_accumulate": 0,
     }
     dom = max(fam_avg, key=fam_avg.get)
     achieved = fam_bytes[dom] / (fam_avg[dom] / 1000.0) / 1e9
-    traffic = None
+    traffic, traffic_src, inst_per_read = None, None, None
     prof = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(prof):
         try:
-            tj = json.load(open(prof))
-            traffic = tj.get(dom, {}).get("dram_bytes_per_read", None)
-            if traffic is not None:
-                traffic = traffic * n
+            tj = json.load(open(prof)).get(dom, {})
+            if tj.get("dram_bytes_per_read") is not None:
+                traffic = tj["dram_bytes_per_read"] * n
+                traffic_src = "ncu --set full capture %s (%d reads per launch), scaled to this launch; not re-measured in this run" % (tj.get("source"), tj.get("reads_in_profiled_launch", 0))
+            inst_per_read = tj.get("warp_inst_per_read")
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+            pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": dom, "kernel_ms": fam_avg[dom], "algorithmic_bytes_per_launch": fam_bytes[dom], "peak_source": peak_src,
-                "note": "integer / pointer-chasing kernels: the HBM fraction is small by construction (DESIGN.md Rooflines); "
-                        "seed_kernel is INT-ALU bound (%d integer ops per read)" % ((L - info["k"] + 1) * ((S - 1) * 12 + 20)),
                 "all_kernels": {k: {"ms": fam_avg[k], "algorithmic_GBps": (fam_bytes[k] / (fam_avg[k] / 1000.0) / 1e9) if fam_avg[k] > 0 else 0.0}
                                 for k in api.KERNEL_FAMILIES}}
+    if rank == 0:
+        # the resource that really bounds the sketch kernel: integer instruction issue. Peak = measured here
+        # (grootgpu_int_issue_peak: 16 independent IMAD / SHF / LOP3 chains per thread, full occupancy); the kernel's
+        # instruction count per read comes from the committed ncu capture (smsp__inst_executed.sum).
+        try:
+            ip = api.int_issue_peak(ctx.local)
+            roofline["int_issue_peak_warp_inst_per_s"] = ip
+            if inst_per_read and dom == "seed":
+                rate = inst_per_read * n / (fam_avg["seed"] / 1000.0)
+                roofline["int_issue"] = {"warp_inst_per_read": inst_per_read, "achieved_warp_inst_per_s": rate, "frac": rate / ip["mixed"],
+                                         "note": "seed_kernel is integer-issue bound: this fraction, not the HBM one, says how close it is to its roofline"}
+                roofline["int_issue_frac"] = rate / ip["mixed"]
+        except Exception as e:   # noqa: BLE001
+            roofline["int_issue_peak_error"] = str(e)
 
-    # ---- CPU baseline (rank 0, N == 1): the oracle port on all host threads, bounded sample ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and cpu_baseline:
         from oracle import pyoracle as po
         cores = os.cpu_count() or 1
-        oidx = po.Index(msa_dir=msa_dir, k=INDEX_PARAMS["k"], S=INDEX_PARAMS["S"], w=INDEX_PARAMS["w"])
+        oidx = po.Index(msa_dir=msa_dir, **cfg["index"])
         pn = 20000
-        t0 = time.time(); oidx.map_reads(blob[: pn * L], off[: pn + 1], THRESHOLD, threads=cores); rate = pn / (time.time() - t0)
+        t0 = time.time(); oidx.map_reads(blob[: pn * L], off[: pn + 1], THRESHOLD, no_align=no_align, threads=cores); rate = pn / (time.time() - t0)
         sn = int(max(pn, min(n, rate * 15.0)))
-        t0 = time.time(); oidx.map_reads(blob[: sn * L], off[: sn + 1], THRESHOLD, threads=cores); dt = time.time() - t0
+        t0 = time.time(); oidx.map_reads(blob[: sn * L], off[: sn + 1], THRESHOLD, no_align=no_align, threads=cores); dt = time.time() - t0
         cpu = {"value": sn / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d reads of the step's batch, oracle/ C++ restatement, %d threads, %.1fs" % (sn, cores, dt)}
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic",
-            "config": {"workload": "10M x 100bp synthetic reads vs arg-annot.90 (-w 100 -k 31 -s 21 -x 8 -y 4, t=0.99), full align path "
-                                   "(sketch + LSH Ensemble query + exact graph alignment) [BASELINE.json configs[2]]",
-                       "reads_per_gpu_per_step": n, "read_len": L, "threshold": THRESHOLD, "index_windows": info["windows"],
-                       "l2": "inputs (%.2f GB of reads per step) are larger than the 126 MB L2; no explicit flush" % (n * L / 1e9),
-                       "parallelism": "reads sharded over %d GPU(s), index replicated%s" % (world, ", one NCCL gather of results to rank 0 per step" if world > 1 else ""),
-                       "per_read": stats, "index_build_s": t_index},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "includes": "pinned host buffers -> grootgpu_align_batch (H2D, sketch+query+align+ordered graph weighting kernels, D2H of hits/pairs/records); "
-                                "inside the call the batch is streamed through the device in chunks on two lanes, copies overlapped with kernels",
-                    "per_step_ms": e2e_parts},
-            "gpu_launches": launches,
-            "kernel_ms": fam_avg,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        }
-        print(json.dumps(line))
+    if comm:
+        comm.close()
+    idx.close()
+    del d_seq, d_off, h_seq, h_off
+    torch.cuda.empty_cache()
+    par = "reads sharded over %d GPU(s), index replicated" % world
     if world > 1:
-        dist.destroy_process_group()
+        par += "; per step ONE NCCL gather of the result arrays to rank 0 (merged on its device) + the weight vector sent rank to rank (f64 chains in global read order)"
+    return {
+        "value": value, "ms_per_step": dev_ms / steps, "mapping_stream_ms_per_step": map_ms / steps,
+        "config": {"workload": cfg["workload"], "config_id": name, "reads_per_gpu_per_step": n, "read_len": L, "threshold": THRESHOLD, "index_windows": info["windows"],
+                   "l2": "inputs (%.2f GB of reads per step) are larger than the 126 MB L2; no explicit flush" % (n * L / 1e9),
+                   "parallelism": par, "per_read": stats, "index_build_s": t_index, "merged_on_rank0": merged_check},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(d2h),
+                "h2d_GBps_per_rank": h2d / (e2e_s / steps) / 1e9, "d2h_GBps_rank0": d2h / (e2e_s / steps) / 1e9,
+                "includes": "pinned host buffers -> grootgpu_align_batch (H2D in chunks on two lanes overlapped with the kernels: sketch + query + align + ordered graph "
+                            "weighting) -> compact result (16-byte pairs + %d-byte path ids) to the host%s" % (recw, "; N > 1: results kept on the device, gathered to rank 0 over "
+                            "NVLink, merged, copied to rank 0's host (asynchronously, drained inside the timed region)" if world > 1 else ""),
+                "per_step_ms": e2e_parts},
+        "gpu_launches": launches, "kernel_ms": fam_avg, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+    }
+
+
+def run_ours(args):
+    ctx = Ctx()
+    res = run_config(ctx, args.config, args.steps, args.warmup, args.reads, True, not args.no_cpu_baseline)
+    others = {}
+    extra = [] if args.extra in ("none", "") else [c for c in args.extra.split(",") if c != args.config]
+    if ctx.world == 1:
+        for name in extra:   # the other BASELINE configs, shorter runs; same measurement
+            r = run_config(ctx, name, max(3, args.steps // 4), 3, args.reads, False, not args.no_cpu_baseline)
+            others[name] = {k: r[k] for k in ("value", "ms_per_step", "config", "e2e", "kernel_ms", "cpu_baseline", "gpu_launches")}
+            others[name]["roofline"] = {k: r["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernel", "kernel_ms") if k in r["roofline"]}
+            if "int_issue_frac" in r["roofline"]:
+                others[name]["roofline"]["int_issue_frac"] = r["roofline"]["int_issue_frac"]
+    if ctx.rank == 0:
+        line = {
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic", "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "kernel_ms": res["kernel_ms"],
+            "mapping_stream_ms_per_step": res["mapping_stream_ms_per_step"],
+            "roofline": res["roofline"], "cpu_baseline": res["cpu_baseline"], "clocks": res["clocks"],
+        }
+        if others:
+            line["other_configs"] = others
+        print(json.dumps(line))
+    if ctx.world > 1:
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -378,8 +440,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(CONFIGS))
+    ap.add_argument("--extra", default="C2,C4", help="further BASELINE configs measured at N = 1 (shorter runs), or 'none'")
     ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU per step")
-    ap.add_argument("--read-len", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

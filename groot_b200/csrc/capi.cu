@@ -110,6 +110,10 @@ MultTable make_mult(uint32_t k) {
     const uint64_t C = static_cast<uint64_t>(k) * GROOT_MULTI_SEED;
     for (uint64_t i = 0; i < 32; i++) { m.c[i] = i ^ C; m.low[i] = static_cast<uint32_t>((C & 31u) ^ i); }
     m.c0 = C & ~31ull; m.m32 = 32; m.one = 1;
+    m.c_hi = static_cast<uint32_t>(C >> 32);
+    int keybits = 27;
+    if (const char* e = getenv("GROOTGPU_KHF_KEYBITS")) { const int v = atoi(e); if (v >= 1 && v <= 27) keybits = v; }
+    m.key_low = (1u << (32 - keybits)) - 1u;
     return m;
 }
 
@@ -186,7 +190,6 @@ bool sketch_dispatch(uint32_t S, const uint8_t* d_seq, const uint64_t* d_off, co
         default: return false;
     }
 }
-const char* kSupportedS = "8, 10, 16, 20, 21, 24, 30, 32";
 
 // sketches n sequences (host in, host out) on the current device
 void sketch_host(const uint8_t* seqs, size_t seqs_len, const uint64_t* off, const uint32_t* lens, uint32_t fixed_len, uint32_t n,
@@ -198,8 +201,13 @@ void sketch_host(const uint8_t* seqs, size_t seqs_len, const uint64_t* off, cons
     if (lens) { d_lens.need(sizeof(uint32_t) * n); CK(cudaMemcpy(d_lens.p, lens, sizeof(uint32_t) * n, cudaMemcpyHostToDevice)); }
     CK(cudaMemset(d_err.p, 0, 8));
     if (!sketch_dispatch(S, d_seq.as<uint8_t>(), d_off.as<uint64_t>(), lens ? d_lens.as<uint32_t>() : nullptr, fixed_len, n, k,
-                         d_out.as<uint64_t>(), d_err.as<int>(), 0))
-        throw std::runtime_error(std::string("unsupported sketch size (compiled: ") + kSupportedS + ")");
+                         d_out.as<uint64_t>(), d_err.as<int>(), 0)) {
+        // any other sketch size: the run-time-S kernel (seed_kernels.cuh, "any sketch size, any maxK")
+        if (S < 1 || S > static_cast<uint32_t>(kMaxSketch)) throw std::length_error("sketch size must be in 1.." + std::to_string(kMaxSketch) + " (documented limit)");
+        const int blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, 148ull * 16));
+        sketch_generic_kernel<<<std::max(blocks, 1), kSeedThreads>>>(d_seq.as<uint8_t>(), d_off.as<uint64_t>(), lens ? d_lens.as<uint32_t>() : nullptr, fixed_len, n, k, S,
+                                                                      d_out.as<uint64_t>(), d_err.as<int>());
+    }
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());
     int err[2];
@@ -289,7 +297,7 @@ struct grootgpu_index {
     // LSH tables, built lazily per K (all bands)
     std::vector<LshTable> h_tables;    // [(K-1)*n_bands + band]
     LshTable* d_tables = nullptr;
-    bool tables_built[8] = {};
+    bool tables_built[17] = {};
     // per (q, threshold) parameter cache
     std::map<std::pair<uint32_t, double>, LenParam> param_cache;
     DBuf len_params;                   // per read length: (K, L, eq_min), shared by the lanes (prepare_params, under params_mu)
@@ -327,6 +335,8 @@ struct grootgpu_index {
     }
 };
 
+constexpr int kCountWords = 8;   // per rank, exchanged by every gather: n_reads, n_hits, n_pairs, n_records, mapped, multimapped, slow_path_pairs, format
+
 // One rank of a multi-GPU run (include/grootgpu.h "multi-GPU"). Two NCCL communicators, so that the weight ring (stream
 // st_acc of the index) and the result gather (st_gather) never serialise behind each other.
 struct grootgpu_comm {
@@ -340,8 +350,8 @@ struct grootgpu_comm {
     DBuf d_counts;                         // [world * 4] u64: n_reads, n_hits, n_pairs, n_records of every rank
     uint64_t* h_counts = nullptr;          // pinned, [4 + world * 4]
     DBuf m_hit_off, m_hits, m_pairs, m_rec_path, m_rec_pos, m_cpairs, m_rec_c;   // rank 0: the merged batch
-    HBuf h_hit_off, h_hits, h_pairs, h_rec_path, h_rec_pos, h_cpairs, h_rec_c;
-    DBuf d_total_tmp;
+    struct HostSet { HBuf hit_off, hits, pairs, rec_path, rec_pos, cpairs, rec_c; } hs[2];   // host copies of the merged batch: alternating,
+    int hs_i = 0;                                                                             // so that an asynchronous copy never lands in the arrays the caller is still reading
     ~grootgpu_comm() {
         if (ring) nccl().CommDestroy(ring);
         if (gath) nccl().CommDestroy(gath);
@@ -378,8 +388,9 @@ void zero_words(cudaStream_t st, std::initializer_list<std::pair<void*, uint32_t
 void index_to_device(grootgpu_index* ix) {
     pick_device(ix->device);
     FlatIndex& h = ix->h;
-    if (h.p.max_k < 1 || h.p.max_k > 4) throw std::runtime_error("max_k must be in 1..4 (documented limit)");
+    if (h.p.max_k < 1 || h.p.max_k > 16) throw std::length_error("maxK must be in 1..16 (documented limit)");
     if (h.p.S / h.p.max_k < 1) throw std::runtime_error("sketch size must be >= max_k");
+    if (h.p.S > static_cast<uint32_t>(kMaxSketch)) throw std::length_error("sketch size must be <= " + std::to_string(kMaxSketch) + " (documented limit)");
     DevIndex& d = ix->d;
     d.nodes = upload(h.nodes, ix->owned);
     std::vector<uint8_t> seq_padded = h.node_seq; seq_padded.resize(seq_padded.size() + 16, 0);
@@ -466,7 +477,7 @@ void build_tables(grootgpu_index* ix, uint32_t K) {
         std::vector<uint32_t> order(W);
         for (uint32_t i = 0; i < W; i++) order[i] = i;
         auto keyof = [&](uint32_t w, uint32_t key[4]) {
-            for (uint32_t j = 0; j < 4; j++) key[j] = j < K ? static_cast<uint32_t>(h.sketches[static_cast<size_t>(w) * S + b * maxk + j]) : 0u;
+            for (uint32_t j = 0; j < 4; j++) key[j] = j < K ? static_cast<uint32_t>(h.sketches[static_cast<size_t>(w) * S + b * maxk + j]) : 0u;   // K > 4: the first four (lsh_probe_generic checks the rest)
         };
         std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
             uint32_t kx[4], ky[4]; keyof(x, kx); keyof(y, ky);
@@ -732,7 +743,6 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
     const bool copy_back = out && !prm->results_on_device;
     const FlatIndex& h = ix->h;
     const uint32_t S = h.p.S, k = h.p.k;
-    if (h.p.max_k != 4) throw std::runtime_error("this build supports max_k == 4 only (documented limit)");
     if (max_len > 60000) throw std::runtime_error("read longer than 60000 bases (documented limit)");
     prepare_params(ix, std::max(min_len, 1u), max_len, prm->containment_threshold);
     const int sms = g_num_sms(ix->device);
@@ -768,12 +778,15 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
     if (tile_bytes > 20 * 1024) tile_bytes = 0;  // very long reads: no staging, threads read global memory
     sa.tile_bytes = tile_bytes;
     const size_t seed_smem = sizeof(SeedTabs) + 64 + 2ull * tile_bytes * (kSeedThreads / 32);
-    int occ = seed_occupancy_dispatch(S, seed_smem);
-    if (occ <= 0) throw std::runtime_error(std::string("unsupported sketch size (compiled: ") + kSupportedS + ")");
+    // the register-resident kernels exist for maxK == 4 and the sketch sizes of GROOT_S_LIST; anything else `groot index`
+    // accepts (cmd/index.go:48-49) takes the run-time-S kernels
+    int occ = h.p.max_k == 4 ? seed_occupancy_dispatch(S, seed_smem) : 0;
+    const bool generic = occ <= 0;
+    if (generic) occ = 8;
     const uint32_t n_tiles = (n + kTileReads - 1) / kTileReads;
     int seed_blocks = static_cast<int>(std::min<uint64_t>((n_tiles + kSeedThreads / 32 - 1) / (kSeedThreads / 32), static_cast<uint64_t>(sms) * occ));
     // two passes when the optimiser probes a single band for every read length of the batch (see SEED_PRESCREEN)
-    bool two_pass = !prm->keep_sketches && getenv("GROOTGPU_SEED_ONEPASS") == nullptr;
+    bool two_pass = !generic && !prm->keep_sketches && getenv("GROOTGPU_SEED_ONEPASS") == nullptr;
     {
         std::lock_guard<std::mutex> lock(ix->params_mu);
         for (uint32_t len = std::max(min_len, k); len <= max_len && two_pass; len++) {
@@ -797,6 +810,9 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         sq.tile_bytes = qstride * kTileReads <= 20 * 1024 ? qstride * kTileReads : 0u;   // per warp; very long reads: straight from global
         const size_t qsmem = sizeof(SeedTabs) + 64 + 2ull * sq.tile_bytes * (kSeedThreads / 32);
         kbegin(0); seed_queued_dispatch(S, ix->d, sq, k, qsmem, std::max(seed_blocks, 1), st); launches++; kend();
+    } else if (generic) {
+        const int gblocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
+        kbegin(0); seed_generic_kernel<<<std::max(gblocks, 1), kSeedThreads, 0, st>>>(ix->d, sa); launches++; kend();
     } else {
         kbegin(0); seed_dispatch(S, ix->d, sa, k, seed_smem, std::max(seed_blocks, 1), st); launches++; kend();
     }
@@ -828,13 +844,20 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         fa.hit_off = w->hit_off.as<uint32_t>(); fa.stage = w->stage.as<uint32_t>(); fa.hits = w->hits.as<uint32_t>();
         fa.hit_read = w->hit_read.as<uint32_t>(); fa.seg_flag = w->seg_flag.as<uint8_t>(); fa.counters = d_counters;
         fa.n_overflow = w->qcount.as<uint32_t>() + 5;   // zeroed with the other scalars at the start of the batch
+        w->seed_q.need(4ull * n);                       // the prescreen's queue is free again: reused for the reads with more than HSTAGE hits
+        fa.overflow_q = w->seed_q.as<uint32_t>();
         // 2-bit copies of the seeded reads (both orientations) for the packed walk; reads longer than 256 bases go byte-wise
         uint32_t nw32 = 0;   // words of 16 bases per orientation: 8 (<= 128 bases) .. 64 (<= 1024); longer reads go byte-wise
         if (!prm->no_align && max_len <= 1024) { nw32 = 8; while (nw32 * 16u < max_len) nw32 *= 2; }
         if (nw32) { w->reads2.need(8ull * nw32 * n + 64); w->read_ok2.need(n); w->read_oh.need(16ull * n); }
         fa.reads2 = w->reads2.as<uint32_t>(); fa.read_ok2 = w->read_ok2.as<uint8_t>(); fa.read_oh = w->read_oh.as<uint4>(); fa.nw32 = nw32;
         int fill_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
-        kbegin(1); fill_dispatch(S, ix->d, fa, k, fill_blocks, st); launches += 2;
+        kbegin(1);
+        if (generic) {
+            fill_kernel<8, 4, false><<<fill_blocks, kSeedThreads, 0, st>>>(ix->d, fa, make_mult(k));   // the staged hits: no sketch involved
+            fill_refill_generic_kernel<<<fill_blocks, kSeedThreads, 0, st>>>(ix->d, fa);
+        } else fill_dispatch(S, ix->d, fa, k, fill_blocks, st);
+        launches += 2;
         if (nw32) { pack_reads_kernel<<<std::max(1, std::min<int>((n + 31) / 32, sms * 8)), 256, 0, st>>>(fa); launches++; }
         kend();
         CK(cudaGetLastError());
@@ -1313,8 +1336,7 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
 // into their place in the merged arrays — contiguous shards in rank order, so merging is concatenation), a small kernel
 // per rank turns shard-local indices into batch-wide ones. Everything runs on the communicator's own stream: the
 // transfer of batch b overlaps the mapping of batch b + 1, whose result arrays are the other set.
-constexpr int kCountWords = 8;   // per rank: n_reads, n_hits, n_pairs, n_records, mapped, multimapped, slow_path_pairs, format
-void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, bool to_host, grootgpu_batch_result* merged) {
+void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, int to_host, grootgpu_batch_result* merged) {
     grootgpu_index* ix = c->ix;
     const NcclApi& N = nccl();
     cudaStream_t sg = c->st_gather;
@@ -1365,12 +1387,13 @@ void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, bool to_
     HBuf* hbuf[5];
     size_t elem[5], base_of[5][2];   // element size; per section: which prefix array gives the base
     (void)base_of;
+    grootgpu_comm::HostSet& hs = c->hs[c->hs_i ^= 1];
     if (compact) {
-        mb[0] = &c->m_cpairs; mb[1] = &c->m_rec_c; hbuf[0] = &c->h_cpairs; hbuf[1] = &c->h_rec_c; elem[0] = sizeof(CPairOut); elem[1] = recw;
+        mb[0] = &c->m_cpairs; mb[1] = &c->m_rec_c; hbuf[0] = &hs.cpairs; hbuf[1] = &hs.rec_c; elem[0] = sizeof(CPairOut); elem[1] = recw;
         c->m_cpairs.need(std::max<size_t>(16, pb[W] * sizeof(CPairOut))); c->m_rec_c.need(std::max<size_t>(16, cb[W] * recw));
     } else {
         mb[0] = &c->m_hit_off; mb[1] = &c->m_hits; mb[2] = &c->m_pairs; mb[3] = &c->m_rec_path; mb[4] = &c->m_rec_pos;
-        hbuf[0] = &c->h_hit_off; hbuf[1] = &c->h_hits; hbuf[2] = &c->h_pairs; hbuf[3] = &c->h_rec_path; hbuf[4] = &c->h_rec_pos;
+        hbuf[0] = &hs.hit_off; hbuf[1] = &hs.hits; hbuf[2] = &hs.pairs; hbuf[3] = &hs.rec_path; hbuf[4] = &hs.rec_pos;
         elem[0] = 4; elem[1] = 4; elem[2] = sizeof(PairOut); elem[3] = 4; elem[4] = 4;
         c->m_hit_off.need(4 * (rb[W] + 1)); c->m_hits.need(std::max<size_t>(16, 4 * hb[W])); c->m_pairs.need(std::max<size_t>(32, pb[W] * sizeof(PairOut)));
         c->m_rec_path.need(std::max<size_t>(16, 4 * cb[W])); c->m_rec_pos.need(std::max<size_t>(16, 4 * cb[W]));
@@ -1414,11 +1437,11 @@ void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, bool to_
             hbuf[sec]->need(std::max<size_t>(16, total_elems * elem[sec]));
             if (total_elems) CK(cudaMemcpyAsync(hbuf[sec]->p, mb[sec]->p, total_elems * elem[sec], cudaMemcpyDeviceToHost, sg));
         }
-        CK(cudaStreamSynchronize(sg));
-        if (compact) { merged->cpairs = reinterpret_cast<const grootgpu_cpair*>(c->h_cpairs.p); merged->rec_path_c = c->h_rec_c.p; }
+        if (to_host == 1) CK(cudaStreamSynchronize(sg));     // 2: asynchronous, complete after the next grootgpu_gather / grootgpu_comm_sync
+        if (compact) { merged->cpairs = reinterpret_cast<const grootgpu_cpair*>(hs.cpairs.p); merged->rec_path_c = hs.rec_c.p; }
         else {
-            merged->hit_off = c->h_hit_off.as<uint32_t>(); merged->hits = c->h_hits.as<uint32_t>(); merged->pairs = reinterpret_cast<const grootgpu_pair*>(c->h_pairs.p);
-            merged->rec_path = c->h_rec_path.as<uint32_t>(); merged->rec_pos = c->h_rec_pos.as<int32_t>();
+            merged->hit_off = hs.hit_off.as<uint32_t>(); merged->hits = hs.hits.as<uint32_t>(); merged->pairs = reinterpret_cast<const grootgpu_pair*>(hs.pairs.p);
+            merged->rec_path = hs.rec_path.as<uint32_t>(); merged->rec_pos = hs.rec_pos.as<int32_t>();
         }
     }
 }
@@ -1659,8 +1682,25 @@ int grootgpu_comm_create(grootgpu_index* idx, const uint8_t id[GROOTGPU_COMM_ID_
         NK(nccl().CommInitRank(&c->gath, world_size, b, rank));
         CK(cudaStreamCreateWithFlags(&c->st_gather, cudaStreamNonBlocking));
         for (cudaEvent_t* e : {&c->ev_sent[0], &c->ev_sent[1], &c->ev_local}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        c->d_counts.need(8ull * 4 * (world_size + 1));
-        CK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 8ull * 4 * (world_size + 1), cudaHostAllocDefault));
+        c->d_counts.need(8ull * kCountWords * (world_size + 2));
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 8ull * kCountWords * (world_size + 2), cudaHostAllocDefault));
+        if (world_size > 1) {
+            // NCCL connects two peers the first time they exchange something, and that handshake blocks the HOST until
+            // both sides have issued a matching operation. In steady state the last rank's weight vector is sent one
+            // batch before rank 0 asks for it (and rank 0 sits in the gather meanwhile): every connection the run will
+            // use is therefore opened here, where all ranks issue their side at the same time.
+            uint64_t* scratch = c->d_counts.as<uint64_t>();
+            NK(nccl().GroupStart());
+            NK(nccl().Send(scratch, 1, ncclUint64, (rank + 1) % world_size, c->ring, c->st_gather));
+            NK(nccl().Recv(scratch + 1, 1, ncclUint64, (rank + world_size - 1) % world_size, c->ring, c->st_gather));
+            NK(nccl().GroupEnd());
+            NK(nccl().GroupStart());
+            if (rank == 0) { for (int r = 1; r < world_size; r++) NK(nccl().Recv(scratch + 2 + r, 1, ncclUint64, r, c->gath, c->st_gather)); }
+            else NK(nccl().Send(scratch, 1, ncclUint64, 0, c->gath, c->st_gather));
+            NK(nccl().GroupEnd());
+            NK(nccl().AllGather(scratch, scratch + kCountWords, 1, ncclUint64, c->gath, c->st_gather));
+            CK(cudaStreamSynchronize(c->st_gather));
+        }
         // every rank starts from its own weights; only rank 0's enter the ring (the others' are replaced by what arrives)
         if (rank != 0) { sync_weights_to_host(idx); idx->weights_on_device = false; std::fill(idx->h.kmer_freq.begin(), idx->h.kmer_freq.end(), 0.0); std::fill(idx->h.kmer_total.begin(), idx->h.kmer_total.end(), 0); }
     });
@@ -1682,7 +1722,7 @@ int grootgpu_gather(grootgpu_comm* c, const grootgpu_batch_result* local, int to
     return guarded([&] {
         grootgpu_index* ix = c->ix;
         pick_device(ix->device);
-        gather_results(c, local, to_host != 0, merged);
+        gather_results(c, local, to_host, merged);
     });
 }
 

@@ -79,6 +79,9 @@ struct MultTable {
     uint32_t low[32];
     uint32_t m32;  // == 32, kept as a runtime value so that >>27 can be issued as multiplies (FMA pipe) instead of shifts (ALU pipe)
     uint32_t one;  // == 1, a runtime value for the same reason: the running-minimum update as predicated multiply-adds
+    uint32_t c_hi;      // high word of every c_i (the xor with i < 32 only touches the low word)
+    uint32_t key_low;   // low bits of a product's high word that do NOT decide the order of x ^ (x >> 27): 31 (GROOTGPU_KHF_KEYBITS lowers the
+                        // number of deciding bits in test runs, so that the exact tie path is exercised)
 };
 
 enum : int { HSTAGE = 4 };  // hits per read staged by the seed kernel before the exact-size fill

@@ -62,7 +62,8 @@ __device__ inline void build_seed_tabs(SeedTabs* T, unsigned k) {
 
 // ---- the sketch: registers only -------------------------------------------------------------
 #ifndef GROOT_KHF_VARIANT
-#define GROOT_KHF_VARIANT 3
+#define GROOT_KHF_VARIANT 6   // 6: raw products tracked, order decided by their top 27 bits (below); 3: every value finished and compared in full;
+                               // 4 / 5: c0 + low_i split of the multiplier (ptxas splits the 64-bit addend off again: no gain, kept for reference)
 #endif
 // m = min(m, x) with the two conditional moves issued as predicated multiply-adds (x * 1 + 0): they go to the FMA
 // pipe, which has room, instead of the ALU pipe, which is the one that bounds this kernel (2 SEL per hash out of 8 ALU
@@ -77,8 +78,14 @@ __device__ __forceinline__ void min_u64_fma(uint64_t& m, uint64_t x, uint32_t on
     m = (static_cast<uint64_t>(mhi) << 32) | mlo;
 }
 
+// One k-mer hash h into the S running minima: m_0 = h, m_i = x ^ (x >> 27) with x = h * c_i, c_i = i ^ (k * multiSeed)
+// (khf.go:44-53 / nthash MultiHash). For i < 32 the xor only touches the low 5 bits of the multiplier: c_i = c0 + low_i
+// with c0 = C & ~31 and low_i = (C & 31) ^ i < 32, hence h * c_i = h * c0 + h * low_i (exact mod 2^64): ONE 64-bit
+// product per k-mer (A = h * c0) and per hash a 32x32+64 multiply-add plus the high-word correction — 2 FMA-pipe
+// instructions instead of the 4 of a full 64x64 product. lw[] holds the low_i in REGISTERS (21 of them: the sketch
+// itself is 42): from the constant bank every use costs an extra LDC issue slot.
 template <int S>
-__device__ __forceinline__ void khf_update(uint64_t h, const MultTable& M, uint64_t (&sk)[S]) {
+__device__ __forceinline__ void khf_update(uint64_t h, const MultTable& M, const uint32_t (&lw)[S], uint64_t (&sk)[S]) {
 #if GROOT_KHF_VARIANT == 3
     min_u64_fma(sk[0], h, M.one);
 #pragma unroll
@@ -87,61 +94,117 @@ __device__ __forceinline__ void khf_update(uint64_t h, const MultTable& M, uint6
         x ^= x >> GROOT_MULTI_SHIFT;
         min_u64_fma(sk[i], x, M.one);
     }
-    return;
-#endif
-    sk[0] = h < sk[0] ? h : sk[0];
-#if GROOT_KHF_VARIANT == 0 || GROOT_KHF_VARIANT == 3
-#pragma unroll
-    for (int i = 1; i < S; i++) {
-        uint64_t x = h * M.c[i];
-        x ^= x >> GROOT_MULTI_SHIFT;
-        sk[i] = x < sk[i] ? x : sk[i];
-    }
 #else
-    // x_i = h*c0 + h*low_i  (exact mod 2^64, see MultTable)
+    min_u64_fma(sk[0], h, M.one);
     const uint32_t h_lo = static_cast<uint32_t>(h), h_hi = static_cast<uint32_t>(h >> 32);
     const uint64_t A = h * M.c0;
 #pragma unroll
     for (int i = 1; i < S; i++) {
-        uint32_t x_lo, x_hi;
-        asm("{\n .reg .u64 w;\n mad.wide.u32 w, %2, %3, %4;\n mov.b64 {%0, %1}, w;\n}" : "=r"(x_lo), "=r"(x_hi) : "r"(h_lo), "r"(M.low[i]), "l"(A));
-        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x_hi) : "r"(h_hi), "r"(M.low[i]));
-        uint64_t x;
-#if GROOT_KHF_VARIANT == 1
-        x = (static_cast<uint64_t>(x_hi) << 32) | x_lo;
-        x ^= x >> GROOT_MULTI_SHIFT;
+#if GROOT_KHF_VARIANT == 4
+        const uint32_t li = M.low[i];
 #else
-        // x >> 27 through the FMA pipe: (x_lo >> 27) = mulhi(x_lo, 32); (x_hi << 5) = x_hi * 32; (x_hi >> 27) = mulhi(x_hi, 32)
-        const uint32_t a = __umulhi(x_lo, M.m32);
-        uint32_t t_lo;
-        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t_lo) : "r"(x_hi), "r"(M.m32), "r"(a));
-        const uint32_t t_hi = __umulhi(x_hi, M.m32);
-        x = (static_cast<uint64_t>(x_hi ^ t_hi) << 32) | (x_lo ^ t_lo);
+        const uint32_t li = lw[i];
 #endif
-        sk[i] = x < sk[i] ? x : sk[i];
+        uint32_t x_lo, x_hi;
+        asm("{\n .reg .u64 w;\n mad.wide.u32 w, %2, %3, %4;\n mov.b64 {%0, %1}, w;\n}" : "=r"(x_lo), "=r"(x_hi) : "r"(h_lo), "r"(li), "l"(A));
+        asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(x_hi) : "r"(h_hi), "r"(li));
+        uint64_t x = (static_cast<uint64_t>(x_hi) << 32) | x_lo;
+        x ^= x >> GROOT_MULTI_SHIFT;
+        min_u64_fma(sk[i], x, M.one);
     }
 #endif
+}
+
+// ---- variant 6: the sketch tracked as RAW products ------------------------------------------------------------------
+// Slot i >= 1 is min over the k-mers of f(m), m = h * c_i mod 2^64, f(m) = m ^ (m >> 27). The shift only reaches bits
+// 36..0, so bits 63..37 of f(m) ARE bits 63..37 of m: two products whose top 27 bits differ are ordered like their f
+// values, and no k-mer has to be finished (2 shifts + 2 xors) or compared in full (2 set-predicates) to lose the race.
+// Per slot the thread keeps the raw product that currently wins; per k-mer and slot it computes the product (the high
+// word of c_i is the same for every i < 32, so h_lo * c_hi is shared: one wide multiply + one multiply-add + one add),
+// compares the top 27 bits, overwrites on "smaller" (predicated multiply-adds: FMA pipe) and raises a flag on "equal".
+// A raised flag (probability ~2^-27 per comparison) re-runs that k-mer with the exact comparison of f values for every
+// slot — idempotent for the slots already updated. f is applied once per slot at the end. 4 FMA-pipe + 4-5 ALU-pipe
+// instructions per hash instead of 6 + 6 and a constant load.
+__device__ __forceinline__ uint64_t khf_finish(uint32_t lo, uint32_t hi) {
+    const uint64_t m = (static_cast<uint64_t>(hi) << 32) | lo;
+    return m ^ (m >> GROOT_MULTI_SHIFT);
+}
+template <int S>
+__device__ __forceinline__ void khf_update_exact(uint64_t h, const MultTable& M, uint32_t (&rlo)[S], uint32_t (&rhi)[S]) {
+#pragma unroll   // static indices: the raw products stay in registers (a call taking the arrays by reference would put them in local memory)
+    for (int i = 1; i < S; i++) {
+        const uint64_t m = h * M.c[i];
+        if ((m ^ (m >> GROOT_MULTI_SHIFT)) < khf_finish(rlo[i], rhi[i])) { rlo[i] = static_cast<uint32_t>(m); rhi[i] = static_cast<uint32_t>(m >> 32); }
+    }
+}
+template <int S, bool FIRST>
+__device__ __forceinline__ void khf_update_raw(uint64_t h, const MultTable& M, uint64_t& s0, uint32_t (&rlo)[S], uint32_t (&rhi)[S]) {
+    const uint32_t h_lo = static_cast<uint32_t>(h), h_hi = static_cast<uint32_t>(h >> 32);
+    if (FIRST) s0 = h; else min_u64_fma(s0, h, M.one);
+    const uint32_t P = h_lo * M.c_hi;
+    const uint32_t kl = M.key_low;
+    bool tie = false;
+#pragma unroll
+    for (int i = 1; i < S; i++) {
+        const uint32_t clo = static_cast<uint32_t>(M.c[i]);
+        uint32_t xl, xh;
+        asm("{\n .reg .u64 w;\n mul.wide.u32 w, %2, %3;\n mov.b64 {%0, %1}, w;\n}" : "=r"(xl), "=r"(xh) : "r"(h_lo), "r"(clo));
+        uint32_t t;
+        asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(t) : "r"(h_hi), "r"(clo), "r"(P));
+        xh += t;
+        if (FIRST) { rlo[i] = xl; rhi[i] = xh; continue; }      // MaxUint64 (khf.go:18-32) loses to anything
+        const uint32_t v = xh | kl, b = rhi[i] | kl;
+        tie |= (v == b);
+        asm("{\n .reg .pred p;\n setp.lt.u32 p, %2, %3;\n @p mad.lo.u32 %0, %4, %6, 0;\n @p mad.lo.u32 %1, %5, %6, 0;\n}"
+            : "+r"(rlo[i]), "+r"(rhi[i])
+            : "r"(v), "r"(b), "r"(xl), "r"(xh), "r"(M.one));
+    }
+    if (!FIRST && tie) khf_update_exact<S>(h, M, rlo, rhi);
 }
 
 // p: read bases (shared or global), len >= k
 template <int S>
 __device__ __forceinline__ void khf_sketch(const uint8_t* __restrict__ p, uint32_t len, uint32_t k, const SeedTabs& T,
                                            const MultTable& M, uint64_t (&sk)[S]) {
-#pragma unroll
-    for (int i = 0; i < S; i++) sk[i] = ~0ULL;
     uint64_t fh = 0, rh = 0;
     for (uint32_t j = 0; j < k; j++) {
         fh = ((fh << 1) | (fh >> 63)) ^ T.in[p[j]];
         rh = ((rh << 1) | (rh >> 63)) ^ T.c0[p[k - 1 - j] & 7u];
     }
-    khf_update<S>(rh < fh ? rh : fh, M, sk);
     const uint32_t n = len - k + 1;
+#if GROOT_KHF_VARIANT == 6
+    uint32_t rlo[S], rhi[S];
+    uint64_t s0;
+    khf_update_raw<S, true>(rh < fh ? rh : fh, M, s0, rlo, rhi);
     for (uint32_t j = 1; j < n; j++) {
         const uint32_t bo = p[j - 1], bi = p[j + k - 1];
         fh = ((fh << 1) | (fh >> 63)) ^ T.out[bo] ^ T.in[bi];
         rh = ((rh >> 1) | (rh << 63)) ^ T.cout[bo & 7u] ^ T.cin[bi & 7u];
-        khf_update<S>(rh < fh ? rh : fh, M, sk);
+        khf_update_raw<S, false>(rh < fh ? rh : fh, M, s0, rlo, rhi);
     }
+    sk[0] = s0;
+#pragma unroll
+    for (int i = 1; i < S; i++) sk[i] = khf_finish(rlo[i], rhi[i]);
+#else
+#pragma unroll
+    for (int i = 0; i < S; i++) sk[i] = ~0ULL;
+    uint32_t lw[S];
+#pragma unroll
+    for (int i = 0; i < S; i++) {
+#if GROOT_KHF_VARIANT == 5
+        asm volatile("mov.u32 %0, %1;" : "=r"(lw[i]) : "r"(M.low[i & 31]));   // volatile: stays a register, is not re-read from the constant bank per use
+#else
+        lw[i] = 0;
+#endif
+    }
+    khf_update<S>(rh < fh ? rh : fh, M, lw, sk);
+    for (uint32_t j = 1; j < n; j++) {
+        const uint32_t bo = p[j - 1], bi = p[j + k - 1];
+        fh = ((fh << 1) | (fh >> 63)) ^ T.out[bo] ^ T.in[bi];
+        rh = ((rh >> 1) | (rh << 63)) ^ T.cout[bo & 7u] ^ T.cin[bi & 7u];
+        khf_update<S>(rh < fh ? rh : fh, M, lw, sk);
+    }
+#endif
 }
 
 // ---- the probe: LSH band lookup + containment check, all per thread ----------------------------
@@ -518,7 +581,8 @@ struct FillArgs {
     uint32_t* hit_read;
     uint8_t* seg_flag;
     unsigned long long* counters;  // [0]=mapped reads, [1]=multimapped reads
-    uint32_t* n_overflow;          // device scalar: reads with more than HSTAGE hits, counted by the lean kernel, read by the refill kernel
+    uint32_t* n_overflow;          // device scalar: reads with more than HSTAGE hits, queued by the lean kernel, taken by the refill kernel
+    uint32_t* overflow_q;          // [n] those reads (a dense queue: the refill kernel runs with full warps instead of scanning all reads)
     uint32_t* reads2;              // [n * 2 * nw32 + 1] packed copies of the seeded reads (pack_reads_kernel), or nullptr
     uint8_t* read_ok2;             // [n] 1 when reads2 holds the read
     uint4* read_oh;                // [n] one-hot prefixes for the screen: x/y = bases [0,8) / [1,9) of the read, z/w = of its reverse complement
@@ -609,21 +673,43 @@ __global__ void __launch_bounds__(256) pack_reads_kernel(FillArgs a) {
     }
 }
 
+// sorts a read's hits ascending (== graph, Node, OffSet order), marks (read, graph) segment starts; returns the number of graphs
+__device__ __forceinline__ uint32_t finish_read_hits(const DevIndex& ix, const FillArgs& a, uint32_t r, uint32_t nh, uint32_t base) {
+    for (uint32_t i = 1; i < nh; i++) {  // insertion sort, tiny
+        uint32_t v = a.hits[base + i];
+        uint32_t j = i;
+        while (j > 0 && a.hits[base + j - 1] > v) { a.hits[base + j] = a.hits[base + j - 1]; j--; }
+        a.hits[base + j] = v;
+    }
+    uint32_t segs = 0, prev_g = 0xffffffffu;
+    for (uint32_t i = 0; i < nh; i++) {
+        uint32_t g = ix.wins[a.hits[base + i]].graph;
+        a.hit_read[base + i] = r;
+        a.seg_flag[base + i] = (g != prev_g);
+        segs += (g != prev_g);
+        prev_g = g;
+    }
+    return segs;
+}
+
 // REFILL = false: the reads whose hits were all staged (the lean, common kernel). REFILL = true: only the rare reads
 // with more than HSTAGE hits, whose probe is redone (kept apart so that its sketch registers do not set the
 // occupancy of the common case).
 template <int S, int MAXK, bool REFILL>
 __global__ void __launch_bounds__(kSeedThreads) fill_kernel(DevIndex ix, FillArgs a, MultTable M) {
     __shared__ SeedTabs T;
+    uint32_t n_units = a.n_reads;
     if (REFILL) {
-        if (*a.n_overflow == 0) return;                 // the usual case: nothing to redo, the whole grid leaves at once
+        n_units = *a.n_overflow;
+        if (n_units == 0) return;                       // the usual case: nothing to redo, the whole grid leaves at once
         build_seed_tabs(&T, ix.k); __syncthreads();
     }
-    unsigned mapped = 0, multi = 0, overflow = 0;
-    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
+    unsigned mapped = 0, multi = 0;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+        const uint32_t r = REFILL ? a.overflow_q[u] : u;
         const uint32_t nh = a.n_hits[r];
-        if (!REFILL && nh > HSTAGE) overflow++;
-        if (nh == 0 || (nh > HSTAGE) != REFILL) continue;
+        if (nh == 0) continue;
+        if (!REFILL && nh > HSTAGE) { a.overflow_q[atomicAdd(a.n_overflow, 1u)] = r; continue; }
         const uint32_t base = a.hit_off[r];
         if (!REFILL) {
             for (uint32_t i = 0; i < nh; i++) a.hits[base + i] = a.stage[static_cast<size_t>(r) * HSTAGE + i];
@@ -634,30 +720,146 @@ __global__ void __launch_bounds__(kSeedThreads) fill_kernel(DevIndex ix, FillArg
             uint32_t c = 0;
             lsh_probe<S, MAXK>(ix, sk, a.len_params[len], [&](uint32_t w) { if (c < nh) a.hits[base + c] = w; c++; });
         }
-        for (uint32_t i = 1; i < nh; i++) {  // insertion sort, tiny
-            uint32_t v = a.hits[base + i];
-            uint32_t j = i;
-            while (j > 0 && a.hits[base + j - 1] > v) { a.hits[base + j] = a.hits[base + j - 1]; j--; }
-            a.hits[base + j] = v;
-        }
-        uint32_t segs = 0, prev_g = 0xffffffffu;
-        for (uint32_t i = 0; i < nh; i++) {
-            uint32_t g = ix.wins[a.hits[base + i]].graph;
-            a.hit_read[base + i] = r;
-            a.seg_flag[base + i] = (g != prev_g);
-            segs += (g != prev_g);
-            prev_g = g;
-        }
+        const uint32_t segs = finish_read_hits(ix, a, r, nh, base);
         mapped++;
         multi += segs > 1;
     }
     mapped = __reduce_add_sync(0xffffffffu, mapped);
     multi = __reduce_add_sync(0xffffffffu, multi);
-    overflow = __reduce_add_sync(0xffffffffu, overflow);
-    if ((threadIdx.x & 31) == 0 && overflow) atomicAdd(a.n_overflow, overflow);
     if ((threadIdx.x & 31) == 0) {
         if (mapped) atomicAdd(&a.counters[0], static_cast<unsigned long long>(mapped));
         if (multi) atomicAdd(&a.counters[1], static_cast<unsigned long long>(multi));
+    }
+}
+
+// ---- any sketch size, any maxK -----------------------------------------------------------------------------------
+// `groot index` accepts any -s / -y (cmd/index.go:48-49). The kernels above are compiled for the sketch sizes in common
+// use with maxK == 4 (sketch and band keys in registers); every other combination runs here: the same arithmetic with
+// run-time S and maxK, the sketch in thread-local memory, the probe per thread. Slower per read, bit-identical results.
+// Band tables are keyed on the first min(K, 4) hashes of a band (LshSlot holds four); the remaining hashes of a longer
+// prefix are compared against the candidate's sketch, so a bucket is exactly lshensemble's prefix match.
+constexpr int kMaxSketch = 256;
+
+__device__ inline void khf_sketch_generic(const uint8_t* __restrict__ p, uint32_t len, uint32_t k, const SeedTabs& T, uint32_t S, uint64_t* __restrict__ sk) {
+    const uint64_t C = static_cast<uint64_t>(k) * GROOT_MULTI_SEED;
+    for (uint32_t i = 0; i < S; i++) sk[i] = ~0ULL;
+    uint64_t fh = 0, rh = 0;
+    for (uint32_t j = 0; j < k; j++) {
+        fh = ((fh << 1) | (fh >> 63)) ^ T.in[p[j]];
+        rh = ((rh << 1) | (rh >> 63)) ^ T.c0[p[k - 1 - j] & 7u];
+    }
+    const uint32_t n = len - k + 1;
+    for (uint32_t j = 0; j < n; j++) {
+        if (j) {
+            const uint32_t bo = p[j - 1], bi = p[j + k - 1];
+            fh = ((fh << 1) | (fh >> 63)) ^ T.out[bo] ^ T.in[bi];
+            rh = ((rh >> 1) | (rh << 63)) ^ T.cout[bo & 7u] ^ T.cin[bi & 7u];
+        }
+        const uint64_t h = rh < fh ? rh : fh;
+        if (h < sk[0]) sk[0] = h;
+        for (uint32_t i = 1; i < S; i++) {                       // khf.go:44-53 / nthash MultiHash
+            uint64_t x = h * (static_cast<uint64_t>(i) ^ C);
+            x ^= x >> GROOT_MULTI_SHIFT;
+            if (x < sk[i]) sk[i] = x;
+        }
+    }
+}
+
+template <class Emit>
+__device__ inline void lsh_probe_generic(const DevIndex& ix, const uint64_t* __restrict__ sk, LenParam lp, Emit emit) {
+    const uint32_t S = ix.S, maxk = ix.max_k, NB = ix.n_bands, K = lp.K;
+    if (lp.eq_min > S || K == 0) return;
+    auto band_match = [&](const uint64_t* ws, uint32_t b, uint32_t from) {   // hashes [from, K) of band b equal (low 32 bits: lshensemble's hash key)
+        for (uint32_t j = from; j < K; j++)
+            if (static_cast<uint32_t>(ws[b * maxk + j]) != static_cast<uint32_t>(sk[b * maxk + j])) return false;
+        return true;
+    };
+    for (uint32_t b = 0; b < NB && b < lp.L; b++) {
+        uint32_t key[4] = {0, 0, 0, 0};
+        for (uint32_t j = 0; j < 4 && j < K; j++) key[j] = static_cast<uint32_t>(sk[b * maxk + j]);
+        const LshTable tab = ix.tables[(K - 1) * NB + b];
+        uint32_t h = band_key_hash(key) & tab.mask;
+        uint32_t start = 0, count = 0;
+        while (true) {
+            const uint4* sp = reinterpret_cast<const uint4*>(tab.slots + h);
+            const uint4 kq = __ldg(sp), rest = __ldg(sp + 1);
+            if (rest.y == 0) break;  // empty
+            if (kq.x == key[0] && kq.y == key[1] && kq.z == key[2] && kq.w == key[3]) { start = rest.x; count = rest.y; break; }
+            h = (h + 1) & tab.mask;
+        }
+        for (uint32_t c = 0; c < count; c++) {
+            const uint32_t w = __ldg(tab.wins + start + c);
+            const uint64_t* ws = ix.sketches + static_cast<size_t>(w) * S;
+            if (K > 4 && !band_match(ws, b, 4)) continue;       // the table groups by the first four hashes only
+            uint32_t eq = 0;
+            for (uint32_t i = 0; i < S; i++) eq += (__ldg(ws + i) == sk[i]);
+            bool dup = false;                                    // already reported through an earlier band
+            for (uint32_t b2 = 0; b2 < b && !dup; b2++) dup = band_match(ws, b2, 0);
+            if (eq >= lp.eq_min && !dup) emit(w);
+        }
+    }
+}
+
+// one thread per read: sketch + probe, hits staged (<= HSTAGE) and counted, like seed_kernel<S, MAXK, SEED_FULL>
+__global__ void __launch_bounds__(kSeedThreads) seed_generic_kernel(DevIndex ix, SeedArgs a) {
+    __shared__ SeedTabs T;
+    build_seed_tabs(&T, ix.k);
+    __syncthreads();
+    uint64_t sk[kMaxSketch];
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += gridDim.x * blockDim.x) {
+        const uint32_t o = a.off[r], len = a.off[r + 1] - o;
+        if (len < ix.k || len > a.max_len) { set_error(a.error, len < ix.k ? -5 : -7, r); a.n_hits[r] = 0; continue; }
+        khf_sketch_generic(a.seq + o, len, ix.k, T, ix.S, sk);
+        if (a.sketches_out)
+            for (uint32_t i = 0; i < ix.S; i++) a.sketches_out[static_cast<size_t>(r) * ix.S + i] = sk[i];
+        uint32_t nh = 0;
+        lsh_probe_generic(ix, sk, a.len_params[len], [&](uint32_t w) { if (nh < HSTAGE) a.stage[static_cast<size_t>(r) * HSTAGE + nh] = w; nh++; });
+        a.n_hits[r] = nh;
+    }
+}
+
+// the reads with more than HSTAGE hits: probe redone with the hits written at their final place
+__global__ void __launch_bounds__(kSeedThreads) fill_refill_generic_kernel(DevIndex ix, FillArgs a) {
+    __shared__ SeedTabs T;
+    if (*a.n_overflow == 0) return;
+    build_seed_tabs(&T, ix.k);
+    __syncthreads();
+    uint64_t sk[kMaxSketch];
+    unsigned mapped = 0, multi = 0;
+    const uint32_t n_units = *a.n_overflow;
+    for (uint32_t u = blockIdx.x * blockDim.x + threadIdx.x; u < n_units; u += gridDim.x * blockDim.x) {
+        const uint32_t r = a.overflow_q[u];
+        const uint32_t nh = a.n_hits[r];
+        const uint32_t base = a.hit_off[r];
+        const uint32_t o = a.off[r], len = a.off[r + 1] - o;
+        khf_sketch_generic(a.seq + o, len, ix.k, T, ix.S, sk);
+        uint32_t c = 0;
+        lsh_probe_generic(ix, sk, a.len_params[len], [&](uint32_t w) { if (c < nh) a.hits[base + c] = w; c++; });
+        const uint32_t segs = finish_read_hits(ix, a, r, nh, base);
+        mapped++;
+        multi += segs > 1;
+    }
+    mapped = __reduce_add_sync(0xffffffffu, mapped);
+    multi = __reduce_add_sync(0xffffffffu, multi);
+    if ((threadIdx.x & 31) == 0) {
+        if (mapped) atomicAdd(&a.counters[0], static_cast<unsigned long long>(mapped));
+        if (multi) atomicAdd(&a.counters[1], static_cast<unsigned long long>(multi));
+    }
+}
+
+// window sketching / grootgpu_sketch_batch for any sketch size
+__global__ void __launch_bounds__(kSeedThreads) sketch_generic_kernel(const uint8_t* __restrict__ seq, const uint64_t* __restrict__ off,
+                                                                      const uint32_t* __restrict__ lens, uint32_t fixed_len, uint32_t n,
+                                                                      uint32_t k, uint32_t S, uint64_t* __restrict__ out, int* error) {
+    __shared__ SeedTabs T;
+    build_seed_tabs(&T, k);
+    __syncthreads();
+    uint64_t sk[kMaxSketch];
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const uint32_t len = lens ? lens[r] : fixed_len;
+        if (len < k) { set_error(error, -5, r); continue; }
+        khf_sketch_generic(seq + off[r], len, k, T, S, sk);
+        for (uint32_t i = 0; i < S; i++) out[static_cast<size_t>(r) * S + i] = sk[i];
     }
 }
 

@@ -252,9 +252,11 @@ int grootgpu_comm_id(uint8_t id[GROOTGPU_COMM_ID_BYTES]);
 int grootgpu_comm_create(grootgpu_index* idx, const uint8_t id[GROOTGPU_COMM_ID_BYTES], int rank, int world_size, grootgpu_comm** out);
 /* Collective: `local` is the result of this rank's last align call (results_on_device = 1; either output format, the same
  * on all ranks). On rank 0 `merged` receives the batch-wide result: read indices global (rank 0's reads first), hit /
- * record offsets rebased, counters summed; d_* pointers always, host arrays too when to_host != 0 (the call then returns
- * after the copy; otherwise it only enqueues, and the arrays are complete after grootgpu_comm_sync). Valid until the next
- * grootgpu_gather on the communicator. Other ranks may pass merged = NULL. The transfer overlaps the next align call. */
+ * record offsets rebased, counters summed; d_* pointers always (complete once the communicator's stream has run: after
+ * the next grootgpu_gather or grootgpu_comm_sync), valid until the next grootgpu_gather. to_host = 1: host arrays too, the
+ * call returns after the copy; to_host = 2: host arrays too, copied asynchronously — complete after the next
+ * grootgpu_gather / grootgpu_comm_sync and valid until the gather after that (two alternating sets). Other ranks may pass
+ * merged = NULL. The transfer overlaps the next align call of every rank. */
 int grootgpu_gather(grootgpu_comm* comm, const grootgpu_batch_result* local, int to_host, grootgpu_batch_result* merged);
 /* Collective: waits for the gathers and the weight ring; afterwards rank 0's index holds the graph weights of everything
  * mapped so far on all ranks (grootgpu_weights / _prune / _graph_save_gfa on rank 0), the other ranks' weights are zero. */

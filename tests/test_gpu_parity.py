@@ -78,6 +78,29 @@ def test_sketch_matches_oracle_random():
         assert np.array_equal(api.sketch_batch(b1, o1, k, S), api.sketch_batch(b2, o2, k, S))
 
 
+def test_sketch_tie_path_is_exact(monkeypatch, argannot, db_dirs):
+    """The sketch kernel orders k-mer products by their top 27 bits and only finishes / compares in full on a tie
+    (seed_kernels.cuh, variant 6) — about once in 10^5 reads. GROOTGPU_KHF_KEYBITS lowers the number of deciding bits so
+    that nearly every comparison ties and takes the exact path: sketches, hits and records must not change."""
+    rng = np.random.default_rng(11)
+    seqs = [bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(31, 300)))) for _ in range(400)]
+    seqs.append(b"A" * 120)                       # one k-mer repeated: every comparison is an exact tie
+    seqs.append(b"ACGTN" * 30)
+    blob, off = pack_reads(seqs)
+    want = {(k, S): np.stack([po.sketch(s, k, S) for s in seqs]) for k, S in ((31, 21), (21, 32), (31, 8))}
+    g, o = argannot
+    rb, ro = _c1_reads(db_dirs["arg-annot.90"], 3000, 100, seed=21)
+    orr = o.map_reads(rb, ro, 0.99, threads=8)
+    for bits in ("27", "12", "3", "1"):
+        monkeypatch.setenv("GROOTGPU_KHF_KEYBITS", bits)
+        for (k, S), w in want.items():
+            assert np.array_equal(api.sketch_batch(blob, off, k, S), w), (bits, k, S)
+        for keep in (False, True):               # two-pass (prescreen + queued) and one-pass seed kernels
+            gr = g.map_reads(rb, ro, 0.99, keep_sketches=keep)
+            assert_same_result(gr, orr)
+    monkeypatch.delenv("GROOTGPU_KHF_KEYBITS")
+
+
 def test_sketch_short_sequence_is_an_error():
     blob, off = pack_reads([b"ACGTACGTAC", b"ACG"])
     with pytest.raises(api.GrootGpuError) as e:
@@ -545,3 +568,42 @@ def test_compact_output_decodes_to_the_full_records(argannot, db_dirs, monkeypat
     g.map_reads(b1, o1, 0.99, compact=True, project_on_device=True)
     o.map_reads(b1, o1, 0.99, threads=8)
     assert np.array_equal(g.weights()[0], o.weights()[0]) and np.array_equal(g.weights()[1], o.weights()[1])
+
+
+def test_any_sketch_size_and_maxk(root, db_dirs):
+    """`groot index` accepts any -s / -y (cmd/index.go:48-49). Combinations outside the compiled register-resident kernels
+    (maxK == 4, eight sketch sizes) run the run-time-S kernels: index dump, sketches, hits, records and weights must equal
+    the oracle's — maxK 2 with S = 25 (12 bands of 2), maxK 6 (band prefixes longer than a table slot's four words),
+    maxK 1, and a compiled S with maxK 3."""
+    msa = [os.path.join(root, "data", "graph", "test-genes.msa")]
+    names, seqs, quals = load_fastq(os.path.join(root, "data", "reads", "test-reads-OXA90-OXA106-100bp-with-errors.fastq"))
+    blob, off = pack_reads(seqs[:600])
+    rng = np.random.default_rng(1)
+    rs = [bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=int(rng.integers(31, 200)))) for _ in range(50)]
+    rblob, roff = pack_reads(rs)
+    for S, max_k, k, t in ((25, 2, 31, 0.99), (25, 2, 31, 0.9), (30, 6, 31, 0.95), (13, 1, 21, 0.9), (21, 3, 31, 0.97), (40, 4, 31, 0.99)):
+        g = api.Index.build(msa_files=msa, k=k, S=S, w=100, max_k=max_k)
+        o = po.Index(msa_files=msa, k=k, S=S, w=100, max_k=max_k)
+        assert g.dump_hash() == o.dump_hash(), (S, max_k)
+        assert np.array_equal(api.sketch_batch(rblob, roff, k, S), np.stack([po.sketch(r, k, S) for r in rs]))
+        gr = g.map_reads(blob, off, t, project=True, keep_sketches=True)
+        orr = o.map_reads(blob, off, t, threads=8, keep_sketches=True)
+        assert orr.counts["mapped"] > 50, (S, max_k, orr.counts)
+        assert_same_result(gr, orr)
+        assert np.array_equal(gr.sketches, orr.sketches)
+        assert np.array_equal(g.weights()[0], o.weights()[0])
+        gr2 = g.map_reads(blob, off, t)           # without keep_sketches (the two-pass switch must not matter here)
+        assert np.array_equal(gr2.hits, orr.hits) and np.array_equal(gr2.records_table(), oracle_records_table(orr))
+        g.close()
+    # arg-annot.90 at -y 2 -s 25: reads with many hits (the refill kernel), several graphs per read
+    d = db_dirs["arg-annot.90"]
+    g = api.Index.build(msa_dir=d, k=31, S=25, w=100, max_k=2)
+    o = po.Index(msa_dir=d, k=31, S=25, w=100, max_k=2)
+    assert g.dump_hash() == o.dump_hash()
+    blob, off = _c1_reads(d, 3000, 100, seed=8)
+    for t in (0.99, 0.9):
+        g.reset_weights(); o.reset_weights()
+        gr = g.map_reads(blob, off, t, project_on_device=True)
+        orr = o.map_reads(blob, off, t, threads=8)
+        assert_same_result(gr, orr)
+        assert np.array_equal(g.weights()[0], o.weights()[0])

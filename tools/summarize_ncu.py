@@ -85,6 +85,7 @@ for r in rd[2:]:
     try:   # a family's traffic = the sum over its distinct kernels of one batch (e.g. seed = prescreen + queued pass)
         t = traffic.setdefault(fam, {"dram_bytes_per_read": 0.0, "reads_in_profiled_launch": n_reads, "source": os.path.basename(rep), "kernels": []})
         t["dram_bytes_per_read"] += (num("dram__bytes_read.sum") + num("dram__bytes_write.sum")) / n_reads
+        t["warp_inst_per_read"] = t.get("warp_inst_per_read", 0.0) + float(r[ix["smsp__inst_executed.sum"]].replace(",", "")) / n_reads
         t["kernels"].append(name[:60])
     except Exception:
         pass
