@@ -96,6 +96,8 @@ def lib():
         L.grootgpu_graphs_dump.argtypes = [C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(IndexParams), C.c_char_p, C.POINTER(C.c_uint64)]
         L.grootgpu_index_save.argtypes = [vp, C.c_char_p]
         L.grootgpu_index_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.grootgpu_index_load_gob.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
+        L.grootgpu_gob_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64)]
         L.grootgpu_index_destroy.argtypes = [vp]
         L.grootgpu_index_destroy.restype = None
         L.grootgpu_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
@@ -132,7 +134,7 @@ EXPORTED_SYMBOLS = [
     "grootgpu_weights", "grootgpu_reset_weights", "grootgpu_sketch_batch", "grootgpu_prune", "grootgpu_graph_save_gfa",
     "grootgpu_host_alloc", "grootgpu_host_free", "grootgpu_device_count", "grootgpu_last_error", "grootgpu_version",
     "grootgpu_int_issue_peak", "grootgpu_index_node_paths", "grootgpu_comm_id", "grootgpu_comm_create", "grootgpu_comm_destroy", "grootgpu_comm_sync",
-    "grootgpu_gather",
+    "grootgpu_gather", "grootgpu_index_load_gob", "grootgpu_gob_dump",
 ]
 
 
@@ -269,6 +271,13 @@ class Index:
     def load(cls, path, device=0):
         h = C.c_void_p()
         _check(lib().grootgpu_index_load(path.encode(), device, C.byref(h)))
+        return cls(h.value, device)
+
+    @classmethod
+    def load_gob(cls, gg_path, lshe_path, device=0):
+        """The reference's own index files (groot.gg + groot.lshe, Go gob): cmd/align.go:94-107."""
+        h = C.c_void_p()
+        _check(lib().grootgpu_index_load_gob(gg_path.encode(), lshe_path.encode(), device, C.byref(h)))
         return cls(h.value, device)
 
     def save(self, path):
@@ -415,6 +424,13 @@ def graphs_dump(msa_files, dump_path=None, k=31, S=21, w=100, num_part=8, max_k=
     arr = (C.c_char_p * len(msa_files))(*[f.encode() for f in msa_files])
     h = C.c_uint64()
     _check(lib().grootgpu_graphs_dump(arr, len(msa_files), C.byref(p), dump_path.encode() if dump_path else None, C.byref(h)))
+    return h.value
+
+
+def gob_dump(gg_path, lshe_path, dump_path=None):
+    """Host-only: decode groot.gg + groot.lshe, return the FNV-1a-64 hash of the canonical dump (and write it)."""
+    h = C.c_uint64()
+    _check(lib().grootgpu_gob_dump(gg_path.encode(), lshe_path.encode(), dump_path.encode() if dump_path else None, C.byref(h)))
     return h.value
 
 

@@ -8,6 +8,7 @@
 #include <dirent.h>
 
 #include <algorithm>
+#include <array>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -436,6 +437,29 @@ void index_to_device(grootgpu_index* ix) {
         d.node_seq2 = upload(seq2, ix->owned); d.node_n2 = upload(n2, ix->owned); d.graph_has_n = upload(has_n, ix->owned);
     }
     d.k = h.p.k; d.S = h.p.S; d.max_k = h.p.max_k; d.n_bands = h.p.S / h.p.max_k; d.n_wins = static_cast<uint32_t>(h.wins.size());
+    {   // windows grouped by identical sketch (DevIndex::full): key = sketch_digest, bucket = window ids ascending
+        const uint32_t S = h.p.S, W = static_cast<uint32_t>(h.wins.size());
+        std::vector<std::array<uint32_t, 4>> dig(W);
+        for (uint32_t w = 0; w < W; w++) sketch_digest(&h.sketches[static_cast<size_t>(w) * S], S, dig[w].data());
+        std::vector<uint32_t> order(W);
+        for (uint32_t i = 0; i < W; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return dig[x] != dig[y] ? dig[x] < dig[y] : x < y; });
+        uint32_t uniq = 0;
+        for (uint32_t i = 0; i < W; i++) if (i == 0 || dig[order[i]] != dig[order[i - 1]]) uniq++;
+        uint32_t cap = 16;
+        while (cap < 2 * uniq) cap <<= 1;
+        std::vector<LshSlot> slots(cap);
+        memset(slots.data(), 0, slots.size() * sizeof(LshSlot));
+        for (uint32_t i = 0; i < W;) {
+            uint32_t j = i + 1;
+            while (j < W && dig[order[j]] == dig[order[i]]) j++;
+            uint32_t hsh = band_key_hash(dig[order[i]].data()) & (cap - 1);
+            while (slots[hsh].count != 0) hsh = (hsh + 1) & (cap - 1);
+            memcpy(slots[hsh].key, dig[order[i]].data(), 16); slots[hsh].start = i; slots[hsh].count = j - i;
+            i = j;
+        }
+        d.full.slots = upload(slots, ix->owned); d.full.wins = upload(order, ix->owned); d.full.mask = cap - 1; d.full.pad = 0;
+    }
     ix->h_tables.assign(static_cast<size_t>(h.p.max_k) * d.n_bands, LshTable{nullptr, nullptr, 0, 0});
     void* dt = nullptr;
     CK(cudaMalloc(&dt, ix->h_tables.size() * sizeof(LshTable)));
@@ -1558,6 +1582,30 @@ int grootgpu_index_load(const char* path, int device, grootgpu_index** out) {
     if (rc != GROOTGPU_OK) { delete ix; return rc; }
     *out = ix;
     return GROOTGPU_OK;
+}
+int grootgpu_index_load_gob(const char* gg_path, const char* lshe_path, int device, grootgpu_index** out) {
+    if (!gg_path || !lshe_path || !out) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    *out = nullptr;
+    grootgpu_index* ix = new grootgpu_index();
+    int rc = guarded([&] { load_index_gob(ix->h, gg_path, lshe_path); validate_index(ix->h); pick_device(device); ix->device = device; index_to_device(ix); });
+    if (rc != GROOTGPU_OK) { delete ix; return rc; }
+    *out = ix;
+    return GROOTGPU_OK;
+}
+int grootgpu_gob_dump(const char* gg_path, const char* lshe_path, const char* dump_path, uint64_t* hash) {
+    if (!gg_path || !lshe_path) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    return guarded([&] {
+        FlatIndex h;
+        load_index_gob(h, gg_path, lshe_path);
+        validate_index(h);
+        if (hash) { *hash = 1469598103934665603ULL; dump_index(h, fnv_sink, hash); }
+        if (dump_path) {
+            FILE* f = fopen(dump_path, "wb");
+            if (!f) throw std::ios_base::failure(std::string("cannot create ") + dump_path);
+            dump_index(h, file_sink, f);
+            fclose(f);
+        }
+    });
 }
 void grootgpu_index_destroy(grootgpu_index* idx) {
     if (!idx) return;

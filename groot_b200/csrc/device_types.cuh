@@ -48,6 +48,18 @@ __host__ __device__ inline uint32_t band_key_hash(const uint32_t key[4]) {
     return h;
 }
 
+// 128-bit digest of a whole sketch: the key of the "identical sketch" table (below). Any mixing function works — a
+// collision only adds a candidate that the verification rejects — but host and device must agree bit for bit.
+__host__ __device__ inline void sketch_digest(const uint64_t* sk, uint32_t S, uint32_t key[4]) {
+    uint32_t a[4] = {0x243F6A88u, 0x85A308D3u, 0x13198A2Eu, 0x03707344u};
+    for (uint32_t i = 0; i < S; i++) {
+        const uint32_t lo = static_cast<uint32_t>(sk[i]), hi = static_cast<uint32_t>(sk[i] >> 32);
+        uint32_t& x = a[i & 3u];
+        x = ((x << 13) | (x >> 19)) ^ (lo * 0x9E3779B1u + hi);
+    }
+    for (int j = 0; j < 4; j++) key[j] = a[j];
+}
+
 struct DevIndex {
     const NodeRec* nodes;
     const uint8_t* node_seq;
@@ -64,6 +76,11 @@ struct DevIndex {
     const uint32_t* node_seq2;    // node_seq packed 2 bits per base (pack_base2), 16 bases per word, same positions as node_seq
     const uint32_t* node_n2;      // same layout: bit 2i of a word set when base i is an 'N' wildcard (alignment.go:212-215)
     const uint8_t* graph_has_n;   // [G] 1 when a node of the graph holds an 'N' (only then node_n2 is consulted)
+    // Windows grouped by IDENTICAL sketch (key = sketch_digest). When a query needs every slot equal (eq_min == S: a read as
+    // long as the index window at the default threshold) and probes one band, "in the band's bucket and all S slots equal"
+    // is the same set as "identical sketch": this table yields ~1 candidate per seeded read where the band bucket holds ~11
+    // (neighbouring windows share their first K minima), i.e. a tenth of the verification loads.
+    LshTable full;
     uint32_t k, S, max_k, n_bands, n_wins;
 };
 

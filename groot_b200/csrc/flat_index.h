@@ -91,6 +91,9 @@ void build_windows(FlatIndex& idx, SketchFn sketch, void* ctx);
 
 void save_index(const FlatIndex& idx, const std::string& path);
 void load_index(FlatIndex& idx, const std::string& path);
+void validate_index(const FlatIndex& idx);   // range checks of every offset / index; throws std::runtime_error
+// groot.gg + groot.lshe (Go gob, host/gob_reader.cpp)
+void load_index_gob(FlatIndex& idx, const std::string& gg_path, const std::string& lshe_path);
 // canonical text dump shared (as a FORMAT) with the oracle; sink(line incl. '\n')
 void dump_index(const FlatIndex& idx, void (*sink)(void* ctx, const char* data, size_t n), void* ctx);
 

@@ -54,7 +54,7 @@ void save_index(const FlatIndex& idx, const std::string& path) {
 // Every CSR offset / count and every node, path or window index of a loaded file is range-checked against the array it
 // points into, and the parameters against each other: a truncated, corrupt or version-skewed file must fail here
 // (GROOTGPU_ERR_FORMAT) instead of reading out of bounds on the host (index_to_device, build_prefix_sets) or in the kernels.
-static void validate_index(const FlatIndex& idx) {
+void validate_index(const FlatIndex& idx) {
     auto bad = [](const char* what) { throw std::runtime_error(std::string("inconsistent index file: ") + what); };
     const IndexParams& p = idx.p;
     if (p.k < 1 || p.w < p.k || p.max_k < 1 || p.S < p.max_k) bad("parameters (need 1 <= k <= w, 1 <= maxK <= sketch size)");

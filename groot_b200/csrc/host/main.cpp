@@ -91,9 +91,14 @@ static int run_align(const Args& a) {
     std::vector<std::string> fastq = split_commas(a.get("-f", "--fastq", ""));
     const double t0 = now_s();
     std::vector<grootgpu_index*> replicas;       // the index is replicated on every GPU of the run; replicas[0] ends up with the results
+    // the library's own flat index file when `groot-b200 index` wrote one, else the reference's groot.gg + groot.lshe (cmd/align.go:94-107)
+    struct stat sb;
+    const bool own = stat((info.IndexDir + "/groot.grootb200").c_str(), &sb) == 0;
     for (int dev : info.Devices) {
         grootgpu_index* r = nullptr;
-        if (grootgpu_index_load((info.IndexDir + "/groot.grootb200").c_str(), dev, &r)) fatal(grootgpu_last_error());
+        const int rc = own ? grootgpu_index_load((info.IndexDir + "/groot.grootb200").c_str(), dev, &r)
+                           : grootgpu_index_load_gob((info.IndexDir + "/groot.gg").c_str(), (info.IndexDir + "/groot.lshe").c_str(), dev, &r);
+        if (rc) fatal(grootgpu_last_error());
         replicas.push_back(r);
     }
     grootgpu_index* idx = replicas[0];

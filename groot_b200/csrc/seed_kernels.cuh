@@ -265,6 +265,7 @@ __device__ __forceinline__ uint32_t warp_probe(const DevIndex& ix, const uint64_
     constexpr uint32_t FULL = 0xffffffffu;
     const bool probing = valid && lp.eq_min <= S && lp.K != 0;
     const uint32_t myL = probing ? lp.L : 0u;
+    const bool use_full = probing && lp.eq_min == S && lp.L == 1 && ix.full.slots != nullptr;   // every slot has to match: look the whole sketch up (DevIndex::full)
     const uint32_t maxL = __reduce_max_sync(FULL, myL);
     const uint32_t lt_mask = (1u << lane) - 1u;
     uint32_t nh = 0;
@@ -274,14 +275,18 @@ __device__ __forceinline__ uint32_t warp_probe(const DevIndex& ix, const uint64_
         uint32_t start = 0, count = 0;
         if (b < myL) {
             uint32_t key[4] = {0, 0, 0, 0};
+            if (use_full) {
+                sketch_digest(sk, S, key);
+            } else {
 #pragma unroll
-            for (int bb = 0; bb < NB; bb++) {
-                if (bb == static_cast<int>(b)) {
+                for (int bb = 0; bb < NB; bb++) {
+                    if (bb == static_cast<int>(b)) {
 #pragma unroll
-                    for (int j = 0; j < MAXK; j++) key[j] = j < lp.K ? static_cast<uint32_t>(sk[bb * MAXK + j]) : 0u;
+                        for (int j = 0; j < MAXK; j++) key[j] = j < lp.K ? static_cast<uint32_t>(sk[bb * MAXK + j]) : 0u;
+                    }
                 }
             }
-            const LshTable tab = ix.tables[(lp.K - 1) * NB + b];
+            const LshTable tab = use_full ? ix.full : ix.tables[(lp.K - 1) * NB + b];
             uint32_t h = band_key_hash(key) & tab.mask;
             while (true) {
                 const uint4* sp = reinterpret_cast<const uint4*>(tab.slots + h);
@@ -313,10 +318,12 @@ __device__ __forceinline__ uint32_t warp_probe(const DevIndex& ix, const uint64_
             const uint32_t o_start = __shfl_sync(FULL, start, o);
             const uint32_t o_K = __shfl_sync(FULL, static_cast<uint32_t>(lp.K), o), o_eqmin = __shfl_sync(FULL, static_cast<uint32_t>(lp.eq_min), o);
             const uint32_t o_nh = __shfl_sync(FULL, nh, o), o_r = __shfl_sync(FULL, r, o);
+            const bool o_full = __shfl_sync(FULL, static_cast<uint32_t>(use_full), o) != 0;
             uint32_t w = 0;
             const uint64_t* ws = ix.sketches;
             if (live) {
-                w = __ldg(ix.tables[(o_K - 1) * NB + b].wins + o_start + (item - o_excl));
+                const uint32_t* bucket = o_full ? ix.full.wins : ix.tables[(o_K - 1) * NB + b].wins;
+                w = __ldg(bucket + o_start + (item - o_excl));
                 ws += static_cast<size_t>(w) * S;
             }
             uint32_t eq = 0, low = 0;

@@ -78,6 +78,12 @@ int grootgpu_index_build_dir(const char* msa_dir, const grootgpu_index_params* p
  * is this library's own flat little-endian format (".grootb200"), not Go gob. */
 int grootgpu_index_save(const grootgpu_index* idx, const char* path);
 int grootgpu_index_load(const char* path, int device, grootgpu_index** out);
+/* The same from the reference's OWN index files: groot.gg (Info + graph Store) and groot.lshe (ContainmentIndex), Go gob
+ * streams (src/pipeline/runtime.go:64-91, src/lshe/lshe.go:72-146; cmd/align.go:94-107). The graphs are adopted as the Go
+ * host wrote them — node order, segment ids, path ids — so results index straight into the host's info.Store. */
+int grootgpu_index_load_gob(const char* gg_path, const char* lshe_path, int device, grootgpu_index** out);
+/* Host-only (no device): decodes and validates the two gob files and writes the canonical dump and/or its hash. */
+int grootgpu_gob_dump(const char* gg_path, const char* lshe_path, const char* dump_path, uint64_t* hash);
 void grootgpu_index_destroy(grootgpu_index* idx);
 int grootgpu_index_get_info(const grootgpu_index* idx, grootgpu_index_info* out);
 

@@ -1,0 +1,69 @@
+"""The library's reader for the reference's own index files (groot.gg / groot.lshe, Go encoding/gob:
+src/pipeline/runtime.go:64-91, src/lshe/lshe.go:72-146). No Go toolchain exists here, so the streams come from
+tests/gob_writer.py, a restatement of the gob ENCODER that is itself pinned to the byte sequence the encoding/gob
+documentation gives for Point{22, 33}. CPU only: grootgpu_gob_dump decodes, validates and dumps without a device."""
+import glob
+import os
+
+import pytest
+
+from groot_b200 import api
+from oracle import pyoracle as po
+from tests import gob_writer as gw
+
+
+def test_gob_writer_reproduces_the_documented_stream():
+    want = bytes.fromhex("1fff8103010105506f696e7401ff82000102010158010400010159010400000007ff82012c014200")
+    got = gw.Encoder().encode(gw.Struct("Point", [("X", gw.INT), ("Y", gw.INT)]), {"X": 22, "Y": 33})
+    assert got == want
+    assert gw.uvarint(7) == b"\x07" and gw.uvarint(256) == b"\xfe\x01\x00" and gw.varint(-129) == b"\xfe\x01\x01"     # doc: 256 -> FE 01 00, -129 -> FE 01 01
+    assert gw.gfloat(17.0) == b"\xfe\x31\x40"                                                                          # doc: float64 17 -> FE 31 40
+
+
+def test_gob_index_roundtrip(root, db_dirs, tmp_path):
+    """An index written the way `groot index` writes it (maps in random order) must come back as the same index: graphs
+    in Store order, nodes in SortedNodes order, out-edges in the stored order, windows sorted (graph, Node, OffSet, the
+    counter of the lookup string)."""
+    cases = [([os.path.join(root, "data", "graph", "test-genes.msa")], dict(k=51, S=30, w=100)),
+             (sorted(glob.glob(os.path.join(db_dirs["arg-annot.90"], "cluster*.msa")))[:25], dict(k=31, S=21, w=100)),
+             (sorted(glob.glob(os.path.join(db_dirs["card.90"], "cluster*.msa")))[:12], dict(k=31, S=20, w=150, max_k=2))]
+    for i, (files, prm) in enumerate(cases):
+        o = po.Index(msa_files=files, **prm)
+        dump = str(tmp_path / ("o%d.txt" % i))
+        o.dump_file(dump)
+        gg, lshe = str(tmp_path / "groot.gg"), str(tmp_path / "groot.lshe")
+        for seed in (1, 2):
+            gw.write_reference_index(dump, gg, lshe, seed=seed)
+            out = str(tmp_path / "g.txt")
+            assert api.gob_dump(gg, lshe, out) == o.dump_hash()
+            assert open(out).read() == open(dump).read()
+
+
+def test_gob_errors(root, tmp_path):
+    o = po.Index(msa_files=[os.path.join(root, "data", "graph", "test-genes.msa")], k=51, S=30, w=100)
+    dump = str(tmp_path / "o.txt")
+    o.dump_file(dump)
+    gg, lshe = str(tmp_path / "groot.gg"), str(tmp_path / "groot.lshe")
+    gw.write_reference_index(dump, gg, lshe)
+    with pytest.raises(api.GrootGpuError) as e:
+        api.gob_dump(str(tmp_path / "missing.gg"), lshe)
+    assert e.value.code == -3
+    raw = open(gg, "rb").read()
+    open(tmp_path / "cut.gg", "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(api.GrootGpuError) as e:
+        api.gob_dump(str(tmp_path / "cut.gg"), lshe)
+    assert e.value.code == -4
+    open(tmp_path / "empty.gg", "wb").write(b"")
+    with pytest.raises(api.GrootGpuError) as e:                     # runtime.go:86-88 "groot graph store appears empty"
+        api.gob_dump(str(tmp_path / "empty.gg"), lshe)
+    assert e.value.code == -4
+    with pytest.raises(api.GrootGpuError) as e:                     # the two files swapped: wrong top-level type
+        api.gob_dump(lshe, gg)
+    assert e.value.code == -4
+    # a groot.lshe of another index (different sketch size) must be refused
+    o2 = po.Index(msa_files=[os.path.join(root, "data", "graph", "test-genes.msa")], k=51, S=21, w=100)
+    o2.dump_file(str(tmp_path / "o2.txt"))
+    gw.write_reference_index(str(tmp_path / "o2.txt"), str(tmp_path / "g2.gg"), str(tmp_path / "g2.lshe"))
+    with pytest.raises(api.GrootGpuError) as e:
+        api.gob_dump(gg, str(tmp_path / "g2.lshe"))
+    assert e.value.code == -4

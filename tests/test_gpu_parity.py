@@ -607,3 +607,30 @@ def test_any_sketch_size_and_maxk(root, db_dirs):
         orr = o.map_reads(blob, off, t, threads=8)
         assert_same_result(gr, orr)
         assert np.array_equal(g.weights()[0], o.weights()[0])
+
+
+def test_index_from_reference_gob_files(oxa, root, tmp_path):
+    """grootgpu_index_load_gob: groot.gg + groot.lshe as `groot index` writes them (here: written by tests/gob_writer.py
+    from the oracle's index, maps in random order) give the same index and the same alignments as the natively built one;
+    the driver picks them up when the index directory holds no groot.grootb200."""
+    import subprocess
+    from tests import gob_writer as gw
+    g, o = oxa
+    dump = str(tmp_path / "o.txt")
+    o.dump_file(dump)
+    d = tmp_path / "idx"; d.mkdir()
+    gw.write_reference_index(dump, str(d / "groot.gg"), str(d / "groot.lshe"), seed=7)
+    gg = api.Index.load_gob(str(d / "groot.gg"), str(d / "groot.lshe"))
+    assert gg.dump_hash() == o.dump_hash()          # (the shared GPU index `g` has been pruned by an earlier test: its path lengths differ)
+    names, seqs, quals = load_fastq(os.path.join(root, "data", "reads", "test-reads-OXA90-OXA106-100bp-with-errors.fastq"))
+    blob, off = pack_reads(seqs[:500])
+    o.reset_weights()
+    orr = o.map_reads(blob, off, 0.99)
+    gr = gg.map_reads(blob, off, 0.99, project_on_device=True)
+    assert_same_result(gr, orr)
+    assert np.array_equal(gg.weights()[0], o.weights()[0])
+    cli = os.path.join(os.path.dirname(api.LIB_PATH), "groot-b200")
+    fq = os.path.join(root, "data", "reads", "test-reads-OXA90-OXA106-100bp-with-errors.fastq")
+    r = subprocess.run([cli, "align", "-i", str(d), "-f", fq, "-g", str(tmp_path / "graphs"), "--bamOut", str(tmp_path / "out.bam")], stderr=subprocess.PIPE, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"number of reads received from input: 2062" in r.stderr

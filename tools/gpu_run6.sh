@@ -1,0 +1,6 @@
+set -x
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02a_launches.csv python tools/prof_step.py 10000000 > gpurun_out/r02a_ncu_launches.log 2>&1
+tail -2 gpurun_out/r02a_ncu_launches.log
+timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:'seed_kernel|fill_kernel|pack_reads|align_|project_' -f -o gpurun_out/r02a_prof python tools/prof_step.py 2000000 > gpurun_out/r02a_ncu_full.log 2>&1
+tail -2 gpurun_out/r02a_ncu_full.log
+ls -la gpurun_out/
