@@ -250,13 +250,30 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
     d_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).to(dev)
     stream = torch.cuda.current_stream().cuda_stream
 
+    # The gather call waits for every rank's sizes (one small all-gather), i.e. for the slowest rank of the batch: it is
+    # issued from a helper thread while this thread already maps the next batch (include/grootgpu.h, grootgpu_gather). At
+    # most one gather is outstanding: gather b has returned before align b + 2 starts.
+    from concurrent.futures import ThreadPoolExecutor
+    pool = ThreadPoolExecutor(max_workers=1) if comm else None
+    pending = [None]
+    last_merged = [None]
+
+    def gather_async(raw, to_host):
+        if pending[0] is not None:
+            last_merged[0] = pending[0].result()
+        pending[0] = pool.submit(comm.gather, raw, to_host)
+
     def step_device():
         raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, THRESHOLD, no_align=no_align, stream=stream, project_on_device=True)
-        merged = comm.gather(raw, to_host=0) if comm else None     # the one collective of the path: result arrays to rank 0 over NVLink, merged there
-        return raw, merged
+        if comm:
+            gather_async(raw, 0)   # the one collective of the path: result arrays to rank 0 over NVLink, merged there
+        return raw, last_merged[0]
 
     def drain():
         if comm:
+            if pending[0] is not None:
+                last_merged[0] = pending[0].result()
+                pending[0] = None
             comm.sync()            # gathers done, the weight vector has been round every rank, rank 0 holds the weights
         else:
             idx.weights()          # the f64 chains run behind the batches: wait for the last ones
@@ -269,10 +286,11 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
         raw = idx.map_reads_raw(h_seq.data_ptr(), h_off.data_ptr(), n, THRESHOLD, no_align=no_align, project_on_device=True, compact=True,
                                 results_on_device=comm is not None)
         t1 = time.perf_counter()
-        merged = comm.gather(raw, to_host=2) if comm else None     # rank 0: merged compact batch -> host, asynchronously (complete at the next gather / sync)
+        if comm:
+            gather_async(raw, 2)   # rank 0: merged compact batch -> host, asynchronously (complete at the next gather / sync)
         e2e_parts["align_batch_ms"] += (t1 - t0) * 1e3
         e2e_parts["gather_ms"] += (time.perf_counter() - t1) * 1e3
-        return raw, merged
+        return raw, last_merged[0]
 
     # ---- value: inputs resident in HBM ----
     sampler = ClockSampler(ctx.local) if sample_clocks else None
@@ -307,6 +325,7 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
     stats = dict(hits=raw.n_hits / n, pairs=raw.n_pairs / n, records=raw.n_records / n, mapped=raw.mapped / n)
     merged_check = None
     if comm and rank == 0:
+        merged = last_merged[0]
         merged_check = dict(reads=int(merged.n_reads), pairs=int(merged.n_pairs), records=int(merged.n_records), mapped=int(merged.mapped))
 
     # ---- e2e: pinned host buffers through the C ABI, compact result to the host ----
@@ -384,6 +403,8 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
         t0 = time.time(); oidx.map_reads(blob[: sn * L], off[: sn + 1], THRESHOLD, no_align=no_align, threads=cores); dt = time.time() - t0
         cpu = {"value": sn / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "first %d reads of the step's batch, oracle/ C++ restatement, %d threads, %.1fs" % (sn, cores, dt)}
+    if pool:
+        pool.shutdown()
     if comm:
         comm.close()
     idx.close()

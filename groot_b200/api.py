@@ -70,7 +70,7 @@ class BatchResultC(C.Structure):
                 ("d_hit_off", C.c_void_p), ("d_hits", C.c_void_p), ("d_pairs", C.c_void_p), ("d_rec_path", C.c_void_p),
                 ("d_rec_pos", C.c_void_p),
                 ("cpairs", C.POINTER(CPair)), ("rec_path_c", C.c_void_p), ("rec_path_bytes", C.c_uint32),
-                ("d_cpairs", C.c_void_p), ("d_rec_path_c", C.c_void_p)]
+                ("d_cpairs", C.c_void_p), ("d_rec_path_c", C.c_void_p), ("result_set", C.c_uint32)]
 
 
 KERNEL_FAMILIES = ("seed", "fill", "align_screen", "align_walk", "align_finish", "align_emit", "project", "project_accumulate")
@@ -400,14 +400,15 @@ class Comm:
         _check(lib().grootgpu_comm_id(buf))
         return buf.raw
 
-    def gather(self, raw, to_host=False):
-        """raw: BatchResultC of this rank's last align call (results_on_device). Rank 0 gets the merged batch: a
-        BatchResult with host arrays when to_host, else the raw C struct (device pointers)."""
+    def gather(self, raw, to_host=0):
+        """raw: BatchResultC of this rank's last align call (results_on_device). Rank 0 gets the merged batch: with
+        to_host = 1 a BatchResult (numpy copies of the host arrays); with 0 (device pointers only) or 2 (host arrays
+        copied asynchronously: complete after the next gather / sync) the raw C struct."""
         merged = BatchResultC()
         _check(lib().grootgpu_gather(self.h, C.byref(raw), int(to_host), C.byref(merged)))
         if self.rank != 0:
             return None
-        return BatchResult(merged, self.index.info()["S"], True) if to_host else merged
+        return BatchResult(merged, self.index.info()["S"], True) if int(to_host) == 1 else merged
 
     def sync(self):
         _check(lib().grootgpu_comm_sync(self.h))

@@ -1052,6 +1052,7 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         }
         if (copy_back) out->sketches = prm->keep_sketches ? ix->r_sketches.as<uint64_t>() : nullptr;
         out->rec_path_bytes = compact ? recw : 0u;
+        out->result_set = static_cast<uint32_t>(ix->call_parity);
         out->received = n; out->mapped = counters[0]; out->multimapped = counters[1]; out->alignments = R;
         float seed_ms = 0, align_ms = 0, dev_ms = 0, all_ms = 0;
         cudaEventElapsedTime(&seed_ms, w->ev[0], w->ev[1]);
@@ -1126,7 +1127,7 @@ __global__ void __launch_bounds__(256) chunk_rebase_compact_kernel(CPairOut* __r
 uint32_t chunk_reads_setting() {   // reads per pipeline chunk; GROOTGPU_CHUNK_READS overrides (tests force many small chunks)
     const char* e = getenv("GROOTGPU_CHUNK_READS");
     const long x = e ? atol(e) : 0;
-    return static_cast<uint32_t>(x > 0 ? x : 1600000l);
+    return static_cast<uint32_t>(x > 0 ? x : 2000000l);
 }
 
 // Host buffers in, host results out, as a pipeline over chunks of reads on TWO LANES (workspaces with their own
@@ -1154,24 +1155,28 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
                        grootgpu_batch_result* out) {
     cudaStream_t st_in = ix->st_in, st_out = ix->st_out;
     const uint32_t S = ix->h.p.S;
-    // chunk boundaries (always < 4 GiB of bases per chunk). The copy-in link is only ~1.25x faster than the kernels,
-    // so the schedule starts with a small chunk (the first copy-in is a transfer nothing overlaps), grows by at most
-    // that factor per chunk up to chunk_reads_setting() — the next chunk's bases then arrive before the current one
-    // is done — and ends with a small chunk again (the last copy-out is the other exposed transfer).
+    // chunk boundaries (always < 4 GiB of bases per chunk). The copy-in link is only ~1.25x faster than the kernels, so
+    // the schedule starts with a small chunk (the first copy-in is a transfer nothing overlaps) and grows up to
+    // chunk_reads_setting() — the next chunk's bases then arrive before the current one is done. The end depends on what
+    // is copied out: the full result arrays are ~90 bytes per read, so the batch ends with a small chunk (the last
+    // copy-out is the other exposed transfer); the compact output and device-resident results have no copy-out to speak
+    // of, so the last TWO chunks — one per lane, running side by side — are made equal and the lanes finish together.
     std::vector<uint32_t> cb{0};
     {
+        const bool light_out = prm->compact_records != 0 || prm->results_on_device != 0;
         const uint32_t target = chunk_reads_setting(), edge = std::max(1u, target / 4);
         const uint64_t max_bytes = (1ull << 32) - 4096;
-        uint32_t want = std::max(1u, target / 2);
+        uint32_t want = std::max(1u, light_out ? target / 4 : target / 2);
         while (cb.back() < n) {
             const uint32_t r0 = cb.back(), left = n - r0;
             uint32_t take = std::min(want, left);
-            if (left > edge && left - take < edge) take = left - edge;   // leave a last chunk of `edge` reads
+            if (light_out) { if (left > want && left <= 2ull * want) take = (left + 1) / 2; }              // two last chunks of equal size
+            else if (left > edge && left - take < edge) take = left - edge;                             // leave a last chunk of `edge` reads
             uint32_t r1 = r0 + std::max(1u, take);
             while (r1 > r0 + 1 && seq_off[r1] - seq_off[r0] >= max_bytes) r1 = r0 + (r1 - r0) / 2;
             if (seq_off[r1] - seq_off[r0] >= max_bytes) throw std::length_error("a read of 4 GiB or more");
             cb.push_back(r1);
-            want = std::min<uint64_t>(target, static_cast<uint64_t>(want) + want / 4 + 1);
+            want = std::min<uint64_t>(target, static_cast<uint64_t>(want) + (light_out ? want / 2 : want / 4) + 1);
         }
     }
     const uint32_t C = static_cast<uint32_t>(cb.size()) - 1;
@@ -1184,13 +1189,14 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
         }
     } drain{ix};
     const bool on_device = prm->results_on_device != 0, compact = prm->compact_records != 0;
-    grootgpu_index::DevResult& dres = ix->bres[ix->call_parity];
+    const int parity = ix->call_parity;
+    grootgpu_index::DevResult& dres = ix->bres[parity];
     if (on_device) { if (!compact) dres.hit_off.need(4ull * (static_cast<size_t>(n) + 1)); }
     else if (!compact) ix->r_hit_off.need(4ull * (static_cast<size_t>(n) + 1));
     if (on_device && prm->keep_sketches) throw std::runtime_error("keep_sketches needs host results");
     if (prm->keep_sketches) ix->r_sketches.need(8ull * S * n);
     if (prm->project_on_device) push_weights_to_device(ix);
-    if (on_device && ix->comm) CK(cudaStreamWaitEvent(st_out, ix->comm->ev_sent[ix->call_parity], 0));   // the gather of two calls ago has read this result set
+    if (on_device && ix->comm) CK(cudaStreamWaitEvent(st_out, ix->comm->ev_sent[parity], 0));   // the gather of two calls ago has read this result set
     grootgpu_align_params cprm = *prm;
     cprm.results_on_device = 1;
     ChunkShared sh;
@@ -1337,6 +1343,7 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
     *out = sh.total;
     out->n_reads = n; out->n_hits = sh.hit_end[C - 1]; out->n_pairs = sh.pair_end[C - 1]; out->n_records = sh.rec_end[C - 1];
     out->rec_path_bytes = compact ? ix->rec_width : 0u;
+    out->result_set = static_cast<uint32_t>(parity);
     if (on_device) {
         if (compact) { out->d_cpairs = reinterpret_cast<const grootgpu_cpair*>(dres.cpairs.p); out->d_rec_path_c = dres.rec_c.p; }
         else {
@@ -1365,10 +1372,13 @@ void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, int to_h
     const NcclApi& N = nccl();
     cudaStream_t sg = c->st_gather;
     const bool compact = loc->rec_path_bytes != 0;
-    const int W = c->world, parity = ix->call_parity;
+    const int W = c->world, parity = static_cast<int>(loc->result_set & 1u);
     const uint32_t recw = ix->rec_width;
     if (loc->n_pairs && !(compact ? static_cast<const void*>(loc->d_cpairs) : static_cast<const void*>(loc->d_pairs)))
         throw std::runtime_error("grootgpu_gather needs a result with device pointers (results_on_device = 1)");
+    const bool trace = getenv("GROOTGPU_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     // 1. everybody's sizes (one small all-gather; the host needs them to lay the merged arrays out)
     uint64_t* hc = c->h_counts;
     hc[0] = loc->n_reads; hc[1] = loc->n_hits; hc[2] = loc->n_pairs; hc[3] = loc->n_records;
@@ -1378,6 +1388,7 @@ void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, int to_h
     NK(N.AllGather(dc, dc + kCountWords, kCountWords, ncclUint64, c->gath, sg));
     CK(cudaMemcpyAsync(hc + kCountWords, dc + kCountWords, 8ull * kCountWords * W, cudaMemcpyDeviceToHost, sg));
     CK(cudaStreamSynchronize(sg));   // also: the previous gather (it had the whole mapping of this batch to finish) is done
+    const double t_counts = now_ms();
     const uint64_t* all = hc + kCountWords;
     std::vector<uint64_t> rb(W + 1, 0), hb(W + 1, 0), pb(W + 1, 0), cb(W + 1, 0);
     uint64_t mapped = 0, multi = 0, slow = 0;
@@ -1404,6 +1415,7 @@ void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, int to_h
         NK(N.GroupEnd());
         CK(cudaEventRecord(c->ev_sent[parity], sg));
         if (merged) memset(merged, 0, sizeof *merged);
+        if (trace) fprintf(stderr, "[grootgpu] gather rank %d: sizes known at %.2f ms, sends enqueued at %.2f ms\n", c->rank, t_counts, now_ms());
         return;
     }
     // 2. rank 0: receive every shard at its place
@@ -1455,6 +1467,7 @@ void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, int to_h
         merged->d_hit_off = c->m_hit_off.as<uint32_t>(); merged->d_hits = c->m_hits.as<uint32_t>(); merged->d_pairs = reinterpret_cast<const grootgpu_pair*>(c->m_pairs.p);
         merged->d_rec_path = c->m_rec_path.as<uint32_t>(); merged->d_rec_pos = c->m_rec_pos.as<int32_t>();
     }
+    const double t_enq = now_ms();
     if (to_host) {
         for (int sec = 0; sec < n_sec; sec++) {
             const uint64_t total_elems = compact ? (sec == 0 ? pb[W] : cb[W]) : (sec == 0 ? rb[W] + 1 : sec == 1 ? hb[W] : sec == 2 ? pb[W] : cb[W]);
@@ -1468,6 +1481,8 @@ void gather_results(grootgpu_comm* c, const grootgpu_batch_result* loc, int to_h
             merged->rec_path = hs.rec_path.as<uint32_t>(); merged->rec_pos = hs.rec_pos.as<int32_t>();
         }
     }
+    if (trace) fprintf(stderr, "[grootgpu] gather rank 0: sizes known at %.2f ms, receives + merge enqueued at %.2f ms, host copies %s at %.2f ms\n", t_counts, t_enq,
+                       to_host == 1 ? "done" : to_host ? "enqueued" : "not asked for", now_ms());
 }
 
 void fnv_sink(void* ctx, const char* d, size_t n) { uint64_t& hsh = *static_cast<uint64_t*>(ctx); for (size_t i = 0; i < n; i++) { hsh ^= static_cast<uint8_t>(d[i]); hsh *= 1099511628211ULL; } }

@@ -193,6 +193,7 @@ typedef struct {
     uint32_t rec_path_bytes;
     const grootgpu_cpair* d_cpairs;
     const void* d_rec_path_c;
+    uint32_t result_set;               /* which of the handle's two alternating sets of result arrays this batch wrote (used by grootgpu_gather) */
 } grootgpu_batch_result;
 
 /* Replaces the per-read loop of theBoss.mapReads (src/pipeline/boss.go:134-203: RunMinHash ->
@@ -262,7 +263,10 @@ int grootgpu_comm_create(grootgpu_index* idx, const uint8_t id[GROOTGPU_COMM_ID_
  * the next grootgpu_gather or grootgpu_comm_sync), valid until the next grootgpu_gather. to_host = 1: host arrays too, the
  * call returns after the copy; to_host = 2: host arrays too, copied asynchronously — complete after the next
  * grootgpu_gather / grootgpu_comm_sync and valid until the gather after that (two alternating sets). Other ranks may pass
- * merged = NULL. The transfer overlaps the next align call of every rank. */
+ * merged = NULL. The transfer overlaps the next align call of every rank; the call itself waits for every rank's sizes
+ * (one small all-gather), so a host that does not want to wait for the slowest rank may issue it from a second thread
+ * while the first already runs the next align call on the same handle — the one exception to "calls on a handle are
+ * serialised" (a gather must have returned before the align call after next starts). */
 int grootgpu_gather(grootgpu_comm* comm, const grootgpu_batch_result* local, int to_host, grootgpu_batch_result* merged);
 /* Collective: waits for the gathers and the weight ring; afterwards rank 0's index holds the graph weights of everything
  * mapped so far on all ranks (grootgpu_weights / _prune / _graph_save_gfa on rank 0), the other ranks' weights are zero. */

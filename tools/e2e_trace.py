@@ -18,9 +18,13 @@ idx = api.Index.build(msa_dir=msa_dir, k=31, S=21, w=L)
 blob, off = synth.synth_reads(n, L, synth.db_sequences(msa_dir), seed=42)
 h_seq = torch.from_numpy(blob).pin_memory()
 h_off = torch.from_numpy(off.view(np.int64)).pin_memory()
-for it in range(4):
-    if it == 3:
-        os.environ["GROOTGPU_TRACE"] = "1"
-    t0 = time.perf_counter()
-    raw = idx.map_reads_raw(h_seq.data_ptr(), h_off.data_ptr(), n, 0.99, project_on_device=True)
-    print("call %d: %.2f ms wall, %.2f ms first copy-in to last copy-out, device %.2f ms" % (it, (time.perf_counter() - t0) * 1e3, raw.ms[0], raw.ms[1] + raw.ms[2] + raw.ms[3]))
+for chunk in (os.environ.get("GROOTGPU_CHUNK_READS", "1600000"), "2000000", "2500000"):
+    os.environ["GROOTGPU_CHUNK_READS"] = chunk
+    os.environ.pop("GROOTGPU_TRACE", None)
+    for it in range(5):
+        if it == 4 and chunk == "1600000":
+            os.environ["GROOTGPU_TRACE"] = "1"
+        t0 = time.perf_counter()
+        raw = idx.map_reads_raw(h_seq.data_ptr(), h_off.data_ptr(), n, 0.99, project_on_device=True, compact=True)
+        wall = (time.perf_counter() - t0) * 1e3
+    print("chunk %s: %.2f ms wall (%.1f M reads/s), %.2f ms first copy-in to last copy-out, device %.2f ms" % (chunk, wall, n / wall / 1e3, raw.ms[0], raw.ms[1] + raw.ms[2] + raw.ms[3]))
