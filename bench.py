@@ -6,10 +6,12 @@ alignment -> ordered graph weighting) over one batch of synthetic reads per GPU.
 BASELINE.json configs[2] (C3: 10 M x 100 bp, arg-annot.90 -w 100, full align path); at N = 1 the line also carries
 C2 (seeding only, --noAlign) and C4 (10 M x 150 bp vs card.90 -w 150) under "other_configs".
 
-  value   the batch already resident in HBM, full result arrays left on the device, CUDA events on the launching
-          stream. N > 1: every rank maps its own shard, the result arrays are gathered to rank 0 over NCCL / NVLink
-          (grootgpu_gather) and merged there, the order-dependent f64 graph weights are chained rank after rank
-          (weight ring) — all of it, and the final drain, inside the timed region.
+  value   the batch already resident in HBM, result arrays (the compact BAM-oriented form: what the BAM writer consumes
+          and what crosses NVLink and PCIe) left on the device, CUDA events on the launching stream. N > 1: every rank
+          maps its own shard, the result arrays are gathered to rank 0 over NCCL / NVLink (grootgpu_gather) and merged
+          there, the order-dependent f64 graph weights are chained rank after rank (weight ring) — all of it, and the
+          final drain, inside the timed region. At N = 1 the line also gives the step with the full result arrays
+          (hit lists, 32-byte pairs, 8-byte records: round 1's output format) as `full_format`.
   e2e     the call a user makes: pinned HOST buffers -> grootgpu_align_batch (H2D, kernels, compact BAM-oriented result)
           -> host. N > 1: + gather to rank 0 and rank 0's device->host copy of the merged batch.
   --impl reference   the CPU restatement of the reference (oracle/, all host threads) on a bounded sample of the
@@ -243,10 +245,11 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
 
     seqs = synth.db_sequences(msa_dir)
     blob, off = synth.synth_reads(n, L, seqs, seed=42 + rank)      # weak scaling: rank r maps reads [r*n, (r+1)*n) of the global batch
-    h_seq = torch.from_numpy(blob).pin_memory()
-    h_off = torch.from_numpy(off.view(np.int64)).pin_memory()
+    p_seq, p_off = api.PinnedBuffer(n * L), api.PinnedBuffer(8 * (n + 1))      # pinned host input buffers (grootgpu_host_alloc)
+    p_seq.array[:] = blob
+    p_off.array[:] = off.view(np.uint8)
     d_seq = torch.zeros(n * L + 64, dtype=torch.uint8, device=dev)
-    d_seq[: n * L].copy_(h_seq)
+    d_seq[: n * L].copy_(torch.from_numpy(blob))
     d_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).to(dev)
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -263,8 +266,8 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
             last_merged[0] = pending[0].result()
         pending[0] = pool.submit(comm.gather, raw, to_host)
 
-    def step_device():
-        raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, THRESHOLD, no_align=no_align, stream=stream, project_on_device=True)
+    def step_device(compact=True):
+        raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, THRESHOLD, no_align=no_align, stream=stream, project_on_device=True, compact=compact)
         if comm:
             gather_async(raw, 0)   # the one collective of the path: result arrays to rank 0 over NVLink, merged there
         return raw, last_merged[0]
@@ -283,7 +286,7 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
 
     def step_e2e():
         t0 = time.perf_counter()
-        raw = idx.map_reads_raw(h_seq.data_ptr(), h_off.data_ptr(), n, THRESHOLD, no_align=no_align, project_on_device=True, compact=True,
+        raw = idx.map_reads_raw(p_seq.ptr, p_off.ptr, n, THRESHOLD, no_align=no_align, project_on_device=True, compact=True,
                                 results_on_device=comm is not None)
         t1 = time.perf_counter()
         if comm:
@@ -328,6 +331,24 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
         merged = last_merged[0]
         merged_check = dict(reads=int(merged.n_reads), pairs=int(merged.n_pairs), records=int(merged.n_records), mapped=int(merged.mapped))
 
+    # ---- the same step with the full result arrays (round 1's output format), N = 1 only ----
+    full_format = None
+    if world == 1:
+        for _ in range(3):
+            step_device(compact=False)
+        drain()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fsteps = max(3, steps // 2)
+        f0.record()
+        for _ in range(fsteps):
+            step_device(compact=False)
+        drain()
+        f1.record()
+        torch.cuda.synchronize()
+        fms = f0.elapsed_time(f1) / fsteps
+        full_format = {"value": n / (fms / 1000.0), "unit": UNIT, "ms_per_step": fms, "steps": fsteps,
+                       "output": "hit_off / hits / 32-byte pairs / (u32 path, i32 pos) records, left on the device"}
+
     # ---- e2e: pinned host buffers through the C ABI, compact result to the host ----
     for _ in range(max(1, warmup // 2)):
         raw_e, merged_e = step_e2e()
@@ -356,7 +377,7 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
         "align_screen": raw.n_pairs * (L + 16 + 8) + raw.n_hits * 32,            # read + pair bookkeeping + window records
         "align_walk": raw.n_pairs * (L + 16 + 32 + 8 + 32),                      # re-read read + window meta + pair out + locus + path bitset
         "align_finish": 0,
-        "align_emit": raw.n_pairs * (32 + 8 + 32) + raw.n_records * 8,           # pair + locus + bitset in, 8-byte records out
+        "align_emit": raw.n_pairs * (32 + 8 + 32 + 16) + raw.n_records * raw.rec_path_bytes,   # pair + locus + bitset in, 16-byte compact pair + path ids out
         "project": raw.n_pairs * 40,                                             # pair in; the (node, f64) items are internal traffic
         "project_accumulate": 0,
     }
@@ -408,18 +429,20 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
     if comm:
         comm.close()
     idx.close()
-    del d_seq, d_off, h_seq, h_off
+    del d_seq, d_off
+    p_seq.free(); p_off.free()
     torch.cuda.empty_cache()
     par = "reads sharded over %d GPU(s), index replicated" % world
     if world > 1:
         par += "; per step ONE NCCL gather of the result arrays to rank 0 (merged on its device) + the weight vector sent rank to rank (f64 chains in global read order)"
     return {
-        "value": value, "ms_per_step": dev_ms / steps, "mapping_stream_ms_per_step": map_ms / steps,
+        "value": value, "ms_per_step": dev_ms / steps, "mapping_stream_ms_per_step": map_ms / steps, "full_format": full_format,
         "config": {"workload": cfg["workload"], "config_id": name, "reads_per_gpu_per_step": n, "read_len": L, "threshold": THRESHOLD, "index_windows": info["windows"],
+                   "output": "compact records (16-byte pairs + %d-byte path ids); graph weights on the device" % raw.rec_path_bytes,
                    "l2": "inputs (%.2f GB of reads per step) are larger than the 126 MB L2; no explicit flush" % (n * L / 1e9),
                    "parallelism": par, "per_read": stats, "index_build_s": t_index, "merged_on_rank0": merged_check},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(d2h),
-                "h2d_GBps_per_rank": h2d / (e2e_s / steps) / 1e9, "d2h_GBps_rank0": d2h / (e2e_s / steps) / 1e9,
+                "h2d_GBps_per_rank": h2d / (e2e_s / steps) / 1e9, "h2d_GBps_all_ranks": h2d * world / (e2e_s / steps) / 1e9, "d2h_GBps_rank0": d2h / (e2e_s / steps) / 1e9,
                 "includes": "pinned host buffers -> grootgpu_align_batch (H2D in chunks on two lanes overlapped with the kernels: sketch + query + align + ordered graph "
                             "weighting) -> compact result (16-byte pairs + %d-byte path ids) to the host%s" % (recw, "; N > 1: results kept on the device, gathered to rank 0 over "
                             "NVLink, merged, copied to rank 0's host (asynchronously, drained inside the timed region)" if world > 1 else ""),
@@ -445,7 +468,7 @@ def run_ours(args):
             "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": ctx.world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic", "config": res["config"], "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "kernel_ms": res["kernel_ms"],
-            "mapping_stream_ms_per_step": res["mapping_stream_ms_per_step"],
+            "mapping_stream_ms_per_step": res["mapping_stream_ms_per_step"], "full_format": res["full_format"],
             "roofline": res["roofline"], "cpu_baseline": res["cpu_baseline"], "clocks": res["clocks"],
         }
         if others:

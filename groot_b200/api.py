@@ -156,6 +156,21 @@ def int_issue_peak(device=0):
     return dict(imad=out[0], alu=out[1], mixed=out[2])
 
 
+class PinnedBuffer:
+    """Pinned host memory from grootgpu_host_alloc, viewed as a numpy uint8 array (`.array`); `.ptr` for the raw-pointer calls."""
+
+    def __init__(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().grootgpu_host_alloc(C.byref(p), max(1, int(nbytes))))
+        self.ptr, self.nbytes = p.value, int(nbytes)
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(max(1, int(nbytes)),))[: int(nbytes)]
+
+    def free(self):
+        if self.ptr:
+            lib().grootgpu_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+
 def _np(ptr, n, dtype):
     if n == 0:
         return np.zeros(0, dtype=dtype)

@@ -1516,7 +1516,9 @@ int grootgpu_device_count(int* n) {
 }
 int grootgpu_host_alloc(void** ptr, size_t bytes) {
     if (!ptr) return fail(GROOTGPU_ERR_ARG, "null argument");
-    if (cudaHostAlloc(ptr, bytes, cudaHostAllocDefault) != cudaSuccess) return fail(GROOTGPU_ERR_CUDA, "cudaHostAlloc failed");
+    // GROOTGPU_HOST_ALLOC_WC=1: write-combined pinned memory (input buffers the host only writes: the DMA reads skip the CPU caches)
+    const char* wc = getenv("GROOTGPU_HOST_ALLOC_WC");
+    if (cudaHostAlloc(ptr, bytes, wc && *wc == '1' ? cudaHostAllocWriteCombined : cudaHostAllocDefault) != cudaSuccess) return fail(GROOTGPU_ERR_CUDA, "cudaHostAlloc failed");
     return GROOTGPU_OK;
 }
 int grootgpu_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? GROOTGPU_OK : fail(GROOTGPU_ERR_CUDA, "cudaFreeHost failed"); }
