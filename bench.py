@@ -267,7 +267,10 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
         pending[0] = pool.submit(comm.gather, raw, to_host)
 
     def step_device(compact=True):
-        raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, THRESHOLD, no_align=no_align, stream=stream, project_on_device=True, compact=compact)
+        # stream=None: the library's own compute stream (it sits between the priorities of the f64 chains and of the gather).
+        # The call returns after the batch's kernels have finished, so the events recorded on torch's stream around the
+        # loop still bracket all of the device work.
+        raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, THRESHOLD, no_align=no_align, stream=None, project_on_device=True, compact=compact)
         if comm:
             gather_async(raw, 0)   # the one collective of the path: result arrays to rank 0 over NVLink, merged there
         return raw, last_merged[0]

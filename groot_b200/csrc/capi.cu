@@ -269,8 +269,14 @@ struct Workspace {
         rset ^= 1;
     }
     void create() {
-        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&st_side, cudaStreamNonBlocking));
+        // priorities: the ordered f64 chains (st_acc of the index: short, latency-bound, and on N GPUs the one serial
+        // resource of the whole job) run first, the mapping kernels next, the multi-GPU gather (st_gather of the
+        // communicator) takes what is left — it has a whole batch time to finish
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        const int prio_map = prio_hi < prio_lo ? prio_lo - 1 : prio_lo;
+        CK(cudaStreamCreateWithPriority(&stream, cudaStreamNonBlocking, prio_map));
+        CK(cudaStreamCreateWithPriority(&st_side, cudaStreamNonBlocking, prio_map));
         for (auto& e : ev) CK(cudaEventCreate(&e));
         for (auto& e : kev) CK(cudaEventCreate(&e));
         for (cudaEvent_t* e : {&ev_fork, &ev_join, &ev_done, &ev_out[0], &ev_out[1], &acc[0].ev_sorted, &acc[0].ev_done, &acc[1].ev_sorted, &acc[1].ev_done})
@@ -471,7 +477,11 @@ void index_to_device(grootgpu_index* ix) {
     ix->len_params.need(60002 * sizeof(LenParam));   // never reallocated: the lanes' kernels read it while prepare_params extends it
     CK(cudaStreamCreateWithFlags(&ix->st_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&ix->st_out, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&ix->st_acc, cudaStreamNonBlocking));
+    {
+        int prio_lo = 0, prio_hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CK(cudaStreamCreateWithPriority(&ix->st_acc, cudaStreamNonBlocking, prio_hi));   // see Workspace::create
+    }
     {
         uint32_t max_paths = 0;
         for (uint32_t g = 0; g < h.n_graphs; g++) max_paths = std::max(max_paths, h.n_paths_of(g));
@@ -717,7 +727,7 @@ void acc_enqueue(grootgpu_index* ix, Workspace* w, AccSlot* slot, uint32_t n_ite
             const uint32_t n_nodes = static_cast<uint32_t>(ix->h.nodes.size());
             const int ablocks = std::max(1, std::min<int>(static_cast<int>((n_nodes + 7) / 8), sms * 8));
             CK(cudaEventRecord(slot->ev_t0, sa));
-            project_accumulate_kernel<<<ablocks, 256, 0, sa>>>(slot->keys.as<uint32_t>(), slot->vals.as<double>(), n_items, n_nodes, ix->d_kmer_freq); launches++;
+            project_accumulate_kernel<<<ablocks, kAccWarps * 32, 0, sa>>>(slot->keys.as<uint32_t>(), slot->vals.as<double>(), n_items, n_nodes, ix->d_kmer_freq); launches++;
             CK(cudaGetLastError());
             CK(cudaEventRecord(slot->ev_t1, sa));
             slot->timed = true;
@@ -1745,7 +1755,11 @@ int grootgpu_comm_create(grootgpu_index* idx, const uint8_t id[GROOTGPU_COMM_ID_
         memcpy(&a, id, NCCL_UNIQUE_ID_BYTES); memcpy(&b, id + NCCL_UNIQUE_ID_BYTES, NCCL_UNIQUE_ID_BYTES);
         NK(nccl().CommInitRank(&c->ring, world_size, a, rank));
         NK(nccl().CommInitRank(&c->gath, world_size, b, rank));
-        CK(cudaStreamCreateWithFlags(&c->st_gather, cudaStreamNonBlocking));
+        {
+            int prio_lo = 0, prio_hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            CK(cudaStreamCreateWithPriority(&c->st_gather, cudaStreamNonBlocking, prio_lo));   // lowest: see Workspace::create
+        }
         for (cudaEvent_t* e : {&c->ev_sent[0], &c->ev_sent[1], &c->ev_local}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         c->d_counts.need(8ull * kCountWords * (world_size + 2));
         CK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 8ull * kCountWords * (world_size + 2), cudaHostAllocDefault));

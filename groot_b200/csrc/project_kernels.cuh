@@ -100,16 +100,21 @@ __global__ void __launch_bounds__(256) project_expand_kernel(DevIndex ix, Projec
 }
 
 // keys sorted (stable): ONE WARP PER NODE. The additions of one node form a dependent DADD chain by definition (that IS
-// the reference's order), and the hottest node's chain is the critical path of the whole kernel — so everything else
-// is taken off it: lanes 0/1 find the node's segment [lower_bound(node), lower_bound(node + 1)) by binary search, the
-// 32 lanes load 32 addends at a time (coalesced, the next 32 prefetched while the current ones are added) and every
-// lane runs the same chain, fetching addend l from lane l by shuffle (shuffles do not depend on the accumulator, so
-// they pipeline under the DADD latency). One thread per segment with loads ahead of use took ~90 cycles per addend
-// (profiles/r01_ncu_summary.md); this form is bounded by the DADD latency alone.
-__global__ void __launch_bounds__(256) project_accumulate_kernel(const uint32_t* __restrict__ keys, const double* __restrict__ vals,
-                                                                 uint32_t n, uint32_t n_nodes,
-                                                                 double* __restrict__ kmer_freq) {
-    const uint32_t lane = threadIdx.x & 31;
+// the reference's order), and the hottest node's chain is the critical path of the whole kernel — on N GPUs of the whole
+// job, since the chains of the ranks run one after the other — so everything else is taken off it: lanes 0/1 find the
+// node's segment [lower_bound(node), lower_bound(node + 1)) by binary search, the 32 lanes load 64 addends at a time
+// (coalesced 16-byte loads, the next 64 requested before the current ones are added) and park them in the warp's slice of
+// shared memory; the chain itself is then one 16-byte shared-memory load per two additions. 1.5 issue slots per addend
+// (a shuffle-fed chain needs 3): the kernel shares its SMs with the mapping kernels of the following batch, and every
+// instruction of the chain has to win an issue slot against them.
+constexpr int kAccWarps = 8;     // warps (nodes in flight) per block
+constexpr int kAccChunk = 64;    // addends per shared-memory refill
+
+__global__ void __launch_bounds__(kAccWarps * 32) project_accumulate_kernel(const uint32_t* __restrict__ keys, const double* __restrict__ vals,
+                                                                            uint32_t n, uint32_t n_nodes,
+                                                                            double* __restrict__ kmer_freq) {
+    __shared__ double2 park[kAccWarps][kAccChunk / 2];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t gwarp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, total_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t node = gwarp; node < n_nodes; node += total_warps) {
         uint32_t lo = 0, hi = n;                              // lower_bound(node + (lane & 1))
@@ -118,17 +123,30 @@ __global__ void __launch_bounds__(256) project_accumulate_kernel(const uint32_t*
         const uint32_t start = __shfl_sync(0xffffffffu, lo, 0), end = __shfl_sync(0xffffffffu, lo, 1);
         if (start >= end) continue;
         double acc = kmer_freq[node];
-        double v = start + lane < end ? vals[start + lane] : 0.0;
-        for (uint32_t base = start; base < end; base += 32) {
-            const uint32_t nxt = base + 32 + lane;
-            const double vn = nxt < end ? vals[nxt] : 0.0;
-            const uint32_t cnt = end - base < 32u ? end - base : 32u;
+        auto fetch = [&](uint32_t base) {                     // this lane's two addends of the chunk starting at `base` (0.0 past the end: never added)
+            const uint32_t i = base + 2 * lane;
+            double2 v;
+            v.x = i < end ? vals[i] : 0.0;
+            v.y = i + 1 < end ? vals[i + 1] : 0.0;
+            return v;
+        };
+        double2 mine = fetch(start);
+        for (uint32_t base = start; base < end; base += kAccChunk) {
+            __syncwarp();                                     // the previous chunk has been consumed by every lane
+            park[wib][lane] = mine;
+            __syncwarp();
+            mine = fetch(base + kAccChunk);                   // in flight while this chunk is added
+            const uint32_t cnt = end - base < static_cast<uint32_t>(kAccChunk) ? end - base : static_cast<uint32_t>(kAccChunk);
+            if (cnt == kAccChunk) {
 #pragma unroll
-            for (uint32_t l = 0; l < 32; l++) {
-                const double x = __shfl_sync(0xffffffffu, v, l);
-                if (l < cnt) acc = __dadd_rn(acc, x);        // node.go:25-28, in read order
+                for (uint32_t j = 0; j < kAccChunk / 2; j++) {
+                    const double2 v = park[wib][j];
+                    acc = __dadd_rn(acc, v.x);                // node.go:25-28, in read order
+                    acc = __dadd_rn(acc, v.y);
+                }
+            } else {
+                for (uint32_t j = 0; j < cnt; j++) acc = __dadd_rn(acc, reinterpret_cast<const double*>(park[wib])[j]);
             }
-            v = vn;
         }
         if (lane == 0) kmer_freq[node] = acc;
     }
