@@ -363,6 +363,11 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
     drain()
     e2e_s = ctx.reduce(time.perf_counter() - t0, "MAX")
     e2e_parts = {k: v / steps for k, v in e2e_parts.items()}
+    if world > 1:          # every rank's time inside grootgpu_align_batch (H2D + kernels): shows how evenly the host feeds the GPUs
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = e2e_parts["align_batch_ms"]
+        ctx.dist.all_reduce(t)
+        e2e_parts["align_batch_ms_by_rank"] = [round(x, 2) for x in t.tolist()]
     ctx.barrier()
     e2e_value = total_reads * steps / e2e_s
     recw = raw_e.rec_path_bytes
