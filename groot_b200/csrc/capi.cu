@@ -310,7 +310,8 @@ struct grootgpu_index {
     DBuf len_params;                   // per read length: (K, L, eq_min), shared by the lanes (prepare_params, under params_mu)
     std::mutex params_mu;
     HBuf r_hit_off, r_hits, r_pairs, r_rec_path, r_rec_pos, r_sketches, r_cpairs, r_rec_c;   // batch-wide host result arrays
-    Workspace ws[2];                   // two lanes: the chunked host path runs consecutive chunks on alternating lanes
+    static constexpr uint32_t kLanes = 3, kInBufs = 2 * kLanes;
+    Workspace ws[kLanes];              // lanes: the chunked host path runs consecutive chunks on the lanes in turn
     cudaStream_t st_in = nullptr, st_out = nullptr;   // copy-in / copy-out of the chunked host path
     cudaStream_t st_acc = nullptr;     // the ordered f64 chains of the graph weighting (and the multi-GPU weight ring): runs behind the batches
     std::mutex acc_mu;                 // enqueues on st_acc come from both lanes' host threads
@@ -320,8 +321,8 @@ struct grootgpu_index {
     // batch-wide result arrays on the DEVICE (chunked host path with results_on_device): two sets, alternating per call
     struct DevResult { DBuf hit_off, hits, pairs, rec_path, rec_pos, cpairs, rec_c; } bres[2];
     int call_parity = 0;               // flips with every align call: which result set (workspace or bres) the call writes
-    DBuf in_seq[4], in_off64[4], in_off32[4];
-    cudaEvent_t ev_in[4] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
+    DBuf in_seq[kInBufs], in_off64[kInBufs], in_off32[kInBufs];
+    cudaEvent_t ev_in[kInBufs] = {}, ev_t0 = nullptr, ev_t1 = nullptr;
     // graph weights live on the device once a batch was projected there; the host copy is refreshed lazily
     double* d_kmer_freq = nullptr;
     unsigned long long* d_kmer_total = nullptr;
@@ -566,7 +567,7 @@ LenParam param_for(grootgpu_index* ix, uint32_t q, double t) {
 
 // make sure len_params[len] is on the device for every len in [min_len, max_len] and the tables exist
 void prepare_params(grootgpu_index* ix, uint32_t min_len, uint32_t max_len, double t) {
-    std::lock_guard<std::mutex> lock(ix->params_mu);   // the two lanes of the chunked host path share the tables
+    std::lock_guard<std::mutex> lock(ix->params_mu);   // the lanes of the chunked host path share the tables
     const uint32_t k = ix->h.p.k;
     if (ix->lp_threshold == t && min_len >= ix->lp_min && max_len <= ix->lp_max) return;
     uint32_t lo = std::min(min_len, ix->lp_threshold == t ? ix->lp_min : min_len);
@@ -717,7 +718,7 @@ void ring_send(grootgpu_index* ix) {
 
 // slot == nullptr: the batch / chunk has nothing to add, but still takes its turn (ordering hooks, ring)
 void acc_enqueue(grootgpu_index* ix, Workspace* w, AccSlot* slot, uint32_t n_items, int sms, uint32_t& launches) {
-    if (w->acc_before) w->acc_before();                            // chunk order across the two lanes (host side)
+    if (w->acc_before) w->acc_before();                            // chunk order across the lanes (host side)
     {
         std::lock_guard<std::mutex> lock(ix->acc_mu);
         cudaStream_t sa = ix->st_acc;
@@ -828,6 +829,11 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
             if (lp.eq_min <= S && lp.K != 0 && lp.L != 1) two_pass = false;
         }
     }
+    // 2-bit copies of the seeded reads (both orientations) for the packed walk; reads longer than 1 024 bases go byte-wise
+    uint32_t nw32 = 0;   // words of 16 bases per orientation: 8 (<= 128 bases) .. 64 (<= 1024)
+    if (!prm->no_align && max_len <= 1024) { nw32 = 8; while (nw32 * 16u < max_len) nw32 *= 2; }
+    if (nw32) { w->reads2.need(8ull * nw32 * n + 64); w->read_ok2.need(n); w->read_oh.need(16ull * n); }
+    bool packed_by_seed = false;
     CK(cudaEventRecord(w->ev[0], st));
     if (two_pass) {
         w->seed_q.need(4ull * n);
@@ -843,6 +849,10 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         const uint32_t qstride = (((max_len + 7u) >> 2) | 1u) * 4u;                 // bytes per read slot: odd number of words
         sq.tile_bytes = qstride * kTileReads <= 20 * 1024 ? qstride * kTileReads : 0u;   // per warp; very long reads: straight from global
         const size_t qsmem = sizeof(SeedTabs) + 64 + 2ull * sq.tile_bytes * (kSeedThreads / 32);
+        if (nw32 && sq.tile_bytes) {   // the queued pass holds every read it hashes in shared memory: it packs the seeded ones on the way
+            sq.reads2 = w->reads2.as<uint32_t>(); sq.read_ok2 = w->read_ok2.as<uint8_t>(); sq.read_oh = w->read_oh.as<uint4>(); sq.nw32 = nw32;
+            packed_by_seed = true;
+        }
         kbegin(0); seed_queued_dispatch(S, ix->d, sq, k, qsmem, std::max(seed_blocks, 1), st); launches++; kend();
     } else if (generic) {
         const int gblocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
@@ -880,10 +890,6 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
         fa.n_overflow = w->qcount.as<uint32_t>() + 5;   // zeroed with the other scalars at the start of the batch
         w->seed_q.need(4ull * n);                       // the prescreen's queue is free again: reused for the reads with more than HSTAGE hits
         fa.overflow_q = w->seed_q.as<uint32_t>();
-        // 2-bit copies of the seeded reads (both orientations) for the packed walk; reads longer than 256 bases go byte-wise
-        uint32_t nw32 = 0;   // words of 16 bases per orientation: 8 (<= 128 bases) .. 64 (<= 1024); longer reads go byte-wise
-        if (!prm->no_align && max_len <= 1024) { nw32 = 8; while (nw32 * 16u < max_len) nw32 *= 2; }
-        if (nw32) { w->reads2.need(8ull * nw32 * n + 64); w->read_ok2.need(n); w->read_oh.need(16ull * n); }
         fa.reads2 = w->reads2.as<uint32_t>(); fa.read_ok2 = w->read_ok2.as<uint8_t>(); fa.read_oh = w->read_oh.as<uint4>(); fa.nw32 = nw32;
         int fill_blocks = static_cast<int>(std::min<uint64_t>((static_cast<uint64_t>(n) + kSeedThreads - 1) / kSeedThreads, static_cast<uint64_t>(sms) * 8));
         kbegin(1);
@@ -892,7 +898,7 @@ void run_batch(grootgpu_index* ix, Workspace* w, const uint8_t* d_seq, const uin
             fill_refill_generic_kernel<<<fill_blocks, kSeedThreads, 0, st>>>(ix->d, fa);
         } else fill_dispatch(S, ix->d, fa, k, fill_blocks, st);
         launches += 2;
-        if (nw32) { pack_reads_kernel<<<std::max(1, std::min<int>((n + 31) / 32, sms * 8)), 256, 0, st>>>(fa); launches++; }
+        if (nw32 && !packed_by_seed) { pack_reads_kernel<<<std::max(1, std::min<int>((n + 31) / 32, sms * 8)), 256, 0, st>>>(fa); launches++; }
         kend();
         CK(cudaGetLastError());
         // ---- (read, graph) segment starts ----
@@ -1140,12 +1146,12 @@ uint32_t chunk_reads_setting() {   // reads per pipeline chunk; GROOTGPU_CHUNK_R
     return static_cast<uint32_t>(x > 0 ? x : 2000000l);
 }
 
-// Host buffers in, host results out, as a pipeline over chunks of reads on TWO LANES (workspaces with their own
-// streams, each driven by its own host thread): chunk c runs on lane c & 1 while
+// Host buffers in, host results out, as a pipeline over chunks of reads on kLanes LANES (workspaces with their own
+// streams, each driven by its own host thread): chunk c runs on lane c % kLanes while
 //   * the bases and offsets of the next chunks are copied in (st_in, up to two chunks ahead),
 //   * the result arrays of finished chunks are copied out (st_out) straight to their final place in the batch-wide
 //     host arrays, after a small kernel has rebased the chunk-local indices,
-//   * the other lane runs the neighbouring chunk: its kernels fill the GPU during this chunk's latency-bound tails
+//   * the other lanes run the neighbouring chunks: their kernels fill the GPU during this chunk's latency-bound tails
 //     (stragglers of the walk, the ordered f64 chains) and during the host round trips that size its buffers.
 // What stays ordered: chunk c's graph weighting chain runs after chunk c-1's (an event between the lanes' side
 // streams), and the batch-wide offsets of chunk c are fixed once chunk c-1 has published its totals — so every
@@ -1216,11 +1222,11 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
     auto now_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(); };
     const int device = ix->device;
 
-    // copy-in of chunk c into input buffer c & 3; issued in chunk order, at most two chunks ahead of the chunk that
-    // is starting (buffer c & 3 was last read by chunk c - 4, which completed before chunk c - 2 could start)
+    // copy-in of chunk c into input buffer c % kInBufs; issued in chunk order, at most kLanes chunks ahead of the chunk that
+    // is starting (that buffer was last read by chunk c - 2 * kLanes, which completed before chunk c - kLanes — same lane — could start)
     auto issue_inputs_upto = [&](uint32_t last) {   // sh.mu held
         for (; sh.inputs_issued <= last && sh.inputs_issued < C; sh.inputs_issued++) {
-            const uint32_t c = sh.inputs_issued, r0 = cb[c], nc = cb[c + 1] - r0, b = c & 3;
+            const uint32_t c = sh.inputs_issued, r0 = cb[c], nc = cb[c + 1] - r0, b = c % grootgpu_index::kInBufs;
             const uint64_t bytes = seq_off[cb[c + 1]] - seq_off[r0];
             ix->in_seq[b].need(bytes + 64); ix->in_off64[b].need(8ull * (nc + 1)); ix->in_off32[b].need(4ull * (nc + 1));
             CK(cudaMemcpyAsync(ix->in_seq[b].p, seq + seq_off[r0], bytes, cudaMemcpyHostToDevice, st_in));
@@ -1235,13 +1241,13 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
         cudaStream_t st = w->stream;
         try {
             pick_device(device);
-            for (uint32_t c = lane; c < C; c += 2) {
-                const uint32_t r0 = cb[c], nc = cb[c + 1] - r0, b = c & 3;
+            for (uint32_t c = lane; c < C; c += grootgpu_index::kLanes) {
+                const uint32_t r0 = cb[c], nc = cb[c + 1] - r0, b = c % grootgpu_index::kInBufs;
                 const double t_c0 = now_ms();
                 {
                     std::unique_lock<std::mutex> lk(sh.mu);
                     if (sh.failed) return;
-                    issue_inputs_upto(c + 2);
+                    issue_inputs_upto(c + grootgpu_index::kLanes);
                 }
                 CK(cudaStreamWaitEvent(st, ix->ev_in[b], 0));
                 poke(st, {{w->len_minmax.as<uint32_t>(), 0xffffffffu}, {w->len_minmax.as<uint32_t>() + 1, 0u}});
@@ -1337,12 +1343,11 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
 
     CK(cudaEventRecord(ix->ev_t0, st_in));
     for (Workspace& w : ix->ws) { w.len_minmax.need(16); w.acc_before = nullptr; w.acc_after = nullptr; }
-    if (C > 1) {
-        std::thread helper(lane_main, 1u);
+    {
+        std::vector<std::thread> helpers;
+        for (uint32_t l = 1; l < grootgpu_index::kLanes && l < C; l++) helpers.emplace_back(lane_main, l);
         lane_main(0u);
-        helper.join();
-    } else {
-        lane_main(0u);
+        for (auto& t : helpers) t.join();
     }
     for (Workspace& w : ix->ws) { w.acc_before = nullptr; w.acc_after = nullptr; }
     if (sh.failed) std::rethrow_exception(sh.error);

@@ -373,7 +373,53 @@ struct SeedArgs {
     uint32_t tile_bytes;       // shared-memory bytes per tile buffer (0 => read straight from global)
     uint32_t* queue;           // SEED_PRESCREEN: reads whose first band found a bucket (out); SEED_QUEUED: the reads to process (in)
     uint32_t* n_queue;         // device scalar
+    // SEED_QUEUED with staged reads: the 2-bit copies of the seeded reads for the align kernels are written here, from the
+    // bases the warp already holds in shared memory (layout: pack_reads_kernel); nw32 == 0: not wanted / done by pack_reads_kernel
+    uint32_t* reads2;
+    uint8_t* read_ok2;
+    uint4* read_oh;
+    uint32_t nw32;
 };
+
+// reverse the order of the sixteen 2-bit groups of a word
+__device__ __forceinline__ uint32_t rev_pairs16(uint32_t x) {
+    const uint32_t r = __brev(x);
+    return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+}
+
+// One thread packs one read whose bases lie in shared memory: the same output as pack_reads_kernel (2-bit forward copy,
+// reverse complement shifted to the end of its words, validity flag, one-hot 9-base prefixes of both strands).
+__device__ __forceinline__ void pack_read_from_smem(const uint8_t* __restrict__ p, uint32_t len, uint32_t nw32, uint32_t* __restrict__ out,
+                                                    uint8_t* __restrict__ ok_out, uint4* __restrict__ oh_out) {
+    bool ok = len <= nw32 * 16u;
+    if (ok) {
+        for (uint32_t j = 0; j < nw32; j++) {
+            uint32_t acc = 0;
+            const uint32_t b0 = 16u * j;
+            const uint32_t nb = b0 < len ? (len - b0 < 16u ? len - b0 : 16u) : 0u;
+#pragma unroll
+            for (uint32_t t = 0; t < 16u; t++) {
+                if (t < nb) {
+                    const uint32_t b = p[b0 + t];
+                    const uint32_t c = (b >> 1) & 3u;
+                    ok = ok && b == ((0x47544341u >> (8u * c)) & 0xffu);     // 'A' 'C' 'T' 'G' by code: anything else (lower case, N) goes byte-wise
+                    acc |= c << (2u * t);
+                }
+            }
+            out[j] = acc;
+            out[nw32 + (nw32 - 1u - j)] = rev_pairs16(acc) ^ 0xAAAAAAAAu;
+        }
+    }
+    uint64_t f = 0, c = 0;
+    if (ok) {
+        for (uint32_t i = 0; i < 9u && i < len; i++) {
+            f |= static_cast<uint64_t>(1u << ((p[i] >> 1) & 3u)) << (4 * i);
+            c |= static_cast<uint64_t>(1u << (((p[len - 1u - i] >> 1) & 3u) ^ 2u)) << (4 * i);
+        }
+    }
+    *ok_out = ok ? 1 : 0;
+    *oh_out = make_uint4(static_cast<uint32_t>(f), static_cast<uint32_t>(f >> 4), static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 4));
+}
 
 // seed_kernel modes. SEED_FULL: every read gets its full sketch and probe in one pass. The two-pass form exploits
 // that most reads of a metagenome seed nowhere: SEED_PRESCREEN computes only the first band's MAXK sketch slots (a
@@ -547,6 +593,8 @@ __global__ void __launch_bounds__(kSeedThreads, MODE == SEED_PRESCREEN ? 8 : GRO
             // ---- probe + containment check: the warp's 32 reads pool their candidates (warp_probe) ----
             const uint32_t nh = warp_probe<S, MAXK>(ix, sk, lp, valid, lane, a.stage, r);
             if (live) a.n_hits[r] = nh;
+            if (MODE == SEED_QUEUED && a.nw32 != 0 && qread != nullptr && valid && nh != 0)   // a seeded read: its 2-bit copies for the align kernels, while the bases are at hand
+                pack_read_from_smem(qread, len, a.nw32, a.reads2 + static_cast<size_t>(r) * 2u * a.nw32, a.read_ok2 + r, a.read_oh + r);
         }
         __syncwarp();  // every lane is done with buffer `cur`
         cur ^= 1;
@@ -595,12 +643,6 @@ struct FillArgs {
     uint4* read_oh;                // [n] one-hot prefixes for the screen: x/y = bases [0,8) / [1,9) of the read, z/w = of its reverse complement
     uint32_t nw32;                 // words per orientation (16 bases each); 0 = packing off
 };
-
-// reverse the order of the sixteen 2-bit groups of a word
-__device__ __forceinline__ uint32_t rev_pairs16(uint32_t x) {
-    const uint32_t r = __brev(x);
-    return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
-}
 
 // 2-bit copies of the seeded reads for the align kernels, per read r at reads2 + r * 2 * nw32:
 //   words [0, nw32)        the read: base i in word i >> 4 at bits 2 * (i & 15), code pack_base2
