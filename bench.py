@@ -380,8 +380,8 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
     S = info["S"]
     fam_avg = {k: sum(v) / len(v) for k, v in fam_ms.items()}
     fam_bytes = {   # per launch family, for n reads
-        "seed": n * (L + 8 + 32 + 4) + raw.n_hits * (8 * S + 8),                # L + 8 + 32 + 8*S*c + 4 + 8*h with c := h
-        "fill": 4 * n + raw.n_hits * 13 + raw.mapped * (L + L // 2),            # hit counts in, hits + owner + segment flag out; seeded reads in, their 2-bit copies (both strands) out
+        "seed": n * (L + 8 + 32 + 4) + raw.n_hits * (8 * S + 8) + (0 if no_align else raw.mapped * (L // 2 + 17)),   # L + 8 + 32 + 8*S*c + 4 + 8*h with c := h; + the 2-bit copies (both strands), flag and one-hot prefixes of the seeded reads, written by the queued pass
+        "fill": 4 * n + raw.n_hits * 13,                                         # hit counts in, hits + owner + segment flag out
         "align_screen": raw.n_pairs * (L + 16 + 8) + raw.n_hits * 32,            # read + pair bookkeeping + window records
         "align_walk": raw.n_pairs * (L + 16 + 32 + 8 + 32),                      # re-read read + window meta + pair out + locus + path bitset
         "align_finish": 0,
