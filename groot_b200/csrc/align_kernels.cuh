@@ -321,12 +321,22 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
                                            uint32_t max_depth, DfsResult* res, uint32_t* __restrict__ trav_masks,
                                            PT* __restrict__ out_path = nullptr, int32_t* __restrict__ out_pos = nullptr) {
     uint32_t nrec = 0, ntrav = 0, depth = 0;
-    const uint32_t p0_off = ix.nodes[node0].path_off, p0_cnt = ix.nodes[node0].path_cnt;
+    uint32_t p0_off = 0, p0_cnt = 0;
+    if (EMIT) { p0_off = ix.nodes[node0].path_off; p0_cnt = ix.nodes[node0].path_cnt; }
     uint32_t cur = node0, off = off0, dist = 0;
     uint32_t cm[kMaskWordsInline];
 #pragma unroll
     for (int wi = 0; wi < kMaskWordsInline; wi++) cm[wi] = 0xffffffffu;
-    NodeRec nd = ix.nodes[cur];
+    // one 32-byte record per node step: sequence range, path bitset (graphs of <= 128 paths) and the out-edge of a linear chain
+    auto load_node = [&](uint32_t n) {
+        const uint4* q = reinterpret_cast<const uint4*>(ix.wnodes + n);
+        const uint4 a = __ldg(q), b = __ldg(q + 1);
+        WalkNode w;
+        w.seq_off = a.x; w.seq_len = a.y; w.edge = a.z; w.edge_cnt = a.w; w.mask[0] = b.x; w.mask[1] = b.y; w.mask[2] = b.z; w.mask[3] = b.w;
+        return w;
+    };
+    const bool inline_mask = mw <= kWalkMaskWords;
+    WalkNode nd = load_node(cur);
     if (off >= nd.seq_len || rlen == 0) { res->nrec = 0; res->ntrav = 0; return; }   // alignment.go:199-201
     while (true) {
         // ---- up to 16 bases of the current node ----
@@ -344,9 +354,15 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
         bool descend = false;
         if (mism == 0u) {
             uint32_t any = 0;
+            if (inline_mask) {
 #pragma unroll
-            for (int wi = 0; wi < kMaskWordsInline; wi++)
-                if (wi < mw) { cm[wi] &= ix.node_mask[nd.mask_off + wi]; any |= cm[wi]; }
+                for (int wi = 0; wi < static_cast<int>(kWalkMaskWords); wi++)
+                    if (wi < mw) { cm[wi] &= nd.mask[wi]; any |= cm[wi]; }
+            } else {
+#pragma unroll
+                for (int wi = 0; wi < kMaskWordsInline; wi++)
+                    if (wi < mw) { cm[wi] &= ix.node_mask[nd.mask[0] + wi]; any |= cm[wi]; }
+            }
             if (any != 0u) {
                 if (dist == rlen || nd.edge_cnt == 0) {           // alignment.go:229: full read matched OR sink node
                     if (EMIT) {
@@ -378,14 +394,14 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
                     }
                     ntrav++;
                 } else if (nd.edge_cnt == 1) {
-                    cur = ix.edges[nd.edge_off]; descend = true;
+                    cur = nd.edge; descend = true;                // the target itself: no edges[] access on a linear chain
                 } else if (depth < max_depth) {
-                    stack[depth].node = nd.edge_off + 1; stack[depth].edge_i = static_cast<uint16_t>(nd.edge_cnt - 1);
+                    stack[depth].node = nd.edge + 1; stack[depth].edge_i = static_cast<uint16_t>(nd.edge_cnt - 1);
                     stack[depth].dist = static_cast<uint16_t>(dist);
 #pragma unroll
                     for (int wi = 0; wi < kMaskWordsInline; wi++) if (wi < mw) mask_ws[depth * kMaskWordsInline + wi] = cm[wi];
                     depth++;
-                    cur = ix.edges[nd.edge_off]; descend = true;
+                    cur = ix.edges[nd.edge]; descend = true;
                 }
             }
         }
@@ -398,7 +414,7 @@ __device__ __forceinline__ void dfs_packed(const DevIndex& ix, uint32_t node0, u
             top.node++;
             if (--top.edge_i == 0) depth--;
         }
-        nd = ix.nodes[cur];
+        nd = load_node(cur);
         off = 0;
     }
     res->nrec = nrec; res->ntrav = ntrav;
@@ -626,9 +642,13 @@ __global__ void __launch_bounds__(256, 4) align_screen_kernel(DevIndex ix, Round
 // walk one try of pair s: 1 = aligned (the pair's outputs are filled), 0 = no path id from this try, -1 (PACKED_ONLY)
 // = the pair cannot take the packed walk (read with other bytes than ACGT or longer than the packed copy, graph of
 // more than 256 paths) and is left to the byte-wise walk of align_finish_kernel.
+// srow: 9 words of shared memory owned by this thread (or nullptr): reads of up to 128 bases are walked from a copy of their
+// packed words there — the walk touches them at every node step, and from global memory that was a sector per step.
+constexpr uint32_t kWalkReadWords = 9;
 template <bool PACKED_ONLY>
 __device__ __forceinline__ int walk_try(const DevIndex& ix, const AlignArgs& a, const uint8_t* lut, uint32_t s, uint32_t hb,
-                                        uint32_t m, uint32_t strand, uint32_t t, DfsFrame* stack, uint32_t* mask_ws, uint32_t depth_cap) {
+                                        uint32_t m, uint32_t strand, uint32_t t, DfsFrame* stack, uint32_t* mask_ws, uint32_t depth_cap,
+                                        uint32_t* srow = nullptr) {
     const WinRec wr = ix.wins[a.hits[m]];
     const uint32_t r = a.hit_read[hb];
     const uint32_t o = a.off[r], len = a.off[r + 1] - o;
@@ -642,6 +662,12 @@ __device__ __forceinline__ int walk_try(const DevIndex& ix, const AlignArgs& a, 
     if (a.nw32 && mw <= kMaskWordsInline && a.read_ok2[r]) {
         const uint32_t* rd2 = a.reads2 + static_cast<size_t>(r) * 2u * a.nw32 + (strand ? a.nw32 : 0u);
         const uint32_t base0 = (strand ? a.nw32 * 16u - len : 0u) + (stage == 3 ? 1u : 0u);
+        if (srow != nullptr && a.nw32 == 8u) {               // one sector in, then shared memory only
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(rd2)), hi = __ldg(reinterpret_cast<const uint4*>(rd2) + 1);
+            srow[0] = lo.x; srow[1] = lo.y; srow[2] = lo.z; srow[3] = lo.w; srow[4] = hi.x; srow[5] = hi.y; srow[6] = hi.z; srow[7] = hi.w;
+            srow[8] = 0u;                                      // only ever shifted into bases past the end of the read
+            rd2 = srow;
+        }
         dfs_packed<false>(ix, node, off0, rd2, base0, rlen, mw, ix.graph_has_n[wr.graph] != 0, stack, mask_ws, depth_cap, &res,
                           a.seg_mask + static_cast<size_t>(s) * kTravWords);
         inline_masks = res.ntrav * mw <= static_cast<uint32_t>(kTravWords);
@@ -670,6 +696,8 @@ __device__ __forceinline__ int walk_try(const DevIndex& ix, const AlignArgs& a, 
 }
 
 __global__ void __launch_bounds__(128, 8) align_walk_kernel(DevIndex ix, RoundArgs ra) {
+    __shared__ uint32_t s_read[128 * kWalkReadWords];          // row stride 9 words: conflict-free
+    uint32_t* srow = s_read + threadIdx.x * kWalkReadWords;
     const AlignArgs& a = ra.a;
     const uint32_t n_queue = *ra.n_queue;
     const uint32_t gthread = blockIdx.x * blockDim.x + threadIdx.x, total = gridDim.x * blockDim.x;
@@ -682,7 +710,7 @@ __global__ void __launch_bounds__(128, 8) align_walk_kernel(DevIndex ix, RoundAr
         const uint2 cand = ra.cand[s];
         if (cand.x == kNoCand) continue;                        // try list exhausted: the default (unaligned) result stands
         const uint32_t hb = a.seg_begin[s];
-        const int rc = walk_try<true>(ix, a, nullptr, s, hb, hb + (cand.x >> 1), cand.x & 1u, cand.y, stack, mask_ws, depth_cap);
+        const int rc = walk_try<true>(ix, a, nullptr, s, hb, hb + (cand.x >> 1), cand.x & 1u, cand.y, stack, mask_ws, depth_cap, srow);
         if (rc == 0) {
             ra.cursor[s] = PairCursor{cand.x, cand.y + 1};      // resume just past this try (the screen handles t == T)
             ra.queue_next[atomicAdd(ra.n_queue_next, 1u)] = s;

@@ -443,6 +443,22 @@ void index_to_device(grootgpu_index* ix) {
                 }
         d.node_seq2 = upload(seq2, ix->owned); d.node_n2 = upload(n2, ix->owned); d.graph_has_n = upload(has_n, ix->owned);
     }
+    {   // one-sector node records for the packed walk (device_types.cuh, WalkNode)
+        std::vector<WalkNode> wn(h.nodes.size());
+        for (uint32_t g = 0; g < h.n_graphs; g++) {
+            const uint32_t mw = h.graph_mask_words[g];
+            for (uint32_t n = h.graph_node_base[g]; n < h.graph_node_base[g + 1]; n++) {
+                const NodeRec& nr = h.nodes[n];
+                WalkNode& x = wn[n];
+                x.seq_off = nr.seq_off; x.seq_len = nr.seq_len; x.edge_cnt = nr.edge_cnt;
+                x.edge = nr.edge_cnt == 1 ? h.edges[nr.edge_off] : nr.edge_off;
+                for (uint32_t j = 0; j < kWalkMaskWords; j++) x.mask[j] = 0;
+                if (mw <= kWalkMaskWords) { for (uint32_t j = 0; j < mw; j++) x.mask[j] = h.node_mask[nr.mask_off + j]; }
+                else x.mask[0] = nr.mask_off;
+            }
+        }
+        d.wnodes = upload(wn, ix->owned);
+    }
     d.k = h.p.k; d.S = h.p.S; d.max_k = h.p.max_k; d.n_bands = h.p.S / h.p.max_k; d.n_wins = static_cast<uint32_t>(h.wins.size());
     {   // windows grouped by identical sketch (DevIndex::full): key = sketch_digest, bucket = window ids ascending
         const uint32_t S = h.p.S, W = static_cast<uint32_t>(h.wins.size());

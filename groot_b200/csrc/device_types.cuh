@@ -60,6 +60,19 @@ __host__ __device__ inline void sketch_digest(const uint64_t* sk, uint32_t S, ui
     for (int j = 0; j < 4; j++) key[j] = a[j];
 }
 
+// What one step of the packed walk needs from a node, in ONE 32-byte sector (align_kernels.cuh, dfs_packed): the walk is
+// bound by the number of sectors it pulls through L1 / L2 per node step (measured: 134 per pair), and NodeRec + path
+// bitset + out-edge were three of them.
+struct WalkNode {
+    uint32_t seq_off;    // NodeRec::seq_off (position in node_seq2 / node_n2)
+    uint32_t seq_len;
+    uint32_t edge;       // edge_cnt == 1: the target node itself; otherwise NodeRec::edge_off (index into edges[])
+    uint32_t edge_cnt;
+    uint32_t mask[4];    // path bitset of the node when its graph has <= 128 paths; otherwise mask[0] = NodeRec::mask_off
+};
+static_assert(sizeof(WalkNode) == 32, "WalkNode must be one 32-byte sector");
+constexpr uint32_t kWalkMaskWords = 4;
+
 struct DevIndex {
     const NodeRec* nodes;
     const uint8_t* node_seq;
@@ -76,6 +89,7 @@ struct DevIndex {
     const uint32_t* node_seq2;    // node_seq packed 2 bits per base (pack_base2), 16 bases per word, same positions as node_seq
     const uint32_t* node_n2;      // same layout: bit 2i of a word set when base i is an 'N' wildcard (alignment.go:212-215)
     const uint8_t* graph_has_n;   // [G] 1 when a node of the graph holds an 'N' (only then node_n2 is consulted)
+    const WalkNode* wnodes;       // [n_nodes] the packed walk's view of nodes[] + edges[] + node_mask[]
     // Windows grouped by IDENTICAL sketch (key = sketch_digest). When a query needs every slot equal (eq_min == S: a read as
     // long as the index window at the default threshold) and probes one band, "in the band's bucket and all S slots equal"
     // is the same set as "identical sketch": this table yields ~1 candidate per seeded read where the band bucket holds ~11

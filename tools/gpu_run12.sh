@@ -1,5 +1,6 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw,temperature.gpu,clocks_event_reasons.active --format=csv
+(for i in 1 2 3 4 5 6 7 8 9 10 11 12; do nvidia-smi --query-gpu=clocks.sm,power.draw,clocks_event_reasons.active --format=csv,noheader; sleep 2; done) > gpurun_out/clk.txt &
 timeout 200 python tools/kernel_times.py 10000000 100 2>&1 | tail -2
-timeout 300 python tools/e2e_trace.py 10000000 > gpurun_out/r02_e2e_trace.txt 2>&1
-grep -E "^chunk|chunk [0-9]+ \(lane" gpurun_out/r02_e2e_trace.txt | tail -14
+wait
+sort gpurun_out/clk.txt | uniq -c
