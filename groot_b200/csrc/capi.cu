@@ -1658,6 +1658,11 @@ int grootgpu_gob_dump(const char* gg_path, const char* lshe_path, const char* du
 void grootgpu_index_destroy(grootgpu_index* idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);
+    if (idx->comm) {   // a communicator that outlives its index: detach it (grootgpu_comm_destroy then only releases NCCL)
+        if (idx->st_acc) cudaStreamSynchronize(idx->st_acc);
+        if (idx->comm->st_gather) cudaStreamSynchronize(idx->comm->st_gather);
+        idx->comm->ix = nullptr;
+    }
     delete idx;
 }
 
