@@ -467,7 +467,7 @@ struct ScreenDesc {
     WinRec w0;                   // the first mapping's window
     uint32_t sn_seq_off, sn_seq_len;   // its seed node
     uint32_t packed;             // the read has a packed copy (upper-case ACGT, fits)
-    uint32_t pad;
+    uint32_t win0;               // window id of the first mapping
 };
 static_assert(sizeof(ScreenDesc) == 80, "ScreenDesc is five 16-byte words");
 
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(256) align_init_kernel(DevIndex ix, AlignArgs 
             d.sn_seq_off = sn.seq_off; d.sn_seq_len = sn.seq_len;
             d.packed = a.nw32 && a.read_ok2[p.read] ? 1u : 0u;
             d.oh = d.packed ? a.read_oh[p.read] : make_uint4(0, 0, 0, 0);
-            d.pad = 0;
+            d.win0 = a.hits[hb];
             a.sdesc[s] = d;
         }
     }
@@ -542,9 +542,27 @@ __device__ __forceinline__ void warp_read_prefix(const AlignArgs& a, uint32_t r,
 // are never enumerated: stage 1 covers only the offsets that exist on the seed node, stage 2 pools the existing
 // offsets 0..10 of up to 32 contained nodes at a time (inclusive scan + owner search, as in warp_probe); the try
 // NUMBERING stays the reference's (decode_try), so cursors and results are unchanged. wr, sn, t0, len are uniform.
-__device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinRec& wr, uint32_t sn_seq_off, uint32_t sn_seq_len, uint32_t t0,
+__device__ __forceinline__ uint32_t screen_strand(const DevIndex& ix, const WinRec& wr, uint32_t win, uint32_t sn_seq_off, uint32_t sn_seq_len, uint32_t t0,
                                                   const uint32_t (&oh)[2], uint32_t len, uint32_t lane) {
     constexpr uint32_t FULL = 0xffffffffu;
+    {   // can ANY try of this (window, strand) pass? The window's set of possible 5-base prefixes answers with one load
+        // (lane 0: the read as it is — stages 1, 2, 4; lane 1: without its first base — stage 3). A base that is not ACGT has
+        // an empty one-hot nibble and passes the allele-set test, so such a read is not filtered.
+        bool may = false;
+        if (lane < 2u) {
+            const uint32_t o = oh[lane];
+            uint32_t idx = 0;
+            bool known = true;
+#pragma unroll
+            for (uint32_t i = 0; i < 5u; i++) {
+                const uint32_t nib = (o >> (4u * i)) & 0xFu;
+                known = known && nib != 0u;
+                idx |= ((static_cast<uint32_t>(__ffs(static_cast<int>(nib))) - 1u) & 3u) << (2u * i);
+            }
+            may = !known || ((__ldg(ix.win_kmers + static_cast<size_t>(win) * 32u + (idx >> 5)) >> (idx & 31u)) & 1u) != 0u;
+        }
+        if (!__any_sync(FULL, may)) return kNoCand;
+    }
     const uint32_t T1 = wr.merge_span + wr.win_size + 1u;
     // stage 1: offsets OffSet + t on the seed node
     const uint32_t room = sn_seq_len > wr.offset ? sn_seq_len - wr.offset : 0u;
@@ -619,16 +637,18 @@ __global__ void __launch_bounds__(256, 4) align_screen_kernel(DevIndex ix, Round
         uint2 cand = make_uint2(kNoCand, 0u);
         while (m < he) {
             WinRec wr = d.w0;
+            uint32_t win = d.win0;
             uint32_t sn_off = d.sn_seq_off, sn_len = d.sn_seq_len;
             if (m != hb) {                                             // further mappings of the pair (rare): fetched on demand
-                wr = ix.wins[a.hits[m]];
+                win = a.hits[m];
+                wr = ix.wins[win];
                 const NodeRec sn = ix.nodes[wr.node];
                 sn_off = sn.seq_off; sn_len = sn.seq_len;
             }
             uint32_t oh[2];
             if (d.packed) { oh[0] = strand ? d.oh.z : d.oh.x; oh[1] = strand ? d.oh.w : d.oh.y; }
             else warp_read_prefix(a, r, rp, len, strand != 0, lane, oh);
-            const uint32_t t = screen_strand(ix, wr, sn_off, sn_len, t0, oh, len, lane);
+            const uint32_t t = screen_strand(ix, wr, win, sn_off, sn_len, t0, oh, len, lane);
             if (t != kNoCand) { cand = make_uint2(((m - hb) << 1) | strand, t); break; }
             t0 = 0;
             if (strand == 0) { strand = 1; if (!d.packed) check_revcomp_bytes(a, r, rp, len, lane); }
@@ -749,12 +769,13 @@ __global__ void __launch_bounds__(128, 5) align_finish_kernel(DevIndex ix, Round
         uint32_t m = hb + (cur.m_strand >> 1), strand = cur.m_strand & 1u, t0 = cur.t;
         bool done = false;
         while (m < he && !done) {
-            const WinRec wr = ix.wins[a.hits[m]];
+            const uint32_t win = a.hits[m];
+            const WinRec wr = ix.wins[win];
             const NodeRec sn = ix.nodes[wr.node];
             uint32_t oh[2];
             warp_read_prefix(a, r, rp, len, strand != 0, lane, oh);
             while (!done) {
-                const uint32_t t = screen_strand(ix, wr, sn.seq_off, sn.seq_len, t0, oh, len, lane);
+                const uint32_t t = screen_strand(ix, wr, win, sn.seq_off, sn.seq_len, t0, oh, len, lane);
                 if (t == kNoCand) break;
                 uint32_t okw = 0;
                 if (lane == 0) okw = walk_try<false>(ix, a, lut, s, hb, m, strand, t, stack, mask_ws, depth_cap) > 0 ? 1u : 0u;

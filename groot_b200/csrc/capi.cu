@@ -425,6 +425,9 @@ void index_to_device(grootgpu_index* ix) {
         std::vector<uint32_t> pset;
         build_prefix_sets(h, pset);
         d.pfxset = upload(pset, ix->owned);
+        std::vector<uint32_t> wk;
+        build_window_kmer_sets(h, pset, wk);
+        d.win_kmers = upload(wk, ix->owned);
     }
     {   // 2-bit copy of the node sequences + per-graph 'N' flag for the packed walk (align_kernels.cuh, dfs_packed)
         std::vector<uint32_t> seq2((h.node_seq.size() + 15) / 16 + 2, 0u);

@@ -85,6 +85,7 @@ struct DevIndex {
     const uint64_t* sketches;
     const uint32_t* graph_mask_words;
     const LshTable* tables;  // [(K-1)*n_bands + band]; slots == nullptr when not built yet
+    const uint32_t* win_kmers;    // [n_wins * 32] per window: the 5-base prefixes possible at any of its tries (host/prefix_table.cpp, build_window_kmer_sets)
     const uint32_t* pfxset;  // [node_seq bytes + 1] allele sets of the first 8 steps from a position (host/prefix_table.cpp), position = NodeRec::seq_off + offset
     const uint32_t* node_seq2;    // node_seq packed 2 bits per base (pack_base2), 16 bases per word, same positions as node_seq
     const uint32_t* node_n2;      // same layout: bit 2i of a word set when base i is an 'N' wildcard (alignment.go:212-215)

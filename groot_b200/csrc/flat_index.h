@@ -99,6 +99,7 @@ void dump_index(const FlatIndex& idx, void (*sink)(void* ctx, const char* data, 
 
 // derived acceleration structure for the align kernel (host/prefix_table.cpp)
 void build_prefix_sets(const FlatIndex& idx, std::vector<uint32_t>& pset);
+void build_window_kmer_sets(const FlatIndex& idx, const std::vector<uint32_t>& pset, std::vector<uint32_t>& wk);
 
 // lshensemble parameter optimiser + containment threshold, exact f64 expressions (host, once per query size)
 void optimal_kl(int max_k, int max_l, int x, int q, double t, int* K, int* L);

@@ -56,4 +56,38 @@ void build_prefix_sets(const FlatIndex& ix, std::vector<uint32_t>& pset) {
     }
 }
 
+// Window 5-mer sets: for every indexed window, WHICH 5-base prefixes a read can start with at ANY of the window's tries —
+// the seed-node offsets of stage 1, offsets 0..10 of the contained nodes of stage 2, the seed position of stages 3 / 4
+// (alignment.go:35-103) — as a 1 024-bit set per window (32 words), every combination of the allele sets of the first five
+// steps of every try position. A read whose first five bases (and, for the start-clipped stage 3, bases 1..5) are not in
+// the set cannot pass the allele-set test at any try of that (window, strand): the screen skips the whole try list
+// with one load. This is what a read costs on the strand it does NOT align on — half of all (pair, strand) scans.
+void build_window_kmer_sets(const FlatIndex& ix, const std::vector<uint32_t>& pset, std::vector<uint32_t>& wk) {
+    wk.assign(ix.wins.size() * 32, 0u);
+    auto add_position = [&](uint32_t* row, uint32_t pos) {
+        const uint32_t sets = pset[pos];
+        uint32_t s[5];
+        for (int i = 0; i < 5; i++) s[i] = (sets >> (4 * i)) & 0xFu;
+        for (uint32_t c0 = 0; c0 < 4; c0++) if (s[0] >> c0 & 1u)
+            for (uint32_t c1 = 0; c1 < 4; c1++) if (s[1] >> c1 & 1u)
+                for (uint32_t c2 = 0; c2 < 4; c2++) if (s[2] >> c2 & 1u)
+                    for (uint32_t c3 = 0; c3 < 4; c3++) if (s[3] >> c3 & 1u)
+                        for (uint32_t c4 = 0; c4 < 4; c4++) if (s[4] >> c4 & 1u) {
+                            const uint32_t idx = c0 | c1 << 2 | c2 << 4 | c3 << 6 | c4 << 8;
+                            row[idx >> 5] |= 1u << (idx & 31u);
+                        }
+    };
+    for (size_t w = 0; w < ix.wins.size(); w++) {
+        const WinRec& wr = ix.wins[w];
+        uint32_t* row = &wk[w * 32];
+        const NodeRec& sn = ix.nodes[wr.node];
+        const uint32_t t1 = wr.merge_span + wr.win_size + 1u;
+        for (uint32_t t = 0; t < t1 && wr.offset + t < sn.seq_len; t++) add_position(row, sn.seq_off + wr.offset + t);
+        for (uint32_t j = 0; j < wr.cn_cnt; j++) {
+            const NodeRec& cn = ix.nodes[ix.cn_node[wr.cn_off + j]];
+            for (uint32_t off = 0; off < 11u && off < cn.seq_len; off++) add_position(row, cn.seq_off + off);
+        }
+    }
+}
+
 }  // namespace groot
