@@ -1,6 +1,8 @@
 // libgrootgpu.so — C ABI implementation (include/grootgpu.h): index bring-up on the device, the
 // batch pipeline  seed (sketch+probe+verify) -> scan -> fill -> segment -> align search -> scan -> emit,
-// result transfer, and the host-side ordered weight replay.
+// the ordered graph weighting (count / expand / sort beside the emit, the f64 chains behind the batch on st_acc),
+// result transfer (full or compact arrays; host, or batch-wide device arrays), the chunked three-lane host path,
+// the multi-GPU gather and weight ring over NCCL, and the host-side ordered weight replay.
 //
 // There is no CPU fallback anywhere in this file: every compute entry point needs a CUDA device and
 // fails with GROOTGPU_ERR_CUDA otherwise.

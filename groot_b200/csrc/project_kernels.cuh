@@ -9,7 +9,8 @@
 //      ((segLen/total)*numKmers)*count, so every addend equals the host's bit for bit.
 //   2. cub::DeviceRadixSort::SortPairs by node id — a STABLE sort, so each node's items stay in read order.
 //   3. project_accumulate  one warp per node adds the node's items to KmerFreq one after the other (the dependent
-//      DADD chain IS the reference's order); KmerTotal is an integer sum (atomics are exact).
+//      DADD chain IS the reference's order); KmerTotal is an integer sum (atomics are exact). The chains run on their
+//      own stream behind the batch (capi.cu, acc_enqueue); on N GPUs the weight vector travels rank to rank between them.
 #pragma once
 #include <cuda_runtime.h>
 

@@ -13,8 +13,11 @@
 // co-prime with the 32 banks so the per-thread byte reads are conflict free. The probe is warp-cooperative: the
 // candidate buckets of the warp's 32 reads are pooled and verified 32 at a time (warp_probe). With a single band
 // probed (the default) the kernel runs in two passes — a first-band prescreen over all reads, the full sketch only
-// for the reads that found a bucket (SEED_PRESCREEN / SEED_QUEUED). Integer-issue bound (~18k integer ops per
-// 100 bp read versus ~320 algorithmic bytes), see DESIGN.md §4.
+// for the reads that found a bucket (SEED_PRESCREEN / SEED_QUEUED); the second pass also writes the 2-bit copies of the
+// seeded reads the align kernels walk (pack_read_from_smem). Integer-issue bound (~18k integer ops per 100 bp read versus
+// ~320 algorithmic bytes), see DESIGN.md §4. The sketch is tracked as raw k-mer products ordered by their top 27 bits
+// (khf_update_raw), queries that need every slot equal look the whole sketch up (DevIndex::full), and sketch sizes /
+// maxK outside the compiled set run the run-time-S kernels at the end of this file.
 #pragma once
 #include <cuda_runtime.h>
 
