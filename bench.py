@@ -245,9 +245,8 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
 
     seqs = synth.db_sequences(msa_dir)
     blob, off = synth.synth_reads(n, L, seqs, seed=42 + rank)      # weak scaling: rank r maps reads [r*n, (r+1)*n) of the global batch
-    p_seq, p_off = api.PinnedBuffer(n * L), api.PinnedBuffer(8 * (n + 1))      # pinned host input buffers (grootgpu_host_alloc)
+    p_seq = api.PinnedBuffer(n * L)                                   # pinned host input buffer (grootgpu_host_alloc)
     p_seq.array[:] = blob
-    p_off.array[:] = off.view(np.uint8)
     d_seq = torch.zeros(n * L + 64, dtype=torch.uint8, device=dev)
     d_seq[: n * L].copy_(torch.from_numpy(blob))
     d_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).to(dev)
@@ -289,8 +288,9 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
 
     def step_e2e():
         t0 = time.perf_counter()
-        raw = idx.map_reads_raw(p_seq.ptr, p_off.ptr, n, THRESHOLD, no_align=no_align, project_on_device=True, compact=True,
-                                results_on_device=comm is not None)
+        # reads of one length: params->fixed_read_len, no offsets array handed over (it would be 8 more bytes per read on the link)
+        raw = idx.map_reads_raw(p_seq.ptr, None, n, THRESHOLD, no_align=no_align, project_on_device=True, compact=True,
+                                results_on_device=comm is not None, fixed_read_len=L)
         t1 = time.perf_counter()
         if comm:
             gather_async(raw, 2)   # rank 0: merged compact batch -> host, asynchronously (complete at the next gather / sync)
@@ -371,7 +371,7 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
     ctx.barrier()
     e2e_value = total_reads * steps / e2e_s
     recw = raw_e.rec_path_bytes
-    h2d = n * L + 8 * (n + 1)                                         # per rank: bases + u64 offsets
+    h2d = n * L                                                       # per rank: the bases (fixed_read_len: no offsets travel)
     d2h_one = 16 * raw_e.n_pairs + recw * raw_e.n_records             # compact: 16-byte pairs + path ids
     d2h = ctx.reduce(float(d2h_one), "SUM")                           # N > 1: all of it leaves through rank 0 after the gather
 
@@ -438,7 +438,7 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
         comm.close()
     idx.close()
     del d_seq, d_off
-    p_seq.free(); p_off.free()
+    p_seq.free()
     torch.cuda.empty_cache()
     par = "reads sharded over %d GPU(s), index replicated" % world
     if world > 1:
@@ -451,7 +451,7 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
                    "parallelism": par, "per_read": stats, "index_build_s": t_index, "merged_on_rank0": merged_check},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": int(d2h),
                 "h2d_GBps_per_rank": h2d / (e2e_s / steps) / 1e9, "h2d_GBps_all_ranks": h2d * world / (e2e_s / steps) / 1e9, "d2h_GBps_rank0": d2h / (e2e_s / steps) / 1e9,
-                "includes": "pinned host buffers -> grootgpu_align_batch (H2D in chunks on two lanes overlapped with the kernels: sketch + query + align + ordered graph "
+                "includes": "pinned host buffer of bases (reads of one length: fixed_read_len, no offsets) -> grootgpu_align_batch (H2D in chunks on two lanes overlapped with the kernels: sketch + query + align + ordered graph "
                             "weighting) -> compact result (16-byte pairs + %d-byte path ids) to the host%s" % (recw, "; N > 1: results kept on the device, gathered to rank 0 over "
                             "NVLink, merged, copied to rank 0's host (asynchronously, drained inside the timed region)" if world > 1 else ""),
                 "per_step_ms": e2e_parts},

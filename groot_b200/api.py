@@ -37,7 +37,8 @@ class IndexInfo(C.Structure):
 
 class AlignParams(C.Structure):
     _fields_ = [("containment_threshold", C.c_double), ("no_align", C.c_int32), ("keep_sketches", C.c_int32),
-                ("project_on_device", C.c_int32), ("results_on_device", C.c_int32), ("compact_records", C.c_int32)]
+                ("project_on_device", C.c_int32), ("results_on_device", C.c_int32), ("compact_records", C.c_int32),
+                ("fixed_read_len", C.c_uint32)]
 
 
 class Pair(C.Structure):
@@ -338,21 +339,25 @@ class Index:
         return K.value, L.value, e.value
 
     # -- the hot path -----------------------------------------------------------------------------
-    def map_reads(self, seqs, off, threshold=0.99, no_align=False, keep_sketches=False, project=False, project_on_device=False, compact=False):
-        """theBoss.mapReads for one batch (src/pipeline/boss.go:108-242): host buffers in, host result out."""
+    def map_reads(self, seqs, off, threshold=0.99, no_align=False, keep_sketches=False, project=False, project_on_device=False, compact=False,
+                  fixed_read_len=0):
+        """theBoss.mapReads for one batch (src/pipeline/boss.go:108-242): host buffers in, host result out. With
+        fixed_read_len the offsets are not handed to the library (reads of one length, back to back)."""
         seqs = np.ascontiguousarray(seqs, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint64)
-        prm = AlignParams(threshold, int(no_align), int(keep_sketches), int(project_on_device), 0, int(compact))
+        prm = AlignParams(threshold, int(no_align), int(keep_sketches), int(project_on_device), 0, int(compact), int(fixed_read_len))
         raw = BatchResultC()
-        _check(lib().grootgpu_align_batch(self.h, seqs.ctypes.data, off.ctypes.data, len(off) - 1, C.byref(prm), C.byref(raw)))
+        _check(lib().grootgpu_align_batch(self.h, seqs.ctypes.data, None if fixed_read_len else off.ctypes.data, len(off) - 1, C.byref(prm), C.byref(raw)))
         res = BatchResult(raw, self.info()["S"], True)
         if project:
             self.project(res, off)
         return res
 
-    def map_reads_raw(self, seq_ptr, off_ptr, n_reads, threshold=0.99, no_align=False, project_on_device=False, compact=False, results_on_device=False):
-        """Same call on raw host pointers (pinned buffers), returning only the C struct: what bench.py times."""
-        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), int(results_on_device), int(compact))
+    def map_reads_raw(self, seq_ptr, off_ptr, n_reads, threshold=0.99, no_align=False, project_on_device=False, compact=False, results_on_device=False,
+                      fixed_read_len=0):
+        """Same call on raw host pointers (pinned buffers), returning only the C struct: what bench.py times. With
+        fixed_read_len the offsets pointer may be None (reads of one length, back to back)."""
+        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), int(results_on_device), int(compact), int(fixed_read_len))
         raw = BatchResultC()
         _check(lib().grootgpu_align_batch(self.h, seq_ptr, off_ptr, n_reads, C.byref(prm), C.byref(raw)))
         return raw
@@ -360,7 +365,7 @@ class Index:
     def map_reads_device(self, d_seq_ptr, d_off_ptr, n_reads, min_len, max_len, threshold=0.99, no_align=False, stream=None, copy_back=False,
                          project_on_device=False, compact=False):
         """Reads already resident in HBM (device pointers as ints)."""
-        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), 0 if copy_back else 1, int(compact))
+        prm = AlignParams(threshold, int(no_align), 0, int(project_on_device), 0 if copy_back else 1, int(compact), 0)
         raw = BatchResultC()
         _check(lib().grootgpu_align_batch_device(self.h, d_seq_ptr, d_off_ptr, n_reads, min_len, max_len, C.byref(prm), stream,
                                                  C.byref(raw)))

@@ -1128,6 +1128,10 @@ __global__ void __launch_bounds__(256) chunk_offsets_kernel(const uint64_t* __re
     if ((threadIdx.x & 31) == 0) { atomicMin(&minmax[0], mn); atomicMax(&minmax[1], mx); }
 }
 
+__global__ void __launch_bounds__(256) chunk_offsets_fixed_kernel(uint32_t* __restrict__ off32, uint32_t n, uint32_t len) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) off32[i] = i * len;
+}
+
 // chunk-local indices -> batch-global ones, before the chunk's arrays are copied to their place in the host result
 __global__ void __launch_bounds__(256) chunk_rebase_kernel(PairOut* __restrict__ pairs, uint32_t n_pairs, uint32_t* __restrict__ hit_off, uint32_t n_off,
                                                            uint32_t read_base, uint32_t hit_base, uint32_t rec_base) {
@@ -1192,6 +1196,15 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
                        grootgpu_batch_result* out) {
     cudaStream_t st_in = ix->st_in, st_out = ix->st_out;
     const uint32_t S = ix->h.p.S;
+    // reads of one length, back to back (params->fixed_read_len): offsets are arithmetic, none travel to the device
+    const uint32_t fixed_len = prm->fixed_read_len;
+    if (!seq_off && fixed_len == 0) throw std::runtime_error("seq_off is NULL and params->fixed_read_len is 0");
+    if (fixed_len != 0 && fixed_len < ix->h.p.k) throw std::invalid_argument("a read is shorter than k (the reference panics at boss.go:164-166)");
+    if (fixed_len != 0 && seq_off)
+        for (uint32_t i : {0u, n / 2, n - 1}) if (seq_off[i + 1] - seq_off[i] != fixed_len || seq_off[i] - seq_off[0] != static_cast<uint64_t>(i) * fixed_len)
+            throw std::runtime_error("params->fixed_read_len does not match seq_off");
+    const uint64_t off_base = fixed_len != 0 && seq_off ? seq_off[0] : 0;
+    auto off_at = [&](uint32_t i) -> uint64_t { return fixed_len != 0 ? off_base + static_cast<uint64_t>(i) * fixed_len : seq_off[i]; };
     // chunk boundaries (always < 4 GiB of bases per chunk). The copy-in link is only ~1.25x faster than the kernels, so
     // the schedule starts with a small chunk (the first copy-in is a transfer nothing overlaps) and grows up to
     // chunk_reads_setting() — the next chunk's bases then arrive before the current one is done. The end depends on what
@@ -1210,8 +1223,8 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
             if (light_out) { if (left > want && left <= 2ull * want) take = (left + 1) / 2; }              // two last chunks of equal size
             else if (left > edge && left - take < edge) take = left - edge;                             // leave a last chunk of `edge` reads
             uint32_t r1 = r0 + std::max(1u, take);
-            while (r1 > r0 + 1 && seq_off[r1] - seq_off[r0] >= max_bytes) r1 = r0 + (r1 - r0) / 2;
-            if (seq_off[r1] - seq_off[r0] >= max_bytes) throw std::length_error("a read of 4 GiB or more");
+            while (r1 > r0 + 1 && off_at(r1) - off_at(r0) >= max_bytes) r1 = r0 + (r1 - r0) / 2;
+            if (off_at(r1) - off_at(r0) >= max_bytes) throw std::length_error("a read of 4 GiB or more");
             cb.push_back(r1);
             want = std::min<uint64_t>(target, static_cast<uint64_t>(want) + (light_out ? want / 2 : want / 4) + 1);
         }
@@ -1248,11 +1261,14 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
     auto issue_inputs_upto = [&](uint32_t last) {   // sh.mu held
         for (; sh.inputs_issued <= last && sh.inputs_issued < C; sh.inputs_issued++) {
             const uint32_t c = sh.inputs_issued, r0 = cb[c], nc = cb[c + 1] - r0, b = c % grootgpu_index::kInBufs;
-            const uint64_t bytes = seq_off[cb[c + 1]] - seq_off[r0];
-            ix->in_seq[b].need(bytes + 64); ix->in_off64[b].need(8ull * (nc + 1)); ix->in_off32[b].need(4ull * (nc + 1));
-            CK(cudaMemcpyAsync(ix->in_seq[b].p, seq + seq_off[r0], bytes, cudaMemcpyHostToDevice, st_in));
+            const uint64_t bytes = off_at(cb[c + 1]) - off_at(r0);
+            ix->in_seq[b].need(bytes + 64); ix->in_off32[b].need(4ull * (nc + 1));
+            CK(cudaMemcpyAsync(ix->in_seq[b].p, seq + off_at(r0), bytes, cudaMemcpyHostToDevice, st_in));
             CK(cudaMemsetAsync(ix->in_seq[b].as<uint8_t>() + bytes, 0, 64, st_in));
-            CK(cudaMemcpyAsync(ix->in_off64[b].p, seq_off + r0, 8ull * (nc + 1), cudaMemcpyHostToDevice, st_in));
+            if (fixed_len == 0) {
+                ix->in_off64[b].need(8ull * (nc + 1));
+                CK(cudaMemcpyAsync(ix->in_off64[b].p, seq_off + r0, 8ull * (nc + 1), cudaMemcpyHostToDevice, st_in));
+            }
             CK(cudaEventRecord(ix->ev_in[b], st_in));
         }
     };
@@ -1271,11 +1287,16 @@ void run_batch_chunked(grootgpu_index* ix, const uint8_t* seq, const uint64_t* s
                     issue_inputs_upto(c + grootgpu_index::kLanes);
                 }
                 CK(cudaStreamWaitEvent(st, ix->ev_in[b], 0));
-                poke(st, {{w->len_minmax.as<uint32_t>(), 0xffffffffu}, {w->len_minmax.as<uint32_t>() + 1, 0u}});
-                chunk_offsets_kernel<<<std::max(1u, std::min<uint32_t>((nc + 256) / 256, 1184u)), 256, 0, st>>>(ix->in_off64[b].as<uint64_t>(), nc, ix->in_off32[b].as<uint32_t>(),
-                                                                                                             w->len_minmax.as<uint32_t>());
-                uint32_t mm[2] = {0, 0};
-                { const uint32_t* pk = peek(w, st, {w->len_minmax.as<uint32_t>(), w->len_minmax.as<uint32_t>() + 1}); mm[0] = pk[0]; mm[1] = pk[1]; }
+                uint32_t mm[2] = {fixed_len, fixed_len};
+                if (fixed_len != 0) {   // offsets generated in place: no copy, no round trip for the length range
+                    chunk_offsets_fixed_kernel<<<std::max(1u, std::min<uint32_t>((nc + 256) / 256, 1184u)), 256, 0, st>>>(ix->in_off32[b].as<uint32_t>(), nc, fixed_len);
+                } else {
+                    poke(st, {{w->len_minmax.as<uint32_t>(), 0xffffffffu}, {w->len_minmax.as<uint32_t>() + 1, 0u}});
+                    chunk_offsets_kernel<<<std::max(1u, std::min<uint32_t>((nc + 256) / 256, 1184u)), 256, 0, st>>>(ix->in_off64[b].as<uint64_t>(), nc, ix->in_off32[b].as<uint32_t>(),
+                                                                                                                 w->len_minmax.as<uint32_t>());
+                    const uint32_t* pk = peek(w, st, {w->len_minmax.as<uint32_t>(), w->len_minmax.as<uint32_t>() + 1});
+                    mm[0] = pk[0]; mm[1] = pk[1];
+                }
                 if (mm[0] < ix->h.p.k) throw std::invalid_argument("a read is shorter than k (the reference panics at boss.go:164-166)");
                 w->swap_result_sets();                                   // write the result set the lane's previous chunk is NOT being copied out of
                 CK(cudaStreamWaitEvent(st, w->ev_out[w->rset], 0));      // ... whose own copy-out (two chunks of this lane ago) has completed
@@ -1745,7 +1766,7 @@ int grootgpu_align_batch_device(grootgpu_index* idx, const uint8_t* d_seq, const
 
 int grootgpu_align_batch(grootgpu_index* idx, const uint8_t* seq, const uint64_t* seq_off, uint32_t n_reads, const grootgpu_align_params* params,
                          grootgpu_batch_result* out) {
-    if (!idx || !seq || !seq_off || !params || !out || n_reads == 0) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    if (!idx || !seq || !params || !out || n_reads == 0 || (!seq_off && params->fixed_read_len == 0)) return fail(GROOTGPU_ERR_ARG, "bad argument");
     return guarded([&] {
         pick_device(idx->device);
         idx->call_parity ^= 1;

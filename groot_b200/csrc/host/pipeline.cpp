@@ -417,6 +417,13 @@ int ReadMapper::Run(FastqStream& reads) {
         struct Release { BatchFeed& f; int i; ~Release() { f.release(i); } } release_slot{feed, slot_i};
         ReadBatch& b = *bp;
         grootgpu_batch_result res;
+        {   // reads of one length (the usual Illumina run): the library then needs no offsets on the device
+            const uint64_t L0 = b.size() ? b.seq_off[1] - b.seq_off[0] : 0;
+            bool same = L0 > 0 && L0 < (1ull << 31);
+            for (uint32_t i = 1; i < b.size() && same; i++) same = b.seq_off[i + 1] - b.seq_off[i] == L0;
+            prm.fixed_read_len = same ? static_cast<uint32_t>(L0) : 0u;
+            team.prm.fixed_read_len = prm.fixed_read_len;
+        }
         if (indexes_.size() > 1) {
             if ((rc = team.run(b.seq.data(), b.seq_off.data(), b.size(), &res, &err_))) return rc;
         } else {

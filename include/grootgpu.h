@@ -123,6 +123,8 @@ typedef struct {
     int32_t compact_records;      /* 1: BAM-oriented compact output — cpairs[] + rec_path_c[] instead of hit_off / hits / pairs /
                                      rec_path / rec_pos (about a fifth of the bytes: what crosses PCIe and NVLink). Needs
                                      project_on_device or no weighting: grootgpu_project_batch wants the full arrays */
+    uint32_t fixed_read_len;      /* > 0: every read of the batch has this many bases, back to back; grootgpu_align_batch then
+                                     accepts seq_off == NULL and does not move 8 bytes of offset per read to the device */
 } grootgpu_align_params;
 
 /* One (read, graph) unit == one graphMinionPair (src/pipeline/graphminion.go:14-17). */
@@ -199,7 +201,8 @@ typedef struct {
 /* Replaces the per-read loop of theBoss.mapReads (src/pipeline/boss.go:134-203: RunMinHash ->
  * db.Query -> dispatch) fused with the graphMinion loop (src/pipeline/graphminion.go:46-102: sort
  * mappings, AlignRead forward then reverse complement, stop at the first mapping that aligns).
- * seq = concatenated read bases (raw FASTQ line 2 bytes), seq_off[n_reads+1] = byte offsets.
+ * seq = concatenated read bases (raw FASTQ line 2 bytes), seq_off[n_reads+1] = byte offsets (NULL allowed with
+ * params->fixed_read_len).
  * Host buffers in, host results out (H2D / D2H inside); pinned buffers from grootgpu_host_alloc make
  * the copies asynchronous. Any batch size: the batch is streamed through the device in chunks on two
  * lanes (copy-in, kernels and copy-out of neighbouring chunks overlap; one helper thread is started and

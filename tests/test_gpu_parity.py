@@ -634,3 +634,25 @@ def test_index_from_reference_gob_files(oxa, root, tmp_path):
     r = subprocess.run([cli, "align", "-i", str(d), "-f", fq, "-g", str(tmp_path / "graphs"), "--bamOut", str(tmp_path / "out.bam")], stderr=subprocess.PIPE, timeout=300)
     assert r.returncode == 0, r.stderr.decode()
     assert b"number of reads received from input: 2062" in r.stderr
+
+
+def test_fixed_read_length_path(argannot, db_dirs, monkeypatch):
+    """params->fixed_read_len: reads of one length, back to back, seq_off == NULL — the offsets are generated on the device
+    instead of travelling there (8 of 108 bytes per read). Same result as with offsets, in ragged chunks too."""
+    g, o = argannot
+    blob, off = _c1_reads(db_dirs["arg-annot.90"], 20_003, 100, seed=12)
+    want = g.map_reads(blob, off, 0.99)
+    for chunk in (None, "3001"):
+        if chunk:
+            monkeypatch.setenv("GROOTGPU_CHUNK_READS", chunk)
+        got = g.map_reads(blob, off, 0.99, fixed_read_len=100)
+        assert got.counts == want.counts
+        for k in ("hit_off", "hits", "pairs", "rec_path", "rec_pos"):
+            assert np.array_equal(getattr(got, k), getattr(want, k)), k
+        c = g.map_reads(blob, off, 0.99, fixed_read_len=100, compact=True, project_on_device=True)
+        assert np.array_equal(c.decode_compact(g), want.records_table())
+        if chunk:
+            monkeypatch.delenv("GROOTGPU_CHUNK_READS")
+    with pytest.raises(api.GrootGpuError) as e:          # shorter than k: the reference panics (boss.go:164-166)
+        g.map_reads(blob, off, 0.99, fixed_read_len=20)
+    assert e.value.code == -5
