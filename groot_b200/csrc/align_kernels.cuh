@@ -844,8 +844,32 @@ __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a
         if (p.rec_count == 0) continue;
         const uint32_t ntrav = a.seg_ntrav[s];
         if (!(ntrav & kTravRewalk)) {
-            const uint2 loc = a.seg_locus[s];
             const uint32_t mw = ix.graph_mask_words[p.graph];
+            if (RECW != 0) {
+                // compact output: the records of a traversal ARE the set bits of its path bitset, ascending (the bitset is an
+                // AND over the traversal's nodes, the start node included, so it is a subset of that node's paths) — no start
+                // node, no path list, no positions. Lane j of the group owns word j of the bitset (mw <= 8 here: larger
+                // graphs re-walk), an exclusive scan of the popcounts over the group places its bits.
+                uint32_t written = 0;
+                for (uint32_t t = 0; t < ntrav; t++) {                 // traversals in DFS order, path ids ascending inside one
+                    uint32_t m = gl < mw ? a.seg_mask[static_cast<size_t>(s) * kTravWords + t * mw + gl] : 0u;
+                    const uint32_t c = __popc(m);
+                    uint32_t incl = c;
+#pragma unroll
+                    for (uint32_t d = 1; d < 8; d <<= 1) { const uint32_t v = __shfl_up_sync(gmask, incl, d, 8); if (gl >= d) incl += v; }
+                    uint32_t slot = rb + written + incl - c;
+                    written += __shfl_sync(gmask, incl, 7, 8);
+                    while (m) {
+                        const uint32_t pid = gl * 32u + static_cast<uint32_t>(__ffs(static_cast<int>(m))) - 1u;
+                        m &= m - 1u;
+                        if (RECW == 1) static_cast<uint8_t*>(a.rec_c)[slot] = static_cast<uint8_t>(pid);
+                        else static_cast<uint16_t*>(a.rec_c)[slot] = static_cast<uint16_t>(pid);
+                        slot++;
+                    }
+                }
+                continue;
+            }
+            const uint2 loc = a.seg_locus[s];
             const NodeRec n0 = ix.nodes[loc.x];
             uint32_t written = 0;
             for (uint32_t t = 0; t < ntrav; t++) {                     // traversals in DFS order, path ids ascending inside one
@@ -857,11 +881,8 @@ __global__ void __launch_bounds__(256) align_emit_kernel(DevIndex ix, EmitArgs a
                     const uint32_t ball = (__ballot_sync(gmask, on) >> gshift) & 0xffu;
                     if (on) {
                         const uint32_t slot = rb + written + __popc(ball & ((1u << gl) - 1u));
-                        if (RECW == 0) {
-                            a.rec_path[slot] = pid;
-                            a.rec_pos[slot] = ix.node_path_pos[n0.path_off + j] + static_cast<int32_t>(loc.y);   // alignment.go:296
-                        } else if (RECW == 1) static_cast<uint8_t*>(a.rec_c)[slot] = static_cast<uint8_t>(pid);
-                        else static_cast<uint16_t*>(a.rec_c)[slot] = static_cast<uint16_t>(pid);
+                        a.rec_path[slot] = pid;
+                        a.rec_pos[slot] = ix.node_path_pos[n0.path_off + j] + static_cast<int32_t>(loc.y);   // alignment.go:296
                     }
                     written += __popc(ball);
                 }

@@ -1,4 +1,3 @@
 set -x
-timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_cli.py -m gpu -x -q -k "fixed_read or cli_oxa or travis or chunked" 2>&1 | tail -3
-timeout 600 python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench.json 2> gpurun_out/r02_bench.err
-tail -c 200 gpurun_out/r02_bench.json; tail -2 gpurun_out/r02_bench.err
+timeout 500 python -m pytest tests/test_gpu_parity.py tests/test_gpu_multi.py tests/test_gpu_cli.py -m gpu -x -q -k "compact or fixed_read or ranks or cli_oxa or travis or walk_variants or card" 2>&1 | tail -3
+KT_COMPACT=1 timeout 200 python tools/kernel_times.py 10000000 100 2>&1 | tail -2

@@ -23,9 +23,9 @@ d_seq[: n * L].copy_(torch.from_numpy(blob))
 d_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).to(dev)
 for it in range(5):
     t0 = time.perf_counter()
-    raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, 0.99, project_on_device=True)
+    raw = idx.map_reads_device(d_seq.data_ptr(), d_off.data_ptr(), n, L, L, 0.99, project_on_device=True, compact=os.environ.get("KT_COMPACT") == "1")
     torch.cuda.synchronize()
     wall = (time.perf_counter() - t0) * 1e3
-print(dict(zip(api.KERNEL_FAMILIES, ["%.3f" % v for v in list(raw.kernel_ms)[:8]])))
+print("compact" if os.environ.get("KT_COMPACT") == "1" else "full", dict(zip(api.KERNEL_FAMILIES, ["%.3f" % v for v in list(raw.kernel_ms)[:8]])))
 print("lib=%s n=%d L=%d seed=%.3f ms align=%.3f ms other=%.3f ms total_dev=%.3f ms wall=%.3f ms slow_path_pairs=%d pairs=%d records=%d"
       % (os.path.basename(api.LIB_PATH), n, L, raw.ms[1], raw.ms[2], raw.ms[3], raw.ms[0], wall, raw.slow_path_pairs, raw.n_pairs, raw.n_records))
