@@ -186,13 +186,15 @@ type CompactResult struct {
 }
 
 // AlignBatchCompact is AlignBatch with the ordered graph weighting on the device and the compact output.
-func (ix *Index) AlignBatchCompact(seq []byte, off []uint64, threshold float64, noAlign bool) (*CompactResult, error) {
+// fixedReadLen > 0 declares that every read has that many bases (then the offsets do not travel to the device).
+func (ix *Index) AlignBatchCompact(seq []byte, off []uint64, threshold float64, noAlign bool, fixedReadLen uint32) (*CompactResult, error) {
 	if len(off) < 2 || len(seq) == 0 {
 		return &CompactResult{}, nil
 	}
 	pin()
 	defer unpin()
-	prm := C.grootgpu_align_params{containment_threshold: C.double(threshold), project_on_device: 1, compact_records: 1}
+	prm := C.grootgpu_align_params{containment_threshold: C.double(threshold), project_on_device: 1, compact_records: 1,
+		fixed_read_len: C.uint32_t(fixedReadLen)}
 	if noAlign {
 		prm.no_align = 1
 	}

@@ -355,10 +355,9 @@ struct grootgpu_comm {
     ncclComm_t ring = nullptr, gath = nullptr;
     cudaStream_t st_gather = nullptr;
     cudaEvent_t ev_sent[2] = {};           // the gather that read result set 0 / 1 of the index has finished with it
-    cudaEvent_t ev_local = nullptr;
     bool ring_pending = false;             // rank 0: the last rank has sent (or will send) a weight vector that was not received yet
-    DBuf d_counts;                         // [world * 4] u64: n_reads, n_hits, n_pairs, n_records of every rank
-    uint64_t* h_counts = nullptr;          // pinned, [4 + world * 4]
+    DBuf d_counts;                         // [kCountWords * (world + 2)] u64: the same on the device (all-gather in place)
+    uint64_t* h_counts = nullptr;          // pinned, [kCountWords * (world + 2)]: this rank's words, then everybody's
     DBuf m_hit_off, m_hits, m_pairs, m_rec_path, m_rec_pos, m_cpairs, m_rec_c;   // rank 0: the merged batch
     struct HostSet { HBuf hit_off, hits, pairs, rec_path, rec_pos, cpairs, rec_c; } hs[2];   // host copies of the merged batch: alternating,
     int hs_i = 0;                                                                             // so that an asynchronous copy never lands in the arrays the caller is still reading
@@ -366,7 +365,7 @@ struct grootgpu_comm {
         if (ring) nccl().CommDestroy(ring);
         if (gath) nccl().CommDestroy(gath);
         if (st_gather) cudaStreamDestroy(st_gather);
-        for (cudaEvent_t e : {ev_sent[0], ev_sent[1], ev_local}) if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : {ev_sent[0], ev_sent[1]}) if (e) cudaEventDestroy(e);
         if (h_counts) cudaFreeHost(h_counts);
     }
 };
@@ -1812,7 +1811,7 @@ int grootgpu_comm_create(grootgpu_index* idx, const uint8_t id[GROOTGPU_COMM_ID_
             CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
             CK(cudaStreamCreateWithPriority(&c->st_gather, cudaStreamNonBlocking, prio_lo));   // lowest: see Workspace::create
         }
-        for (cudaEvent_t* e : {&c->ev_sent[0], &c->ev_sent[1], &c->ev_local}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        for (cudaEvent_t* e : {&c->ev_sent[0], &c->ev_sent[1]}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         c->d_counts.need(8ull * kCountWords * (world_size + 2));
         CK(cudaHostAlloc(reinterpret_cast<void**>(&c->h_counts), 8ull * kCountWords * (world_size + 2), cudaHostAllocDefault));
         if (world_size > 1) {
