@@ -353,7 +353,7 @@ def run_config(ctx, name, steps, warmup, n, sample_clocks, cpu_baseline):
                        "output": "hit_off / hits / 32-byte pairs / (u32 path, i32 pos) records, left on the device"}
 
     # ---- e2e: pinned host buffers through the C ABI, compact result to the host ----
-    for _ in range(max(1, warmup // 2)):
+    for _ in range(max(3, warmup // 2)):      # at least 3: both alternating result sets (device and pinned host) are allocated in the first two calls
         raw_e, merged_e = step_e2e()
     drain(); ctx.barrier()
     e2e_parts.update(align_batch_ms=0.0, gather_ms=0.0)
