@@ -88,6 +88,7 @@ static int run_align(const Args& a) {
     if (info.Devices.empty()) info.Devices.push_back(info.Device);
     info.BatchReads = static_cast<uint32_t>(atoi(a.get("--batchReads", "", "1048576").c_str()));
     info.BamLevel = atoi(a.get("--bamLevel", "", "-1").c_str());   // no counterpart: deflate level of the BAM (default = zlib's, as biogo's writer)
+    info.BamDelta = atoi(a.get("--bamDelta", "", "1").c_str()) != 0;   // no counterpart: 0 = every BGZF block through zlib (host/bgzf.h)
     std::vector<std::string> fastq = split_commas(a.get("-f", "--fastq", ""));
     const double t0 = now_s();
     std::vector<grootgpu_index*> replicas;       // the index is replicated on every GPU of the run; replicas[0] ends up with the results

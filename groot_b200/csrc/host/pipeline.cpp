@@ -3,6 +3,8 @@
 
 #include <zlib.h>
 
+#include "bgzf.h"
+
 #include <algorithm>
 #include <cstring>
 #include <ctime>
@@ -82,12 +84,21 @@ bool FastqStream::getline(const char*& line, size_t& len) {
 }
 
 // ---- FastqHandler (sketch.go:175-238) + FastqChecker (sketch.go:259-282) ---------------------------------------
+namespace {
+// a line goes into the batch with one memmove: iterators of the vector's own element type (a `const char*` range is
+// converted element by element, which was 80 % of the reader's time)
+inline void append(std::vector<uint8_t>& v, const char* p, size_t n) {
+    const uint8_t* q = reinterpret_cast<const uint8_t*>(p);
+    v.insert(v.end(), q, q + n);
+}
+}  // namespace
+
 bool FastqStream::next(ReadBatch& b, uint32_t max_reads) {
     b.clear();
     auto push = [&](const char* id, size_t id_n, const char* seq, size_t seq_n, const char* qual, size_t qual_n) {
-        b.id.insert(b.id.end(), id, id + id_n); b.id_off.push_back(b.id.size());
-        b.seq.insert(b.seq.end(), seq, seq + seq_n); b.seq_off.push_back(b.seq.size());
-        b.qual.insert(b.qual.end(), qual, qual + qual_n); b.qual_off.push_back(b.qual.size());
+        append(b.id, id, id_n); b.id_off.push_back(b.id.size());
+        append(b.seq, seq, seq_n); b.seq_off.push_back(b.seq.size());
+        append(b.qual, qual, qual_n); b.qual_off.push_back(b.qual.size());
         raw_count_++; length_total_ += seq_n;
     };
     const char* p; size_t n;
@@ -115,14 +126,14 @@ bool FastqStream::next(ReadBatch& b, uint32_t max_reads) {
     while (b.size() < max_reads) {
         if (!next_line(p, n)) break;
         const size_t id0 = b.id.size(), seq0 = b.seq.size(), qual0 = b.qual.size();
-        b.id.insert(b.id.end(), p, p + n);
+        append(b.id, p, n);
         bool ok = next_line(p, n);
-        if (ok) { b.seq.insert(b.seq.end(), p, p + n); ok = next_line(p, n); }        // line 3 ('+') is dropped
+        if (ok) { append(b.seq, p, n); ok = next_line(p, n); }        // line 3 ('+') is dropped
         if (ok) ok = next_line(p, n);
         if (!ok) { b.id.resize(id0); b.seq.resize(seq0); b.qual.resize(qual0); break; }   // an incomplete trailing record is dropped (sketch.go:216-236)
         if (b.id.size() == id0 || b.id[id0] != '@')   // only a complete record reaches seqio.NewFASTQread (seqio.go:178-180) -> log.Fatal
             throw std::runtime_error("read ID in fastq file does not begin with @: " + std::string(b.id.begin() + id0, b.id.end()));
-        b.qual.insert(b.qual.end(), p, p + n);
+        append(b.qual, p, n);
         b.id_off.push_back(b.id.size()); b.seq_off.push_back(b.seq.size()); b.qual_off.push_back(b.qual.size());
         raw_count_++; length_total_ += b.seq.size() - seq0;
     }
@@ -132,7 +143,6 @@ bool FastqStream::next(ReadBatch& b, uint32_t max_reads) {
 // ---- BAM / BGZF ------------------------------------------------------------------------------------------------
 namespace {
 void put32(std::vector<uint8_t>& v, uint32_t x) { for (int i = 0; i < 4; i++) v.push_back(static_cast<uint8_t>(x >> (8 * i))); }
-void put16(std::vector<uint8_t>& v, uint16_t x) { v.push_back(static_cast<uint8_t>(x)); v.push_back(static_cast<uint8_t>(x >> 8)); }
 int reg2bin(int64_t beg, int64_t end) {  // SAM spec 5.3
     --end;
     if (beg >> 14 == end >> 14) return static_cast<int>(((1 << 15) - 1) / 7 + (beg >> 14));
@@ -142,7 +152,6 @@ int reg2bin(int64_t beg, int64_t end) {  // SAM spec 5.3
     if (beg >> 26 == end >> 26) return static_cast<int>(((1 << 3) - 1) / 7 + (beg >> 26));
     return 0;
 }
-const size_t kBgzfBlock = 0xff00;
 }  // namespace
 
 BamWriter::BamWriter(FILE* out, const std::string& text, const std::vector<std::pair<std::string, int32_t>>& refs, int level) : out_(out), level_(level) {
@@ -160,25 +169,7 @@ BamWriter::BamWriter(FILE* out, const std::string& text, const std::vector<std::
 BamWriter::~BamWriter() { if (!closed_) close(); }
 
 void BamWriter::compress_blocks(const uint8_t* data, size_t n, int level, std::vector<uint8_t>& out) {
-    std::vector<uint8_t> comp(compressBound(kBgzfBlock) + 64);
-    for (size_t at = 0; at < n; at += kBgzfBlock) {
-        const size_t m = std::min(n - at, kBgzfBlock);
-        z_stream zs{};
-        if (deflateInit2(&zs, level < 0 ? Z_DEFAULT_COMPRESSION : level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY) != Z_OK) throw std::runtime_error("deflateInit2 failed");
-        zs.next_in = const_cast<Bytef*>(data + at); zs.avail_in = static_cast<uInt>(m);
-        zs.next_out = comp.data(); zs.avail_out = static_cast<uInt>(comp.size());
-        if (deflate(&zs, Z_FINISH) != Z_STREAM_END) { deflateEnd(&zs); throw std::runtime_error("deflate failed"); }
-        const size_t clen = zs.total_out;
-        deflateEnd(&zs);
-        uint8_t hdr[18] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0, 'B', 'C', 2, 0, 0, 0};
-        const uint16_t bsize = static_cast<uint16_t>(clen + 25);
-        hdr[16] = static_cast<uint8_t>(bsize); hdr[17] = static_cast<uint8_t>(bsize >> 8);
-        out.insert(out.end(), hdr, hdr + 18);
-        out.insert(out.end(), comp.data(), comp.data() + clen);
-        const uint32_t crc = static_cast<uint32_t>(crc32(crc32(0L, Z_NULL, 0), data + at, static_cast<uInt>(m)));
-        for (int i = 0; i < 4; i++) out.push_back(static_cast<uint8_t>(crc >> (8 * i)));
-        for (int i = 0; i < 4; i++) out.push_back(static_cast<uint8_t>(static_cast<uint32_t>(m) >> (8 * i)));
-    }
+    BgzfDeflater::compress_plain(data, n, level, out);
 }
 
 void BamWriter::flush_block() {
@@ -194,8 +185,18 @@ void BamWriter::append_blocks(const std::vector<uint8_t>& bgzf) {
     fwrite(bgzf.data(), 1, bgzf.size(), out_);
 }
 
-void BamWriter::format_record(std::vector<uint8_t>& buf, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
-                              uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual) {
+size_t BamWriter::record_size(uint32_t name_len, uint32_t clip_start, uint32_t match_len, uint32_t clip_end) {
+    const uint32_t n_cigar = 1 + (clip_start ? 1 : 0) + (clip_end ? 1 : 0);
+    return 36u + name_len + 1u + 4u * n_cigar + (match_len + 1u) / 2u + match_len;
+}
+
+namespace {
+inline void st32(uint8_t* p, uint32_t x) { memcpy(p, &x, 4); }     // little-endian hosts only (x86-64 / aarch64), as the rest of the library
+inline void st16(uint8_t* p, uint16_t x) { memcpy(p, &x, 2); }
+}  // namespace
+
+uint8_t* BamWriter::format_record_at(uint8_t* p, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
+                                     uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual) {
     static const struct Nt16 {
         uint8_t t[256];
         Nt16() {
@@ -205,28 +206,46 @@ void BamWriter::format_record(std::vector<uint8_t>& buf, const uint8_t* name, ui
         }
     } nt16;
     const uint32_t n_cigar = 1 + (clip_start ? 1 : 0) + (clip_end ? 1 : 0);
-    const uint32_t block = 32 + name_len + 1 + 4 * n_cigar + (match_len + 1) / 2 + match_len;
-    put32(buf, block);
-    put32(buf, static_cast<uint32_t>(ref_id));
-    put32(buf, static_cast<uint32_t>(pos));
-    buf.push_back(static_cast<uint8_t>(name_len + 1));
-    buf.push_back(30);                                               // MapQ (alignment.go:143)
-    put16(buf, static_cast<uint16_t>(reg2bin(pos, pos + std::max<int64_t>(1, match_len))));
-    put16(buf, static_cast<uint16_t>(n_cigar));
-    put16(buf, flag);
-    put32(buf, match_len);
-    put32(buf, 0xffffffffu);                                         // MateRef nil
-    put32(buf, 0xffffffffu);                                         // no mate position
-    put32(buf, 0);                                                   // TempLen
-    buf.insert(buf.end(), name, name + name_len); buf.push_back(0);
-    if (clip_start) put32(buf, (clip_start << 4) | 5);               // H (alignment.go:132-134)
-    put32(buf, (match_len << 4) | 0);                                // M (alignment.go:135)
-    if (clip_end) put32(buf, (clip_end << 4) | 5);                   // H (alignment.go:136-138)
-    for (uint32_t i = 0; i < match_len; i += 2) {
-        const uint8_t hi = nt16.t[seq[i]], lo = i + 1 < match_len ? nt16.t[seq[i + 1]] : 0;
-        buf.push_back(static_cast<uint8_t>((hi << 4) | lo));
-    }
-    buf.insert(buf.end(), qual, qual + match_len);                  // raw ASCII, not de-offset (alignment.go:121)
+    st32(p, static_cast<uint32_t>(record_size(name_len, clip_start, match_len, clip_end) - 4));   // block_size
+    st32(p + 4, static_cast<uint32_t>(ref_id));
+    st32(p + 8, static_cast<uint32_t>(pos));
+    p[12] = static_cast<uint8_t>(name_len + 1);
+    p[13] = 30;                                                      // MapQ (alignment.go:143)
+    st16(p + 14, record_bin(pos, match_len));
+    st16(p + 16, static_cast<uint16_t>(n_cigar));
+    st16(p + 18, flag);
+    st32(p + 20, match_len);
+    st32(p + 24, 0xffffffffu);                                       // MateRef nil
+    st32(p + 28, 0xffffffffu);                                       // no mate position
+    st32(p + 32, 0);                                                 // TempLen
+    p += 36;
+    memcpy(p, name, name_len); p[name_len] = 0; p += name_len + 1;
+    if (clip_start) { st32(p, (clip_start << 4) | 5); p += 4; }      // H (alignment.go:132-134)
+    st32(p, (match_len << 4) | 0); p += 4;                           // M (alignment.go:135)
+    if (clip_end) { st32(p, (clip_end << 4) | 5); p += 4; }          // H (alignment.go:136-138)
+    for (uint32_t i = 0; i + 1 < match_len; i += 2) *p++ = static_cast<uint8_t>((nt16.t[seq[i]] << 4) | nt16.t[seq[i + 1]]);
+    if (match_len & 1u) *p++ = static_cast<uint8_t>(nt16.t[seq[match_len - 1]] << 4);
+    memcpy(p, qual, match_len);                                      // raw ASCII, not de-offset (alignment.go:121)
+    return p + match_len;
+}
+
+uint16_t BamWriter::record_bin(int32_t pos, uint32_t match_len) { return static_cast<uint16_t>(reg2bin(pos, pos + std::max<int64_t>(1, match_len))); }
+
+// the next record of the same read against another path: everything but refID, pos, bin and the flag is the same
+// (alignment.go:296-315 builds them from one read in a loop over the paths of the start node)
+void BamWriter::repeat_record_at(uint8_t* p, const uint8_t* prev, size_t len, int32_t ref_id, int32_t pos, uint16_t flag, uint32_t match_len) {
+    memcpy(p, prev, len);
+    st32(p + 4, static_cast<uint32_t>(ref_id));
+    st32(p + 8, static_cast<uint32_t>(pos));
+    st16(p + 14, record_bin(pos, match_len));
+    st16(p + 18, flag);
+}
+
+void BamWriter::format_record(std::vector<uint8_t>& buf, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
+                              uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual) {
+    const size_t at = buf.size();
+    buf.resize(at + record_size(name_len, clip_start, match_len, clip_end));
+    format_record_at(buf.data() + at, name, name_len, ref_id, pos, flag, clip_start, match_len, clip_end, seq, qual);
 }
 
 void BamWriter::write(const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag, uint32_t clip_start, uint32_t match_len,
@@ -241,6 +260,102 @@ void BamWriter::close() {
     fwrite(eof, 1, 28, out_);
     fflush(out_);
     closed_ = true;
+}
+
+// ---- one batch of compact results -> BGZF blocks (the writer loop of boss.go:225-242 over alignment.go:114-156 records) ----
+// NumProc workers each format and deflate a contiguous slice of the pairs (slices of roughly equal record count) into
+// ready-made BGZF blocks; the slices are appended in order. One worker reproduces the serial writer byte for byte up
+// to block boundaries. The first record of a pair is formatted from the read (reverse-complemented when the pair is on
+// the reverse strand, read.RevComplement(), seqio.go:120-133); its other records are copies with refID / pos / bin / flag
+// patched, and the block writer is told so (bgzf.h).
+std::string format_batch_bam(const BamBatch& in, unsigned workers, int level, bool delta, std::vector<std::vector<uint8_t>>& outs, uint64_t* delta_blocks) {
+    const ReadBatch& b = *in.reads;
+    workers = std::max(1u, workers);
+    uint8_t ctab[256];                     // complementBases (seqio.go:17-23): everything else maps to 0
+    memset(ctab, 0, sizeof ctab);
+    ctab['A'] = 'T'; ctab['T'] = 'A'; ctab['C'] = 'G'; ctab['G'] = 'C'; ctab['N'] = 'N';
+    // first record of every pair (the compact output carries counts only)
+    std::vector<uint64_t> rec_begin(in.n_pairs + 1, 0);
+    for (uint64_t i = 0; i < in.n_pairs; i++) rec_begin[i + 1] = rec_begin[i] + in.cpairs[i].rec_count;
+    const uint8_t* path8 = in.rec_path_bytes == 1 ? static_cast<const uint8_t*>(in.rec_path_c) : nullptr;
+    const uint16_t* path16 = in.rec_path_bytes == 2 ? static_cast<const uint16_t*>(in.rec_path_c) : nullptr;
+    std::vector<uint64_t> cut(workers + 1, in.n_pairs);
+    cut[0] = 0;
+    {
+        uint64_t i = 0;
+        for (unsigned t = 1; t < workers; t++) {
+            const uint64_t want = in.n_records * t / workers;
+            while (i < in.n_pairs && rec_begin[i] < want) i++;
+            cut[t] = i;
+        }
+    }
+    outs.assign(workers, {});
+    std::vector<std::string> errs(workers);
+    std::vector<uint64_t> n_delta(workers, 0);
+    auto work = [&](unsigned t) {
+        std::vector<uint8_t> rc_seq, rc_qual;
+        std::vector<uint8_t>& out = outs[t];
+        try {
+            BgzfDeflater z(level, delta);
+            size_t prev_len = 0;               // length of the record in front of the next one (0: none pending)
+            for (uint64_t i = cut[t]; i < cut[t + 1]; i++) {
+                const grootgpu_cpair& p = in.cpairs[i];
+                if (p.rec_count == 0) continue;
+                const bool reverse = (p.offset_flags & GROOTGPU_CPAIR_REVERSE) != 0;
+                const uint32_t clip_start = (p.offset_flags & GROOTGPU_CPAIR_CLIP_START) ? 1u : 0u, clip_end = (p.offset_flags & GROOTGPU_CPAIR_CLIP_END) ? 1u : 0u;
+                const int32_t offset = static_cast<int32_t>(p.offset_flags & GROOTGPU_CPAIR_OFFSET_MASK);
+                NodePathsView np;
+                if (!in.node_paths(p.node, &np)) { errs[t] = grootgpu_last_error(); return; }
+                const uint64_t so = b.seq_off[p.read], sl = b.seq_off[p.read + 1] - so;
+                const uint64_t qo = b.qual_off[p.read], ql = b.qual_off[p.read + 1] - qo;
+                const uint8_t* seq = b.seq.data() + so;
+                const uint8_t* qual = b.qual.data() + qo;
+                if (ql < sl) {   // FASTA mode / truncated qualities: the reference panics in RevComplement or when slicing Qual (seqio.go:125-127, alignment.go:121)
+                    errs[t] = "read without a full quality string reached the BAM writer (the reference panics here)";
+                    return;
+                }
+                if (reverse) {                                             // read.RevComplement() (seqio.go:120-133)
+                    rc_seq.resize(sl); rc_qual.resize(sl);
+                    for (uint64_t k = 0; k < sl; k++) { rc_seq[k] = ctab[seq[sl - 1 - k]]; rc_qual[k] = qual[sl - 1 - k]; }
+                    seq = rc_seq.data(); qual = rc_qual.data();
+                }
+                const uint32_t match = static_cast<uint32_t>(sl) - clip_start - clip_end;         // alignment.go:117
+                const uint64_t io = b.id_off[p.read], il = b.id_off[p.read + 1] - io;
+                const uint32_t name_len = static_cast<uint32_t>(il ? il - 1 : 0);                 // Name = ID[1:] (alignment.go:119)
+                const size_t rl = BamWriter::record_size(name_len, clip_start, match, clip_end);
+                for (uint32_t j = 0; j < p.rec_count; j++) {
+                    uint16_t flag = 0;
+                    if (p.rec_count > 1 && j != 0) flag |= 0x100;          // sam.Secondary (alignment.go:147-149)
+                    if (reverse) flag |= 0x10;                             // sam.Reverse (alignment.go:150-152)
+                    const uint32_t path = path8 ? path8[rec_begin[i] + j] : path16[rec_begin[i] + j];
+                    const uint32_t* it = std::lower_bound(np.ids, np.ids + np.n, path);   // Position[pathID] of the start node (alignment.go:296)
+                    const int32_t pos = (it != np.ids + np.n && *it == path ? np.pos[it - np.ids] : 0) + offset;
+                    const int32_t ref_id = static_cast<int32_t>(in.graph_ref_base[np.graph] + path);
+                    uint8_t* dst = z.reserve(rl);
+                    if (j == 0) {
+                        BamWriter::format_record_at(dst, b.id.data() + io + 1, name_len, ref_id, pos, flag, clip_start, match, clip_end, seq, qual);   // Seq/Qual = read[0:seqLength] (alignment.go:120-121)
+                        z.commit(rl, static_cast<uint32_t>(prev_len));     // the record of another read in front: header fields and the name's prefix usually match
+                    } else {
+                        BamWriter::repeat_record_at(dst, dst - rl, rl, ref_id, pos, flag, match);
+                        z.commit(rl, static_cast<uint32_t>(rl));
+                    }
+                    prev_len = rl;
+                }
+                if (z.pending() >= (1u << 20)) { z.drain(false, out); if (z.pending() < rl) prev_len = 0; }   // whole blocks; the remainder stays pending
+            }
+            z.drain(true, out);
+            n_delta[t] = z.delta_blocks();
+        } catch (std::exception& e) { errs[t] = e.what(); }
+    };
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < workers; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
+    }
+    if (delta_blocks) { *delta_blocks = 0; for (uint64_t v : n_delta) *delta_blocks += v; }
+    for (unsigned t = 0; t < workers; t++) if (!errs[t].empty()) return errs[t];
+    return "";
 }
 
 // ---- ReadMapper (sketch.go:308-351 -> boss.go:45-242, graphminion.go:40-103) ------------------------------------
@@ -373,9 +488,6 @@ int ReadMapper::Run(FastqStream& reads) {
         team.prm = prm; team.prm.results_on_device = 1;
         if ((rc = team.start(&err_))) return rc;
     }
-    uint8_t ctab[256];                     // complementBases (seqio.go:17-23): everything else maps to 0
-    memset(ctab, 0, sizeof ctab);
-    ctab['A'] = 'T'; ctab['T'] = 'A'; ctab['C'] = 'G'; ctab['G'] = 'C'; ctab['N'] = 'N';
     // DataStreamer/FastqHandler run ahead on their own thread, as the reference's stages do (pipeline.go:36-45): the
     // next batch is parsed while this one is on the GPU and in the BAM workers. Two batch buffers, handed back and forth.
     struct BatchFeed {
@@ -433,85 +545,18 @@ int ReadMapper::Run(FastqStream& reads) {
         read_stats_[0] += res.received; read_stats_[1] += res.mapped; read_stats_[2] += res.multimapped;
         alignment_count_ += res.alignments;
         if (!bam) continue;
-        // first record of every pair (the compact output carries counts only)
-        std::vector<uint64_t> rec_begin(res.n_pairs + 1, 0);
-        for (uint64_t i = 0; i < res.n_pairs; i++) rec_begin[i + 1] = rec_begin[i] + res.cpairs[i].rec_count;
-        const uint8_t* path8 = res.rec_path_bytes == 1 ? static_cast<const uint8_t*>(res.rec_path_c) : nullptr;
-        const uint16_t* path16 = res.rec_path_bytes == 2 ? static_cast<const uint16_t*>(res.rec_path_c) : nullptr;
-        // Records of the batch, in pair order == (read, graph) order. NumProc workers each format and deflate a
-        // contiguous slice of the pairs (slices of roughly equal record count) into ready-made BGZF blocks; the slices
-        // are appended in order. One worker reproduces the serial writer byte for byte up to block boundaries.
-        const unsigned workers = static_cast<unsigned>(std::max(1, info_->NumProc));
-        std::vector<uint64_t> cut(workers + 1, res.n_pairs);
-        cut[0] = 0;
-        {
-            uint64_t i = 0;
-            for (unsigned t = 1; t < workers; t++) {
-                const uint64_t want = res.n_records * t / workers;
-                while (i < res.n_pairs && rec_begin[i] < want) i++;
-                cut[t] = i;
-            }
-        }
-        std::vector<std::vector<uint8_t>> outs(workers);
-        std::vector<std::string> errs(workers);
-        auto work = [&](unsigned t) {
-            std::vector<uint8_t> raw, rc_seq, rc_qual;
-            std::vector<uint8_t>& out = outs[t];
-            try {
-                for (uint64_t i = cut[t]; i < cut[t + 1]; i++) {
-                    const grootgpu_cpair& p = res.cpairs[i];
-                    if (p.rec_count == 0) continue;
-                    const bool reverse = (p.offset_flags & GROOTGPU_CPAIR_REVERSE) != 0;
-                    const uint32_t clip_start = (p.offset_flags & GROOTGPU_CPAIR_CLIP_START) ? 1u : 0u, clip_end = (p.offset_flags & GROOTGPU_CPAIR_CLIP_END) ? 1u : 0u;
-                    const int32_t offset = static_cast<int32_t>(p.offset_flags & GROOTGPU_CPAIR_OFFSET_MASK);
-                    uint32_t graph = 0, n_node_paths = 0;
-                    const uint32_t* node_ids = nullptr; const int32_t* node_pos = nullptr;
-                    if (grootgpu_index_node_paths(index_, p.node, &graph, &node_ids, &node_pos, &n_node_paths)) { errs[t] = grootgpu_last_error(); return; }
-                    const uint64_t so = b.seq_off[p.read], sl = b.seq_off[p.read + 1] - so;
-                    const uint64_t qo = b.qual_off[p.read], ql = b.qual_off[p.read + 1] - qo;
-                    const uint8_t* seq = b.seq.data() + so;
-                    const uint8_t* qual = b.qual.data() + qo;
-                    if (ql < sl) {   // FASTA mode / truncated qualities: the reference panics in RevComplement or when slicing Qual (seqio.go:125-127, alignment.go:121)
-                        errs[t] = "read without a full quality string reached the BAM writer (the reference panics here)";
-                        return;
-                    }
-                    if (reverse) {                                             // read.RevComplement() (seqio.go:120-133)
-                        rc_seq.resize(sl); rc_qual.resize(sl);
-                        for (uint64_t k = 0; k < sl; k++) { rc_seq[k] = ctab[seq[sl - 1 - k]]; rc_qual[k] = qual[sl - 1 - k]; }
-                        seq = rc_seq.data(); qual = rc_qual.data();
-                    }
-                    const uint32_t match = static_cast<uint32_t>(sl) - clip_start - clip_end;         // alignment.go:117
-                    const uint64_t io = b.id_off[p.read], il = b.id_off[p.read + 1] - io;
-                    for (uint32_t j = 0; j < p.rec_count; j++) {
-                        uint16_t flag = 0;
-                        if (p.rec_count > 1 && j != 0) flag |= 0x100;          // sam.Secondary (alignment.go:147-149)
-                        if (reverse) flag |= 0x10;                             // sam.Reverse (alignment.go:150-152)
-                        const uint32_t path = path8 ? path8[rec_begin[i] + j] : path16[rec_begin[i] + j];
-                        const uint32_t* it = std::lower_bound(node_ids, node_ids + n_node_paths, path);   // Position[pathID] of the start node (alignment.go:296)
-                        const int32_t pos = (it != node_ids + n_node_paths && *it == path ? node_pos[it - node_ids] : 0) + offset;
-                        BamWriter::format_record(raw, b.id.data() + io + 1, static_cast<uint32_t>(il ? il - 1 : 0),          // Name = ID[1:] (alignment.go:119)
-                                                 static_cast<int32_t>(graph_ref_base[graph] + path), pos, flag,
-                                                 clip_start, match, clip_end, seq, qual);    // Seq/Qual = read[0:seqLength] (alignment.go:120-121)
-                    }
-                    if (raw.size() >= (1u << 20)) {                            // deflate whole blocks, keep the remainder
-                        const size_t whole = raw.size() / kBgzfBlock * kBgzfBlock;
-                        BamWriter::compress_blocks(raw.data(), whole, info_->BamLevel, out);
-                        raw.erase(raw.begin(), raw.begin() + whole);
-                    }
-                }
-                BamWriter::compress_blocks(raw.data(), raw.size(), info_->BamLevel, out);
-            } catch (std::exception& e) { errs[t] = e.what(); }
+        // Records of the batch, in pair order == (read, graph) order: NumProc workers, ready-made BGZF blocks (format_batch_bam)
+        BamBatch bb;
+        bb.reads = &b; bb.cpairs = res.cpairs; bb.n_pairs = res.n_pairs; bb.n_records = res.n_records;
+        bb.rec_path_c = res.rec_path_c; bb.rec_path_bytes = res.rec_path_bytes; bb.graph_ref_base = graph_ref_base.data();
+        bb.node_paths = [this](uint32_t node, NodePathsView* v) {
+            return grootgpu_index_node_paths(index_, node, &v->graph, &v->ids, &v->pos, &v->n) == 0;
         };
-        {
-            std::vector<std::thread> th;
-            for (unsigned t = 1; t < workers; t++) th.emplace_back(work, t);
-            work(0);
-            for (auto& x : th) x.join();
-        }
-        for (unsigned t = 0; t < workers; t++) {
-            if (!errs[t].empty()) { err_ = errs[t]; return GROOTGPU_ERR_FORMAT; }
-            bam->append_blocks(outs[t]);
-        }
+        const unsigned workers = static_cast<unsigned>(std::max(1, info_->NumProc));
+        std::vector<std::vector<uint8_t>> outs;
+        const std::string werr = format_batch_bam(bb, workers, info_->BamLevel, info_->BamDelta, outs);
+        if (!werr.empty()) { err_ = werr; return GROOTGPU_ERR_FORMAT; }
+        for (unsigned t = 0; t < workers; t++) bam->append_blocks(outs[t]);
     }
     if (reads.rawCount() == 0) { err_ = "no fastq reads received"; return GROOTGPU_ERR_EMPTY; }   // sketch.go:275-277
     if (bam) { bam->close(); if (fh != stdout) fclose(fh); }

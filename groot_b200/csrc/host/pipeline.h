@@ -14,6 +14,7 @@
 #pragma once
 #include <cstdint>
 #include <cstdio>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -38,6 +39,7 @@ struct Info {
     int Device = 0;
     std::vector<int> Devices;                 // --devices 0,1,...: one index replica per GPU, reads sharded, results gathered to the first (empty = {Device})
     int BamLevel = -1;                        // deflate level of the BGZF blocks (-1 = zlib default, like bam.NewWriter; 0..9)
+    bool BamDelta = true;                     // repeated records of one read as back-references written directly (bgzf.h); false = zlib only
 };
 
 // seqio.FASTQread for a whole batch (src/seqio/seqio.go:26-37), struct-of-arrays
@@ -88,6 +90,13 @@ class BamWriter {
                uint32_t clip_end, const uint8_t* seq, const uint8_t* qual);
     void append_blocks(const std::vector<uint8_t>& bgzf);   // flushes what write() buffered, then appends the blocks as they are
     void close();  // flushes and appends the BGZF EOF block
+    // the same record written at p (record_size bytes); returns the end
+    static size_t record_size(uint32_t name_len, uint32_t clip_start, uint32_t match_len, uint32_t clip_end);
+    static uint8_t* format_record_at(uint8_t* p, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
+                                     uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual);
+    // a further record of the same read (another path): a copy of prev with refID / pos / bin / flag replaced
+    static void repeat_record_at(uint8_t* p, const uint8_t* prev, size_t len, int32_t ref_id, int32_t pos, uint16_t flag, uint32_t match_len);
+    static uint16_t record_bin(int32_t pos, uint32_t match_len);
     // the same record, appended to a caller-owned buffer of uncompressed BAM bytes
     static void format_record(std::vector<uint8_t>& buf, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
                               uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual);
@@ -100,6 +109,23 @@ class BamWriter {
     int level_;
     bool closed_ = false;
 };
+
+// One batch of compact results (grootgpu_batch_result with compact_records) -> BGZF blocks. node_paths is
+// grootgpu_index_node_paths (graph, sorted path ids and Position[pathID] of a node); false = error (grootgpu_last_error).
+struct NodePathsView { uint32_t graph = 0; const uint32_t* ids = nullptr; const int32_t* pos = nullptr; uint32_t n = 0; };
+struct BamBatch {
+    const ReadBatch* reads = nullptr;
+    const grootgpu_cpair* cpairs = nullptr;
+    uint64_t n_pairs = 0, n_records = 0;
+    const void* rec_path_c = nullptr;
+    uint32_t rec_path_bytes = 1;
+    const uint32_t* graph_ref_base = nullptr;          // first @SQ of every graph
+    std::function<bool(uint32_t node, NodePathsView*)> node_paths;
+};
+// outs[t] = the blocks of worker t (append in order). Returns "" or the error text. level = deflate level of zlib
+// (-1 default); delta = let the block writer encode repeated records as back-references itself (bgzf.h).
+std::string format_batch_bam(const BamBatch& in, unsigned workers, int level, bool delta, std::vector<std::vector<uint8_t>>& outs,
+                             uint64_t* delta_blocks = nullptr);
 
 class ReadMapper {
   public:
