@@ -5,13 +5,13 @@
 // Why it is not just zlib: theBoss writes one sam.Record per (read, path) — alignment.go:296-315 emits the SAME read
 // once for every path through the start node, 17 records per aligned read against arg-annot.90 — so consecutive
 // records of one (read, graph) pair are byte-identical except for refID, pos, bin and the secondary flag. zlib finds
-// those repeats again by hashing every byte (~60-150 MB/s per thread); the writer below is TOLD where the previous
-// record lies (a hint: "this record probably equals the bytes `dist` back") and turns equal stretches into LZ77 matches
-// with one 8-byte-wide compare — one fixed-Huffman deflate block per BGZF block. It is correct by construction: a match
-// is only emitted for bytes that WERE compared equal, whatever the hints say; bytes without a usable hint are literals
-// (with run-length matches at distance 1). A block the hints do not help (single-path databases: every record is a
-// different read) is handed to zlib at the configured level instead, so the default output is never much larger than
-// the reference's.
+// those repeats again by hashing every byte; the writer below is TOLD where the previous record lies (a hint: "this
+// record probably equals the bytes `dist` back") and turns equal stretches into LZ77 matches with a 16-byte-wide
+// compare. The tokens of a block (literals, matches, runs of one byte as matches at distance 1) are then written as ONE
+// deflate block, with the fixed code of RFC 1951 3.2.6 or a Huffman code built for the block (3.2.7), whichever is
+// shorter. It is correct by construction: a match is only emitted for bytes that WERE compared equal, whatever the
+// hints say. A block the hints do not help (single-path databases: every record is a different read) is handed to zlib
+// at the configured level instead, so the default output is never much larger than the reference's.
 #pragma once
 #include <zlib.h>
 #if defined(__SSE2__)
@@ -32,30 +32,37 @@ constexpr size_t kBgzfMaxData = 65536 - 26; // deflate bytes that fit behind the
 namespace bgzf_detail {
 inline uint32_t bit_reverse(uint32_t v, int n) { uint32_t r = 0; for (int i = 0; i < n; i++) r |= ((v >> i) & 1u) << (n - 1 - i); return r; }
 
-// RFC 1951 3.2.6 fixed Huffman codes, stored ready for an LSB-first bit stream (code bit-reversed, extra bits behind it)
-struct FixedTables {
-    uint16_t lit_bits[256]; uint8_t lit_n[256];
-    uint32_t len_bits[259]; uint8_t len_n[259];
-    FixedTables() {
-        for (int b = 0; b < 256; b++) {
-            if (b < 144) { lit_bits[b] = static_cast<uint16_t>(bit_reverse(0x30u + b, 8)); lit_n[b] = 8; }
-            else { lit_bits[b] = static_cast<uint16_t>(bit_reverse(0x190u + (b - 144), 9)); lit_n[b] = 9; }
-        }
+constexpr int kLitLen = 286, kDist = 30, kCodeLen = 19;
+
+// RFC 1951 3.2.5 length symbols and the fixed codes of 3.2.6, ready for an LSB-first bit stream (Huffman codes are
+// stored bit-reversed, extra bits behind them)
+struct Tables {
+    uint8_t len_sym[259], len_extra_n[29]; uint16_t len_base[29];     // match length -> symbol - 257; extra bits of a symbol
+    uint16_t fix_lit_bits[256]; uint8_t fix_lit_n[256];
+    uint32_t fix_len_bits[259]; uint8_t fix_len_n[259];               // code + extra bits of a match length
+    uint8_t fix_sym_n[kLitLen];
+    Tables() {
         static const uint16_t base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
         static const uint8_t extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+        for (int c = 0; c < 29; c++) { len_base[c] = base[c]; len_extra_n[c] = extra[c]; }
+        for (int s = 0; s < kLitLen; s++) fix_sym_n[s] = s < 144 ? 8 : s < 256 ? 9 : s < 280 ? 7 : 8;
+        for (int b = 0; b < 256; b++) {
+            fix_lit_bits[b] = static_cast<uint16_t>(b < 144 ? bit_reverse(0x30u + b, 8) : bit_reverse(0x190u + (b - 144), 9));
+            fix_lit_n[b] = fix_sym_n[b];
+        }
+        memset(len_sym, 0, sizeof len_sym);
         for (int len = 3; len <= 258; len++) {
             int c = 28;
             if (len < 258) { c = 0; while (c + 1 < 28 && base[c + 1] <= len) c++; }
-            const int sym = 257 + c;
-            uint32_t code; int n;
-            if (sym < 280) { code = bit_reverse(static_cast<uint32_t>(sym - 256), 7); n = 7; }
-            else { code = bit_reverse(0xC0u + (sym - 280), 8); n = 8; }
-            len_bits[len] = code | static_cast<uint32_t>(len - base[c]) << n;
-            len_n[len] = static_cast<uint8_t>(n + extra[c]);
+            len_sym[len] = static_cast<uint8_t>(c);
+            const int sym = 257 + c, n = fix_sym_n[sym];
+            const uint32_t code = sym < 280 ? bit_reverse(static_cast<uint32_t>(sym - 256), 7) : bit_reverse(0xC0u + (sym - 280), 8);
+            fix_len_bits[len] = code | static_cast<uint32_t>(len - base[c]) << n;
+            fix_len_n[len] = static_cast<uint8_t>(n + extra[c]);
         }
     }
 };
-inline const FixedTables& tables() { static const FixedTables t; return t; }
+inline const Tables& tables() { static const Tables t; return t; }
 
 struct BitWriter {
     uint8_t* p; uint64_t acc = 0; int nb = 0;
@@ -67,14 +74,54 @@ struct BitWriter {
     inline uint8_t* finish() { while (nb > 0) { *p++ = static_cast<uint8_t>(acc); acc >>= 8; nb -= 8; } nb = 0; return p; }
 };
 
-// distance 1..32768 -> 5-bit code (reversed) + extra bits
-inline void dist_code(uint32_t d, uint32_t* bits, int* n) {
-    if (d <= 4) { *bits = bit_reverse(d - 1, 5); *n = 5; return; }
+// distance 1..32768 -> symbol 0..29, number of extra bits, their value (RFC 1951 3.2.5)
+inline void dist_symbol(uint32_t d, uint32_t* sym, int* extra_n, uint32_t* extra) {
+    if (d <= 4) { *sym = d - 1; *extra_n = 0; *extra = 0; return; }
     const uint32_t x = d - 1;
     const int hb = 31 - __builtin_clz(x);
-    const uint32_t code = 2u * hb + ((x >> (hb - 1)) & 1u);
-    *bits = bit_reverse(code, 5) | (x & ((1u << (hb - 1)) - 1u)) << 5;
-    *n = 5 + hb - 1;
+    *sym = 2u * hb + ((x >> (hb - 1)) & 1u);
+    *extra_n = hb - 1;
+    *extra = x & ((1u << (hb - 1)) - 1u);
+}
+
+// Huffman code lengths of at most max_bits for the symbols with freq != 0 (at least two symbols get a code, so the code
+// is always complete: what zlib's build_tree does for inflaters that insist on it). Plain two-queue Huffman; if the tree
+// comes out too deep the frequencies are halved (rounding up) and it is built again — that flattens it until it fits.
+inline void huffman_lengths(const uint32_t* freq, int n, int max_bits, uint8_t* len) {
+    struct Leaf { uint32_t f; int s; };
+    Leaf leaf[288];
+    int m = 0;
+    for (int s = 0; s < n; s++) if (freq[s]) leaf[m++] = {freq[s], s};
+    for (int s = 0; m < 2 && s < n; s++) if (!freq[s]) leaf[m++] = {1u, s};
+    std::sort(leaf, leaf + m, [](const Leaf& a, const Leaf& b) { return a.f != b.f ? a.f < b.f : a.s < b.s; });
+    memset(len, 0, static_cast<size_t>(n));
+    uint64_t f[576]; int parent[576], depth[576];
+    while (true) {
+        for (int i = 0; i < m; i++) f[i] = leaf[i].f;
+        int a = 0, b = m, k = m;                       // next unmerged leaf / internal node, next free internal slot
+        while (k < 2 * m - 1) {
+            int pick[2];
+            for (int j = 0; j < 2; j++) pick[j] = (a < m && (b >= k || f[a] <= f[b])) ? a++ : b++;
+            f[k] = f[pick[0]] + f[pick[1]];
+            parent[pick[0]] = parent[pick[1]] = k;
+            k++;
+        }
+        depth[2 * m - 2] = 0;
+        int deepest = 0;
+        for (int i = 2 * m - 3; i >= 0; i--) { depth[i] = depth[parent[i]] + 1; if (i < m) deepest = std::max(deepest, depth[i]); }
+        if (deepest <= max_bits) break;
+        for (int i = 0; i < m; i++) leaf[i].f = (leaf[i].f + 1u) >> 1;     // monotone: the order stays sorted
+    }
+    for (int i = 0; i < m; i++) len[leaf[i].s] = static_cast<uint8_t>(depth[i]);
+}
+// canonical codes of RFC 1951 3.2.2, bit-reversed for the LSB-first stream
+inline void canonical_codes(const uint8_t* len, int n, uint16_t* code) {
+    uint32_t count[16] = {0}, next[16] = {0};
+    for (int s = 0; s < n; s++) count[len[s]]++;
+    count[0] = 0;
+    uint32_t c = 0;
+    for (int bits = 1; bits < 16; bits++) { c = (c + count[bits - 1]) << 1; next[bits] = c; }
+    for (int s = 0; s < n; s++) code[s] = len[s] ? static_cast<uint16_t>(bit_reverse(next[len[s]]++, len[s])) : 0;
 }
 }  // namespace bgzf_detail
 
@@ -83,7 +130,7 @@ inline void dist_code(uint32_t d, uint32_t* bits, int* n) {
 class BgzfDeflater {
   public:
     // level: zlib's (-1 default, 0 stored .. 9); delta: use the hint-driven encoder where it pays (never at level 0)
-    BgzfDeflater(int level, bool delta) : level_(level), delta_(delta && level != 0), scratch_(kBgzfBlock * 4 / 3 + 256) {}   // worst case: every 3 bytes a 31-bit match
+    BgzfDeflater(int level, bool delta) : level_(level), delta_(delta && level != 0), scratch_(kBgzfBlock * 4 / 3 + 1024) {}   // worst case: every 3 bytes a 31-bit match
 
     // room for one record behind the pending bytes; the pointer is valid until the next reserve / drain, and the bytes
     // in front of it are the previous records (a caller may copy from `ptr - len_of_previous`)
@@ -111,6 +158,7 @@ class BgzfDeflater {
                 clen = encode_delta(at, m, h);
                 done = clen <= kBgzfMaxData && clen * 3 <= m + 64;          // worth it: at most a third of the input
                 delta_blocks_ += done ? 1 : 0;
+                dynamic_blocks_ += done && last_dynamic_ ? 1 : 0;
             }
             if (!done) clen = encode_zlib(raw_.data() + at, m);
             zlib_blocks_ += done ? 0 : 1;
@@ -128,6 +176,7 @@ class BgzfDeflater {
     }
     uint64_t delta_blocks() const { return delta_blocks_; }
     uint64_t zlib_blocks() const { return zlib_blocks_; }
+    uint64_t dynamic_blocks() const { return dynamic_blocks_; }    // of the delta blocks: written with a code of their own
 
     // deflate + BGZF framing of data[0, n) with zlib only (what the header and single records use)
     static void compress_plain(const uint8_t* data, size_t n, int level, std::vector<uint8_t>& out) {
@@ -140,6 +189,7 @@ class BgzfDeflater {
 
   private:
     struct Hint { int64_t off; uint32_t len, dist; };
+    static constexpr uint32_t kMatch = 0x80000000u;        // token: literal byte, or kMatch | length << 16 | (distance - 1)
 
     size_t encode_zlib(const uint8_t* data, size_t m) {
         z_stream zs{};
@@ -165,32 +215,32 @@ class BgzfDeflater {
         memcpy(out.data() + o + 18 + clen, tail, 8);
     }
 
+    // ---- tokens of one block -------------------------------------------------------------------------------------
+    // a match of n >= 3 bytes at distance dist, cut into pieces of at most 258 bytes none of which is shorter than 3
+    inline void tok_match(size_t n, uint32_t dist) {
+        const bgzf_detail::Tables& T = bgzf_detail::tables();
+        if (dist != ds_dist_) { ds_dist_ = dist; int en; uint32_t ev; bgzf_detail::dist_symbol(dist, &ds_sym_, &en, &ev); }    // a block sees few distinct distances
+        while (n > 0) {
+            size_t take = std::min<size_t>(n, 258);
+            if (n - take > 0 && n - take < 3) take = n - 3;
+            *tok_end_++ = kMatch | static_cast<uint32_t>(take) << 16 | (dist - 1u);
+            lfreq_[257 + T.len_sym[take]]++; dfreq_[ds_sym_]++;
+            n -= take;
+        }
+    }
     // literals of raw_[p, q), runs of one byte as matches at distance 1 (the run's first byte stays a literal)
-    inline void put_literals(bgzf_detail::BitWriter& bw, size_t p, size_t q) {
-        const bgzf_detail::FixedTables& T = bgzf_detail::tables();
+    inline void tok_literals(size_t p, size_t q) {
         const uint8_t* d = raw_.data();
         while (p < q) {
             const uint8_t b = d[p];
-            bw.put(T.lit_bits[b], T.lit_n[b]);
+            *tok_end_++ = b; lfreq_[b]++;
             p++;
             if (p + 3 <= q && d[p] == b && d[p + 1] == b && d[p + 2] == b) {
                 size_t r = 3;
                 while (p + r < q && d[p + r] == b) r++;
-                put_match(bw, r, 1);
+                tok_match(r, 1);
                 p += r;
             }
-        }
-    }
-    // a match of n >= 3 bytes at distance dist, cut into pieces of at most 258 bytes none of which is shorter than 3
-    inline void put_match(bgzf_detail::BitWriter& bw, size_t n, uint32_t dist) {
-        const bgzf_detail::FixedTables& T = bgzf_detail::tables();
-        if (dist != dc_dist_) { dc_dist_ = dist; bgzf_detail::dist_code(dist, &dc_bits_, &dc_n_); }    // a block sees few distinct distances
-        while (n > 0) {
-            size_t take = std::min<size_t>(n, 258);
-            if (n - take > 0 && n - take < 3) take = n - 3;
-            bw.put(T.len_bits[take], T.len_n[take]);
-            bw.put(dc_bits_, dc_n_);
-            n -= take;
         }
     }
     // length of the common prefix of a[0, n) and b[0, n)
@@ -214,44 +264,138 @@ class BgzfDeflater {
         return e;
     }
     // raw_[p, q) against the bytes dist back: equal stretches of 3+ bytes become matches, the rest literals
-    inline void put_compared(bgzf_detail::BitWriter& bw, size_t p, size_t q, uint32_t dist) {
+    inline void tok_compared(size_t p, size_t q, uint32_t dist) {
         const uint8_t* d = raw_.data();
         size_t lit0 = p;                       // start of the literal stretch not written yet
         while (p < q) {
             if (d[p] != d[p - dist]) { p++; continue; }
             const size_t e = p + equal_prefix(d + p, d + p - dist, q - p);      // [p, e) equals the bytes dist back
             if (e - p >= 3) {
-                if (lit0 < p) put_literals(bw, lit0, p);
-                put_match(bw, e - p, dist);
+                if (lit0 < p) tok_literals(lit0, p);
+                tok_match(e - p, dist);
                 lit0 = e;
             }
             p = e;                              // shorter: too short to pay for a match, stays in the literal stretch
         }
-        if (lit0 < q) put_literals(bw, lit0, q);
+        if (lit0 < q) tok_literals(lit0, q);
     }
 
-    // one fixed-Huffman block for raw_[at, at + m); h = first hint that reaches into it. Returns the deflate size
-    // (in scratch_), which may exceed kBgzfMaxData — the caller then falls back to zlib.
+    // ---- one deflate block for raw_[at, at + m); h = first hint that reaches into it --------------------------------
+    // Returns the deflate size (in scratch_), which may exceed kBgzfMaxData — the caller then falls back to zlib.
     size_t encode_delta(size_t at, size_t m, size_t h) {
-        bgzf_detail::BitWriter bw(scratch_.data());
-        bw.put(3u, 3);                                                   // BFINAL = 1, BTYPE = 01
+        using namespace bgzf_detail;
+        const Tables& T = tables();
+        if (tok_.size() < m + 16) tok_.resize(m + 16);                    // at most one token per byte
+        tok_end_ = tok_.data();
+        memset(lfreq_, 0, sizeof lfreq_); memset(dfreq_, 0, sizeof dfreq_);
+        ds_dist_ = 0;
         const int64_t b0 = static_cast<int64_t>(at), b1 = static_cast<int64_t>(at + m);
         int64_t p = b0;
         for (size_t i = h; i < hints_.size() && hints_[i].off < b1; i++) {
             const Hint& hn = hints_[i];
             const int64_t s = std::max(hn.off, b0), e = std::min(hn.off + static_cast<int64_t>(hn.len), b1);
             if (e <= s) continue;
-            if (p < s) put_literals(bw, static_cast<size_t>(p), static_cast<size_t>(s));      // bytes no record claims
+            if (p < s) tok_literals(static_cast<size_t>(p), static_cast<size_t>(s));      // bytes no record claims
             // a reference may not reach in front of the block: literal up to b0 + dist
             const int64_t ms = hn.dist ? std::max(s, b0 + static_cast<int64_t>(hn.dist)) : e;
             if (ms < e) {
-                if (s < ms) put_literals(bw, static_cast<size_t>(s), static_cast<size_t>(ms));
-                put_compared(bw, static_cast<size_t>(ms), static_cast<size_t>(e), hn.dist);
-            } else put_literals(bw, static_cast<size_t>(s), static_cast<size_t>(e));
+                if (s < ms) tok_literals(static_cast<size_t>(s), static_cast<size_t>(ms));
+                tok_compared(static_cast<size_t>(ms), static_cast<size_t>(e), hn.dist);
+            } else tok_literals(static_cast<size_t>(s), static_cast<size_t>(e));
             p = e;
         }
-        if (p < b1) put_literals(bw, static_cast<size_t>(p), static_cast<size_t>(b1));
-        bw.put(0u, 7);                                                   // end of block (symbol 256)
+        if (p < b1) tok_literals(static_cast<size_t>(p), static_cast<size_t>(b1));
+        lfreq_[256] = 1;                                                  // end of block
+
+        // the block's own code (RFC 1951 3.2.7) and what it costs against the fixed one
+        uint8_t llen[kLitLen], dlen[kDist];
+        huffman_lengths(lfreq_, kLitLen, 15, llen);
+        huffman_lengths(dfreq_, kDist, 15, dlen);
+        int nlit = kLitLen, ndist = kDist;
+        while (nlit > 257 && !llen[nlit - 1]) nlit--;
+        while (ndist > 1 && !dlen[ndist - 1]) ndist--;
+        // the code lengths themselves, run-length coded with the symbols 16 (repeat), 17 / 18 (zeros)
+        uint8_t seq[kLitLen + kDist];
+        memcpy(seq, llen, static_cast<size_t>(nlit)); memcpy(seq + nlit, dlen, static_cast<size_t>(ndist));
+        struct ClTok { uint8_t sym, extra; };
+        ClTok cl[kLitLen + kDist];
+        int ncl_tok = 0;
+        uint32_t clfreq[kCodeLen] = {0};
+        auto emit = [&](int sym, int extra) { cl[ncl_tok++] = {static_cast<uint8_t>(sym), static_cast<uint8_t>(extra)}; clfreq[sym]++; };
+        for (int i = 0, n = nlit + ndist; i < n;) {
+            const int v = seq[i];
+            int run = 1;
+            while (i + run < n && seq[i + run] == v) run++;
+            i += run;
+            if (v == 0) {
+                while (run >= 11) { const int t = std::min(run, 138); emit(18, t - 11); run -= t; }
+                if (run >= 3) { emit(17, run - 3); run = 0; }
+            } else {
+                emit(v, 0); run--;
+                while (run >= 3) { const int t = std::min(run, 6); emit(16, t - 3); run -= t; }
+            }
+            while (run-- > 0) emit(v, 0);
+        }
+        uint8_t cllen[kCodeLen];
+        huffman_lengths(clfreq, kCodeLen, 7, cllen);
+        static const uint8_t order[kCodeLen] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+        int ncl = kCodeLen;
+        while (ncl > 4 && !cllen[order[ncl - 1]]) ncl--;
+        uint64_t extra_bits = 0, dyn_bits = 3 + 5 + 5 + 4 + 3 * static_cast<uint64_t>(ncl), fix_bits = 3;
+        for (int c = 0; c < 29; c++) extra_bits += static_cast<uint64_t>(lfreq_[257 + c]) * T.len_extra_n[c];
+        for (int d = 4; d < kDist; d++) extra_bits += static_cast<uint64_t>(dfreq_[d]) * static_cast<uint64_t>(d / 2 - 1);
+        for (int i = 0; i < ncl_tok; i++) dyn_bits += cllen[cl[i].sym] + (cl[i].sym == 16 ? 2 : cl[i].sym == 17 ? 3 : cl[i].sym == 18 ? 7 : 0);
+        for (int s = 0; s < kLitLen; s++) { dyn_bits += static_cast<uint64_t>(lfreq_[s]) * llen[s]; fix_bits += static_cast<uint64_t>(lfreq_[s]) * T.fix_sym_n[s]; }
+        for (int d = 0; d < kDist; d++) { dyn_bits += static_cast<uint64_t>(dfreq_[d]) * dlen[d]; fix_bits += static_cast<uint64_t>(dfreq_[d]) * 5u; }
+        dyn_bits += extra_bits; fix_bits += extra_bits;
+
+        BitWriter bw(scratch_.data());
+        last_dynamic_ = false;
+        if (fix_bits <= dyn_bits) {
+            bw.put(3u, 3);                                                   // BFINAL = 1, BTYPE = 01
+            uint32_t last_dist = 0, dbits = 0; int dn = 0;
+            for (const uint32_t* tp = tok_.data(); tp != tok_end_; tp++) {
+                const uint32_t t = *tp;
+                if (!(t & kMatch)) { bw.put(T.fix_lit_bits[t], T.fix_lit_n[t]); continue; }
+                const uint32_t len = (t >> 16) & 0x1ffu, dist = (t & 0x7fffu) + 1u;
+                if (dist != last_dist) {
+                    uint32_t sym, ev; int en;
+                    dist_symbol(dist, &sym, &en, &ev);
+                    last_dist = dist; dbits = bit_reverse(sym, 5) | ev << 5; dn = 5 + en;
+                }
+                bw.put(T.fix_len_bits[len], T.fix_len_n[len]);
+                bw.put(dbits, dn);
+            }
+            bw.put(0u, 7);                                                   // end of block (symbol 256)
+            return static_cast<size_t>(bw.finish() - scratch_.data());
+        }
+        last_dynamic_ = true;
+        uint16_t lcode[kLitLen], dcode[kDist], clcode[kCodeLen];
+        canonical_codes(llen, kLitLen, lcode); canonical_codes(dlen, kDist, dcode); canonical_codes(cllen, kCodeLen, clcode);
+        bw.put(5u, 3);                                                       // BFINAL = 1, BTYPE = 10
+        bw.put(static_cast<uint32_t>(nlit - 257), 5); bw.put(static_cast<uint32_t>(ndist - 1), 5); bw.put(static_cast<uint32_t>(ncl - 4), 4);
+        for (int i = 0; i < ncl; i++) bw.put(cllen[order[i]], 3);
+        for (int i = 0; i < ncl_tok; i++) {
+            bw.put(clcode[cl[i].sym], cllen[cl[i].sym]);
+            if (cl[i].sym >= 16) bw.put(cl[i].extra, cl[i].sym == 16 ? 2 : cl[i].sym == 17 ? 3 : 7);
+        }
+        uint32_t last_dist = 0, dbits = 0; int dn = 0;
+        uint32_t lit[256];                                                   // code | length << 16 of the literals
+        for (int b = 0; b < 256; b++) lit[b] = lcode[b] | static_cast<uint32_t>(llen[b]) << 16;
+        for (const uint32_t* tp = tok_.data(); tp != tok_end_; tp++) {
+            const uint32_t t = *tp;
+            if (!(t & kMatch)) { bw.put(lit[t] & 0xffffu, static_cast<int>(lit[t] >> 16)); continue; }
+            const uint32_t len = (t >> 16) & 0x1ffu, dist = (t & 0x7fffu) + 1u;
+            if (dist != last_dist) {
+                uint32_t sym, ev; int en;
+                dist_symbol(dist, &sym, &en, &ev);
+                last_dist = dist; dbits = dcode[sym] | ev << dlen[sym]; dn = dlen[sym] + en;
+            }
+            const int c = T.len_sym[len], ls = 257 + c;
+            bw.put(lcode[ls] | static_cast<uint32_t>(len - T.len_base[c]) << llen[ls], llen[ls] + T.len_extra_n[c]);
+            bw.put(dbits, dn);
+        }
+        bw.put(lcode[256], llen[256]);
         return static_cast<size_t>(bw.finish() - scratch_.data());
     }
 
@@ -260,8 +404,12 @@ class BgzfDeflater {
     std::vector<uint8_t> raw_, scratch_;
     size_t fill_ = 0;
     std::vector<Hint> hints_;
-    uint64_t delta_blocks_ = 0, zlib_blocks_ = 0;
-    uint32_t dc_dist_ = 0, dc_bits_ = 0; int dc_n_ = 0;   // last distance code
+    std::vector<uint32_t> tok_;
+    uint32_t* tok_end_ = nullptr;
+    uint32_t lfreq_[bgzf_detail::kLitLen], dfreq_[bgzf_detail::kDist];
+    uint32_t ds_dist_ = 0, ds_sym_ = 0;                    // last distance -> symbol
+    uint64_t delta_blocks_ = 0, zlib_blocks_ = 0, dynamic_blocks_ = 0;
+    bool last_dynamic_ = false;
 };
 
 }  // namespace groot_host

@@ -268,7 +268,7 @@ void BamWriter::close() {
 // to block boundaries. The first record of a pair is formatted from the read (reverse-complemented when the pair is on
 // the reverse strand, read.RevComplement(), seqio.go:120-133); its other records are copies with refID / pos / bin / flag
 // patched, and the block writer is told so (bgzf.h).
-std::string format_batch_bam(const BamBatch& in, unsigned workers, int level, bool delta, std::vector<std::vector<uint8_t>>& outs, uint64_t* delta_blocks) {
+std::string format_batch_bam(const BamBatch& in, unsigned workers, int level, bool delta, std::vector<std::vector<uint8_t>>& outs, BamBlockStats* stats) {
     const ReadBatch& b = *in.reads;
     workers = std::max(1u, workers);
     uint8_t ctab[256];                     // complementBases (seqio.go:17-23): everything else maps to 0
@@ -291,7 +291,7 @@ std::string format_batch_bam(const BamBatch& in, unsigned workers, int level, bo
     }
     outs.assign(workers, {});
     std::vector<std::string> errs(workers);
-    std::vector<uint64_t> n_delta(workers, 0);
+    std::vector<BamBlockStats> wstats(workers);
     auto work = [&](unsigned t) {
         std::vector<uint8_t> rc_seq, rc_qual;
         std::vector<uint8_t>& out = outs[t];
@@ -344,7 +344,7 @@ std::string format_batch_bam(const BamBatch& in, unsigned workers, int level, bo
                 if (z.pending() >= (1u << 20)) { z.drain(false, out); if (z.pending() < rl) prev_len = 0; }   // whole blocks; the remainder stays pending
             }
             z.drain(true, out);
-            n_delta[t] = z.delta_blocks();
+            wstats[t].zlib = z.zlib_blocks(); wstats[t].delta = z.delta_blocks(); wstats[t].delta_own_code = z.dynamic_blocks();
         } catch (std::exception& e) { errs[t] = e.what(); }
     };
     {
@@ -353,7 +353,7 @@ std::string format_batch_bam(const BamBatch& in, unsigned workers, int level, bo
         work(0);
         for (auto& x : th) x.join();
     }
-    if (delta_blocks) { *delta_blocks = 0; for (uint64_t v : n_delta) *delta_blocks += v; }
+    if (stats) { *stats = BamBlockStats(); for (const BamBlockStats& w : wstats) { stats->zlib += w.zlib; stats->delta += w.delta; stats->delta_own_code += w.delta_own_code; } }
     for (unsigned t = 0; t < workers; t++) if (!errs[t].empty()) return errs[t];
     return "";
 }

@@ -124,8 +124,9 @@ struct BamBatch {
 };
 // outs[t] = the blocks of worker t (append in order). Returns "" or the error text. level = deflate level of zlib
 // (-1 default); delta = let the block writer encode repeated records as back-references itself (bgzf.h).
+struct BamBlockStats { uint64_t zlib = 0, delta = 0, delta_own_code = 0; };   // BGZF blocks by encoder (delta_own_code: of the delta blocks, those with a Huffman code of their own)
 std::string format_batch_bam(const BamBatch& in, unsigned workers, int level, bool delta, std::vector<std::vector<uint8_t>>& outs,
-                             uint64_t* delta_blocks = nullptr);
+                             BamBlockStats* stats = nullptr);
 
 class ReadMapper {
   public:

@@ -1,6 +1,6 @@
 // Test / timing harness for the host driver's BAM output (format_batch_bam + BamWriter, host only — no device): reads a
 // fabricated batch (reads, compact pairs, path ids, node -> path table, @SQ list) from a file written by
-// tests/test_bam_cpu.py, writes the BAM, prints "<seconds> <uncompressed record bytes> <bam bytes> <delta blocks>".
+// tests/test_bam_cpu.py, writes the BAM, prints "<seconds> <uncompressed record bytes> <bam bytes> <delta blocks> <of those: own Huffman code> <zlib blocks>".
 //   bam_batch <batch file> <out.bam> <workers> <level> <delta 0|1> [repeats]
 #include <chrono>
 #include <cstdio>
@@ -75,11 +75,12 @@ int main(int argc, char** argv) {
         FILE* out = fopen(argv[2], "wb");
         if (!out) throw std::runtime_error("cannot open output");
         double best = 1e30;
-        uint64_t bam_bytes = 0, delta_blocks = 0;
+        uint64_t bam_bytes = 0;
+        BamBlockStats st;
         for (int it = 0; it < repeats; it++) {
             std::vector<std::vector<uint8_t>> outs;
             const auto t0 = std::chrono::steady_clock::now();
-            const std::string err = format_batch_bam(bb, workers, level, delta, outs, &delta_blocks);
+            const std::string err = format_batch_bam(bb, workers, level, delta, outs, &st);
             const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             if (!err.empty()) throw std::runtime_error(err);
             best = std::min(best, dt);
@@ -90,7 +91,8 @@ int main(int argc, char** argv) {
             }
         }
         fclose(out);
-        printf("%.6f %llu %llu %llu\n", best, static_cast<unsigned long long>(raw_bytes), static_cast<unsigned long long>(bam_bytes), static_cast<unsigned long long>(delta_blocks));
+        printf("%.6f %llu %llu %llu %llu %llu\n", best, static_cast<unsigned long long>(raw_bytes), static_cast<unsigned long long>(bam_bytes),
+               static_cast<unsigned long long>(st.delta), static_cast<unsigned long long>(st.delta_own_code), static_cast<unsigned long long>(st.zlib));
     } catch (std::exception& e) {
         fprintf(stderr, "%s\n", e.what());
         return 2;

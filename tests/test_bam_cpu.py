@@ -132,10 +132,14 @@ def _check_blocks(raw):
     return b"".join(out)
 
 
+COVERAGE = {"fixed": 0, "own": 0, "zlib": 0}       # blocks by encoder over the whole module (checked by the last test)
+
+
 def _run(harness, batch_file, out, workers, level, delta):
     r = subprocess.run([harness, batch_file, out, str(workers), str(level), str(delta)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert r.returncode == 0, r.stderr.decode()
-    secs, raw_bytes, bam_bytes, delta_blocks = r.stdout.decode().split()
+    secs, raw_bytes, bam_bytes, delta_blocks, own_code, zlib_blocks = r.stdout.decode().split()
+    COVERAGE["fixed"] += int(delta_blocks) - int(own_code); COVERAGE["own"] += int(own_code); COVERAGE["zlib"] += int(zlib_blocks)
     return int(raw_bytes), int(bam_bytes), int(delta_blocks)
 
 
@@ -163,6 +167,20 @@ def test_bam_stream_equals_independent_writer(harness, tmp_path, case):
             assert delta_blocks == 0
         if case in ("many_paths", "binned_quals") and delta and level != 0:
             assert delta_blocks > 0 and bam_bytes < raw_bytes // 4            # the repeats are found: most blocks go through the hint-driven encoder
+
+
+def test_bam_tiny_batch_takes_the_fixed_code(harness, tmp_path):
+    """A block of a few short records: a code of its own would cost more than it saves (RFC 1951 3.2.6 block)."""
+    rng = np.random.default_rng(3)
+    b = Batch(rng, 1, 12, 12, 1, zero_frac=0.0)
+    b.cpairs, b.rec_path = [(0, 0, 5, 4)], [int(b.nodes[0][1][0])] * 4
+    f = str(tmp_path / "batch.bin")
+    b.write(f)
+    out = str(tmp_path / "o.bam")
+    before = dict(COVERAGE)
+    _run(harness, f, out, 1, -1, 1)
+    assert COVERAGE["fixed"] == before["fixed"] + 1
+    assert _check_blocks(open(out, "rb").read()) == b.expected()
 
 
 def test_bam_empty_batch(harness, tmp_path):
@@ -193,3 +211,21 @@ def test_report_reads_what_the_block_writer_wrote(harness, root, tmp_path):
         assert r.returncode == 0, r.stderr.decode()
         lines.append(r.stdout.decode())
     assert lines[0] == lines[1] and lines[0].count("\n") > 10
+
+
+def test_every_block_encoder_was_exercised():
+    """The cases above went through all three ways a block is written: fixed code, a code of its own, zlib."""
+    assert COVERAGE["fixed"] > 0 and COVERAGE["own"] > 0 and COVERAGE["zlib"] > 0, COVERAGE
+
+
+def test_block_writer_fuzz(root, tmp_path):
+    """bgzf.h on random streams with right, wrong and absent hints, under AddressSanitizer / UBSan: every block inflates
+    (zlib) to exactly the bytes that went in — the encoder never trusts a hint."""
+    exe = str(tmp_path / "bgzf_fuzz")
+    subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-Wall", "-o", exe,
+                           os.path.join(root, "tests", "cpp", "bgzf_fuzz.cpp"), "-lz"])
+    for seed in (11, 12, 13):
+        r = subprocess.run([exe, str(seed), "25"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0 and r.stdout.decode().startswith("ok "), r.stdout.decode() + r.stderr.decode()
+        _, blocks, delta, own = r.stdout.decode().split()
+        assert int(delta) > 100 and int(own) > 100

@@ -53,7 +53,7 @@ print("batch: %d reads, %d pairs, %d records" % (n, len(cpairs), len(rec_path)))
 for level, delta in ((0, 0), (1, 0), (-1, 0), (1, 1), (-1, 1)):
     out = os.path.join(tmp, "o.bam")
     r = subprocess.run([exe, f, out, str(workers), str(level), str(delta), "3"], stdout=subprocess.PIPE, check=True)
-    secs, raw_bytes, bam_bytes, delta_blocks = r.stdout.decode().split()
+    secs, raw_bytes, bam_bytes, delta_blocks, own_code, zlib_blocks = r.stdout.decode().split()
     secs = float(secs)
     print("workers %2d level %2d delta %d: %.3f s  %.2f M reads/s  %.2f GB/s of records  BAM/raw %.3f  delta blocks %s" %
           (workers, level, delta, secs, n / secs / 1e6, int(raw_bytes) / secs / 1e9, int(bam_bytes) / int(raw_bytes), delta_blocks))
