@@ -488,12 +488,15 @@ int ReadMapper::Run(FastqStream& reads) {
         team.prm = prm; team.prm.results_on_device = 1;
         if ((rc = team.start(&err_))) return rc;
     }
-    // DataStreamer/FastqHandler run ahead on their own thread, as the reference's stages do (pipeline.go:36-45): the
-    // next batch is parsed while this one is on the GPU and in the BAM workers. Two batch buffers, handed back and forth.
+    // Three stages, as the reference's pipeline has them (pipeline.go:36-45; boss.go:225-242 writes the BAM from its own
+    // goroutine): DataStreamer/FastqHandler parse batch i+2 on the reader thread while batch i+1 is on the GPU (this thread)
+    // and the BAM stage formats, deflates and writes batch i. Three batch buffers go round; a buffer is released by the
+    // last stage that needs it (the BAM stage reads names, bases and qualities from it).
+    constexpr int kSlots = 3;
     struct BatchFeed {
         FastqStream& reads; uint32_t batch_reads;
-        ReadBatch slot[2];
-        int state[2] = {0, 0};             // 0 = free, 1 = filled, 2 = end of input
+        ReadBatch slot[kSlots];
+        int state[kSlots] = {0, 0, 0};     // 0 = free, 1 = filled, 2 = end of input
         bool stop = false;
         std::exception_ptr error;
         std::mutex mu; std::condition_variable cv;
@@ -501,7 +504,7 @@ int ReadMapper::Run(FastqStream& reads) {
         BatchFeed(FastqStream& r, uint32_t n) : reads(r), batch_reads(n) {
             th = std::thread([this] {
                 try {
-                    for (int i = 0;; i ^= 1) {
+                    for (int i = 0;; i = (i + 1) % kSlots) {
                         { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || state[i] == 0; }); if (stop) return; }
                         const bool ok = reads.next(slot[i], batch_reads);
                         { std::lock_guard<std::mutex> lk(mu); state[i] = ok ? 1 : 2; }
@@ -509,7 +512,7 @@ int ReadMapper::Run(FastqStream& reads) {
                         if (!ok) return;
                     }
                 } catch (...) {
-                    { std::lock_guard<std::mutex> lk(mu); error = std::current_exception(); state[0] = state[1] = 2; }
+                    { std::lock_guard<std::mutex> lk(mu); error = std::current_exception(); for (int& st : state) st = 2; }
                     cv.notify_all();
                 }
             });
@@ -523,10 +526,65 @@ int ReadMapper::Run(FastqStream& reads) {
         void release(int i) { { std::lock_guard<std::mutex> lk(mu); state[i] = 0; } cv.notify_all(); }
         ~BatchFeed() { { std::lock_guard<std::mutex> lk(mu); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); }
     } feed(reads, info_->BatchReads);
-    for (int slot_i = 0;; slot_i ^= 1) {
+    // The BAM stage: one batch at a time, in order. The library's result arrays are only valid until the next align call
+    // on the handle (include/grootgpu.h), which this thread makes while the stage is still working: the compact records
+    // (16 bytes per pair + 1-2 bytes per record) are copied into the stage's own buffers at the hand-over.
+    struct BamStage {
+        BatchFeed& feed; BamWriter* bam; Info* info; grootgpu_index* index; const uint32_t* graph_ref_base;
+        std::vector<grootgpu_cpair> cpairs; std::vector<uint8_t> rec_path;
+        uint64_t n_records = 0; uint32_t path_bytes = 1;
+        ReadBatch* batch = nullptr; int slot = 0;
+        bool busy = false, stop = false;
+        std::string error;
+        std::mutex mu; std::condition_variable cv;
+        std::thread th;
+        BamStage(BatchFeed& f, BamWriter* w, Info* inf, grootgpu_index* ix, const uint32_t* grb) : feed(f), bam(w), info(inf), index(ix), graph_ref_base(grb) {
+            th = std::thread([this] {
+                while (true) {
+                    { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || busy; }); if (!busy) return; }
+                    std::string e;
+                    try {
+                        BamBatch bb;
+                        bb.reads = batch; bb.cpairs = cpairs.data(); bb.n_pairs = cpairs.size(); bb.n_records = n_records;
+                        bb.rec_path_c = rec_path.data(); bb.rec_path_bytes = path_bytes; bb.graph_ref_base = graph_ref_base;
+                        bb.node_paths = [this](uint32_t node, NodePathsView* v) {
+                            return grootgpu_index_node_paths(index, node, &v->graph, &v->ids, &v->pos, &v->n) == 0;
+                        };
+                        const unsigned workers = static_cast<unsigned>(std::max(1, info->NumProc));
+                        std::vector<std::vector<uint8_t>> outs;
+                        e = format_batch_bam(bb, workers, info->BamLevel, info->BamDelta, outs);
+                        if (e.empty()) for (unsigned t = 0; t < workers; t++) bam->append_blocks(outs[t]);
+                    } catch (std::exception& ex) { e = ex.what(); }
+                    feed.release(slot);
+                    { std::lock_guard<std::mutex> lk(mu); busy = false; if (error.empty()) error = e; }
+                    cv.notify_all();
+                }
+            });
+        }
+        // waits for the batch in front, then takes this one; returns the first error of the stage so far ("" = none)
+        std::string submit(int slot_i, ReadBatch* b, const grootgpu_batch_result& res) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !busy; });
+            if (!error.empty()) return error;
+            cpairs.assign(res.cpairs, res.cpairs + res.n_pairs);
+            const uint8_t* rp = static_cast<const uint8_t*>(res.rec_path_c);
+            rec_path.assign(rp, rp + res.n_records * res.rec_path_bytes);
+            n_records = res.n_records; path_bytes = res.rec_path_bytes; batch = b; slot = slot_i;
+            busy = true;
+            lk.unlock();
+            cv.notify_all();
+            return "";
+        }
+        std::string drain() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !busy; }); return error; }
+        ~BamStage() { { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !busy; }); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); }
+    };
+    std::unique_ptr<BamStage> stage;
+    if (bam) stage.reset(new BamStage(feed, bam.get(), info_, index_, graph_ref_base.data()));
+    for (int slot_i = 0;; slot_i = (slot_i + 1) % kSlots) {
         ReadBatch* bp = feed.take(slot_i);
         if (!bp) break;
-        struct Release { BatchFeed& f; int i; ~Release() { f.release(i); } } release_slot{feed, slot_i};
+        bool handed_over = false;
+        struct Release { BatchFeed& f; int i; bool& handed; ~Release() { if (!handed) f.release(i); } } release_slot{feed, slot_i, handed_over};
         ReadBatch& b = *bp;
         grootgpu_batch_result res;
         {   // reads of one length (the usual Illumina run): the library then needs no offsets on the device
@@ -544,19 +602,15 @@ int ReadMapper::Run(FastqStream& reads) {
         }
         read_stats_[0] += res.received; read_stats_[1] += res.mapped; read_stats_[2] += res.multimapped;
         alignment_count_ += res.alignments;
-        if (!bam) continue;
-        // Records of the batch, in pair order == (read, graph) order: NumProc workers, ready-made BGZF blocks (format_batch_bam)
-        BamBatch bb;
-        bb.reads = &b; bb.cpairs = res.cpairs; bb.n_pairs = res.n_pairs; bb.n_records = res.n_records;
-        bb.rec_path_c = res.rec_path_c; bb.rec_path_bytes = res.rec_path_bytes; bb.graph_ref_base = graph_ref_base.data();
-        bb.node_paths = [this](uint32_t node, NodePathsView* v) {
-            return grootgpu_index_node_paths(index_, node, &v->graph, &v->ids, &v->pos, &v->n) == 0;
-        };
-        const unsigned workers = static_cast<unsigned>(std::max(1, info_->NumProc));
-        std::vector<std::vector<uint8_t>> outs;
-        const std::string werr = format_batch_bam(bb, workers, info_->BamLevel, info_->BamDelta, outs);
+        if (!stage) continue;
+        const std::string werr = stage->submit(slot_i, bp, res);
         if (!werr.empty()) { err_ = werr; return GROOTGPU_ERR_FORMAT; }
-        for (unsigned t = 0; t < workers; t++) bam->append_blocks(outs[t]);
+        handed_over = true;
+    }
+    if (stage) {
+        const std::string werr = stage->drain();
+        stage.reset();
+        if (!werr.empty()) { err_ = werr; return GROOTGPU_ERR_FORMAT; }
     }
     if (reads.rawCount() == 0) { err_ = "no fastq reads received"; return GROOTGPU_ERR_EMPTY; }   // sketch.go:275-277
     if (bam) { bam->close(); if (fh != stdout) fclose(fh); }

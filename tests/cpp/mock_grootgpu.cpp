@@ -8,6 +8,7 @@
 //     that reads them after the next call fails the comparison;
 //   * the multi-GPU calls are emulated with threads: grootgpu_gather merges the ranks' shards on rank 0.
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -88,10 +89,11 @@ int grootgpu_align_batch(grootgpu_index* ix, const uint8_t* seq, const uint64_t*
     ix->cpairs.clear(); ix->rec_path.clear();
     memset(out, 0, sizeof *out);
     const uint32_t P = ix->paths_per_graph;
+    static const bool fast = getenv("MOCK_FAST") != nullptr;          // timing runs: hash 16 bases only, the fake device should cost next to nothing
     for (uint32_t r = 0; r < n_reads; r++) {
         const uint64_t a = seq_off ? seq_off[r] : static_cast<uint64_t>(r) * prm->fixed_read_len, b = seq_off ? seq_off[r + 1] : a + prm->fixed_read_len;
         if (prm->fixed_read_len && b - a != prm->fixed_read_len) return fail(GROOTGPU_ERR_ARG, "fixed_read_len does not match the offsets");
-        const uint64_t h = fnv1a(seq + a, b - a);
+        const uint64_t h = fnv1a(seq + a, fast ? std::min<uint64_t>(b - a, 16) : b - a);
         if (h % 100 >= 52) continue;
         out->mapped++;
         if (prm->no_align) continue;
