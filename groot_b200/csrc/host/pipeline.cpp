@@ -1,7 +1,11 @@
 // Implementation of the host-side pipeline mirror (see pipeline.h for the reference file:line of every stage).
 #include "pipeline.h"
 
+#include <fcntl.h>
+#include <unistd.h>
 #include <zlib.h>
+
+#include <cerrno>
 
 #include "bgzf.h"
 
@@ -25,23 +29,52 @@ void ReadBatch::clear() {
 FastqStream::FastqStream(const std::vector<std::string>& files, bool fasta) : files_(files), fasta_(fasta) {
     use_stdin_ = files.empty();   // no input file: scan STDIN (sketch.go:45-53)
 }
-FastqStream::~FastqStream() { if (gz_) gzclose(static_cast<gzFile>(gz_)); }
+FastqStream::~FastqStream() { close_current(); }
+
+void FastqStream::close_current() {
+    if (gz_) { gzclose(static_cast<gzFile>(gz_)); gz_ = nullptr; }
+    if (fd_ > 0) ::close(fd_);
+    fd_ = -1; open_ = false;
+}
 
 bool FastqStream::open_next() {
-    if (gz_) { gzclose(static_cast<gzFile>(gz_)); gz_ = nullptr; }
+    close_current();
+    if (buf_.size() < (8u << 20)) buf_.resize(8u << 20);
+    pos_ = end_ = 0; eof_ = false;
     if (use_stdin_) {
         if (stdin_done_) return false;
         stdin_done_ = true;
-        gz_ = gzdopen(0, "rb");
-    } else {
-        if (file_i_ >= files_.size()) return false;
-        gz_ = gzopen(files_[file_i_].c_str(), "rb");       // gz decided by content; the reference keys on the ".gz" extension (sketch.go:60-68)
-        if (!gz_) throw std::runtime_error("open " + files_[file_i_] + ": no such file or directory");   // misc.ErrorCheck(err) -> log.Fatal
-        file_i_++;
+        gz_ = gzdopen(0, "rb");                 // a pipe cannot be rewound after a look at it: zlib's transparent mode takes plain and gzip alike
+        if (!gz_) throw std::runtime_error("cannot open input");
+        gzbuffer(static_cast<gzFile>(gz_), 1 << 20);
+        open_ = true;
+        return true;
     }
-    if (!gz_) throw std::runtime_error("cannot open input");
-    gzbuffer(static_cast<gzFile>(gz_), 1 << 20);
-    pos_ = end_ = 0; eof_ = false;
+    if (file_i_ >= files_.size()) return false;
+    fd_ = ::open(files_[file_i_].c_str(), O_RDONLY);
+    if (fd_ < 0) throw std::runtime_error("open " + files_[file_i_] + ": no such file or directory");   // misc.ErrorCheck(err) -> log.Fatal
+    file_i_++;
+    // gzip is decided by content (the reference keys on the ".gz" extension, sketch.go:60-68): the first block is read
+    // here; a gzip magic hands the descriptor to zlib, anything else is read straight into the block buffer (one copy
+    // less than gzread's transparent mode; the reader's time is in the line scan and the per-line copies either way).
+    size_t got = 0;
+    while (got < 2) {
+        const ssize_t r = ::read(fd_, buf_.data() + got, buf_.size() - got);
+        if (r < 0) { if (errno == EINTR) continue; throw std::runtime_error("error reading input file"); }
+        if (r == 0) break;
+        got += static_cast<size_t>(r);
+    }
+    if (got >= 2 && static_cast<uint8_t>(buf_[0]) == 0x1f && static_cast<uint8_t>(buf_[1]) == 0x8b) {
+        if (::lseek(fd_, 0, SEEK_SET) != 0) throw std::runtime_error("cannot rewind input file");
+        gz_ = gzdopen(fd_, "rb");               // zlib owns the descriptor from here
+        if (!gz_) throw std::runtime_error("cannot open input");
+        fd_ = -1;
+        gzbuffer(static_cast<gzFile>(gz_), 1 << 20);
+    } else {
+        end_ = got;
+        if (got == 0) eof_ = true;
+    }
+    open_ = true;
     return true;
 }
 
@@ -51,8 +84,14 @@ bool FastqStream::refill() {
     if (buf_.size() < (8u << 20)) buf_.resize(8u << 20);
     if (pos_ > 0) { memmove(buf_.data(), buf_.data() + pos_, end_ - pos_); end_ -= pos_; pos_ = 0; }
     if (end_ == buf_.size()) buf_.resize(buf_.size() * 2);           // one line longer than the buffer
-    const int got = gzread(static_cast<gzFile>(gz_), buf_.data() + end_, static_cast<unsigned>(std::min<size_t>(buf_.size() - end_, 1u << 30)));
-    if (got < 0) throw std::runtime_error("error reading input file");
+    ssize_t got;
+    if (gz_) {
+        got = gzread(static_cast<gzFile>(gz_), buf_.data() + end_, static_cast<unsigned>(std::min<size_t>(buf_.size() - end_, 1u << 30)));
+        if (got < 0) throw std::runtime_error("error reading input file");
+    } else {
+        do got = ::read(fd_, buf_.data() + end_, std::min<size_t>(buf_.size() - end_, 1u << 30)); while (got < 0 && errno == EINTR);
+        if (got < 0) throw std::runtime_error("error reading input file");
+    }
     if (got == 0) { eof_ = true; return false; }
     end_ += static_cast<size_t>(got);
     return true;
@@ -62,7 +101,7 @@ bool FastqStream::refill() {
 // every file is scanned on its own (sketch.go:55-75)
 bool FastqStream::getline(const char*& line, size_t& len) {
     while (true) {
-        if (!gz_ && !open_next()) return false;
+        if (!open_ && !open_next()) return false;
         while (true) {
             const char* nl = pos_ < end_ ? static_cast<const char*>(memchr(buf_.data() + pos_, '\n', end_ - pos_)) : nullptr;
             if (nl) {
@@ -79,7 +118,7 @@ bool FastqStream::getline(const char*& line, size_t& len) {
             if (len && line[len - 1] == '\r') len--;
             return true;
         }
-        gzclose(static_cast<gzFile>(gz_)); gz_ = nullptr;           // end of this file
+        close_current();                                            // end of this file
     }
 }
 

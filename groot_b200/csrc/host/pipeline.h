@@ -66,7 +66,10 @@ class FastqStream {
     bool refill();
     std::vector<std::string> files_;
     size_t file_i_ = 0;
-    void* gz_ = nullptr;  // gzFile: zlib reads plain files transparently
+    void* gz_ = nullptr;  // gzFile when the current file starts with the gzip magic
+    int fd_ = -1;         // else the descriptor itself (0 = STDIN)
+    bool open_ = false;
+    void close_current();
     bool fasta_;
     bool use_stdin_ = false, stdin_done_ = false;
     std::string pending_header_, fasta_seq_;
