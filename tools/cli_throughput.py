@@ -35,7 +35,8 @@ print("fastq: %d reads, %.1f MB" % (n, os.path.getsize(fq) / 1e6))
 t0 = time.time()
 subprocess.run([CLI, "index", "-m", msa_dir, "-i", os.path.join(tmp, "idx"), "-w", "100", "-k", "31", "-s", "21"], check=True, stderr=subprocess.DEVNULL)
 print("index: %.2f s" % (time.time() - t0))
-for extra in (["--noAlign"], ["-p", "1", "--bamLevel", "1"], ["-p", "16", "--bamLevel", "1"], ["-p", "16"], ["-p", "16", "--bamLevel", "0"]):
+for extra in (["--noAlign"], ["-p", "1"], ["-p", "16"], ["-p", "16", "--bamDelta", "0"], ["-p", "16", "--bamDelta", "0", "--bamLevel", "1"],
+              ["-p", "16", "--bamLevel", "0"]):
     out = os.path.join(tmp, "out.bam")
     t0 = time.time()
     with open(out, "wb") as f:
