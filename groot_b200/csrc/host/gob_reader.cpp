@@ -160,8 +160,19 @@ class GobDecoder {
         types_[id] = t;
     }
 
+    // Info / Store / ContainmentIndex nest six deep; a damaged type table can make a type contain itself, and every level
+    // of a struct costs only one byte of input — so the depth is bounded here, not by the file size
+    static constexpr int kMaxDepth = 64;
+    int depth_ = 0;
+    struct DepthGuard {
+        int& d;
+        explicit DepthGuard(int& depth) : d(depth) { if (++d > kMaxDepth) { --d; throw std::runtime_error("gob: values nested too deeply"); } }
+        ~DepthGuard() { --d; }
+    };
+
     GobValue value(int id) {
         GobValue v;
+        const DepthGuard guard(depth_);
         switch (id) {
             case tBool: v.kind = GobValue::Bool; v.u = get_uint(); return v;
             case tInt: v.kind = GobValue::Int; v.i = get_int(); return v;
@@ -199,7 +210,7 @@ class GobDecoder {
                 v.kind = GobValue::Nums; v.nums.resize(n);
                 for (uint64_t k = 0; k < n; k++) v.nums[k] = t.elem == tInt ? get_int() : static_cast<int64_t>(get_uint());
             } else {
-                v.kind = GobValue::List; v.list.reserve(n);
+                v.kind = GobValue::List; v.list.reserve(std::min<uint64_t>(n, 1u << 16));   // n is only bounded by the bytes left
                 for (uint64_t k = 0; k < n; k++) v.list.push_back(value(t.elem));
             }
             return v;
@@ -215,7 +226,7 @@ class GobDecoder {
                 else v.nums[2 * k + 1] = t.elem == tInt ? get_int() : static_cast<int64_t>(get_uint());
             }
         } else {
-            v.kind = GobValue::Map; v.map.reserve(n);
+            v.kind = GobValue::Map; v.map.reserve(std::min<uint64_t>(n, 1u << 16));
             for (uint64_t k = 0; k < n; k++) { GobValue key = value(t.key); GobValue val = value(t.elem); v.map.push_back({std::move(key), std::move(val)}); }
         }
         return v;

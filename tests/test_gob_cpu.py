@@ -67,3 +67,40 @@ def test_gob_errors(root, tmp_path):
     with pytest.raises(api.GrootGpuError) as e:
         api.gob_dump(gg, str(tmp_path / "g2.lshe"))
     assert e.value.code == -4
+
+
+def test_damaged_index_files_are_refused_not_crashed_on(root, tmp_path):
+    """Fuzz (tests/cpp/gob_fuzz.cpp, ASan + UBSan): a groot.gg / groot.lshe pair — and the library's own flat index file —
+    with flipped, inserted, duplicated, zeroed or cut-off bytes either loads and validates or raises; it never crashes
+    (a damaged type table can make a gob type contain itself: the decoder bounds its depth)."""
+    import subprocess
+    host = os.path.join(root, "groot_b200", "csrc", "host")
+    exe = str(tmp_path / "gob_fuzz")
+    subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-o", exe,
+                           os.path.join(root, "tests", "cpp", "gob_fuzz.cpp")] +
+                          [os.path.join(host, f) for f in ("gob_reader.cpp", "index_io.cpp", "graph_build.cpp", "lshe_params.cpp", "replay.cpp", "prefix_table.cpp")])
+    o = po.Index(msa_files=[os.path.join(root, "data", "graph", "test-genes.msa")], k=51, S=30, w=100)
+    o.dump_file(str(tmp_path / "o.txt"))
+    gg, lshe = str(tmp_path / "groot.gg"), str(tmp_path / "groot.lshe")
+    gw.write_reference_index(str(tmp_path / "o.txt"), gg, lshe)
+    env = dict(os.environ, ASAN_OPTIONS="allocator_may_return_null=1")
+    for args in ((gg, lshe, str(tmp_path), "6", "40"), (gg, lshe, str(tmp_path), "3", "40", "flat")):
+        r = subprocess.run([exe] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+        assert r.returncode == 0 and r.stdout.decode().startswith("ok "), r.stderr.decode()[-2000:]
+        assert int(r.stdout.decode().split()[2]) > 20                               # most damaged files are refused
+
+
+def test_gob_type_that_contains_itself(root, tmp_path):
+    """What the fuzz found: a type table in which a struct has a field of its own type lets every input byte open another
+    level — the decoder must refuse at a fixed depth instead of running out of stack."""
+    u, i = gw.uvarint, gw.varint
+    tdef = i(-65) + u(3) + u(1) + gw.Encoder._common("T", 65) + u(1) + u(1) + (u(1) + u(1) + b"X" + u(1) + i(65) + b"\x00") + b"\x00" + b"\x00"
+    val = i(65) + u(1) * 300000
+    stream = u(len(tdef)) + tdef + u(len(val)) + val
+    open(tmp_path / "self.gg", "wb").write(stream)
+    o = po.Index(msa_files=[os.path.join(root, "data", "graph", "test-genes.msa")], k=51, S=30, w=100)
+    o.dump_file(str(tmp_path / "o.txt"))
+    gw.write_reference_index(str(tmp_path / "o.txt"), str(tmp_path / "groot.gg"), str(tmp_path / "groot.lshe"))
+    with pytest.raises(api.GrootGpuError) as e:
+        api.gob_dump(str(tmp_path / "self.gg"), str(tmp_path / "groot.lshe"))
+    assert e.value.code == -4 and "nested too deeply" in str(e.value)
