@@ -212,3 +212,29 @@ def test_fastq_stream_edge_cases(root, tmp_path):
     assert rc == 0 and out == ["@s1 d\tACGTAC\t", "@s2\tGG\t", "#2 8"]
     rc, _, err = run(tmp_path / "missing.fq")
     assert rc == 2 and "no such file" in err
+
+
+def test_header_is_c99_and_matches_the_ctypes_mirror(root, tmp_path):
+    """include/grootgpu.h is what cgo and any C host compile: it must be plain C, and the Python mirror
+    of its structs (groot_b200/api.py) must agree with the C compiler on every field offset and size."""
+    import ctypes as C
+    import subprocess
+    from groot_b200 import api
+    mirrors = {"grootgpu_index_params": api.IndexParams, "grootgpu_index_info": api.IndexInfo, "grootgpu_align_params": api.AlignParams,
+               "grootgpu_pair": api.Pair, "grootgpu_cpair": api.CPair, "grootgpu_batch_result": api.BatchResultC}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "grootgpu.h"', "int main(void) {"]
+    for cname, cls in mirrors.items():
+        lines.append('    printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('    printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['    printf("COMM_ID %d\\n", GROOTGPU_COMM_ID_BYTES);', "    return 0;", "}"]
+    src = tmp_path / "abi.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = str(tmp_path / "abi")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"), "-o", exe, str(src)])
+    got = dict(l.split() for l in subprocess.check_output([exe]).decode().splitlines())
+    for cname, cls in mirrors.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
+    assert int(got["COMM_ID"]) == api.COMM_ID_BYTES
