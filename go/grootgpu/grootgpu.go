@@ -84,6 +84,17 @@ func (ix *Index) Save(path string) error {
 	return lastErr(C.grootgpu_index_save(ix.h, cp))
 }
 
+// SaveGob writes the index as the reference's own groot.gg + groot.lshe (Info.Dump + ContainmentIndex.Dump,
+// src/pipeline/runtime.go:64-73, src/lshe/lshe.go:72-92).
+func (ix *Index) SaveGob(ggPath, lshePath string) error {
+	pin()
+	defer unpin()
+	cg, cl := C.CString(ggPath), C.CString(lshePath)
+	defer C.free(unsafe.Pointer(cg))
+	defer C.free(unsafe.Pointer(cl))
+	return lastErr(C.grootgpu_index_save_gob(ix.h, cg, cl))
+}
+
 func (ix *Index) Close() { C.grootgpu_index_destroy(ix.h); ix.h = nil }
 
 // Pair is one (read, graph) unit == one graphMinionPair (src/pipeline/graphminion.go:14-17).

@@ -99,6 +99,9 @@ def lib():
         L.grootgpu_index_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(vp)]
         L.grootgpu_index_load_gob.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(vp)]
         L.grootgpu_gob_dump.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64)]
+        L.grootgpu_index_save_gob.argtypes = [vp, C.c_char_p, C.c_char_p]
+        L.grootgpu_flat_to_gob.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
+        L.grootgpu_gob_to_flat.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p]
         L.grootgpu_index_destroy.argtypes = [vp]
         L.grootgpu_index_destroy.restype = None
         L.grootgpu_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
@@ -135,7 +138,7 @@ EXPORTED_SYMBOLS = [
     "grootgpu_weights", "grootgpu_reset_weights", "grootgpu_sketch_batch", "grootgpu_prune", "grootgpu_graph_save_gfa",
     "grootgpu_host_alloc", "grootgpu_host_free", "grootgpu_device_count", "grootgpu_last_error", "grootgpu_version",
     "grootgpu_int_issue_peak", "grootgpu_index_node_paths", "grootgpu_comm_id", "grootgpu_comm_create", "grootgpu_comm_destroy", "grootgpu_comm_sync",
-    "grootgpu_gather", "grootgpu_index_load_gob", "grootgpu_gob_dump",
+    "grootgpu_gather", "grootgpu_index_load_gob", "grootgpu_gob_dump", "grootgpu_index_save_gob", "grootgpu_flat_to_gob", "grootgpu_gob_to_flat",
 ]
 
 
@@ -299,6 +302,10 @@ class Index:
     def save(self, path):
         _check(lib().grootgpu_index_save(self.h, path.encode()))
 
+    def save_gob(self, gg_path, lshe_path):
+        """The index as the reference's own files (Info.Dump + ContainmentIndex.Dump, runtime.go:64-73, lshe.go:72-92)."""
+        _check(lib().grootgpu_index_save_gob(self.h, gg_path.encode(), lshe_path.encode()))
+
     def close(self):
         if self.h:
             lib().grootgpu_index_destroy(self.h)
@@ -453,6 +460,16 @@ def gob_dump(gg_path, lshe_path, dump_path=None):
     h = C.c_uint64()
     _check(lib().grootgpu_gob_dump(gg_path.encode(), lshe_path.encode(), dump_path.encode() if dump_path else None, C.byref(h)))
     return h.value
+
+
+def flat_to_gob(flat_path, gg_path, lshe_path):
+    """Host-only: the library's flat index file -> groot.gg + groot.lshe."""
+    _check(lib().grootgpu_flat_to_gob(flat_path.encode(), gg_path.encode(), lshe_path.encode()))
+
+
+def gob_to_flat(gg_path, lshe_path, flat_path):
+    """Host-only: groot.gg + groot.lshe -> the library's flat index file."""
+    _check(lib().grootgpu_gob_to_flat(gg_path.encode(), lshe_path.encode(), flat_path.encode()))
 
 
 def query_params_host(query_kmers, threshold, k=31, S=21, w=100, num_part=8, max_k=4):

@@ -13,7 +13,7 @@ CLI = os.path.join(HERE, "groot-b200")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 CU = ["capi.cu"]
-CPP = ["host/graph_build.cpp", "host/index_io.cpp", "host/lshe_params.cpp", "host/replay.cpp", "host/prefix_table.cpp", "host/gob_reader.cpp"]
+CPP = ["host/graph_build.cpp", "host/index_io.cpp", "host/lshe_params.cpp", "host/replay.cpp", "host/prefix_table.cpp", "host/gob_reader.cpp", "host/gob_writer.cpp"]
 
 
 def sources():

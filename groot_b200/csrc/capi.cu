@@ -1680,6 +1680,20 @@ int grootgpu_gob_dump(const char* gg_path, const char* lshe_path, const char* du
         }
     });
 }
+int grootgpu_index_save_gob(const grootgpu_index* idx, const char* gg_path, const char* lshe_path) {
+    if (!idx || !gg_path || !lshe_path) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    { grootgpu_index* mi = const_cast<grootgpu_index*>(idx); int rc = guarded([&] { if (mi->weights_on_device) { pick_device(mi->device); sync_weights_to_host(mi); } }); if (rc) return rc; }
+    try { save_index_gob(idx->h, gg_path, lshe_path, GROOTGPU_REFERENCE_VERSION); } catch (std::exception& e) { return fail(GROOTGPU_ERR_IO, e.what()); }
+    return GROOTGPU_OK;
+}
+int grootgpu_flat_to_gob(const char* flat_path, const char* gg_path, const char* lshe_path) {
+    if (!flat_path || !gg_path || !lshe_path) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    return guarded([&] { FlatIndex h; load_index(h, flat_path); save_index_gob(h, gg_path, lshe_path, GROOTGPU_REFERENCE_VERSION); });
+}
+int grootgpu_gob_to_flat(const char* gg_path, const char* lshe_path, const char* flat_path) {
+    if (!flat_path || !gg_path || !lshe_path) return fail(GROOTGPU_ERR_ARG, "bad argument");
+    return guarded([&] { FlatIndex h; load_index_gob(h, gg_path, lshe_path); validate_index(h); save_index(h, flat_path); });
+}
 void grootgpu_index_destroy(grootgpu_index* idx) {
     if (!idx) return;
     cudaSetDevice(idx->device);

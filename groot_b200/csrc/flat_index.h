@@ -94,6 +94,7 @@ void load_index(FlatIndex& idx, const std::string& path);
 void validate_index(const FlatIndex& idx);   // range checks of every offset / index; throws std::runtime_error
 // groot.gg + groot.lshe (Go gob, host/gob_reader.cpp)
 void load_index_gob(FlatIndex& idx, const std::string& gg_path, const std::string& lshe_path);
+void save_index_gob(const FlatIndex& idx, const std::string& gg_path, const std::string& lshe_path, const std::string& version);   // host/gob_writer.cpp
 // canonical text dump shared (as a FORMAT) with the oracle; sink(line incl. '\n')
 void dump_index(const FlatIndex& idx, void (*sink)(void* ctx, const char* data, size_t n), void* ctx);
 

@@ -65,6 +65,10 @@ static int run_index(const Args& a) {
     if (grootgpu_index_build_dir(msaDir.c_str(), &p, atoi(a.get("--device", "", "0").c_str()), &idx)) fatal(grootgpu_last_error());
     mkdir(indexDir.c_str(), 0777);
     if (grootgpu_index_save(idx, (indexDir + "/groot.grootb200").c_str())) fatal(grootgpu_last_error());
+    // and the reference's own pair (Info.Dump + ContainmentIndex.Dump, cmd/index.go:181-186), so that the Go `groot align` can load
+    // an index built here; `groot-b200 align` itself prefers the flat file. --gob=false skips them.
+    if (a.get("--gob", "", "true") != "false" &&
+        grootgpu_index_save_gob(idx, (indexDir + "/groot.gg").c_str(), (indexDir + "/groot.lshe").c_str())) fatal(grootgpu_last_error());
     grootgpu_index_info ii; grootgpu_index_get_info(idx, &ii);
     fprintf(stderr, "\tnumber of groot graphs built: %u\n\t\tgraphs sketched: %u\n\t\tgraph windows processed: %llu\n\tnumber of sketches added to the LSH Ensemble index: %u\nfinished in %.3fs\n",
             ii.n_graphs, ii.n_graphs - ii.n_masked_graphs, static_cast<unsigned long long>(ii.n_raw_windows), ii.n_windows, now_s() - t0);

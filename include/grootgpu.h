@@ -84,6 +84,13 @@ int grootgpu_index_load(const char* path, int device, grootgpu_index** out);
 int grootgpu_index_load_gob(const char* gg_path, const char* lshe_path, int device, grootgpu_index** out);
 /* Host-only (no device): decodes and validates the two gob files and writes the canonical dump and/or its hash. */
 int grootgpu_gob_dump(const char* gg_path, const char* lshe_path, const char* dump_path, uint64_t* hash);
+/* The other direction: writes the index as the reference's own groot.gg + groot.lshe (Info.Dump + ContainmentIndex.Dump,
+ * src/pipeline/runtime.go:64-73, src/lshe/lshe.go:72-92), so that an index built here can be loaded by the Go
+ * `groot align` / `groot haplotype`. Graph weights (KmerFreq, KmerTotal, Marked) are written as they currently are. */
+int grootgpu_index_save_gob(const grootgpu_index* idx, const char* gg_path, const char* lshe_path);
+/* Host-only (no device) conversions between the library's flat index file and the reference's pair of gob files. */
+int grootgpu_flat_to_gob(const char* flat_path, const char* gg_path, const char* lshe_path);
+int grootgpu_gob_to_flat(const char* gg_path, const char* lshe_path, const char* flat_path);
 void grootgpu_index_destroy(grootgpu_index* idx);
 int grootgpu_index_get_info(const grootgpu_index* idx, grootgpu_index_info* out);
 

@@ -53,7 +53,7 @@ class Map:
 class Encoder:
     def __init__(self, seed=0):
         self.ids, self.out, self.next_id = {}, bytearray(), 65
-        self.rng = random.Random(seed)
+        self.rng = random.Random(seed) if seed is not None else None      # None: maps in insertion order (what the C++ writer emits)
 
     # ---- type definitions ----
     def type_id(self, t):
@@ -128,7 +128,8 @@ class Encoder:
         if isinstance(t, Slice):
             return uvarint(len(v)) + b"".join(self._value(t.elem, x) for x in v)
         items = list(v.items())
-        self.rng.shuffle(items)
+        if self.rng is not None:
+            self.rng.shuffle(items)
         return uvarint(len(items)) + b"".join(self._value(t.key, k) + self._value(t.elem, x) for k, x in items)
 
     def encode(self, t, v):
@@ -202,4 +203,4 @@ def write_reference_index(dump_path, gg_path, lshe_path, seed=0, kmer_freq=None)
         lookup["%s-%d" % (base, i)] = {"GraphID": w["graph"], "Node": w["seg"], "OffSet": w["off"], "ContainedNodes": {s: float(c) for s, c in w["cn"]},
                                        "Ref": [0], "Sketch": w["sketch"], "MergeSpan": w["span"], "WindowSize": w["w"]}
     ci = {"NumPart": params["numPart"], "MaxK": params["maxK"], "NumWindowKmers": params["w"] - params["k"] + 1, "SketchSize": params["S"], "WindowLookup": lookup}
-    open(lshe_path, "wb").write(Encoder(seed + 1).encode(CINDEX, ci))
+    open(lshe_path, "wb").write(Encoder(seed + 1 if seed is not None else None).encode(CINDEX, ci))

@@ -104,3 +104,30 @@ def test_gob_type_that_contains_itself(root, tmp_path):
     with pytest.raises(api.GrootGpuError) as e:
         api.gob_dump(str(tmp_path / "self.gg"), str(tmp_path / "groot.lshe"))
     assert e.value.code == -4 and "nested too deeply" in str(e.value)
+
+
+@pytest.mark.parametrize("params", [dict(k=51, S=30, w=100), dict(k=7, S=21, w=20)])
+def test_gob_writer_cpp_equals_the_python_encoder(root, tmp_path, params):
+    """host/gob_writer.cpp against the independent Python encoder, byte for byte: an index goes Python gob (shuffled maps, as Go
+    writes them) -> flat file -> C++ gob, which must equal what the Python encoder writes with its maps in key order; and
+    the C++ files load back to the same canonical dump (oracle hash)."""
+    o = po.Index(msa_files=[os.path.join(root, "data", "graph", "test-genes.msa")], **params)
+    dump = str(tmp_path / "o.txt")
+    o.dump_file(dump)
+    import numpy as np
+    n_nodes = sum(len(g["nodes"]) for g in gw.parse_dump(dump)[1])
+    kf = np.random.default_rng(0).random(n_nodes) * 3                       # graph weights travel too (KmerFreq, zero ones omitted)
+    kf[::3] = 0
+    gw.write_reference_index(dump, str(tmp_path / "py.gg"), str(tmp_path / "py.lshe"), seed=5, kmer_freq=kf)
+    api.gob_to_flat(str(tmp_path / "py.gg"), str(tmp_path / "py.lshe"), str(tmp_path / "x.grootb200"))
+    api.flat_to_gob(str(tmp_path / "x.grootb200"), str(tmp_path / "cpp.gg"), str(tmp_path / "cpp.lshe"))
+    gw.write_reference_index(dump, str(tmp_path / "want.gg"), str(tmp_path / "want.lshe"), seed=None, kmer_freq=kf)
+    assert open(tmp_path / "cpp.gg", "rb").read() == open(tmp_path / "want.gg", "rb").read()
+    assert open(tmp_path / "cpp.lshe", "rb").read() == open(tmp_path / "want.lshe", "rb").read()
+    assert api.gob_dump(str(tmp_path / "cpp.gg"), str(tmp_path / "cpp.lshe")) == o.dump_hash()
+    with pytest.raises(api.GrootGpuError) as e:
+        api.flat_to_gob(str(tmp_path / "missing.grootb200"), str(tmp_path / "a.gg"), str(tmp_path / "a.lshe"))
+    assert e.value.code == -3
+    with pytest.raises(api.GrootGpuError) as e:
+        api.flat_to_gob(str(tmp_path / "x.grootb200"), str(tmp_path / "no_such_dir" / "a.gg"), str(tmp_path / "a.lshe"))
+    assert e.value.code == -3
