@@ -76,18 +76,17 @@ def test_damaged_index_files_are_refused_not_crashed_on(root, tmp_path):
     import subprocess
     host = os.path.join(root, "groot_b200", "csrc", "host")
     exe = str(tmp_path / "gob_fuzz")
-    subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-o", exe,
-                           os.path.join(root, "tests", "cpp", "gob_fuzz.cpp")] +
-                          [os.path.join(host, f) for f in ("gob_reader.cpp", "index_io.cpp", "graph_build.cpp", "lshe_params.cpp", "replay.cpp", "prefix_table.cpp")])
+    subprocess.check_call(["g++", "-O1", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-std=c++17", "-o", exe,
+                           os.path.join(root, "tests", "cpp", "gob_fuzz.cpp")] + [os.path.join(host, f) for f in ("gob_reader.cpp", "index_io.cpp")])
     o = po.Index(msa_files=[os.path.join(root, "data", "graph", "test-genes.msa")], k=51, S=30, w=100)
     o.dump_file(str(tmp_path / "o.txt"))
     gg, lshe = str(tmp_path / "groot.gg"), str(tmp_path / "groot.lshe")
     gw.write_reference_index(str(tmp_path / "o.txt"), gg, lshe)
     env = dict(os.environ, ASAN_OPTIONS="allocator_may_return_null=1")
-    for args in ((gg, lshe, str(tmp_path), "6", "40"), (gg, lshe, str(tmp_path), "3", "40", "flat")):
+    for args in ((gg, lshe, str(tmp_path), "6", "30"), (gg, lshe, str(tmp_path), "3", "30", "flat")):
         r = subprocess.run([exe] + list(args), stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
         assert r.returncode == 0 and r.stdout.decode().startswith("ok "), r.stderr.decode()[-2000:]
-        assert int(r.stdout.decode().split()[2]) > 20                               # most damaged files are refused
+        assert int(r.stdout.decode().split()[2]) > 15                               # most damaged files are refused
 
 
 def test_gob_type_that_contains_itself(root, tmp_path):
