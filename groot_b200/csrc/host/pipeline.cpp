@@ -2,6 +2,7 @@
 #include "pipeline.h"
 
 #include <fcntl.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
 
@@ -54,6 +55,15 @@ bool FastqStream::open_next() {
     fd_ = ::open(files_[file_i_].c_str(), O_RDONLY);
     if (fd_ < 0) throw std::runtime_error("open " + files_[file_i_] + ": no such file or directory");   // misc.ErrorCheck(err) -> log.Fatal
     file_i_++;
+    struct stat sb;
+    if (fstat(fd_, &sb) != 0 || !S_ISREG(sb.st_mode)) {           // a FIFO / process substitution cannot be rewound either: as STDIN
+        gz_ = gzdopen(fd_, "rb");
+        if (!gz_) throw std::runtime_error("cannot open input");
+        fd_ = -1;
+        gzbuffer(static_cast<gzFile>(gz_), 1 << 20);
+        open_ = true;
+        return true;
+    }
     // gzip is decided by content (the reference keys on the ".gz" extension, sketch.go:60-68): the first block is read
     // here; a gzip magic hands the descriptor to zlib, anything else is read straight into the block buffer (one copy
     // less than gzread's transparent mode; the reader's time is in the line scan and the per-line copies either way).

@@ -212,6 +212,17 @@ def test_fastq_stream_edge_cases(root, tmp_path):
     assert rc == 0 and out == ["@s1 d\tACGTAC\t", "@s2\tGG\t", "#2 8"]
     rc, _, err = run(tmp_path / "missing.fq")
     assert rc == 2 and "no such file" in err
+    # a FIFO (process substitution) as a file argument, plain and gzipped: it cannot be rewound after a look at its first bytes
+    for payload in (a.read_bytes(), gzip.compress(a.read_bytes())):
+        fifo = tmp_path / "pipe.fq"
+        if fifo.exists():
+            fifo.unlink()
+        os.mkfifo(fifo)
+        p = subprocess.Popen([exe, str(fifo)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        with open(fifo, "wb") as w:
+            w.write(payload)
+        o, _ = p.communicate(timeout=60)
+        assert p.returncode == 0 and o.decode().splitlines()[-1] == "#3 8"
 
 
 def test_header_is_c99_and_matches_the_ctypes_mirror(root, tmp_path):
