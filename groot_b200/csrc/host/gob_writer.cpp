@@ -94,9 +94,15 @@ class Stream {
         return id;
     }
     void message(const std::string& body) { put_uint(out_, body.size()); out_ += body; }
-    // the value message of a top-level struct
-    void value(const Type* t, const std::string& encoded) { std::string msg; put_int(msg, define(t)); msg += encoded; message(msg); }
-    const std::string& bytes() const { return out_; }
+    // everything in front of the encoded value of a top-level struct: the type definitions, the byte count of the value
+    // message and its type id (the value itself — hundreds of MB for a large index — is written behind it without a copy)
+    const std::string& prefix(const Type* t, size_t encoded_size) {
+        std::string id;
+        put_int(id, define(t));
+        put_uint(out_, id.size() + encoded_size);
+        out_ += id;
+        return out_;
+    }
   private:
     std::string out_;
     int next_id_ = 65;
@@ -115,10 +121,10 @@ struct StructOut {
     void end() { o.push_back(0); }
 };
 
-void write_file(const std::string& path, const std::string& data) {
+void write_file(const std::string& path, const std::string& head, const std::string& data) {
     FILE* f = fopen(path.c_str(), "wb");
     if (!f) throw std::ios_base::failure("cannot create " + path);
-    const bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+    const bool ok = fwrite(head.data(), 1, head.size(), f) == head.size() && fwrite(data.data(), 1, data.size(), f) == data.size();
     if (fclose(f) != 0 || !ok) throw std::ios_base::failure("cannot write " + path);
 }
 
@@ -180,8 +186,7 @@ void save_index_gob(const FlatIndex& ix, const std::string& gg_path, const std::
         I.field(13); v.push_back(0);                                 // Haplotype: HaploCmd{}
         I.end();
         Stream s;
-        s.value(info, v);
-        write_file(gg_path, s.bytes());
+        write_file(gg_path, s.prefix(info, v.size()), v);
     }
     // ---- groot.lshe: lshe.ContainmentIndex ----
     {
@@ -215,8 +220,7 @@ void save_index_gob(const FlatIndex& ix, const std::string& gg_path, const std::
         }
         C.end();
         Stream s;
-        s.value(cindex, v);
-        write_file(lshe_path, s.bytes());
+        write_file(lshe_path, s.prefix(cindex, v.size()), v);
     }
 }
 
