@@ -35,7 +35,7 @@ uint64_t fnv1a(const uint8_t* p, size_t n) { uint64_t h = 1469598103934665603ull
 
 struct CommShared {
     std::mutex mu; std::condition_variable cv;
-    int world = 0, arrived = 0; uint64_t gen = 0;
+    int world = 0, arrived = 0, handles = 0; uint64_t gen = 0, id = 0;
     std::vector<const grootgpu_batch_result*> local;
     std::vector<grootgpu_cpair> m_cpairs; std::vector<uint8_t> m_rec_path;   // rank 0's merged arrays
     void barrier() {
@@ -134,7 +134,7 @@ int grootgpu_comm_id(uint8_t id[GROOTGPU_COMM_ID_BYTES]) {
 int grootgpu_comm_create(grootgpu_index* idx, const uint8_t id[GROOTGPU_COMM_ID_BYTES], int rank, int world, grootgpu_comm** out) {
     uint64_t v; memcpy(&v, id, 8);
     CommShared* sh;
-    { std::lock_guard<std::mutex> lk(g_comm_mu); CommShared*& s = g_comms[v]; if (!s) { s = new CommShared(); s->world = world; s->local.assign(world, nullptr); } sh = s; }
+    { std::lock_guard<std::mutex> lk(g_comm_mu); CommShared*& s = g_comms[v]; if (!s) { s = new CommShared(); s->world = world; s->id = v; s->local.assign(world, nullptr); } s->handles++; sh = s; }
     *out = new grootgpu_comm{sh, rank, idx};
     sh->barrier();
     return 0;
@@ -174,6 +174,9 @@ int grootgpu_comm_sync(grootgpu_comm* c) {          // the weights of all ranks 
     if (c->rank == 0) { std::lock_guard<std::mutex> lk(mu); total = 0; }
     return 0;
 }
-void grootgpu_comm_destroy(grootgpu_comm* c) { delete c; }
+void grootgpu_comm_destroy(grootgpu_comm* c) {
+    { std::lock_guard<std::mutex> lk(g_comm_mu); if (--c->sh->handles == 0) { g_comms.erase(c->sh->id); delete c->sh; } }
+    delete c;
+}
 
 }  // extern "C"
