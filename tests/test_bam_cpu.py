@@ -120,3 +120,15 @@ def test_block_writer_fuzz(root, tmp_path):
         assert r.returncode == 0 and r.stdout.decode().startswith("ok "), r.stdout.decode() + r.stderr.decode()
         _, blocks, delta, own = r.stdout.decode().split()
         assert int(delta) > 100 and int(own) > 100
+
+
+def test_bam_read_without_qualities_is_an_error(harness, tmp_path):
+    """FASTA input reaching the BAM writer: the reference panics when it reverse-complements or slices the empty quality
+    string (src/seqio/seqio.go:125-127, src/graph/alignment.go:121); the driver reports it instead of writing garbage."""
+    rng = np.random.default_rng(4)
+    b = Batch(rng, 20, 50, 60, 3, zero_frac=0.0)
+    b.quals = [b""] * len(b.quals)
+    f = str(tmp_path / "batch.bin")
+    b.write(f)
+    r = subprocess.run([harness, f, str(tmp_path / "o.bam"), "2", "-1", "1"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 2 and "quality string" in r.stderr.decode()
