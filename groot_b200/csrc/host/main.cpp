@@ -116,6 +116,8 @@ static int run_align(const Args& a) {
         const uint64_t* st = mapper.CollectReadStats();
         fprintf(stderr, "\tnumber of reads received from input: %llu\n\tmean read length: %.0f\n", static_cast<unsigned long long>(stream.rawCount()),
                 stream.rawCount() ? static_cast<double>(stream.lengthTotal()) / stream.rawCount() : 0.0);
+        fprintf(stderr, "\tseconds waiting for the FASTQ reader / in device calls / in the BAM stage (the three overlap): %.2f / %.2f / %.2f\n",
+                mapper.StageSeconds()[0], mapper.StageSeconds()[1], mapper.StageSeconds()[2]);    // no counterpart: where the wall clock goes
         if (st[1] == 0) { fprintf(stderr, "no reads could be mapped to the reference graphs\n"); destroy_all(); return 0; }   // sketch.go:328-334
         fprintf(stderr, "\ttotal number of unmapped reads: %llu\n\ttotal number of mapped reads: %llu\n\t\tmapped to one graph: %llu\n\t\tmapped to multiple graphs: %llu\n"
                         "\ttotal number of exact alignments: %llu\n\ttotal number of k-mers projected onto graphs: %llu\n",

@@ -11,6 +11,7 @@
 #include "bgzf.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <ctime>
 #include <memory>
@@ -407,6 +408,10 @@ std::string format_batch_bam(const BamBatch& in, unsigned workers, int level, bo
     return "";
 }
 
+namespace {
+double now_seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
 // ---- ReadMapper (sketch.go:308-351 -> boss.go:45-242, graphminion.go:40-103) ------------------------------------
 ReadMapper::ReadMapper(Info* info, const std::vector<grootgpu_index*>& indexes) : info_(info), indexes_(indexes), index_(indexes.at(0)) {}
 
@@ -584,6 +589,7 @@ int ReadMapper::Run(FastqStream& reads) {
         uint64_t n_records = 0; uint32_t path_bytes = 1;
         ReadBatch* batch = nullptr; int slot = 0;
         bool busy = false, stop = false;
+        double seconds = 0;                // time spent formatting, deflating and writing
         std::string error;
         std::mutex mu; std::condition_variable cv;
         std::thread th;
@@ -592,6 +598,7 @@ int ReadMapper::Run(FastqStream& reads) {
                 while (true) {
                     { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return stop || busy; }); if (!busy) return; }
                     std::string e;
+                    const double t0 = now_seconds();
                     try {
                         BamBatch bb;
                         bb.reads = batch; bb.cpairs = cpairs.data(); bb.n_pairs = cpairs.size(); bb.n_records = n_records;
@@ -605,7 +612,7 @@ int ReadMapper::Run(FastqStream& reads) {
                         if (e.empty()) for (unsigned t = 0; t < workers; t++) bam->append_blocks(outs[t]);
                     } catch (std::exception& ex) { e = ex.what(); }
                     feed.release(slot);
-                    { std::lock_guard<std::mutex> lk(mu); busy = false; if (error.empty()) error = e; }
+                    { std::lock_guard<std::mutex> lk(mu); busy = false; seconds += now_seconds() - t0; if (error.empty()) error = e; }
                     cv.notify_all();
                 }
             });
@@ -624,13 +631,15 @@ int ReadMapper::Run(FastqStream& reads) {
             cv.notify_all();
             return "";
         }
-        std::string drain() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !busy; }); return error; }
+        std::string drain(double* busy_seconds) { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !busy; }); *busy_seconds = seconds; return error; }
         ~BamStage() { { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !busy; }); stop = true; } cv.notify_all(); if (th.joinable()) th.join(); }
     };
     std::unique_ptr<BamStage> stage;
     if (bam) stage.reset(new BamStage(feed, bam.get(), info_, index_, graph_ref_base.data()));
     for (int slot_i = 0;; slot_i = (slot_i + 1) % kSlots) {
+        const double t_take = now_seconds();
         ReadBatch* bp = feed.take(slot_i);
+        stage_seconds_[0] += now_seconds() - t_take;
         if (!bp) break;
         bool handed_over = false;
         struct Release { BatchFeed& f; int i; bool& handed; ~Release() { if (!handed) f.release(i); } } release_slot{feed, slot_i, handed_over};
@@ -643,12 +652,14 @@ int ReadMapper::Run(FastqStream& reads) {
             prm.fixed_read_len = same ? static_cast<uint32_t>(L0) : 0u;
             team.prm.fixed_read_len = prm.fixed_read_len;
         }
+        const double t_dev = now_seconds();
         if (indexes_.size() > 1) {
             if ((rc = team.run(b.seq.data(), b.seq_off.data(), b.size(), &res, &err_))) return rc;
         } else {
             rc = grootgpu_align_batch(index_, b.seq.data(), b.seq_off.data(), b.size(), &prm, &res);
             if (rc) { err_ = grootgpu_last_error(); return rc; }
         }
+        stage_seconds_[1] += now_seconds() - t_dev;
         read_stats_[0] += res.received; read_stats_[1] += res.mapped; read_stats_[2] += res.multimapped;
         alignment_count_ += res.alignments;
         if (!stage) continue;
@@ -657,7 +668,7 @@ int ReadMapper::Run(FastqStream& reads) {
         handed_over = true;
     }
     if (stage) {
-        const std::string werr = stage->drain();
+        const std::string werr = stage->drain(&stage_seconds_[2]);
         stage.reset();
         if (!werr.empty()) { err_ = werr; return GROOTGPU_ERR_FORMAT; }
     }

@@ -140,6 +140,9 @@ class ReadMapper {
     // corresponds to num. reads, total num. mapped, num. multimapped, total k-mers (sketch.go:289,302-305)
     const uint64_t* CollectReadStats() const { return read_stats_; }
     uint64_t alignmentCount() const { return alignment_count_; }
+    // wall-clock seconds of the run spent [0] waiting for the reader, [1] inside the device calls, [2] by the BAM stage
+    // (it runs beside the other two: the largest of the three is what bounds the run)
+    const double* StageSeconds() const { return stage_seconds_; }
     const std::string& error() const { return err_; }
 
   private:
@@ -148,6 +151,7 @@ class ReadMapper {
     grootgpu_index* index_;                   // == indexes_[0]
     uint64_t read_stats_[4] = {0, 0, 0, 0};
     uint64_t alignment_count_ = 0;
+    double stage_seconds_[3] = {0, 0, 0};
     std::string err_;
 };
 

@@ -46,6 +46,7 @@ int main(int argc, char** argv) {
         const uint64_t* st = mapper.CollectReadStats();
         printf("%llu %llu %llu %llu %llu %.4f\n", (unsigned long long)st[0], (unsigned long long)st[1], (unsigned long long)st[2],
                (unsigned long long)mapper.alignmentCount(), (unsigned long long)st[3], dt);
+        fprintf(stderr, "stages: reader wait %.2f s, device calls %.2f s, BAM stage %.2f s\n", mapper.StageSeconds()[0], mapper.StageSeconds()[1], mapper.StageSeconds()[2]);
     } catch (std::exception& e) {
         fprintf(stderr, "%s\n", e.what());
         rc = 2;
