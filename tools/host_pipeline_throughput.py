@@ -1,0 +1,42 @@
+"""Wall-clock throughput of the host driver with the device mocked out (tests/cpp/mock_grootgpu.cpp): FASTQ -> ReadMapper
+(reader thread | device calls | BAM stage) -> BAM, on this machine's cores. It is the ceiling the I/O either side of the
+GPU path puts on `groot-b200 align`; the device itself sustains ~390 M reads/s end to end (bench.py).
+   python tools/host_pipeline_throughput.py [n_reads] [workers]"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
+workers = int(sys.argv[2]) if len(sys.argv) > 2 else os.cpu_count()
+L = 100
+tmp = "/tmp/groot_host_tp"
+os.makedirs(tmp, exist_ok=True)
+exe = os.path.join(tmp, "mapper_mock")
+host = os.path.join(ROOT, "groot_b200", "csrc", "host")
+subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-o", exe, os.path.join(ROOT, "tests", "cpp", "mapper_mock.cpp"),
+                       os.path.join(ROOT, "tests", "cpp", "mock_grootgpu.cpp"), os.path.join(host, "pipeline.cpp"), "-lz"])
+rng = np.random.default_rng(0)
+idx = np.arange(n)
+row = np.empty((n, 5 + 9 + 1 + L + 3 + L + 1), dtype=np.uint8)
+row[:, :5] = np.frombuffer(b"@SYN_", dtype=np.uint8)
+row[:, 5:14] = np.stack([(idx // 10 ** p) % 10 for p in range(8, -1, -1)], axis=1).astype(np.uint8) + ord("0")
+row[:, 14] = ord("\n")
+row[:, 15:15 + L] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), (n, L))
+row[:, 15 + L:18 + L] = np.frombuffer(b"\n+\n", dtype=np.uint8)
+row[:, 18 + L:18 + 2 * L] = np.repeat(rng.choice(np.frombuffer(b"F:,#", dtype=np.uint8), (n, L // 5), p=[0.8, 0.1, 0.07, 0.03]), 5, axis=1)
+row[:, 18 + 2 * L] = ord("\n")
+fq = os.path.join(tmp, "reads.fq")
+row.tofile(fq)
+files = [fq] * 4                                    # the same file four times: steady state without a 3.5 GB temporary
+total = 4 * n
+print("fastq: 4 x %d reads x %d bp, %d host threads for the BAM stage" % (n, L, workers))
+env = dict(os.environ, MOCK_FAST="1")
+for label, extra in (("--noAlign (reader + device calls only)", ["--noAlign"]), ("BAM to /dev/null", ["--bam", "/dev/null"]),
+                     ("BAM to a file", ["--bam", os.path.join(tmp, "out.bam")]), ("BAM to a file, zlib only (--bamDelta 0)", ["--bam", os.path.join(tmp, "out.bam"), "--delta", "0"])):
+    r = subprocess.run([exe, "-p", str(workers), "--batch", "1048576", "--paths", "40"] + extra + files, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, check=True)
+    f = r.stdout.decode().split()
+    secs = float(f[5])
+    print("%-46s %6.2f s  %5.2f M reads/s  (%s records; %s)" % (label, secs, total / secs / 1e6, f[3], r.stderr.decode().strip()))
