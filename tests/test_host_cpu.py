@@ -249,3 +249,55 @@ def test_header_is_c99_and_matches_the_ctypes_mirror(root, tmp_path):
         for fname, _ in cls._fields_:
             assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
     assert int(got["COMM_ID"]) == api.COMM_ID_BYTES
+
+
+def test_fastq_stream_differential_fuzz(root, tmp_path):
+    """FastqStream against a ten-line Python restatement of the reference's reader (DataStreamer: bufio.ScanLines per file,
+    '\\r' stripped, every line forwarded, empty ones as nil; FastqHandler: four non-nil lines make a read, line 1 must start
+    with '@', an incomplete last group is dropped — src/pipeline/sketch.go:41-77,214-238) on random messy files: blank
+    lines anywhere, CRLF, no final newline, '@' and '+' starting quality lines, several files, gzip, tiny batches."""
+    import gzip
+    import random
+    import subprocess
+    exe = str(tmp_path / "fastq_dump")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cpp", "fastq_dump.cpp"),
+                           os.path.join(root, "groot_b200", "csrc", "host", "pipeline.cpp"), "-L" + os.path.join(root, "groot_b200"), "-lgrootgpu", "-lz",
+                           "-pthread", "-Wl,-rpath," + os.path.join(root, "groot_b200")])
+    rng = random.Random(5)
+    alphabet = "ACGTN@+I#!:F"
+    for case in range(40):
+        files, lines_model = [], []
+        for fi in range(rng.randint(1, 3)):
+            lines = []
+            for _ in range(rng.randint(0, 60)):
+                kind = rng.random()
+                if kind < 0.2:
+                    lines.append("")
+                elif kind < 0.45:
+                    lines.append("@" + "".join(rng.choice(alphabet + " _/1") for _ in range(rng.randint(0, 20))))
+                else:
+                    lines.append("".join(rng.choice(alphabet) for _ in range(rng.randint(1, 130))))
+            eol = "\r\n" if rng.random() < 0.3 else "\n"
+            text = eol.join(lines) + (eol if lines and rng.random() < 0.7 else "")
+            path = tmp_path / ("c%d_%d.fq%s" % (case, fi, ".gz" if rng.random() < 0.3 else ""))
+            data = text.encode()
+            path.write_bytes(gzip.compress(data) if str(path).endswith(".gz") else data)
+            files.append(str(path))
+            # bufio.ScanLines: a final empty line (text ending in a newline) is not a line; "\r" before "\n" or at the very end is dropped
+            per_file = text.split("\n")
+            if per_file and per_file[-1] == "":
+                per_file.pop()
+            lines_model += [l[:-1] if l.endswith("\r") else l for l in per_file]
+        non_empty = [l for l in lines_model if l != ""]
+        want, fatal = [], False
+        for i in range(0, len(non_empty) - 3, 4):
+            if not non_empty[i].startswith("@"):
+                fatal = True
+                break
+            want.append("%s\t%s\t%s" % (non_empty[i], non_empty[i + 1], non_empty[i + 3]))
+        r = subprocess.run([exe, "--batch", str(rng.choice([1, 2, 7, 1000]))] + files, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        if fatal:
+            assert r.returncode == 2 and "does not begin with @" in r.stderr.decode(), (case, files)
+        else:
+            assert r.returncode == 0, (case, r.stderr.decode())
+            assert r.stdout.decode().splitlines()[:-1] == want, (case, files)
