@@ -218,14 +218,10 @@ BamWriter::BamWriter(FILE* out, const std::string& text, const std::vector<std::
 }
 BamWriter::~BamWriter() { if (!closed_) close(); }
 
-void BamWriter::compress_blocks(const uint8_t* data, size_t n, int level, std::vector<uint8_t>& out) {
-    BgzfDeflater::compress_plain(data, n, level, out);
-}
-
 void BamWriter::flush_block() {
     const size_t n = std::min(buf_.size(), kBgzfBlock);
     std::vector<uint8_t> blk;
-    compress_blocks(buf_.data(), n, level_, blk);
+    BgzfDeflater::compress_plain(buf_.data(), n, level_, blk);
     fwrite(blk.data(), 1, blk.size(), out_);
     buf_.erase(buf_.begin(), buf_.begin() + n);
 }
@@ -289,19 +285,6 @@ void BamWriter::repeat_record_at(uint8_t* p, const uint8_t* prev, size_t len, in
     st32(p + 8, static_cast<uint32_t>(pos));
     st16(p + 14, record_bin(pos, match_len));
     st16(p + 18, flag);
-}
-
-void BamWriter::format_record(std::vector<uint8_t>& buf, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
-                              uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual) {
-    const size_t at = buf.size();
-    buf.resize(at + record_size(name_len, clip_start, match_len, clip_end));
-    format_record_at(buf.data() + at, name, name_len, ref_id, pos, flag, clip_start, match_len, clip_end, seq, qual);
-}
-
-void BamWriter::write(const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag, uint32_t clip_start, uint32_t match_len,
-                      uint32_t clip_end, const uint8_t* seq, const uint8_t* qual) {
-    format_record(buf_, name, name_len, ref_id, pos, flag, clip_start, match_len, clip_end, seq, qual);
-    while (buf_.size() >= kBgzfBlock) flush_block();
 }
 
 void BamWriter::close() {

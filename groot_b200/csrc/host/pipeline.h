@@ -81,30 +81,22 @@ class FastqStream {
 };
 
 // Minimal BAM writer (what the reference gets from biogo/hts: bam.NewWriter + Write + Close, boss.go:45-105,225-241).
-// Records can be written one by one (write) or formatted and compressed elsewhere — by NumProc worker threads, each
-// on its own slice of a batch — and appended as ready-made BGZF blocks (append_blocks): a BAM stream is a
+// It writes the header; records are formatted and compressed elsewhere — by NumProc worker threads, each on its own
+// slice of a batch (format_batch_bam) — and appended as ready-made BGZF blocks (append_blocks): a BAM stream is a
 // concatenation of independently deflated blocks, and a record may straddle two of them.
 class BamWriter {
   public:
     BamWriter(FILE* out, const std::string& sam_header_text, const std::vector<std::pair<std::string, int32_t>>& refs, int level = -1);
     ~BamWriter();
-    // one sam.Record as AlignRead builds it (src/graph/alignment.go:114-156)
-    void write(const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag, uint32_t clip_start, uint32_t match_len,
-               uint32_t clip_end, const uint8_t* seq, const uint8_t* qual);
-    void append_blocks(const std::vector<uint8_t>& bgzf);   // flushes what write() buffered, then appends the blocks as they are
+    void append_blocks(const std::vector<uint8_t>& bgzf);   // flushes the header if it is still pending, then appends the blocks as they are
     void close();  // flushes and appends the BGZF EOF block
-    // the same record written at p (record_size bytes); returns the end
+    // one sam.Record as AlignRead builds it (src/graph/alignment.go:114-156), written at p (record_size bytes); returns the end
     static size_t record_size(uint32_t name_len, uint32_t clip_start, uint32_t match_len, uint32_t clip_end);
     static uint8_t* format_record_at(uint8_t* p, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
                                      uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual);
     // a further record of the same read (another path): a copy of prev with refID / pos / bin / flag replaced
     static void repeat_record_at(uint8_t* p, const uint8_t* prev, size_t len, int32_t ref_id, int32_t pos, uint16_t flag, uint32_t match_len);
     static uint16_t record_bin(int32_t pos, uint32_t match_len);
-    // the same record, appended to a caller-owned buffer of uncompressed BAM bytes
-    static void format_record(std::vector<uint8_t>& buf, const uint8_t* name, uint32_t name_len, int32_t ref_id, int32_t pos, uint16_t flag,
-                              uint32_t clip_start, uint32_t match_len, uint32_t clip_end, const uint8_t* seq, const uint8_t* qual);
-    // deflates data[0, n) into BGZF blocks of at most 0xff00 input bytes, appended to out
-    static void compress_blocks(const uint8_t* data, size_t n, int level, std::vector<uint8_t>& out);
   private:
     void flush_block();
     FILE* out_;
