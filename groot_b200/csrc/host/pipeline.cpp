@@ -2,6 +2,7 @@
 #include "pipeline.h"
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -17,6 +18,7 @@
 #include <memory>
 #include <mutex>
 #include <condition_variable>
+#include <deque>
 #include <stdexcept>
 #include <thread>
 
@@ -27,109 +29,217 @@ void ReadBatch::clear() {
     id_off.assign(1, 0); seq_off.assign(1, 0); qual_off.assign(1, 0);
 }
 
-// ---- DataStreamer (sketch.go:41-77) ---------------------------------------------------------------------------
-FastqStream::FastqStream(const std::vector<std::string>& files, bool fasta) : files_(files), fasta_(fasta) {
-    use_stdin_ = files.empty();   // no input file: scan STDIN (sketch.go:45-53)
-}
-FastqStream::~FastqStream() { close_current(); }
+// ---- DataStreamer (sketch.go:41-77): I/O and line scan on a thread of their own ----------------------------------
+// The reference's DataStreamer is a goroutine that scans its files line by line and sends every line down a channel.
+// Here it is a thread that takes the input a block at a time — a stretch of the mapped file for plain regular files,
+// read() / gzread into a buffer for gzip (decided by the magic bytes), FIFOs and STDIN —, finds the line ends (one SSE2
+// pass), and hands the block over together with the table of its lines; the consumer (FastqHandler, below) walks the
+// table and copies the lines into the batch. A block holds whole lines only: mapped blocks are cut behind a line end, the
+// unfinished tail of a buffered block is carried over to the front of the next (a line longer than a block makes the next
+// block larger); blocks do not span files; the last line of a file needs no newline, and a "\r" in front of the line end
+// is dropped (bufio.ScanLines, sketch.go:55-75).
+struct FastqStream::Scanner : std::enable_shared_from_this<FastqStream::Scanner> {
+    static constexpr size_t kBlock = 8u << 20;
+    struct Mapping {                       // a whole plain file, mapped read-only
+        const char* p = nullptr; size_t n = 0;
+        ~Mapping() { if (p) munmap(const_cast<char*>(p), n); }
+    };
+    struct Block {
+        const char* base = nullptr;        // the bytes of the block: `own`, or a stretch of a mapped file
+        std::vector<char> own;
+        std::shared_ptr<Mapping> map;      // keeps the file mapped while the block is in use
+        std::vector<uint32_t> off, len;    // the lines of the block
+        bool last = false;                 // nothing comes after this block (end of the input, or error set)
+        std::exception_ptr error;
+        void reset() { off.clear(); len.clear(); last = false; map.reset(); base = nullptr; off.reserve(kBlock / 32); len.reserve(kBlock / 32); }
+    };
+    std::vector<std::string> files;
+    bool use_stdin = false;
+    Block blocks[3];
+    std::deque<Block*> ready, free_blocks;
+    std::mutex mu; std::condition_variable cv;
+    bool stop = false, done = false;
+    std::thread th;
 
-void FastqStream::close_current() {
-    if (gz_) { gzclose(static_cast<gzFile>(gz_)); gz_ = nullptr; }
-    if (fd_ > 0) ::close(fd_);
-    fd_ = -1; open_ = false;
-}
+    // consumer side
+    Block* next_block() { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return !ready.empty(); }); Block* b = ready.front(); ready.pop_front(); return b; }
+    void give_back(Block* b) { b->map.reset(); { std::lock_guard<std::mutex> lk(mu); free_blocks.push_back(b); } cv.notify_all(); }
+    // scanner side
+    Block* take_free() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return stop || !free_blocks.empty(); });
+        if (stop) return nullptr;
+        Block* b = free_blocks.front(); free_blocks.pop_front();
+        lk.unlock();
+        b->reset();
+        return b;
+    }
+    void publish(Block* b) { { std::lock_guard<std::mutex> lk(mu); ready.push_back(b); } cv.notify_all(); }
 
-bool FastqStream::open_next() {
-    close_current();
-    if (buf_.size() < (8u << 20)) buf_.resize(8u << 20);
-    pos_ = end_ = 0; eof_ = false;
-    if (use_stdin_) {
-        if (stdin_done_) return false;
-        stdin_done_ = true;
-        gz_ = gzdopen(0, "rb");                 // a pipe cannot be rewound after a look at it: zlib's transparent mode takes plain and gzip alike
-        if (!gz_) throw std::runtime_error("cannot open input");
-        gzbuffer(static_cast<gzFile>(gz_), 1 << 20);
-        open_ = true;
-        return true;
+    struct Input {                         // one open file: mapped, read through its descriptor, or a gzFile
+        gzFile gz = nullptr; int fd = -1;
+        std::shared_ptr<Mapping> map;
+        ~Input() { if (gz) gzclose(gz); if (fd > 0) ::close(fd); }
+        size_t read(char* dst, size_t n) {             // 0 = end of file
+            if (gz) { const int got = gzread(gz, dst, static_cast<unsigned>(std::min<size_t>(n, 1u << 30))); if (got < 0) throw std::runtime_error("error reading input file"); return static_cast<size_t>(got); }
+            ssize_t got;
+            do got = ::read(fd, dst, std::min<size_t>(n, 1u << 30)); while (got < 0 && errno == EINTR);
+            if (got < 0) throw std::runtime_error("error reading input file");
+            return static_cast<size_t>(got);
+        }
+    };
+    void open(Input& in, size_t file_i) const {
+        auto as_gz = [&](int fd) {              // zlib's transparent mode takes plain and gzip alike; it owns the descriptor
+            in.gz = gzdopen(fd, "rb");
+            if (!in.gz) throw std::runtime_error("cannot open input");
+            gzbuffer(in.gz, 1 << 20);
+        };
+        if (use_stdin) { as_gz(0); return; }   // no input file: scan STDIN (sketch.go:45-53); a pipe cannot be rewound after a look at it
+        in.fd = ::open(files[file_i].c_str(), O_RDONLY);
+        if (in.fd < 0) throw std::runtime_error("open " + files[file_i] + ": no such file or directory");   // misc.ErrorCheck(err) -> log.Fatal
+        struct stat sb;
+        if (fstat(in.fd, &sb) != 0 || !S_ISREG(sb.st_mode)) { const int fd = in.fd; in.fd = -1; as_gz(fd); return; }   // a FIFO / process substitution: as STDIN
+        if (sb.st_size == 0) return;            // nothing to read: the read path meets end-of-file at once
+        // A regular file is mapped: its pages are scanned and copied from where the page cache has them, without the
+        // read() copy into a block first (a third of the scanner's time). gzip is decided by content (the reference keys
+        // on the ".gz" extension, sketch.go:60-68): the magic bytes hand the descriptor to zlib instead.
+        void* m = mmap(nullptr, static_cast<size_t>(sb.st_size), PROT_READ, MAP_PRIVATE, in.fd, 0);
+        if (m == MAP_FAILED) return;            // cannot be mapped: plain read()
+        in.map = std::make_shared<Mapping>();
+        in.map->p = static_cast<const char*>(m); in.map->n = static_cast<size_t>(sb.st_size);
+        if (in.map->n >= 2 && static_cast<uint8_t>(in.map->p[0]) == 0x1f && static_cast<uint8_t>(in.map->p[1]) == 0x8b) {
+            in.map.reset();
+            const int fd = in.fd; in.fd = -1;
+            as_gz(fd);
+            return;
+        }
+        madvise(m, in.map->n, MADV_SEQUENTIAL);
     }
-    if (file_i_ >= files_.size()) return false;
-    fd_ = ::open(files_[file_i_].c_str(), O_RDONLY);
-    if (fd_ < 0) throw std::runtime_error("open " + files_[file_i_] + ": no such file or directory");   // misc.ErrorCheck(err) -> log.Fatal
-    file_i_++;
-    struct stat sb;
-    if (fstat(fd_, &sb) != 0 || !S_ISREG(sb.st_mode)) {           // a FIFO / process substitution cannot be rewound either: as STDIN
-        gz_ = gzdopen(fd_, "rb");
-        if (!gz_) throw std::runtime_error("cannot open input");
-        fd_ = -1;
-        gzbuffer(static_cast<gzFile>(gz_), 1 << 20);
-        open_ = true;
-        return true;
+    static void add_line(Block* b, const char* d, size_t start, size_t n) {
+        if (n && d[start + n - 1] == '\r') n--;
+        b->off.push_back(static_cast<uint32_t>(start)); b->len.push_back(static_cast<uint32_t>(n));
     }
-    // gzip is decided by content (the reference keys on the ".gz" extension, sketch.go:60-68): the first block is read
-    // here; a gzip magic hands the descriptor to zlib, anything else is read straight into the block buffer (one copy
-    // less than gzread's transparent mode; the reader's time is in the line scan and the per-line copies either way).
-    size_t got = 0;
-    while (got < 2) {
-        const ssize_t r = ::read(fd_, buf_.data() + got, buf_.size() - got);
-        if (r < 0) { if (errno == EINTR) continue; throw std::runtime_error("error reading input file"); }
-        if (r == 0) break;
-        got += static_cast<size_t>(r);
-    }
-    if (got >= 2 && static_cast<uint8_t>(buf_[0]) == 0x1f && static_cast<uint8_t>(buf_[1]) == 0x8b) {
-        if (::lseek(fd_, 0, SEEK_SET) != 0) throw std::runtime_error("cannot rewind input file");
-        gz_ = gzdopen(fd_, "rb");               // zlib owns the descriptor from here
-        if (!gz_) throw std::runtime_error("cannot open input");
-        fd_ = -1;
-        gzbuffer(static_cast<gzFile>(gz_), 1 << 20);
-    } else {
-        end_ = got;
-        if (got == 0) eof_ = true;
-    }
-    open_ = true;
-    return true;
-}
-
-// more bytes of the current file behind the unconsumed tail; false when the file has no more
-bool FastqStream::refill() {
-    if (eof_) return false;
-    if (buf_.size() < (8u << 20)) buf_.resize(8u << 20);
-    if (pos_ > 0) { memmove(buf_.data(), buf_.data() + pos_, end_ - pos_); end_ -= pos_; pos_ = 0; }
-    if (end_ == buf_.size()) buf_.resize(buf_.size() * 2);           // one line longer than the buffer
-    ssize_t got;
-    if (gz_) {
-        got = gzread(static_cast<gzFile>(gz_), buf_.data() + end_, static_cast<unsigned>(std::min<size_t>(buf_.size() - end_, 1u << 30)));
-        if (got < 0) throw std::runtime_error("error reading input file");
-    } else {
-        do got = ::read(fd_, buf_.data() + end_, std::min<size_t>(buf_.size() - end_, 1u << 30)); while (got < 0 && errno == EINTR);
-        if (got < 0) throw std::runtime_error("error reading input file");
-    }
-    if (got == 0) { eof_ = true; return false; }
-    end_ += static_cast<size_t>(got);
-    return true;
-}
-
-// bufio.Scanner with ScanLines: strips the trailing "\n" and an optional "\r"; the last line of a file needs no newline;
-// every file is scanned on its own (sketch.go:55-75)
-bool FastqStream::getline(const char*& line, size_t& len) {
-    while (true) {
-        if (!open_ && !open_next()) return false;
-        while (true) {
-            const char* nl = pos_ < end_ ? static_cast<const char*>(memchr(buf_.data() + pos_, '\n', end_ - pos_)) : nullptr;
-            if (nl) {
-                line = buf_.data() + pos_; len = static_cast<size_t>(nl - line);
-                pos_ += len + 1;
-                if (len && line[len - 1] == '\r') len--;
-                return true;
+    // the lines of d[0, n) into the block's table; returns where the unfinished last line starts (n if there is none)
+    static size_t scan_lines(Block* b, const char* d, size_t n) {
+        size_t p = 0, i = 0;
+#if defined(__SSE2__)
+        // every line end in one pass, 16 bytes per step (a memchr call per 15-150 byte line costs more in set-up than in scanning)
+        const __m128i nlv = _mm_set1_epi8('\n');
+        for (; i + 16 <= n; i += 16) {
+            unsigned m = static_cast<unsigned>(_mm_movemask_epi8(_mm_cmpeq_epi8(_mm_loadu_si128(reinterpret_cast<const __m128i*>(d + i)), nlv)));
+            while (m) {
+                const size_t e = i + static_cast<unsigned>(__builtin_ctz(m));
+                add_line(b, d, p, e - p);
+                p = e + 1;
+                m &= m - 1;
             }
-            if (!refill()) break;
         }
-        if (pos_ < end_) {                                          // unterminated last line
-            line = buf_.data() + pos_; len = end_ - pos_;
-            pos_ = end_;
-            if (len && line[len - 1] == '\r') len--;
-            return true;
+#endif
+        for (i = std::max(i, p); i < n;) {
+            const char* nl = static_cast<const char*>(memchr(d + i, '\n', n - i));
+            if (!nl) break;
+            add_line(b, d, p, static_cast<size_t>(nl - d) - p);
+            p = i = static_cast<size_t>(nl - d) + 1;
         }
-        close_current();                                            // end of this file
+        return p;
+    }
+    // a mapped file: blocks are stretches of the mapping cut behind a line end (no tail to carry over)
+    bool run_mapped(const std::shared_ptr<Mapping>& map) {
+        const char* base = map->p;
+        const size_t size = map->n;
+        for (size_t pos = 0; pos < size;) {
+            size_t end = std::min(pos + kBlock, size);
+            if (end < size) {
+                const char* nl = static_cast<const char*>(memchr(base + end - 1, '\n', size - (end - 1)));
+                end = nl ? static_cast<size_t>(nl - base) + 1 : size;
+            }
+            if (end - pos > 0xfff00000u) throw std::runtime_error("a line of the input is longer than 4 GB");
+            Block* b = take_free();
+            if (!b) return false;
+            b->map = map; b->base = base + pos;
+            const size_t n = end - pos, p = scan_lines(b, b->base, n);
+            if (p < n) add_line(b, b->base, p, n - p);                    // unterminated last line of the file
+            publish(b);
+            pos = end;
+        }
+        return true;
+    }
+    // anything else: blocks are filled by read() / gzread; the unfinished tail of one goes to the front of the next
+    bool run_read(Input& in) {
+        std::vector<char> carry;
+        size_t want = kBlock;
+        for (bool eof = false; !eof;) {
+            Block* b = take_free();
+            if (!b) return false;
+            const size_t cap = std::max(want, carry.size() + kBlock / 2);
+            if (cap > 0xfff00000u) throw std::runtime_error("a line of the input is longer than 4 GB");
+            if (b->own.size() < cap) b->own.resize(cap);
+            char* d = b->own.data();
+            b->base = d;
+            size_t n = carry.size();
+            if (n) memcpy(d, carry.data(), n);
+            carry.clear();
+            const size_t got = in.fd >= 0 || in.gz ? in.read(d + n, b->own.size() - n) : 0;   // neither: an empty file
+            if (got == 0) eof = true;
+            n += got;
+            const size_t p = scan_lines(b, d, n);
+            if (p < n) {
+                if (eof) add_line(b, d, p, n - p);                            // unterminated last line of the file
+                else { carry.assign(d + p, d + n); if (p == 0) want = 2 * n + kBlock; }   // a line longer than the block: a larger one next
+            }
+            publish(b);
+        }
+        return true;
+    }
+    void run() {
+        try {
+            const size_t n_files = use_stdin ? 1 : files.size();
+            for (size_t fi = 0; fi < n_files; fi++) {
+                Input in;
+                open(in, fi);
+                if (!(in.map ? run_mapped(in.map) : run_read(in))) return;
+            }
+            if (Block* b = take_free()) { b->last = true; publish(b); }
+        } catch (...) {
+            if (Block* b = take_free()) { b->last = true; b->error = std::current_exception(); publish(b); }
+        }
+        { std::lock_guard<std::mutex> lk(mu); done = true; }
+    }
+    void start() {
+        for (Block& b : blocks) free_blocks.push_back(&b);
+        th = std::thread([self = shared_from_this()] { self->run(); });   // the thread keeps the scanner alive (see ~FastqStream)
+    }
+};
+
+FastqStream::FastqStream(const std::vector<std::string>& files, bool fasta) : files_(files), fasta_(fasta) {}
+
+FastqStream::~FastqStream() {
+    if (!scan_) return;
+    bool finished;
+    { std::lock_guard<std::mutex> lk(scan_->mu); scan_->stop = true; finished = scan_->done; }
+    scan_->cv.notify_all();
+    // A scanner that has run to the end of its input is joined. One that is still going — the consumer gave up early, the
+    // scanner may sit in a read() on a pipe that delivers nothing — is left to notice `stop` on its own: it holds the only
+    // other reference to its state.
+    if (finished) scan_->th.join(); else scan_->th.detach();
+}
+
+// the next line of the input: a view into the current block, valid until the next call
+bool FastqStream::getline(const char*& line, size_t& len) {
+    if (!scan_) {
+        scan_ = std::make_shared<Scanner>();
+        scan_->files = files_; scan_->use_stdin = files_.empty();
+        scan_->start();
+    }
+    while (true) {
+        Scanner::Block* cur = static_cast<Scanner::Block*>(cur_);
+        if (cur) {
+            if (line_i_ < cur->off.size()) { line = cur->base + cur->off[line_i_]; len = cur->len[line_i_]; line_i_++; return true; }
+            if (cur->last) { if (cur->error) std::rethrow_exception(cur->error); return false; }
+            scan_->give_back(cur);
+        }
+        cur_ = scan_->next_block();
+        line_i_ = 0;
     }
 }
 
@@ -137,7 +247,7 @@ bool FastqStream::getline(const char*& line, size_t& len) {
 namespace {
 // a line goes into the batch with one memmove: iterators of the vector's own element type (a `const char*` range is
 // converted element by element, which was 80 % of the reader's time)
-inline void append(std::vector<uint8_t>& v, const char* p, size_t n) {
+inline void append(ByteVec& v, const char* p, size_t n) {
     const uint8_t* q = reinterpret_cast<const uint8_t*>(p);
     v.insert(v.end(), q, q + n);
 }
@@ -168,12 +278,56 @@ bool FastqStream::next(ReadBatch& b, uint32_t max_reads) {
         }
         return b.size() > 0;
     }
-    // a record's four lines are copied into the batch as they are found (a view does not survive the next getline).
-    // An EMPTY line never fills a slot: the DataStreamer forwards it as a nil slice (append([]byte(nil), ...) of nothing,
-    // sketch.go:49,70) and the handler's `l1 == nil / l2 == nil / ...` tests take the next line for the same slot
-    // (sketch.go:216-236), so blank lines anywhere in a FASTQ stream are skipped.
     auto next_line = [&](const char*& q, size_t& m) { while (getline(q, m)) if (m != 0) return true; return false; };
+    std::vector<uint32_t> plan;                      // per planned record: the table entries of its ID, bases and qualities
     while (b.size() < max_reads) {
+        // Fast path: the records that lie completely inside the current block. Their lines are already in the block's
+        // table, so the batch offsets are a running sum (no data touched but the '@'), and the copies — what the reader's
+        // time goes into — are independent per record: with copy_threads_ > 1 they are spread over helper threads.
+        Scanner::Block* cur = static_cast<Scanner::Block*>(cur_);
+        if (cur && line_i_ < cur->off.size()) {
+            const char* d = cur->base;
+            const uint32_t *off = cur->off.data(), *len = cur->len.data();
+            const size_t n_lines = cur->off.size(), first = b.size();
+            size_t li = line_i_;
+            uint64_t id_at = b.id.size(), seq_at = b.seq.size(), qual_at = b.qual.size(), bases = 0;
+            plan.clear();
+            while (first + plan.size() / 3 < max_reads) {
+                size_t q = li; uint32_t idx[4]; int got = 0;
+                while (q < n_lines && got < 4) { if (len[q]) idx[got++] = static_cast<uint32_t>(q); q++; }
+                if (got < 4 || d[off[idx[0]]] != '@') break;      // runs into the next block / not a header: the slow path decides
+                plan.insert(plan.end(), {idx[0], idx[1], idx[3]});
+                id_at += len[idx[0]]; seq_at += len[idx[1]]; qual_at += len[idx[3]]; bases += len[idx[1]];
+                b.id_off.push_back(id_at); b.seq_off.push_back(seq_at); b.qual_off.push_back(qual_at);
+                li = q;
+            }
+            if (!plan.empty()) {
+                b.id.resize(id_at); b.seq.resize(seq_at); b.qual.resize(qual_at);
+                const size_t n_rec = plan.size() / 3;
+                auto copy = [&](size_t r0, size_t r1) {
+                    for (size_t r = r0; r < r1; r++) {
+                        const uint32_t* e = &plan[3 * r];
+                        memcpy(b.id.data() + b.id_off[first + r], d + off[e[0]], len[e[0]]);
+                        memcpy(b.seq.data() + b.seq_off[first + r], d + off[e[1]], len[e[1]]);
+                        memcpy(b.qual.data() + b.qual_off[first + r], d + off[e[2]], len[e[2]]);
+                    }
+                };
+                const unsigned T = n_rec >= 8192 ? copy_threads_ : 1u;
+                if (T > 1) {
+                    std::vector<std::thread> th;
+                    for (unsigned t = 1; t < T; t++) th.emplace_back(copy, n_rec * t / T, n_rec * (t + 1) / T);
+                    copy(0, n_rec / T);
+                    for (auto& x : th) x.join();
+                } else copy(0, n_rec);
+                raw_count_ += n_rec; length_total_ += bases;
+                line_i_ = li;
+                continue;
+            }
+        }
+        // Slow path, one record: its four lines are copied into the batch as they are found (a view does not survive the
+        // next getline). An EMPTY line never fills a slot: the DataStreamer forwards it as a nil slice (append([]byte(nil), ...)
+        // of nothing, sketch.go:49,70) and the handler's `l1 == nil / l2 == nil / ...` tests take the next line for the same
+        // slot (sketch.go:216-236), so blank lines anywhere in a FASTQ stream are skipped.
         if (!next_line(p, n)) break;
         const size_t id0 = b.id.size(), seq0 = b.seq.size(), qual0 = b.qual.size();
         append(b.id, p, n);
@@ -529,6 +683,8 @@ int ReadMapper::Run(FastqStream& reads) {
     // goroutine): DataStreamer/FastqHandler parse batch i+2 on the reader thread while batch i+1 is on the GPU (this thread)
     // and the BAM stage formats, deflates and writes batch i. Three batch buffers go round; a buffer is released by the
     // last stage that needs it (the BAM stage reads names, bases and qualities from it).
+    // the reader's line copies may use helper threads: freely when there is no BAM stage to feed (--noAlign), sparingly beside it
+    reads.set_copy_threads(info_->Sketch.NoExactAlign ? static_cast<unsigned>(std::min(std::max(1, info_->NumProc), 4)) : (info_->NumProc >= 8 ? 2u : 1u));
     constexpr int kSlots = 3;
     struct BatchFeed {
         FastqStream& reads; uint32_t batch_reads;

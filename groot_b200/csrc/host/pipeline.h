@@ -15,6 +15,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <functional>
+#include <memory>
+#include <new>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -42,9 +45,21 @@ struct Info {
     bool BamDelta = true;                     // repeated records of one read as back-references written directly (bgzf.h); false = zlib only
 };
 
+// A byte vector whose resize() leaves new bytes uninitialised: the reader sizes the batch arrays first and then lets
+// several threads copy lines into them; zero-filling 200 MB per batch first would double the memory traffic.
+template <class T> struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { using other = NoInitAlloc<U>; };
+    NoInitAlloc() = default;
+    template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new (static_cast<void*>(p)) U; else ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+};
+using ByteVec = std::vector<uint8_t, NoInitAlloc<uint8_t>>;
+
 // seqio.FASTQread for a whole batch (src/seqio/seqio.go:26-37), struct-of-arrays
 struct ReadBatch {
-    std::vector<uint8_t> id, seq, qual;        // ID lines incl. the leading '@' / bases / raw ASCII qualities
+    ByteVec id, seq, qual;                     // ID lines incl. the leading '@' / bases / raw ASCII qualities
     std::vector<uint64_t> id_off, seq_off, qual_off;
     uint32_t size() const { return seq_off.empty() ? 0 : static_cast<uint32_t>(seq_off.size() - 1); }
     void clear();
@@ -57,25 +72,21 @@ class FastqStream {
     ~FastqStream();
     // fills `b` with up to max_reads reads; false when the input is exhausted and b is empty
     bool next(ReadBatch& b, uint32_t max_reads);
+    // helper threads for copying parsed lines into the batch (1 = none; the I/O + line scan thread is separate)
+    void set_copy_threads(unsigned n) { copy_threads_ = n < 1 ? 1 : n; }
     uint64_t rawCount() const { return raw_count_; }
     uint64_t lengthTotal() const { return length_total_; }
 
   private:
-    bool getline(const char*& line, size_t& len);   // view into the block buffer, valid until the next call
-    bool open_next();
-    bool refill();
+    bool getline(const char*& line, size_t& len);   // view into the current block, valid until the next call
+    struct Scanner;                                 // reads blocks and finds their lines on a thread of its own (pipeline.cpp)
+    std::shared_ptr<Scanner> scan_;
+    void* cur_ = nullptr;                           // Scanner::Block being consumed
+    size_t line_i_ = 0;
+    unsigned copy_threads_ = 1;
     std::vector<std::string> files_;
-    size_t file_i_ = 0;
-    void* gz_ = nullptr;  // gzFile when the current file starts with the gzip magic
-    int fd_ = -1;         // else the descriptor itself (0 = STDIN)
-    bool open_ = false;
-    void close_current();
     bool fasta_;
-    bool use_stdin_ = false, stdin_done_ = false;
     std::string pending_header_, fasta_seq_;
-    std::vector<char> buf_;        // block buffer: lines are found with memchr and copied once, into the batch
-    size_t pos_ = 0, end_ = 0;
-    bool eof_ = true;              // of the current file
     bool fasta_done_ = false;
     uint64_t raw_count_ = 0, length_total_ = 0;
 };

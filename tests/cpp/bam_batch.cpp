@@ -19,7 +19,7 @@ struct Reader {
     FILE* f;
     void get(void* p, size_t n) { if (n && fread(p, 1, n, f) != n) throw std::runtime_error("short batch file"); }
     template <class T> T one() { T v; get(&v, sizeof v); return v; }
-    template <class T> void vec(std::vector<T>& v, size_t n) { v.resize(n); get(v.data(), n * sizeof(T)); }
+    template <class V> void vec(V& v, size_t n) { v.resize(n); get(v.data(), n * sizeof(typename V::value_type)); }
 };
 }  // namespace
 

@@ -1,5 +1,5 @@
 // Test harness: prints every read the host driver's FastqStream (DataStreamer + FastqHandler + FastqChecker mirror)
-// yields, one "id<TAB>seq<TAB>qual" line each, then "#count total_length". argv: [--fasta] [--batch N] [--count] files...
+// yields, one "id<TAB>seq<TAB>qual" line each, then "#count total_length". argv: [--fasta] [--batch N] [--count] [--threads T] files...
 // (--count: only the last line — for timing the reader)
 #include <cstdio>
 #include <cstdlib>
@@ -13,15 +13,18 @@
 int main(int argc, char** argv) {
     bool fasta = false, count_only = false;
     uint32_t batch = 3;
+    unsigned threads = 1;
     std::vector<std::string> files;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--fasta")) fasta = true;
         else if (!strcmp(argv[i], "--count")) count_only = true;
+        else if (!strcmp(argv[i], "--threads")) threads = static_cast<unsigned>(atoi(argv[++i]));
         else if (!strcmp(argv[i], "--batch")) batch = static_cast<uint32_t>(atoi(argv[++i]));
         else files.push_back(argv[i]);
     }
     try {
         groot_host::FastqStream s(files, fasta);
+        s.set_copy_threads(threads);
         groot_host::ReadBatch b;
         while (s.next(b, batch))
             for (uint32_t r = 0; r < b.size() && !count_only; r++)

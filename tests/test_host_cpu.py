@@ -301,3 +301,39 @@ def test_fastq_stream_differential_fuzz(root, tmp_path):
         else:
             assert r.returncode == 0, (case, r.stderr.decode())
             assert r.stdout.decode().splitlines()[:-1] == want, (case, files)
+
+
+def test_fastq_stream_parallel_copy(root, tmp_path):
+    """Blocks with thousands of records take the planned path of FastqStream::next (offsets first, then the line copies
+    spread over helper threads): same reads, same order, for any thread count and batch size, from a mapped plain file,
+    a gzip file and a pipe; also under ThreadSanitizer."""
+    import gzip
+    import subprocess
+    import numpy as np
+    rng = np.random.default_rng(3)
+    n = 60000
+    recs = []
+    for r in range(n):
+        L = int(rng.integers(30, 150))
+        recs.append(("@r%d len=%d" % (r, L), "".join(rng.choice(list("ACGTN"), L)), "".join(rng.choice(list("FI:#@+"), L))))
+    text = "".join("%s\n%s\n+\n%s\n" % rec for rec in recs[:40000]) + "\n\n" + "".join("%s\r\n%s\r\n+x\r\n%s\r\n" % rec for rec in recs[40000:])
+    plain = tmp_path / "big.fq"; plain.write_text(text)
+    gz = tmp_path / "big.fq.gz"; gz.write_bytes(gzip.compress(text.encode(), 1))
+    want = ["%s\t%s\t%s" % rec for rec in recs] + ["#%d %d" % (n, sum(len(r[1]) for r in recs))]
+    src = [os.path.join(root, "tests", "cpp", "fastq_dump.cpp"), os.path.join(root, "groot_b200", "csrc", "host", "pipeline.cpp"),
+           "-L" + os.path.join(root, "groot_b200"), "-lgrootgpu", "-lz", "-pthread", "-Wl,-rpath," + os.path.join(root, "groot_b200")]
+    exe = str(tmp_path / "fastq_dump")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe] + src)
+    for threads, batch, f in ((1, 1000000, plain), (4, 1000000, plain), (3, 7001, plain), (4, 1000000, gz), (2, 20000, gz)):
+        out = subprocess.run([exe, "--threads", str(threads), "--batch", str(batch), str(f)], stdout=subprocess.PIPE, check=True).stdout.decode().splitlines()
+        assert out == want, (threads, batch, str(f))
+    with open(plain, "rb") as fh:                                                  # STDIN: a pipe
+        out = subprocess.run([exe, "--threads", "4", "--batch", "1000000"], stdin=fh, stdout=subprocess.PIPE, check=True).stdout.decode().splitlines()
+    assert out == want
+    tsan = str(tmp_path / "fastq_dump_tsan")
+    subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=thread", "-std=c++17", "-o", tsan] + src)
+    r = subprocess.run([tsan, "--threads", "4", "--batch", "25000", "--count", str(plain), str(gz)], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    if b"FATAL: ThreadSanitizer" in r.stderr:
+        pytest.skip("ThreadSanitizer cannot run in this environment")
+    assert r.returncode == 0 and b"ThreadSanitizer" not in r.stderr, r.stderr.decode()[-3000:]
+    assert r.stdout.decode().split()[0] == "#%d" % (2 * n)
