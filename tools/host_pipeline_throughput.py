@@ -36,7 +36,12 @@ print("fastq: 4 x %d reads x %d bp, %d host threads for the BAM stage" % (n, L, 
 env = dict(os.environ, MOCK_FAST="1")
 for label, extra in (("--noAlign (reader + device calls only)", ["--noAlign"]), ("BAM to /dev/null", ["--bam", "/dev/null"]),
                      ("BAM to a file", ["--bam", os.path.join(tmp, "out.bam")]), ("BAM to a file, zlib only (--bamDelta 0)", ["--bam", os.path.join(tmp, "out.bam"), "--delta", "0"])):
-    r = subprocess.run([exe, "-p", str(workers), "--batch", "1048576", "--paths", "40"] + extra + files, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, check=True)
+    best = None
+    for _ in range(1 if "--delta" in extra else 3):             # a shared box: best of three (the slow zlib-only run once)
+        r = subprocess.run([exe, "-p", str(workers), "--batch", "1048576", "--paths", "40"] + extra + files, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, check=True)
+        if best is None or float(r.stdout.decode().split()[5]) < float(best.stdout.decode().split()[5]):
+            best = r
+    r = best
     f = r.stdout.decode().split()
     secs = float(f[5])
     print("%-46s %6.2f s  %5.2f M reads/s  (%s records; %s)" % (label, secs, total / secs / 1e6, f[3], r.stderr.decode().strip()))
