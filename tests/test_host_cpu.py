@@ -174,16 +174,24 @@ def test_cli_report_matches_reference_logic(root, tmp_path):
     assert r.returncode != 0
 
 
-def test_fastq_stream_edge_cases(root, tmp_path):
+@pytest.fixture(scope="module")
+def fastq_dump(root, tmp_path_factory):
+    """tests/cpp/fastq_dump.cpp linked with the host driver's reader: prints every read FastqStream yields."""
+    import subprocess
+    exe = str(tmp_path_factory.mktemp("fastq") / "fastq_dump")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cpp", "fastq_dump.cpp"),
+                           os.path.join(root, "groot_b200", "csrc", "host", "pipeline.cpp"), "-L" + os.path.join(root, "groot_b200"), "-lgrootgpu", "-lz",
+                           "-pthread", "-Wl,-rpath," + os.path.join(root, "groot_b200")])
+    return exe
+
+
+def test_fastq_stream_edge_cases(root, tmp_path, fastq_dump):
     """The host driver's reader (block buffer + memchr) keeps the reference's line semantics (src/pipeline/sketch.go:41-77,
     175-238): CRLF, a last line without newline, an incomplete trailing record dropped, every file scanned on its own,
     gzip by content, FASTA mode ('>' entries, an empty line ends the input), '@' check -> fatal, batches of any size."""
     import gzip
     import subprocess
-    exe = str(tmp_path / "fastq_dump")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cpp", "fastq_dump.cpp"),
-                           os.path.join(root, "groot_b200", "csrc", "host", "pipeline.cpp"), "-L" + os.path.join(root, "groot_b200"), "-lgrootgpu", "-lz",
-                           "-pthread", "-Wl,-rpath," + os.path.join(root, "groot_b200")])
+    exe = fastq_dump
     def run(*args):
         r = subprocess.run([exe] + [str(a) for a in args], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
         return r.returncode, r.stdout.decode().splitlines(), r.stderr.decode()
@@ -251,7 +259,7 @@ def test_header_is_c99_and_matches_the_ctypes_mirror(root, tmp_path):
     assert int(got["COMM_ID"]) == api.COMM_ID_BYTES
 
 
-def test_fastq_stream_differential_fuzz(root, tmp_path):
+def test_fastq_stream_differential_fuzz(root, tmp_path, fastq_dump):
     """FastqStream against a ten-line Python restatement of the reference's reader (DataStreamer: bufio.ScanLines per file,
     '\\r' stripped, every line forwarded, empty ones as nil; FastqHandler: four non-nil lines make a read, line 1 must start
     with '@', an incomplete last group is dropped — src/pipeline/sketch.go:41-77,214-238) on random messy files: blank
@@ -259,10 +267,7 @@ def test_fastq_stream_differential_fuzz(root, tmp_path):
     import gzip
     import random
     import subprocess
-    exe = str(tmp_path / "fastq_dump")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(root, "tests", "cpp", "fastq_dump.cpp"),
-                           os.path.join(root, "groot_b200", "csrc", "host", "pipeline.cpp"), "-L" + os.path.join(root, "groot_b200"), "-lgrootgpu", "-lz",
-                           "-pthread", "-Wl,-rpath," + os.path.join(root, "groot_b200")])
+    exe = fastq_dump
     rng = random.Random(5)
     alphabet = "ACGTN@+I#!:F"
     for case in range(40):
@@ -303,7 +308,7 @@ def test_fastq_stream_differential_fuzz(root, tmp_path):
             assert r.stdout.decode().splitlines()[:-1] == want, (case, files)
 
 
-def test_fastq_stream_parallel_copy(root, tmp_path):
+def test_fastq_stream_parallel_copy(root, tmp_path, fastq_dump):
     """Blocks with thousands of records take the planned path of FastqStream::next (offsets first, then the line copies
     spread over helper threads): same reads, same order, for any thread count and batch size, from a mapped plain file,
     a gzip file and a pipe; also under ThreadSanitizer."""
@@ -322,8 +327,7 @@ def test_fastq_stream_parallel_copy(root, tmp_path):
     want = ["%s\t%s\t%s" % rec for rec in recs] + ["#%d %d" % (n, sum(len(r[1]) for r in recs))]
     src = [os.path.join(root, "tests", "cpp", "fastq_dump.cpp"), os.path.join(root, "groot_b200", "csrc", "host", "pipeline.cpp"),
            "-L" + os.path.join(root, "groot_b200"), "-lgrootgpu", "-lz", "-pthread", "-Wl,-rpath," + os.path.join(root, "groot_b200")]
-    exe = str(tmp_path / "fastq_dump")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe] + src)
+    exe = fastq_dump
     for threads, batch, f in ((1, 1000000, plain), (4, 1000000, plain), (3, 7001, plain), (4, 1000000, gz), (2, 20000, gz)):
         out = subprocess.run([exe, "--threads", str(threads), "--batch", str(batch), str(f)], stdout=subprocess.PIPE, check=True).stdout.decode().splitlines()
         assert out == want, (threads, batch, str(f))
